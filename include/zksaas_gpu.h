@@ -1,0 +1,154 @@
+/* zksaas_gpu.h -- C ABI of libzksaas_gpu.so: the B200 (sm_100a) replacement for the data-parallel
+ * prover core of zk-SaaS (tangle-network/zk-SaaS).  The reference has no FFI of its own; each
+ * entry point below replaces the *body* of one Rust function (or the arkworks call inside it)
+ * and cites it as  <file>:<line>  relative to the reference root.  INTEGRATION.md shows the
+ * Rust `-sys` binding and the patched function bodies.
+ *
+ * Conventions
+ *   - Memory images are arkworks 0.4 in-memory forms, little-endian:
+ *       Fr / Fq   : 4 x u64 Montgomery limbs (value * 2^256 mod p), fully reduced      32 B
+ *       G1 affine : { x: Fq, y: Fq, infinity: bool }  (x@0, y@32, infinity@64)          72 B
+ *       G2 affine : { x: Fq2{c0,c1}, y: Fq2{c0,c1}, infinity: bool } (infinity@128)    136 B
+ *       G1 / G2 projective result: Jacobian (X, Y, Z) of 3 x 32 B / 3 x 64 B, always returned
+ *       normalised (Z = 1, or (1,1,0) for the identity): a valid `Projective` whose affine form
+ *       is bit-identical to arkworks' `into_affine()` of the reference result.
+ *   - Host-pointer entry points (no suffix) are blocking, re-entrant and thread-safe; the caller
+ *     owns every buffer and the library never retains a pointer after returning.  They use
+ *     pageable or pinned host memory alike (pinned memory avoids a staging copy).
+ *   - `_dev` entry points take DEVICE pointers plus a context created with zkg_ctx_create(); they
+ *     enqueue work on the context's stream and return without synchronising.
+ *   - Every function returns 0 (ZKG_OK) or a negative ZKG_ERR_* code; zkg_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     ZKG_ERR_CUDA.
+ */
+#ifndef ZKSAAS_GPU_H
+#define ZKSAAS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKG_OK 0
+#define ZKG_ERR_LEN_MISMATCH (-1) /* bases.len() != scalars.len(): Rust shim returns Err(min(len)) like G::msm */
+#define ZKG_ERR_BAD_ARG (-2)
+#define ZKG_ERR_CUDA (-3)
+#define ZKG_ERR_OOM (-4)
+#define ZKG_ERR_UNSUPPORTED (-5)
+
+#define ZKG_G1_AFFINE_BYTES 72u
+#define ZKG_G2_AFFINE_BYTES 136u
+
+typedef struct zkg_ctx zkg_ctx;
+
+/* ---- library / context management ------------------------------------------------------- */
+int32_t zkg_version(void);
+int32_t zkg_device_count(int32_t *count);
+const char *zkg_last_error(void);
+/* Context = device ordinal + stream + grow-only device workspace.  `stream` may be an existing
+ * cudaStream_t (e.g. torch's current stream) or NULL to let the library create one. */
+int32_t zkg_ctx_create(int32_t device, void *stream, zkg_ctx **out);
+int32_t zkg_ctx_destroy(zkg_ctx *ctx);
+int32_t zkg_ctx_sync(zkg_ctx *ctx);
+void *zkg_ctx_stream(zkg_ctx *ctx);
+/* Frees the pooled contexts the host-pointer entry points create lazily. */
+int32_t zkg_shutdown(void);
+
+/* ---- MSM: replaces `G::msm(bases, scalars)` at dist-primitives/src/dmsm/mod.rs:73 ---------
+ * (ark-ec 0.4.2 VariableBaseMSM::msm for ark_bn254::{G1,G2}Projective; callers
+ * groth16/src/prove.rs:52,106,154,209,219).  scalars: Fr Montgomery images. */
+int32_t zkg_msm_bn254_g1(int32_t device, const void *bases, size_t base_stride, size_t n_bases,
+                         const uint64_t *scalars, size_t n_scalars, uint64_t out_xyz[12]);
+int32_t zkg_msm_bn254_g2(int32_t device, const void *bases, size_t base_stride, size_t n_bases,
+                         const uint64_t *scalars, size_t n_scalars, uint64_t out_xyz[24]);
+
+/* Device-resident CRS shares (the bases of groth16/src/proving_key.rs:15-45 are static across
+ * proofs): upload + repack once, then run MSMs against the handle.  group: 1 = G1, 2 = G2. */
+int32_t zkg_bases_register(int32_t device, int32_t group, const void *bases, size_t base_stride, size_t n,
+                           uint64_t *handle);
+int32_t zkg_bases_release(uint64_t handle);
+int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t *scalars, size_t n_scalars, uint64_t *out_xyz);
+
+/* Device-pointer MSM.  d_bases: packed affine (x,y) Montgomery, 64 B (G1) / 128 B (G2) per point,
+ * infinity encoded as (0,0) -- produce it with zkg_pack_bases_dev.  d_scalars: n x 32 B.
+ * d_out_xyz: 96 B / 192 B on the device. */
+int32_t zkg_pack_bases_dev(zkg_ctx *ctx, int32_t group, const void *d_bases_ark, size_t base_stride, size_t n,
+                           void *d_bases_packed);
+int32_t zkg_msm_bn254_g1_dev(zkg_ctx *ctx, const void *d_bases_packed, const uint64_t *d_scalars, size_t n,
+                             uint64_t *d_out_xyz);
+int32_t zkg_msm_bn254_g2_dev(zkg_ctx *ctx, const void *d_bases_packed, const uint64_t *d_scalars, size_t n,
+                             uint64_t *d_out_xyz);
+/* Partial MSM for multi-GPU sharding: same as above but leaves the (un-normalised) XYZZ partial sum
+ * (4 x 32 B / 4 x 64 B) in d_out_xyzz; partials from all ranks are combined with
+ * zkg_msm_combine_dev after an all-gather. */
+int32_t zkg_msm_bn254_partial_dev(zkg_ctx *ctx, int32_t group, const void *d_bases_packed, const uint64_t *d_scalars,
+                                  size_t n, uint64_t *d_out_xyzz);
+int32_t zkg_msm_combine_dev(zkg_ctx *ctx, int32_t group, const uint64_t *d_partials_xyzz, size_t n_partials,
+                            uint64_t *d_out_xyz);
+/* bases[i] = scalars[i] * generator, written in packed device form (synthetic CRS for benches
+ * and tests; also the kernel behind `gen * x` in MsmMask::sample, dmsm/mod.rs:32). */
+int32_t zkg_fixed_base_dev(zkg_ctx *ctx, int32_t group, const uint64_t *d_scalars, size_t n, void *d_bases_packed);
+
+/* ---- client-side FFT step: replaces fft1_in_place, dist-primitives/src/dfft/mod.rs:178-208 ----
+ * px: this party's share vector (mbyl = m/l elements), transformed in place.
+ * pre_scale (nullable): every element is first multiplied by it (d_ifft's size_inv, dfft/mod.rs:159).
+ * in_mask (nullable, mbyl elements): added after the transform (fft2_with_rearrange's masking,
+ * dfft/mod.rs:254-258).  gen: dom.group_gen() or dom.group_gen_inv(). */
+int32_t zkg_fft1_bn254(int32_t device, uint64_t *px, size_t mbyl, uint32_t l, const uint64_t gen[4],
+                       const uint64_t *pre_scale, const uint64_t *in_mask);
+int32_t zkg_fft1_bn254_dev(zkg_ctx *ctx, uint64_t *d_px, size_t mbyl, uint32_t l, const uint64_t gen[4],
+                           const uint64_t *pre_scale, const uint64_t *d_in_mask);
+
+/* ---- king closure of fft2_with_rearrange: dist-primitives/src/dfft/mod.rs:264-304 -----------
+ * shares_by_party[r]: the mbyl-element vector received from party parties[r] (r < n_recv; n_recv
+ * == n = 4l uses unpack2, fewer uses the Lagrange matrix of pss.rs:170-207).  rand: mbyl x t
+ * random field elements for re-packing (column i uses rand[i*t .. i*t+t)); the host RNG stays
+ * in Rust.  out_by_party[p]: mbyl elements for each of the n parties.  g: coset shift (one() for
+ * d_fft).  rearrange != 0 selects the bit-reversed, strided re-packing (dfft/mod.rs:284-300). */
+int32_t zkg_king_fft2_bn254(int32_t device, const uint64_t *const *shares_by_party, const uint32_t *parties,
+                            uint32_t n_recv, size_t mbyl, uint32_t l, const uint64_t gen[4], const uint64_t g[4],
+                            int32_t rearrange, const uint64_t *rand, uint64_t *const *out_by_party);
+/* Device form: d_shares is party-major contiguous (n_recv x mbyl), d_out is party-major (n x mbyl). */
+int32_t zkg_king_fft2_bn254_dev(zkg_ctx *ctx, const uint64_t *d_shares, const uint32_t *parties, uint32_t n_recv,
+                                size_t mbyl, uint32_t l, const uint64_t gen[4], const uint64_t g[4],
+                                int32_t rearrange, const uint64_t *d_rand, uint64_t *d_out);
+
+/* ---- king closure of deg_red: dist-primitives/src/utils/deg_red.rs:103-111 ------------------ */
+int32_t zkg_deg_red_king_bn254(int32_t device, const uint64_t *const *shares_by_party, const uint32_t *parties,
+                               uint32_t n_recv, size_t cols, uint32_t l, const uint64_t *rand,
+                               uint64_t *const *out_by_party);
+int32_t zkg_deg_red_king_bn254_dev(zkg_ctx *ctx, const uint64_t *d_shares, const uint32_t *parties, uint32_t n_recv,
+                                   size_t cols, uint32_t l, const uint64_t *d_rand, uint64_t *d_out);
+
+/* ---- PackedSharingParams transforms over Fr, batched over `cols` columns -------------------
+ * secret-sharing/src/pss.rs: pack :90-122 (rand != NULL), det_pack :69-87 (rand == NULL),
+ * unpack :125-138, unpack2 :141-166.  Column-major contiguous: column c reads secrets[c*l..],
+ * rand[c*t..], writes shares[c*n..]. */
+int32_t zkg_pss_pack_bn254_fr(int32_t device, uint32_t l, const uint64_t *secrets, const uint64_t *rand,
+                              uint64_t *shares, size_t cols);
+int32_t zkg_pss_unpack_bn254_fr(int32_t device, uint32_t l, const uint64_t *shares, uint64_t *secrets, size_t cols);
+int32_t zkg_pss_unpack2_bn254_fr(int32_t device, uint32_t l, const uint64_t *shares, uint64_t *secrets, size_t cols);
+
+/* ---- stand-alone pieces (FftMask::sample dfft/mod.rs:30-85, QAP::pss groth16/src/qap.rs:101) ---- */
+/* fft2_in_place, dfft/mod.rs:210-237 (s1: m elements, in place) */
+int32_t zkg_fft2_bn254(int32_t device, uint64_t *s1, size_t m, uint32_t l, const uint64_t gen[4]);
+/* Radix2EvaluationDomain::distribute_powers (dfft/mod.rs:49,279): v[i] *= g^i */
+int32_t zkg_distribute_powers_bn254(int32_t device, uint64_t *v, size_t n, const uint64_t g[4]);
+/* fft_in_place_rearrange, dfft/mod.rs:322-335 (bit-reversal permutation, n = 2^k) */
+int32_t zkg_bitrev_bn254(int32_t device, uint64_t *v, size_t n);
+/* Radix2EvaluationDomain::{fft,ifft}_in_place on n = 2^k elements, optional coset offset (NULL = 1);
+ * the plain transforms of groth16/src/ext_wit.rs:204-285 and the reconstruction side of the tests. */
+int32_t zkg_fr_fft_bn254(int32_t device, uint64_t *v, size_t n, const uint64_t *offset, int32_t inverse);
+
+/* ---- element-wise helpers used by kernel unit tests (out[i] = a[i] op b[i]; op: 0 mul, 1 add,
+ * 2 sub; field: 0 Fr, 1 Fq) ---- */
+int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t *a, const uint64_t *b, uint64_t *out,
+                     size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKSAAS_GPU_H */

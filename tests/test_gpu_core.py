@@ -1,0 +1,344 @@
+"""GPU parity tests (B200): every CUDA entry point of the hot path, through the C ABI, against the
+CPU oracle on the same seeded inputs -- bit-exact (integer arithmetic; no tolerance)."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from oracle_lib import _p, pyref
+
+pytestmark = pytest.mark.gpu
+
+R, Q = pyref.R_MOD, pyref.Q_MOD
+
+
+@pytest.fixture(scope="module")
+def z():
+    import zksaas_b200
+    return zksaas_b200
+
+
+@pytest.fixture(scope="module")
+def o():
+    return ol.oracle()
+
+
+def raw_np(vals):
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        out[i] = [(v >> (64 * k)) & (2**64 - 1) for k in range(4)]
+    return out
+
+
+def unraw(arr):
+    return [sum(int(x) << (64 * k) for k, x in enumerate(r)) for r in arr]
+
+
+# ------------------------------------------------------------------------------------------------
+# field arithmetic (K1)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("field,p", [(0, R), (1, Q)])
+def test_field_ops_bit_exact(z, field, p):
+    from zksaas_b200 import api
+    rng = random.Random(11 + field)
+    edge = [0, 1, 2, p - 1, p - 2, 1 << 253, (1 << 32) - 1, (1 << 64) - 1, 1 << 224, p >> 1, (p >> 1) + 1]
+    a = [rng.randrange(p) for _ in range(5000)] + [x for x in edge for _ in edge]
+    b = [rng.randrange(p) for _ in range(5000)] + [y for _ in edge for y in edge]
+    A, B = raw_np(a), raw_np(b)
+    rinv = pow(1 << 256, -1, p)
+    assert unraw(api._field_op(0, A, B, field)) == [x * y * rinv % p for x, y in zip(a, b)]
+    assert unraw(api._field_op(1, A, B, field)) == [(x + y) % p for x, y in zip(a, b)]
+    assert unraw(api._field_op(2, A, B, field)) == [(x - y) % p for x, y in zip(a, b)]
+
+
+# ------------------------------------------------------------------------------------------------
+# MSM (K2 + K3)
+# ------------------------------------------------------------------------------------------------
+def _g1_points(rng, n):
+    dl = [rng.randrange(R) for _ in range(n)]
+    lib = ol.oracle()
+    out = np.zeros((n, 72), dtype=np.uint8)
+    if n:
+        lib.zko_g1_fixed_base(_p(ol.fr_np(dl)), n, out.ctypes.data, 72)
+    return dl, out
+
+
+def _g2_points(rng, n):
+    dl = [rng.randrange(R) for _ in range(n)]
+    lib = ol.oracle()
+    out = np.zeros((n, 136), dtype=np.uint8)
+    if n:
+        lib.zko_g2_fixed_base(_p(ol.fr_np(dl)), n, out.ctypes.data, 136)
+    return dl, out
+
+
+def test_msm_g1_known_answer(z):
+    """SURVEY 8c derived KAT: MSM([G,2G,3G,4G],[5, r-1, 0, 2^253])."""
+    G = pyref.G1_GEN
+    bases = ol.g1_aff_np([pyref.G1.mul(G, k) for k in (1, 2, 3, 4)])
+    got = ol.g1_xyz_to_point(z.msm_g1(bases, ol.fr_np([5, R - 1, 0, 1 << 253])))
+    assert got == (13029254136549853374917870083460735038808062714769386524861890685576727298910,
+                   8493657113625770995739651764829897578810448832951094624325556898429206321085)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 100, 512, 1000])
+def test_msm_g1_vs_oracle(z, n):
+    rng = random.Random(100 + n)
+    _, bases = _g1_points(rng, n)
+    scalars = ol.fr_np([rng.randrange(R) for _ in range(n)])
+    got = z.msm_g1(bases, scalars)
+    exp = ol.o_g1_msm(bases, scalars, threads=8)
+    assert (got == exp).all()
+
+
+def test_msm_g1_edge_cases(z):
+    """zero / one / r-1 scalars, infinity bases, all-equal bases (dmsm/mod.rs:144-147), P and -P."""
+    rng = random.Random(5)
+    dl, bases = _g1_points(rng, 64)
+    pts = [pyref.G1.mul(pyref.G1_GEN, d) for d in dl[:4]]
+    sc = [rng.randrange(R) for _ in range(64)]
+    sc[0], sc[1], sc[2] = 0, 1, R - 1
+    bases[3] = np.frombuffer(pyref.g1_affine_image(None), dtype=np.uint8)          # infinity base
+    bases[5] = bases[4]; sc[5] = sc[4]                                             # P + P inside a bucket
+    bases[7] = np.frombuffer(pyref.g1_affine_image(pyref.G1.neg(pts[0])), dtype=np.uint8)
+    bases[6] = np.frombuffer(pyref.g1_affine_image(pts[0]), dtype=np.uint8); sc[7] = sc[6]   # P and -P
+    S = ol.fr_np(sc)
+    assert (z.msm_g1(bases, S) == ol.o_g1_msm(bases, S)).all()
+    # all bases identical, all scalars one  (pack_unpack2_test)
+    same = np.repeat(bases[8:9], 256, axis=0)
+    ones = ol.fr_np([1] * 256)
+    assert (z.msm_g1(same, ones) == ol.o_g1_msm(same, ones)).all()
+    # everything cancels -> identity image (1, 1, 0)
+    two = np.stack([bases[6], bases[7]])
+    ident = z.msm_g1(two, ol.fr_np([7, 7]))
+    assert ol.g1_xyz_to_point(ident) is None
+    assert (ident == ol.g1_point_to_xyz(None)).all()
+
+
+def test_msm_length_mismatch(z):
+    rng = random.Random(1)
+    _, bases = _g1_points(rng, 4)
+    with pytest.raises(z.MsmLengthMismatch) as ei:
+        z.msm_g1(bases, ol.fr_np([1, 2, 3]))
+    assert ei.value.min_len == 3
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 33, 200])
+def test_msm_g2_vs_oracle(z, n):
+    rng = random.Random(200 + n)
+    _, bases = _g2_points(rng, n)
+    sc = [rng.randrange(R) for _ in range(n)]
+    if n >= 5:
+        sc[0], sc[1] = 0, R - 1
+        bases[2] = np.frombuffer(pyref.g2_affine_image(None), dtype=np.uint8)
+        bases[4] = bases[3]; sc[4] = sc[3]
+    S = ol.fr_np(sc)
+    assert (z.msm_g2(bases, S) == ol.o_g2_msm(bases, S, threads=8)).all()
+
+
+@pytest.mark.parametrize("c", [5, 8, 11, 13])
+def test_msm_window_sizes_agree(z, c, monkeypatch):
+    """The window size changes the schedule, never the (normalised) result."""
+    rng = random.Random(77)
+    _, bases = _g1_points(rng, 300)
+    S = ol.fr_np([rng.randrange(R) for _ in range(300)])
+    exp = ol.o_g1_msm(bases, S, threads=8)
+    monkeypatch.setenv("ZKG_MSM_C", str(c))
+    assert (z.msm_g1(bases, S) == exp).all()
+
+
+def test_msm_registered_bases(z):
+    from zksaas_b200 import capi
+    rng = random.Random(9)
+    _, bases = _g1_points(rng, 128)
+    S = ol.fr_np([rng.randrange(R) for _ in range(128)])
+    h = C.c_uint64(0)
+    capi.check(z.lib().zkg_bases_register(0, 1, bases.ctypes.data, 72, 128, C.byref(h)))
+    out = np.zeros(12, dtype=np.uint64)
+    capi.check(z.lib().zkg_msm_bn254_registered(h.value, S.ctypes.data, 128, out.ctypes.data))
+    assert (out == ol.o_g1_msm(bases, S)).all()
+    assert z.lib().zkg_msm_bn254_registered(h.value, S.ctypes.data, 127, out.ctypes.data) == capi.ZKG_ERR_LEN_MISMATCH
+    capi.check(z.lib().zkg_bases_release(h.value))
+
+
+# ------------------------------------------------------------------------------------------------
+# fft1 (K4)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("l,mbyl", [(2, 1), (2, 2), (2, 4), (2, 8), (2, 512), (2, 1024), (2, 2048), (2, 1 << 15),
+                                    (4, 16), (4, 1 << 11), (8, 1 << 12), (2, 1 << 17)])
+def test_fft1_vs_literal_oracle(z, o, l, mbyl):
+    rng = np.random.default_rng(mbyl * 7 + l)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(mbyl * l)
+    px = ol.rand_fr(rng, mbyl)
+    exp = px.copy()
+    gen = dom.group_gen()
+    o.zko_fft1_in_place(_p(exp), mbyl, l, _p(gen))
+    got = px.copy()
+    z.fft1_in_place(got, pp, gen)
+    assert (got == exp).all()
+
+
+def test_fft1_fused_scale_and_mask(z, o):
+    l, mbyl = 2, 1 << 12
+    rng = np.random.default_rng(3)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(mbyl * l)
+    px, mask = ol.rand_fr(rng, mbyl), ol.rand_fr(rng, mbyl)
+    sinv = dom.size_inv()
+    exp = px.copy()
+    o.zko_fr_mul(_p(exp), _p(np.repeat(sinv[None], mbyl, axis=0)), _p(exp), mbyl)       # dfft/mod.rs:159
+    o.zko_fft1_in_place(_p(exp), mbyl, l, _p(dom.group_gen_inv()))                       # :162
+    o.zko_fr_add(_p(exp), _p(mask), _p(exp), mbyl)                                       # :254-258
+    got = px.copy()
+    z.fft1_in_place(got, pp, dom.group_gen_inv(), pre_scale=sinv, in_mask=mask)
+    assert (got == exp).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# PSS (K6)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("l", [2, 4, 8])
+def test_pss_pack_unpack_vs_oracle(z, o, l):
+    rng = np.random.default_rng(40 + l)
+    pp = z.PackedSharingParams.new(l)
+    cols = 333
+    sec, rnd = ol.rand_fr(rng, cols * l), ol.rand_fr(rng, cols * l)
+    exp = np.zeros((cols * pp.n, 4), dtype=np.uint64)
+    o.zko_pss_pack_fr(l, _p(sec), _p(rnd), _p(exp), cols)
+    shares = pp.pack(sec, rnd)
+    assert (shares == exp).all()
+    o.zko_pss_pack_fr(l, _p(sec), None, _p(exp), cols)
+    assert (pp.det_pack(sec) == exp).all()
+    assert (pp.unpack(shares) == sec).all()                       # pss.rs:270-271
+    assert (pp.unpack2(shares) == sec).all()
+    assert (pp.unpack(pp.det_pack(sec)) == sec).all()             # pss.rs:287
+    # products of shares unpack2 to products of secrets (pss.rs:299-310)
+    from zksaas_b200 import api
+    sq = api.fr_mul(shares, shares)
+    e2 = np.zeros((cols * l, 4), dtype=np.uint64)
+    o.zko_pss_unpack2_fr(l, _p(sq), _p(e2), cols)
+    assert (pp.unpack2(sq) == e2).all()
+    assert (e2 == api.fr_mul(sec, sec)).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# king pipeline (K5) and deg_red
+# ------------------------------------------------------------------------------------------------
+def _valid_shares(o, rng, l, mbyl):
+    """party-major degree-2(l+t)-2 sharings: squares of random packed sharings."""
+    n = 4 * l
+    sec, rnd = ol.rand_fr(rng, mbyl * l), ol.rand_fr(rng, mbyl * l)
+    sh = np.zeros((mbyl * n, 4), dtype=np.uint64)
+    o.zko_pss_pack_fr(l, _p(sec), _p(rnd), _p(sh), mbyl)
+    o.zko_fr_mul(_p(sh), _p(sh), _p(sh), mbyl * n)
+    cols = sh.reshape(mbyl, n, 4)
+    return [np.ascontiguousarray(cols[:, p, :]) for p in range(n)]
+
+
+def _oracle_king(o, shares, parties, mbyl, l, gen, g, rearrange, rand):
+    n = 4 * l
+    outs = [np.zeros((mbyl, 4), dtype=np.uint64) for _ in range(n)]
+    par = (C.c_uint32 * len(parties))(*parties)
+    rc = o.zko_king_fft2(ol.ptr_array(shares), par, len(shares), mbyl, l, _p(gen), _p(g), rearrange, _p(rand),
+                         ol.ptr_array(outs))
+    assert rc == 0
+    return outs
+
+
+@pytest.mark.parametrize("l,mbyl", [(2, 1), (2, 4), (2, 64), (2, 1 << 10), (2, 1 << 15), (4, 8), (4, 1 << 9), (8, 1 << 6)])
+@pytest.mark.parametrize("rearrange", [0, 1])
+def test_king_fft2_vs_literal_oracle(z, o, l, mbyl, rearrange):
+    rng = np.random.default_rng(l * 1000 + mbyl + rearrange)
+    pp = z.PackedSharingParams.new(l)
+    m = mbyl * l
+    dom = z.Radix2EvaluationDomain.new(m)
+    shares = _valid_shares(o, rng, l, mbyl)
+    rand = ol.rand_fr(rng, mbyl * l)
+    zeta = z.Radix2EvaluationDomain.new(2 * m).element(1)
+    from zksaas_b200 import api
+    for gen in (dom.group_gen(), dom.group_gen_inv()):
+        for g in (api.fr_image(1), zeta, api.fr_image(5)):
+            exp = _oracle_king(o, shares, list(range(pp.n)), mbyl, l, gen, g, rearrange, rand)
+            got = z.king_fft2(shares, list(range(pp.n)), pp, gen, g, rearrange, rand)
+            for p in range(pp.n):
+                assert (got[p] == exp[p]).all(), (p,)
+
+
+def test_king_fft2_dropout_uses_lagrange(z, o):
+    """One party missing: unpack_missing_shares falls back to lagrange_unpack (pss.rs:210-221)."""
+    l, mbyl = 2, 256
+    rng = np.random.default_rng(8)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(mbyl * l)
+    shares = _valid_shares(o, rng, l, mbyl)
+    rand = ol.rand_fr(rng, mbyl * l)
+    from zksaas_b200 import api
+    for missing in (7, 0, 3):
+        parties = [p for p in range(pp.n) if p != missing]
+        sub = [shares[p] for p in parties]
+        exp = _oracle_king(o, sub, parties, mbyl, l, dom.group_gen(), api.fr_image(1), 1, rand)
+        full = _oracle_king(o, shares, list(range(pp.n)), mbyl, l, dom.group_gen(), api.fr_image(1), 1, rand)
+        got = z.king_fft2(sub, parties, pp, dom.group_gen(), api.fr_image(1), True, rand)
+        for p in range(pp.n):
+            assert (got[p] == exp[p]).all() and (got[p] == full[p]).all()
+    with pytest.raises(z.ZkgError):       # two parties missing: not enough shares for degree 2(l+t)-2
+        z.king_fft2(shares[:6], list(range(6)), pp, dom.group_gen(), api.fr_image(1), True, rand)
+
+
+@pytest.mark.parametrize("l,cols", [(2, 1000), (4, 37)])
+def test_deg_red_king_vs_oracle(z, o, l, cols):
+    rng = np.random.default_rng(cols)
+    pp = z.PackedSharingParams.new(l)
+    shares = _valid_shares(o, rng, l, cols)
+    rand = ol.rand_fr(rng, cols * l)
+    outs = [np.zeros((cols, 4), dtype=np.uint64) for _ in range(pp.n)]
+    par = (C.c_uint32 * pp.n)(*range(pp.n))
+    assert o.zko_deg_red_king(ol.ptr_array(shares), par, pp.n, cols, l, _p(rand), ol.ptr_array(outs)) == 0
+    got = z.deg_red_king(shares, list(range(pp.n)), pp, rand)
+    for p in range(pp.n):
+        assert (got[p] == outs[p]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone pieces
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("l,m", [(2, 8), (2, 1 << 12), (4, 1 << 10), (8, 64)])
+def test_fft2_standalone(z, o, l, m):
+    rng = np.random.default_rng(m + l)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    s1 = ol.rand_fr(rng, m)
+    exp = s1.copy()
+    o.zko_fft2_in_place(_p(exp), m, l, _p(dom.group_gen()))
+    assert (z.fft2_in_place(s1.copy(), pp, dom.group_gen()) == exp).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 1 << 13, 1 << 16])
+def test_bitrev_and_powers(z, o, n):
+    rng = np.random.default_rng(n)
+    v = ol.rand_fr(rng, n)
+    exp = v.copy()
+    o.zko_fr_rearrange(_p(exp), n)
+    assert (z.fft_in_place_rearrange(v.copy()) == exp).all()
+    g = ol.rand_fr(rng, 1)[0]
+    exp = v.copy()
+    o.zko_fr_distribute_powers(_p(exp), n, _p(g))
+    assert (z.distribute_powers(v.copy(), g) == exp).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 16, 1 << 10, 1 << 11, 1 << 16, 1 << 21])
+def test_domain_fft_ifft_coset(z, o, n):
+    rng = np.random.default_rng(n + 1)
+    dom = z.Radix2EvaluationDomain.new(n)
+    from zksaas_b200 import api
+    v = ol.rand_fr(rng, n)
+    for off in (None, api.fr_image(5)):
+        for inv in (0, 1):
+            exp = v.copy()
+            o.zko_fr_fft(_p(exp), n, _p(off) if off is not None else None, inv)
+            got = dom.ifft(v, off) if inv else dom.fft(v, off)
+            assert (got == exp).all(), (off is not None, inv)
+    assert (dom.ifft(dom.fft(v)) == v).all()

@@ -1,0 +1,148 @@
+// api.cu -- context management, error reporting and small element-wise entry points of the C ABI.
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace zkg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+static std::mutex g_pool_mu;
+static std::vector<zkg_ctx*> g_pool;     // idle pooled contexts (any device)
+
+static int32_t ctx_new(int device, void* stream, zkg_ctx** out) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); libzksaas_gpu has no CPU fallback", cudaGetErrorString(e));
+        return ZKG_ERR_CUDA;
+    }
+    ZKG_REQUIRE(device >= 0 && device < count, "device ordinal %d out of range (have %d)", device, count);
+    DeviceGuard dg(device);
+    zkg_ctx* c = new zkg_ctx();
+    c->device = device;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess) { delete c; set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e2)); return ZKG_ERR_CUDA; }
+        c->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return ZKG_OK;
+}
+
+static void ctx_free(zkg_ctx* c) {
+    if (!c) return;
+    DeviceGuard dg(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->ws.release(); c->io.release(); c->io2.release(); c->small.release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int32_t PooledCtx::acquire(int device) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i]->device == device) { ctx = g_pool[i]; g_pool.erase(g_pool.begin() + i); return ZKG_OK; }
+    }
+    return ctx_new(device, nullptr, &ctx);
+}
+PooledCtx::~PooledCtx() {
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back(ctx);
+}
+
+int32_t ctx_pinned(zkg_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return ZKG_OK;
+    if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    ZKG_CUDA(cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+    return ZKG_OK;
+}
+
+template <class F>
+__global__ void k_field_op(int op, const F* __restrict__ a, const F* __restrict__ b, F* __restrict__ o, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i], y = b[i];
+    o[i] = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
+}
+
+}  // namespace zkg
+
+using namespace zkg;
+
+extern "C" {
+
+int32_t zkg_version(void) { return 100; }
+
+int32_t zkg_device_count(int32_t* count) {
+    ZKG_REQUIRE(count, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return ZKG_ERR_CUDA; }
+    *count = c;
+    return ZKG_OK;
+}
+
+const char* zkg_last_error(void) { return g_err; }
+
+int32_t zkg_ctx_create(int32_t device, void* stream, zkg_ctx** out) {
+    ZKG_REQUIRE(out, "out is NULL");
+    return ctx_new(device, stream, out);
+}
+int32_t zkg_ctx_destroy(zkg_ctx* ctx) {
+    ZKG_REQUIRE(ctx, "ctx is NULL");
+    ctx_free(ctx);
+    return ZKG_OK;
+}
+int32_t zkg_ctx_sync(zkg_ctx* ctx) {
+    ZKG_REQUIRE(ctx, "ctx is NULL");
+    DeviceGuard dg(ctx->device);
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+void* zkg_ctx_stream(zkg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int32_t zkg_shutdown(void) {
+    std::vector<zkg_ctx*> all;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        all.swap(g_pool);
+    }
+    for (zkg_ctx* c : all) ctx_free(c);
+    return ZKG_OK;
+}
+
+int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    ZKG_REQUIRE((field == 0 || field == 1) && op >= 0 && op <= 2 && (n == 0 || (a && b && out)), "field_op: bad argument");
+    if (n == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    size_t bytes = align_up(n * 32, 256);
+    ZKG_TRY(ctx->io.reserve(3 * bytes));
+    uint8_t* d = (uint8_t*)ctx->io.p;
+    ZKG_CUDA(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_CUDA(cudaMemcpyAsync(d + bytes, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (field == 0) k_field_op<Fr><<<blocks, 256, 0, ctx->stream>>>(op, (const Fr*)d, (const Fr*)(d + bytes), (Fr*)(d + 2 * bytes), n);
+    else k_field_op<Fq><<<blocks, 256, 0, ctx->stream>>>(op, (const Fq*)d, (const Fq*)(d + bytes), (Fq*)(d + 2 * bytes), n);
+    ZKG_CUDA(cudaGetLastError());
+    ZKG_CUDA(cudaMemcpyAsync(out, d + 2 * bytes, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// common.cuh -- contexts, workspaces and error plumbing shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/zksaas_gpu.h"
+
+namespace zkg {
+
+void set_error(const char* fmt, ...);
+
+#define ZKG_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            zkg::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return _e == cudaErrorMemoryAllocation ? ZKG_ERR_OOM : ZKG_ERR_CUDA;                    \
+        }                                                                                           \
+    } while (0)
+
+#define ZKG_TRY(call)                   \
+    do {                                \
+        int32_t _r = (call);            \
+        if (_r != ZKG_OK) return _r;    \
+    } while (0)
+
+#define ZKG_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            zkg::set_error(__VA_ARGS__); \
+            return ZKG_ERR_BAD_ARG;     \
+        }                               \
+    } while (0)
+
+// Grow-only device buffer (one cudaMalloc per high-water mark, never per call)
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int32_t reserve(size_t need) {
+        if (need <= bytes) return ZKG_OK;
+        if (p) { ZKG_CUDA(cudaFree(p)); p = nullptr; bytes = 0; }
+        size_t want = need + need / 8;           // slack so slowly growing sizes do not realloc
+        ZKG_CUDA(cudaMalloc(&p, want));
+        bytes = want;
+        return ZKG_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace zkg
+
+struct zkg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    zkg::DevBuf ws;        // kernel workspace (digits, sorted indices, buckets, NTT scratch ...)
+    zkg::DevBuf io;        // staging for host-pointer entry points
+    zkg::DevBuf io2;
+    zkg::DevBuf small;     // twiddle tables / matrices / results
+    void* pinned = nullptr;   // small pinned bounce buffer for results
+    size_t pinned_bytes = 0;
+    int sm_count = 0;
+};
+
+namespace zkg {
+
+// RAII: borrow a pooled context for a blocking host-pointer call
+struct PooledCtx {
+    zkg_ctx* ctx = nullptr;
+    int32_t acquire(int device);
+    ~PooledCtx();
+};
+
+int32_t ctx_pinned(zkg_ctx* ctx, size_t bytes);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace zkg

@@ -1,0 +1,201 @@
+// ec.cuh -- BN254 G1 (over Fq) and G2 (over Fq2 = Fq[u]/(u^2+1)) group arithmetic for the MSM
+// kernels.  Replaces ark-ec 0.4 `short_weierstrass::{Affine,Projective}` arithmetic underneath
+// `VariableBaseMSM::msm` (reference call site dist-primitives/src/dmsm/mod.rs:73).
+//
+// Working representation is XYZZ (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; identity: ZZ = 0): the
+// mixed addition that dominates bucket accumulation costs 8M + 2S instead of the 7M + 4S of the
+// Jacobian madd-2007-bl arkworks uses, and needs no field inversion.  A group element has a
+// unique normalised affine form, so results are bit-identical to arkworks' after into_affine().
+//
+// Device-side affine bases are stored packed as (x, y) with the point at infinity encoded as
+// (0, 0), which is not on either curve (b != 0).
+#pragma once
+#include "fp.cuh"
+
+namespace zkg {
+
+// --------------------------------------------------------------------------------------------
+// uniform field interface: f_add/f_sub/f_mul/f_sqr/f_dbl/f_neg/f_inv over Fq and Fq2
+// --------------------------------------------------------------------------------------------
+template <class P> ZKG_D Fp<P> f_add(const Fp<P>& a, const Fp<P>& b) { return fp_add(a, b); }
+template <class P> ZKG_D Fp<P> f_sub(const Fp<P>& a, const Fp<P>& b) { return fp_sub(a, b); }
+template <class P> ZKG_D Fp<P> f_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
+template <class P> ZKG_D Fp<P> f_sqr(const Fp<P>& a) { return fp_sqr(a); }
+template <class P> ZKG_D Fp<P> f_dbl(const Fp<P>& a) { return fp_dbl(a); }
+template <class P> ZKG_D Fp<P> f_neg(const Fp<P>& a) { return fp_neg(a); }
+template <class P> ZKG_D Fp<P> f_inv(const Fp<P>& a) { return fp_inv(a); }
+
+struct Fq2 {
+    Fq c0, c1;
+    ZKG_HD static Fq2 zero() { Fq2 r; r.c0 = Fq::zero(); r.c1 = Fq::zero(); return r; }
+    ZKG_HD static Fq2 one() { Fq2 r; r.c0 = Fq::one(); r.c1 = Fq::zero(); return r; }
+    ZKG_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    ZKG_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    ZKG_HD bool operator!=(const Fq2& b) const { return !(*this == b); }
+};
+ZKG_D Fq2 f_add(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = fp_add(a.c0, b.c0); r.c1 = fp_add(a.c1, b.c1); return r; }
+ZKG_D Fq2 f_sub(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = fp_sub(a.c0, b.c0); r.c1 = fp_sub(a.c1, b.c1); return r; }
+ZKG_D Fq2 f_dbl(const Fq2& a) { Fq2 r; r.c0 = fp_dbl(a.c0); r.c1 = fp_dbl(a.c1); return r; }
+ZKG_D Fq2 f_neg(const Fq2& a) { Fq2 r; r.c0 = fp_neg(a.c0); r.c1 = fp_neg(a.c1); return r; }
+// (a0 + a1 u)(b0 + b1 u), u^2 = -1, Karatsuba: 3 base-field products
+ZKG_NI Fq2 f_mul(const Fq2& a, const Fq2& b) {
+    Fq v0 = fp_mul(a.c0, b.c0);
+    Fq v1 = fp_mul(a.c1, b.c1);
+    Fq s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+    Fq2 r;
+    r.c0 = fp_sub(v0, v1);
+    r.c1 = fp_sub(fp_sub(s, v0), v1);
+    return r;
+}
+// (a0 + a1 u)^2 = (a0+a1)(a0-a1) + 2 a0 a1 u : 2 base-field products
+ZKG_NI Fq2 f_sqr(const Fq2& a) {
+    Fq m = fp_mul(a.c0, a.c1);
+    Fq2 r;
+    r.c0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
+    r.c1 = fp_dbl(m);
+    return r;
+}
+ZKG_NI Fq2 f_inv(const Fq2& a) {
+    Fq n = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+    Fq2 r;
+    r.c0 = fp_mul(a.c0, n);
+    r.c1 = fp_neg(fp_mul(a.c1, n));
+    return r;
+}
+
+// --------------------------------------------------------------------------------------------
+// points
+// --------------------------------------------------------------------------------------------
+template <class F>
+struct Affine {
+    F x, y;                                   // infinity <=> x == 0 && y == 0
+    ZKG_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+    ZKG_HD static Affine inf() { Affine r; r.x = F::zero(); r.y = F::zero(); return r; }
+};
+
+template <class F>
+struct XYZZ {
+    F x, y, zz, zzz;
+    ZKG_HD bool is_inf() const { return zz.is_zero(); }
+    ZKG_HD static XYZZ inf() { XYZZ r; r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero(); return r; }
+    ZKG_HD static XYZZ from_affine(const Affine<F>& p) {
+        if (p.is_inf()) return inf();
+        XYZZ r; r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::one(); return r;
+    }
+};
+
+// acc = 2 * (affine p)      (mdbl-2008-s-1, a = 0)
+template <class F>
+ZKG_NI XYZZ<F> xyzz_dbl_affine(const Affine<F>& p) {
+    if (p.is_inf() || p.y.is_zero()) return XYZZ<F>::inf();   // no 2-torsion on BN254, kept for safety
+    XYZZ<F> r;
+    F u = f_dbl(p.y);
+    F v = f_sqr(u);
+    F w = f_mul(u, v);
+    F s = f_mul(p.x, v);
+    F xx = f_sqr(p.x);
+    F m = f_add(f_dbl(xx), xx);
+    r.x = f_sub(f_sub(f_sqr(m), s), s);
+    r.y = f_sub(f_mul(m, f_sub(s, r.x)), f_mul(w, p.y));
+    r.zz = v;
+    r.zzz = w;
+    return r;
+}
+
+// a = 2a      (dbl-2008-s-1, a = 0)
+template <class F>
+ZKG_NI void xyzz_dbl(XYZZ<F>& a) {
+    if (a.is_inf()) return;
+    F u = f_dbl(a.y);
+    F v = f_sqr(u);
+    F w = f_mul(u, v);
+    F s = f_mul(a.x, v);
+    F xx = f_sqr(a.x);
+    F m = f_add(f_dbl(xx), xx);
+    F x3 = f_sub(f_sub(f_sqr(m), s), s);
+    a.y = f_sub(f_mul(m, f_sub(s, x3)), f_mul(w, a.y));
+    a.x = x3;
+    a.zz = f_mul(v, a.zz);
+    a.zzz = f_mul(w, a.zzz);
+}
+
+// acc += (neg ? -p : p), p affine      (madd-2008-s: 8M + 2S)
+template <class F>
+ZKG_D void xyzz_madd(XYZZ<F>& acc, const Affine<F>& p_in, bool neg) {
+    if (p_in.is_inf()) return;
+    Affine<F> p = p_in;
+    if (neg) p.y = f_neg(p.y);
+    if (acc.is_inf()) { acc.x = p.x; acc.y = p.y; acc.zz = F::one(); acc.zzz = F::one(); return; }
+    F u2 = f_mul(p.x, acc.zz);
+    F s2 = f_mul(p.y, acc.zzz);
+    F pp_ = f_sub(u2, acc.x);
+    F r = f_sub(s2, acc.y);
+    if (pp_.is_zero()) {
+        if (r.is_zero()) acc = xyzz_dbl_affine(p);     // P == Q
+        else acc = XYZZ<F>::inf();                     // P == -Q
+        return;
+    }
+    F pp = f_sqr(pp_);
+    F ppp = f_mul(pp_, pp);
+    F q = f_mul(acc.x, pp);
+    F x3 = f_sub(f_sub(f_sub(f_sqr(r), ppp), q), q);
+    acc.y = f_sub(f_mul(r, f_sub(q, x3)), f_mul(acc.y, ppp));
+    acc.x = x3;
+    acc.zz = f_mul(acc.zz, pp);
+    acc.zzz = f_mul(acc.zzz, ppp);
+}
+
+// a += b      (add-2008-s: 12M + 2S)
+template <class F>
+ZKG_NI void xyzz_add(XYZZ<F>& a, const XYZZ<F>& b) {
+    if (b.is_inf()) return;
+    if (a.is_inf()) { a = b; return; }
+    F u1 = f_mul(a.x, b.zz);
+    F u2 = f_mul(b.x, a.zz);
+    F s1 = f_mul(a.y, b.zzz);
+    F s2 = f_mul(b.y, a.zzz);
+    F pp_ = f_sub(u2, u1);
+    F r = f_sub(s2, s1);
+    if (pp_.is_zero()) {
+        if (r.is_zero()) xyzz_dbl(a);
+        else a = XYZZ<F>::inf();
+        return;
+    }
+    F pp = f_sqr(pp_);
+    F ppp = f_mul(pp_, pp);
+    F q = f_mul(u1, pp);
+    F x3 = f_sub(f_sub(f_sub(f_sqr(r), ppp), q), q);
+    a.y = f_sub(f_mul(r, f_sub(q, x3)), f_mul(s1, ppp));
+    a.x = x3;
+    a.zz = f_mul(f_mul(a.zz, b.zz), pp);
+    a.zzz = f_mul(f_mul(a.zzz, b.zzz), ppp);
+}
+
+// unique normal form (into_affine): x = X/ZZ, y = Y/ZZZ with a single inversion
+template <class F>
+ZKG_NI Affine<F> xyzz_to_affine(const XYZZ<F>& a) {
+    if (a.is_inf()) return Affine<F>::inf();
+    F d = f_inv(f_mul(a.zz, a.zzz));
+    Affine<F> r;
+    r.x = f_mul(a.x, f_mul(a.zzz, d));
+    r.y = f_mul(a.y, f_mul(a.zz, d));
+    return r;
+}
+
+// k * p for a small non-negative integer k (bucket-segment offsets); double-and-add, MSB first
+template <class F>
+ZKG_NI XYZZ<F> xyzz_mul_small(const XYZZ<F>& p, uint32_t k) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int b = 31; b >= 0; --b) {
+        xyzz_dbl(acc);
+        if ((k >> b) & 1) xyzz_add(acc, p);
+    }
+    return acc;
+}
+
+typedef Affine<Fq> G1Affine;
+typedef Affine<Fq2> G2Affine;
+typedef XYZZ<Fq> G1XYZZ;
+typedef XYZZ<Fq2> G2XYZZ;
+
+}  // namespace zkg

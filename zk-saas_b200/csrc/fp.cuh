@@ -1,0 +1,302 @@
+// fp.cuh -- 254-bit prime-field arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form
+// (R = 2^256), i.e. bit-identical to ark-ff 0.4 `Fp<MontBackend<_,4>,4>` memory images
+// (4 x u64 little-endian == 8 x u32 little-endian).  Replaces the ark-ff arithmetic under
+// every hot function of the reference.
+//
+// The multiplier runs on the integer-MAD pipe: products are formed as 32x32->64 multiply-adds
+// with hardware carry chains (mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into
+// IMAD.WIDE.U32[.X]).  Partial products of even and odd limbs are kept in two accumulators that
+// are 32 bits out of phase, so every wide MAD lands on a register pair and the Montgomery
+// reduction is interleaved row by row (CIOS).  Both BN254 moduli are < 2^254, which is what lets
+// the per-row top carries be folded with a single addc (see the bounds in mont_mul).
+//
+// The same source compiles for the host when ZKG_HOST_EMU is defined: the PTX carry-flag
+// primitives are then emulated in portable C++ so that the exact limb schedule can be checked
+// on a machine without a GPU (tests/test_host_emulation.py).
+#pragma once
+#include <stdint.h>
+#include "bn254_consts.cuh"
+
+#ifdef ZKG_HOST_EMU
+#define ZKG_HD inline
+#define ZKG_D inline
+#define ZKG_NI inline
+#else
+#define ZKG_HD __host__ __device__ __forceinline__
+#define ZKG_D __device__ __forceinline__
+// out-of-line device function: used for everything that is big but not on the innermost hot
+// path, so that ptxas sees kernels of a few thousand instructions instead of a few hundred thousand
+#define ZKG_NI static __device__ __noinline__
+#endif
+
+namespace zkg {
+
+// --------------------------------------------------------------------------------------------
+// carry-chain primitives
+// --------------------------------------------------------------------------------------------
+#ifdef ZKG_HOST_EMU
+namespace emu { static thread_local uint32_t cf = 0; }
+// d = a + b (sets CF)
+ZKG_D uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; emu::cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+ZKG_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + emu::cf; emu::cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+ZKG_D uint32_t addc(uint32_t a, uint32_t b) { return a + b + emu::cf; }
+ZKG_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; emu::cf = (uint32_t)((t >> 32) & 1); return (uint32_t)t; }
+ZKG_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - emu::cf; emu::cf = (uint32_t)((t >> 32) & 1); return (uint32_t)t; }
+ZKG_D uint32_t subc(uint32_t a, uint32_t b) { return a - b - emu::cf; }
+ZKG_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+ZKG_D uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+ZKG_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(a * b, c); }
+ZKG_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(a * b, c); }
+ZKG_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
+ZKG_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
+ZKG_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b) + c + emu::cf; }
+// 32x32->64 multiply-accumulate pairs (one IMAD.WIDE each on the device)
+ZKG_D void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a * b; lo = (uint32_t)t; hi = (uint32_t)(t >> 32); }
+ZKG_D void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = mad_lo_cc(a, b, lo); hi = madc_hi_cc(a, b, hi); }
+ZKG_D void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = madc_lo_cc(a, b, lo); hi = madc_hi_cc(a, b, hi); }
+ZKG_D void madc_wide_cc_from(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t c0, uint32_t c1) { lo = madc_lo_cc(a, b, c0); hi = madc_hi_cc(a, b, c1); }
+#else
+// NOTE on sub.cc: PTX defines CC.CF after sub.cc as the *borrow* (1 = borrow occurred), and
+// subc consumes it as a borrow; the emulation above follows the same convention.
+ZKG_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t d; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+ZKG_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t d; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+ZKG_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t d; asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+ZKG_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t d; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+ZKG_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t d; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+ZKG_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t d; asm volatile("subc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+ZKG_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+ZKG_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+ZKG_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+ZKG_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+ZKG_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+ZKG_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+ZKG_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+// 32x32->64 multiply-accumulate pairs.  The lo/hi halves MUST sit in one asm statement: that is
+// the pattern ptxas fuses into a single full-rate IMAD.WIDE.U32[.X]; issued as separate statements
+// it emits IMAD + IMAD.HI (half rate on sm_100, measured) + 2 IADD3.X instead.
+ZKG_D void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+ZKG_D void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+ZKG_D void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+ZKG_D void madc_wide_cc_from(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t c0, uint32_t c1) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(c0), "r"(c1));
+}
+#endif
+
+// --------------------------------------------------------------------------------------------
+// Field parameter packs (limbs from the generated bn254_consts.cuh)
+// --------------------------------------------------------------------------------------------
+struct FrParams {
+    static constexpr uint32_t INV = BN254_FR_INV;
+    ZKG_HD static constexpr uint32_t mod(int i) { return BN254_FR_MOD_L(i); }
+    ZKG_HD static constexpr uint32_t one(int i) { return BN254_FR_R_L(i); }
+    ZKG_HD static constexpr uint32_t r2(int i) { return BN254_FR_R2_L(i); }
+};
+struct FqParams {
+    static constexpr uint32_t INV = BN254_FQ_INV;
+    ZKG_HD static constexpr uint32_t mod(int i) { return BN254_FQ_MOD_L(i); }
+    ZKG_HD static constexpr uint32_t one(int i) { return BN254_FQ_R_L(i); }
+    ZKG_HD static constexpr uint32_t r2(int i) { return BN254_FQ_R2_L(i); }
+};
+
+template <class P>
+struct Fp {
+    static constexpr int N = 8;
+    uint32_t v[N];
+
+    ZKG_HD static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = 0;
+        return r;
+    }
+    ZKG_HD static Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = P::one(i);
+        return r;
+    }
+    ZKG_HD static Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = P::r2(i);
+        return r;
+    }
+    ZKG_HD bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) o |= v[i];
+        return o == 0;
+    }
+    ZKG_HD bool operator==(const Fp& b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) o |= v[i] ^ b.v[i];
+        return o == 0;
+    }
+    ZKG_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = a - p if a >= p else a   (a < 2p)
+template <class P>
+ZKG_D void final_sub(uint32_t* a) {
+    uint32_t t[8];
+    t[0] = sub_cc(a[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t[i] = subc_cc(a[i], P::mod(i));
+    uint32_t borrow = subc(0, 0);   // 0 - 0 - CF : 0 if no borrow, 0xffffffff if borrow
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = borrow ? a[i] : t[i];
+}
+
+template <class P>
+ZKG_D Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> r;
+    r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) r.v[i] = addc_cc(a.v[i], b.v[i]);
+    r.v[7] = addc(a.v[7], b.v[7]);     // a + b < 2^255: no carry out
+    final_sub<P>(r.v);
+    return r;
+}
+
+template <class P>
+ZKG_D Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> r;
+    r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r.v[i] = subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = subc(0, 0);
+    // add p back under the borrow mask
+    r.v[0] = add_cc(r.v[0], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) r.v[i] = addc_cc(r.v[i], P::mod(i) & borrow);
+    r.v[7] = addc(r.v[7], P::mod(7) & borrow);
+    return r;
+}
+
+template <class P>
+ZKG_D Fp<P> fp_neg(const Fp<P>& a) {
+    // p - a, with 0 -> 0
+    Fp<P> r;
+    r.v[0] = sub_cc(P::mod(0), a.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) r.v[i] = subc_cc(P::mod(i), a.v[i]);
+    r.v[7] = subc(P::mod(7), a.v[7]);
+    uint32_t nz = a.is_zero() ? 0u : 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] &= nz;
+    return r;
+}
+
+template <class P>
+ZKG_D Fp<P> fp_dbl(const Fp<P>& a) { return fp_add(a, a); }
+
+// ---- wide-MAD row helpers ------------------------------------------------------------------
+// acc[j], acc[j+1] = a[j] * b   for j = 0,2,4,6          (4 x 32x32->64 multiplies)
+ZKG_D void mul_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) mul_wide(acc[j], acc[j + 1], a[j], b);
+}
+// acc += (a[0],a[2],a[4],a[6]) * b as one carry chain; leaves the carry-out in CF
+ZKG_D void cmad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+    mad_wide_cc(acc[0], acc[1], a[0], b);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) madc_wide_cc(acc[j], acc[j + 1], a[j], b);
+}
+// acc = (acc >> 64) + (a[0],a[2],a[4],a[6]) * b, consuming CF as carry-in; carry-out is 0
+// (the top pair only receives a[6]*b, and a[6] < 2^30 for both BN254 moduli)
+ZKG_D void madc_row_rshift(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+    for (int j = 0; j < 6; j += 2) madc_wide_cc_from(acc[j], acc[j + 1], a[j], b, acc[j + 2], acc[j + 3]);
+    madc_wide_cc_from(acc[6], acc[7], a[6], b, 0, 0);
+}
+
+// One CIOS row.  `x` is the accumulator whose limb k sits on column k, `y` the accumulator that is
+// one limb out of phase.  Adds a*bi, then m*p with m chosen so that column 0 cancels; the caller
+// swaps the roles of x and y for the next row (that swap is the division by 2^32).
+template <class P, bool FIRST>
+ZKG_D void mont_row(uint32_t* x, uint32_t* y, const uint32_t* a, uint32_t bi) {
+    uint32_t pm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pm[i] = P::mod(i);
+    if (FIRST) {
+        mul_row(y, a + 1, bi);
+        mul_row(x, a, bi);
+    } else {
+        x[0] = add_cc(x[0], y[1]);          // the limb that falls off y when it is shifted by 64 bits
+        madc_row_rshift(y, a + 1, bi);
+        cmad_row(x, a, bi);
+        y[7] = addc(y[7], 0);
+    }
+    uint32_t m = mul_lo(x[0], P::INV);
+    cmad_row(y, pm + 1, m);                  // top pair: a7*bi + p7*m < 2^63, carry-out is 0
+    cmad_row(x, pm, m);
+    y[7] = addc(y[7], 0);
+}
+
+// r = a * b * 2^-256 mod p, fully reduced
+template <class P>
+ZKG_D Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t even[8], odd[8];
+    mont_row<P, true>(even, odd, a.v, b.v[0]);
+    mont_row<P, false>(odd, even, a.v, b.v[1]);
+#pragma unroll
+    for (int i = 2; i < 8; i += 2) {
+        mont_row<P, false>(even, odd, a.v, b.v[i]);
+        mont_row<P, false>(odd, even, a.v, b.v[i + 1]);
+    }
+    // merge the two out-of-phase accumulators: result limb k = even[k] + odd[k+1]
+    Fp<P> r;
+    r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) r.v[i] = addc_cc(even[i], odd[i + 1]);
+    r.v[7] = addc(even[7], 0);
+    final_sub<P>(r.v);
+    return r;
+}
+
+template <class P>
+ZKG_D Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul(a, a); }
+
+// Montgomery -> canonical (ark-ff into_bigint): multiply by 1
+template <class P>
+ZKG_D Fp<P> fp_from_mont(const Fp<P>& a) {
+    Fp<P> o = Fp<P>::zero();
+    o.v[0] = 1;
+    return fp_mul(a, o);
+}
+template <class P>
+ZKG_D Fp<P> fp_to_mont(const Fp<P>& a) { return fp_mul(a, Fp<P>::r2()); }
+
+// a^e for a canonical 256-bit exponent given as 8 limbs (used for inversion / roots)
+template <class P>
+ZKG_NI Fp<P> fp_pow(const Fp<P>& a, const uint32_t* e, int nlimbs) {
+    Fp<P> acc = Fp<P>::one();
+    for (int i = nlimbs - 1; i >= 0; --i)
+        for (int b = 31; b >= 0; --b) {
+            acc = fp_sqr(acc);
+            if ((e[i] >> b) & 1) acc = fp_mul(acc, a);
+        }
+    return acc;
+}
+
+// Fermat inversion a^(p-2); 0 -> 0
+template <class P>
+ZKG_NI Fp<P> fp_inv(const Fp<P>& a) {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = P::mod(i);
+    e[0] -= 2;   // both moduli are odd and > 2: low limb does not borrow
+    return fp_pow(a, e, 8);
+}
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+}  // namespace zkg

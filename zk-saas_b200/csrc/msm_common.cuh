@@ -1,0 +1,57 @@
+// msm_common.cuh -- window/digit logic shared by the MSM kernels (device) and their host-emulated
+// tests.  Restates the signed-digit recoding of ark-ec 0.4.2 `make_digits` (the algorithm behind
+// `VariableBaseMSM::msm`, reference call site dist-primitives/src/dmsm/mod.rs:73) with our own
+// window-size rule: a group element has one normalised affine form, so the window size changes
+// the schedule, not the result.
+#pragma once
+#include "fp.cuh"
+
+namespace zkg {
+
+static constexpr int MSM_SCALAR_BITS = 254;          // BN254 Fr
+static constexpr uint32_t MSM_DIGIT_NONE = 0xffffffffu;
+
+// number of windows such that W*c >= 255: the top window then always has a spare bit, so the
+// final carry of the signed recoding is absorbed without an extra window.
+ZKG_HD int msm_num_windows(int c) { return MSM_SCALAR_BITS / c + 1; }
+
+// window size for n points: balances n*W mixed adds against W*2^(c-1) bucket-reduction adds
+ZKG_HD int msm_pick_c(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << lg) < n) ++lg;
+    int c = lg - 5;
+    if (c < 5) c = 5;
+    if (c > 20) c = 20;
+    return c;
+}
+
+// c-bit window `w` of a canonical 256-bit scalar held as 8 x u32
+ZKG_HD uint32_t msm_window_bits(const uint32_t* s, int w, int c) {
+    int bit = w * c;
+    int limb = bit >> 5, off = bit & 31;
+    uint64_t lo = limb < 8 ? s[limb] : 0u;
+    uint64_t hi = limb + 1 < 8 ? s[limb + 1] : 0u;
+    uint64_t v = (lo | (hi << 32)) >> off;
+    return (uint32_t)(v & (((uint64_t)1 << c) - 1));
+}
+
+// Signed radix-2^c digits d_w in [-2^(c-1), 2^(c-1)] with sum d_w 2^(cw) = s.
+// Encoding: MSM_DIGIT_NONE for 0, else (|d|-1) | (d<0 ? 1<<31 : 0); |d|-1 is the bucket index.
+ZKG_HD void msm_signed_digits(const uint32_t* s, int c, int W, uint32_t* out) {
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    for (int w = 0; w < W; ++w) {
+        uint32_t coef = msm_window_bits(s, w, c) + carry;
+        uint32_t neg = 0;
+        carry = 0;
+        if (w != W - 1 && coef >= half && coef != 0) {
+            // coef in [2^(c-1), 2^c]: use coef - 2^c (<= 0) and carry one into the next window
+            if (coef == (1u << c)) { coef = 0; }
+            else { coef = (1u << c) - coef; neg = 1; }
+            carry = 1;
+        }
+        out[w] = coef == 0 ? MSM_DIGIT_NONE : ((coef - 1) | (neg << 31));
+    }
+}
+
+}  // namespace zkg

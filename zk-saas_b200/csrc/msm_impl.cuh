@@ -1,0 +1,430 @@
+// msm_impl.cuh -- BN254 G1/G2 multi-scalar multiplication on sm_100a.
+//
+// Replaces `G::msm(bases, scalars)` (ark-ec 0.4.2 VariableBaseMSM::msm -> msm_bigint_wnaf) at
+// dist-primitives/src/dmsm/mod.rs:73 -- the hottest loop of the reference (callers:
+// groth16/src/prove.rs:52,106,154,209,219).
+//
+// Pipeline (all on the context's stream, no host round-trips):
+//   k_digits      scalars: Montgomery -> canonical, signed radix-2^c digits, per-(window,bucket) histogram
+//   k_scan        exclusive scan of the histogram inside each window  -> bucket start offsets
+//   k_scatter     counting-sort the point indices of every window by bucket
+//   k_accumulate  one thread per (window,bucket): gather affine bases (128-bit loads), XYZZ mixed adds
+//   k_reduce_lvl  multi-level running-sum reduction  sum_b (b+1)*B_b  per window (see below)
+//   k_final       Horner over windows (c doublings each) + normalisation to affine
+// The arithmetic is integer-pipe bound (IMAD.WIDE), not HBM bound: per point 96 B of traffic vs
+// ~10 field multiplications per window.
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+#include "msm_common.cuh"
+
+namespace zkg {
+
+// ------------------------------------------------------------------------------------------
+// loads / stores
+// ------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ T load_vec(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = __ldg(s + i);
+    return r;
+}
+template <class T>
+__device__ __forceinline__ T load_vec_rw(const T* p) {     // data written earlier by this launch sequence
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = s[i];
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void store_vec(T* p, const T& v) {
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// arkworks Affine images (72 B / 136 B, `infinity` flag after the coordinates) -> packed (x,y)
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void k_pack_bases(const uint8_t* __restrict__ ark, size_t stride, size_t n, Affine<F>* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = ark + i * stride;
+    Affine<F> a;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&a);
+    constexpr int WORDS = sizeof(Affine<F>) / 4;
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+        const uint2* s = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+        for (int k = 0; k < WORDS / 2; ++k) { uint2 v = s[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k)
+            w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
+    }
+    if (p[sizeof(Affine<F>)] != 0) a = Affine<F>::inf();
+    store_vec(out + i, a);
+}
+
+// ------------------------------------------------------------------------------------------
+// scalars -> signed digits + histogram
+// ------------------------------------------------------------------------------------------
+static __global__ void k_digits(const Fr* __restrict__ scalars, size_t n, int c, int W, uint32_t nb,
+                         uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = fp_from_mont(load_vec(scalars + i));      // into_bigint()
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    for (int w = 0; w < W; ++w) {
+        uint32_t coef = msm_window_bits(s.v, w, c) + carry;
+        uint32_t neg = 0;
+        carry = 0;
+        if (w != W - 1 && coef >= half) {
+            if (coef == (1u << c)) coef = 0;
+            else { coef = (1u << c) - coef; neg = 1; }
+            carry = 1;
+        }
+        uint32_t d = MSM_DIGIT_NONE;
+        if (coef != 0) {
+            d = (coef - 1) | (neg << 31);
+            atomicAdd(&counts[(size_t)w * nb + (coef - 1)], 1u);
+        }
+        digits[(size_t)w * n + i] = d;
+    }
+}
+
+// exclusive scan of counts inside each window (one block per window)
+static __global__ void k_scan(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t part[1024];
+    const uint32_t* in = counts + (size_t)blockIdx.x * nb;
+    uint32_t* out = cursor + (size_t)blockIdx.x * nb;
+    uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
+    uint32_t lo = threadIdx.x * per, hi = min(lo + per, nb);
+    uint32_t s = 0;
+    for (uint32_t k = lo; k < hi; ++k) s += in[k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread partial sums
+    for (uint32_t off = 1; off < blockDim.x; off <<= 1) {
+        uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t base = threadIdx.x == 0 ? 0 : part[threadIdx.x - 1];
+    for (uint32_t k = lo; k < hi; ++k) { out[k] = base; base += in[k]; }
+}
+
+static __global__ void k_scatter(const uint32_t* __restrict__ digits, size_t n, uint32_t nb, uint32_t* __restrict__ cursor,
+                          uint32_t* __restrict__ sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t w = blockIdx.y;
+    if (i >= n) return;
+    uint32_t d = digits[(size_t)w * n + i];
+    if (d == MSM_DIGIT_NONE) return;
+    uint32_t pos = atomicAdd(&cursor[(size_t)w * nb + (d & 0x7fffffffu)], 1u);
+    sorted[(size_t)w * n + pos] = (uint32_t)i | (d & 0x80000000u);
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket accumulation: one thread per (window, bucket)
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+             const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts, size_t n, uint32_t nb, int W,
+             XYZZ<F>* __restrict__ buckets) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)W * nb) return;
+    // top window first: it is the one that can hold up to twice the points per bucket
+    uint32_t w = (uint32_t)(W - 1 - t / nb), b = (uint32_t)(t % nb);
+    size_t slot = (size_t)w * nb + b;
+    uint32_t end = cursor_end[slot], cnt = counts[slot];
+    const uint32_t* idx = sorted + (size_t)w * n;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = end - cnt; k < end; ++k) {
+        uint32_t e = idx[k];
+        Affine<F> p = load_vec(bases + (e & 0x7fffffffu));
+        xyzz_madd(acc, p, (e >> 31) != 0);
+    }
+    store_vec(buckets + slot, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Bucket reduction.  Per window we need  S = sum_b (b+1) B_b = sum_b b*B_b + sum_b B_b.
+// Invariant at level k (M_k = L^k):   sum_b b*B_b = sum_idx [ Cs_k[idx] + M_k * idx * R_k[idx] ]
+// with R_0 = B, Cs_0 = 0.  One level folds L consecutive entries (segment u):
+//   R_{k+1}[u]  = sum_i R_k[uL+i]
+//   Cs_{k+1}[u] = sum_i Cs_k[uL+i] + M_k * sum_i i*R_k[uL+i]        (running-sum trick for the i* term)
+// When one entry is left, S = Cs + R.  Depth is ~3L adds per level, fully parallel inside a level.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce_lvl(const XYZZ<F>* __restrict__ R_in, const XYZZ<F>* __restrict__ Cs_in, uint32_t n_in, uint32_t L,
+             int log2_M, int W, XYZZ<F>* __restrict__ R_out, XYZZ<F>* __restrict__ Cs_out, uint32_t n_out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)W * n_out) return;
+    uint32_t w = (uint32_t)(t / n_out), u = (uint32_t)(t % n_out);
+    uint32_t lo = u * L, hi = min(lo + L, n_in);
+    const XYZZ<F>* Rw = R_in + (size_t)w * n_in;
+    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf(), cs = XYZZ<F>::inf();
+    for (uint32_t k = hi; k-- > lo;) {
+        XYZZ<F> e = load_vec_rw(Rw + k);
+        if (k != lo) {                 // weight (k - lo) >= 1
+            xyzz_add(run, e);
+            xyzz_add(acc, run);
+        } else {
+            xyzz_add(run, e);          // weight 0: only joins the plain sum
+        }
+        if (Cs_in) {
+            XYZZ<F> cc = load_vec_rw(Cs_in + (size_t)w * n_in + k);
+            xyzz_add(cs, cc);
+        }
+    }
+    for (int d = 0; d < log2_M; ++d) xyzz_dbl(acc);
+    xyzz_add(cs, acc);
+    store_vec(R_out + t, run);
+    store_vec(Cs_out + t, cs);
+}
+
+// Horner over the window sums + normalisation.  mode 0: Jacobian image (x, y, 1) / (1, 1, 0);
+// mode 1: raw XYZZ partial (for multi-GPU combination).
+template <class F>
+__global__ void k_final(const XYZZ<F>* __restrict__ R, const XYZZ<F>* __restrict__ Cs, int c, int W, int mode,
+                        F* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int w = W - 1; w >= 0; --w) {
+        for (int d = 0; d < c; ++d) xyzz_dbl(acc);
+        XYZZ<F> s = load_vec_rw(R + w);
+        XYZZ<F> cs = load_vec_rw(Cs + w);
+        xyzz_add(s, cs);
+        xyzz_add(acc, s);
+    }
+    if (mode == 1) {
+        out[0] = acc.x; out[1] = acc.y; out[2] = acc.zz; out[3] = acc.zzz;
+        return;
+    }
+    if (acc.is_inf()) { out[0] = F::one(); out[1] = F::one(); out[2] = F::zero(); return; }
+    Affine<F> a = xyzz_to_affine(acc);
+    out[0] = a.x; out[1] = a.y; out[2] = F::one();
+}
+
+// identity result for n == 0
+template <class F>
+__global__ void k_identity(int mode, F* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (mode == 1) { out[0] = F::zero(); out[1] = F::zero(); out[2] = F::zero(); out[3] = F::zero(); }
+    else { out[0] = F::one(); out[1] = F::one(); out[2] = F::zero(); }
+}
+
+// sum of XYZZ partials (multi-GPU combine) + normalisation
+template <class F>
+__global__ void k_combine(const XYZZ<F>* __restrict__ parts, size_t n, F* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (size_t i = 0; i < n; ++i) xyzz_add(acc, load_vec_rw(parts + i));
+    if (acc.is_inf()) { out[0] = F::one(); out[1] = F::one(); out[2] = F::zero(); return; }
+    Affine<F> a = xyzz_to_affine(acc);
+    out[0] = a.x; out[1] = a.y; out[2] = F::one();
+}
+
+// ------------------------------------------------------------------------------------------
+// fixed-base generation: out[i] = scalars[i] * G  (synthetic CRS; MsmMask::sample's gen * x)
+// 4-bit fixed windows over a shared-memory table of (j * 16^w) * G would be faster; this is a
+// test/bench data generator, a plain double-and-add with one inversion per point is enough.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ Affine<F> generator();
+template <>
+__device__ __forceinline__ Affine<Fq> generator<Fq>() {
+    Affine<Fq> g;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g.x.v[i] = BN254_G1_GEN_X_MONT_L(i); g.y.v[i] = BN254_G1_GEN_Y_MONT_L(i); }
+    return g;
+}
+template <>
+__device__ __forceinline__ Affine<Fq2> generator<Fq2>() {
+    Affine<Fq2> g;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        g.x.c0.v[i] = BN254_G2_GEN_X_C0_MONT_L(i); g.x.c1.v[i] = BN254_G2_GEN_X_C1_MONT_L(i);
+        g.y.c0.v[i] = BN254_G2_GEN_Y_C0_MONT_L(i); g.y.c1.v[i] = BN254_G2_GEN_Y_C1_MONT_L(i);
+    }
+    return g;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_fixed_base(const Fr* __restrict__ scalars, size_t n, Affine<F>* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = fp_from_mont(load_vec(scalars + i));
+    Affine<F> g = generator<F>();
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int b = 253; b >= 0; --b) {
+        xyzz_dbl(acc);
+        if ((s.v[b >> 5] >> (b & 31)) & 1) xyzz_madd(acc, g, false);
+    }
+    store_vec(out + i, xyzz_to_affine(acc));
+}
+
+// ------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <class F>
+static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, F* d_out, int mode) {
+    cudaStream_t st = ctx->stream;
+    if (n == 0) {
+        k_identity<F><<<1, 32, 0, st>>>(mode, d_out);
+        ZKG_CUDA(cudaGetLastError());
+        return ZKG_OK;
+    }
+    ZKG_REQUIRE(n < ((size_t)1 << 31), "msm: n = %zu exceeds 2^31-1", n);
+    int c = env_int("ZKG_MSM_C", 0);
+    if (c < 2 || c > 22) c = msm_pick_c(n);
+    const int W = msm_num_windows(c);
+    const uint32_t nb = 1u << (c - 1);
+    const uint32_t L = 8;
+    const size_t slots = (size_t)W * nb;
+    const uint32_t n1 = (nb + L - 1) / L;
+
+    // workspace carve-up
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_digits = carve(sizeof(uint32_t) * W * n);
+    size_t o_sorted = carve(sizeof(uint32_t) * W * n);
+    size_t o_counts = carve(sizeof(uint32_t) * slots);
+    size_t o_cursor = carve(sizeof(uint32_t) * slots);
+    size_t o_buckets = carve(sizeof(XYZZ<F>) * slots);
+    size_t o_r0 = carve(sizeof(XYZZ<F>) * W * n1);
+    size_t o_c0 = carve(sizeof(XYZZ<F>) * W * n1);
+    size_t o_r1 = carve(sizeof(XYZZ<F>) * W * n1);
+    size_t o_c1 = carve(sizeof(XYZZ<F>) * W * n1);
+    ZKG_TRY(ctx->ws.reserve(off));
+    uint8_t* ws = (uint8_t*)ctx->ws.p;
+    uint32_t* digits = (uint32_t*)(ws + o_digits);
+    uint32_t* sorted = (uint32_t*)(ws + o_sorted);
+    uint32_t* counts = (uint32_t*)(ws + o_counts);
+    uint32_t* cursor = (uint32_t*)(ws + o_cursor);
+    XYZZ<F>* buckets = (XYZZ<F>*)(ws + o_buckets);
+    XYZZ<F>* Rb[2] = {(XYZZ<F>*)(ws + o_r0), (XYZZ<F>*)(ws + o_r1)};
+    XYZZ<F>* Cb[2] = {(XYZZ<F>*)(ws + o_c0), (XYZZ<F>*)(ws + o_c1)};
+
+    ZKG_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * slots, st));
+    const int TB = 256;
+    k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, c, W, nb, digits, counts);
+    k_scan<<<W, 1024, 0, st>>>(counts, nb, cursor);
+    k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), W), TB, 0, st>>>(digits, n, nb, cursor, sorted);
+    k_accumulate<F><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(d_bases, sorted, cursor, counts, n, nb, W, buckets);
+
+    // multi-level bucket reduction
+    const XYZZ<F>* Rin = buckets;
+    const XYZZ<F>* Cin = nullptr;
+    uint32_t n_in = nb;
+    int log2_M = 0, pp = 0;
+    while (true) {
+        uint32_t n_out = (n_in + L - 1) / L;
+        size_t th = (size_t)W * n_out;
+        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(Rin, Cin, n_in, L, log2_M, W, Rb[pp], Cb[pp], n_out);
+        Rin = Rb[pp]; Cin = Cb[pp];
+        pp ^= 1;
+        n_in = n_out;
+        log2_M += 3;           // M *= L (L = 8)
+        if (n_out == 1) break;
+    }
+    k_final<F><<<1, 32, 0, st>>>(Rin, Cin, c, W, mode, d_out);
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+template <class F>
+static int32_t pack_bases(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t n, void* d_packed) {
+    if (n == 0) return ZKG_OK;
+    ZKG_REQUIRE(stride >= sizeof(Affine<F>) + 1, "base stride %zu too small", stride);
+    k_pack_bases<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)d_ark, stride, n, (Affine<F>*)d_packed);
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+// blocking host-pointer MSM (both curves)
+template <class F>
+static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,
+                        size_t n_scalars, uint64_t* out_xyz) {
+    if (n_bases != n_scalars) {
+        set_error("msm: bases.len() = %zu, scalars.len() = %zu", n_bases, n_scalars);
+        return ZKG_ERR_LEN_MISMATCH;
+    }
+    ZKG_REQUIRE(out_xyz != nullptr, "msm: out is NULL");
+    ZKG_REQUIRE(n_bases == 0 || (bases && scalars), "msm: NULL input");
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    size_t n = n_bases;
+    size_t ark_bytes = align_up(n * stride, 256), sc_bytes = align_up(n * 32, 256), pk_bytes = align_up(n * sizeof(Affine<F>), 256);
+    ZKG_TRY(ctx->io.reserve(ark_bytes + sc_bytes + pk_bytes + 256));
+    uint8_t* d_ark = (uint8_t*)ctx->io.p;
+    uint8_t* d_sc = d_ark + ark_bytes;
+    uint8_t* d_pk = d_sc + sc_bytes;
+    F* d_out = (F*)(d_pk + pk_bytes);
+    if (n) {
+        ZKG_CUDA(cudaMemcpyAsync(d_sc, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ZKG_CUDA(cudaMemcpyAsync(d_ark, bases, n * stride, cudaMemcpyHostToDevice, ctx->stream));
+        ZKG_TRY(pack_bases<F>(ctx, d_ark, stride, n, d_pk));
+    }
+    ZKG_TRY(msm_run<F>(ctx, (const Affine<F>*)d_pk, (const Fr*)d_sc, n, d_out, 0));
+    ZKG_CUDA(cudaMemcpyAsync(out_xyz, d_out, 3 * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+
+// per-curve entry points, instantiated in msm_g1.cu (F = Fq) and msm_g2.cu (F = Fq2)
+#define ZKG_MSM_DECLARE(G)                                                                                          \
+    int32_t msm_run_##G(zkg_ctx* ctx, const void* d_bases, const uint64_t* d_scalars, size_t n, void* d_out, int mode); \
+    int32_t pack_bases_##G(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t n, void* d_packed);               \
+    int32_t msm_host_##G(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,     \
+                         size_t n_scalars, uint64_t* out_xyz);                                                      \
+    int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out);                          \
+    int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);
+ZKG_MSM_DECLARE(g1)
+ZKG_MSM_DECLARE(g2)
+
+#define ZKG_MSM_DEFINE(G, F)                                                                                        \
+    int32_t msm_run_##G(zkg_ctx* ctx, const void* d_bases, const uint64_t* d_scalars, size_t n, void* d_out, int mode) { \
+        return msm_run<F>(ctx, (const Affine<F>*)d_bases, (const Fr*)d_scalars, n, (F*)d_out, mode);                \
+    }                                                                                                               \
+    int32_t pack_bases_##G(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t n, void* d_packed) {              \
+        return pack_bases<F>(ctx, d_ark, stride, n, d_packed);                                                      \
+    }                                                                                                               \
+    int32_t msm_host_##G(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,     \
+                         size_t n_scalars, uint64_t* out_xyz) {                                                     \
+        return msm_host<F>(device, bases, stride, n_bases, scalars, n_scalars, out_xyz);                            \
+    }                                                                                                               \
+    int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out) {                         \
+        k_combine<F><<<1, 32, 0, ctx->stream>>>((const XYZZ<F>*)d_parts, n, (F*)d_out);                             \
+        ZKG_CUDA(cudaGetLastError());                                                                               \
+        return ZKG_OK;                                                                                              \
+    }                                                                                                               \
+    int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed) {                     \
+        if (n == 0) return ZKG_OK;                                                                                  \
+        k_fixed_base<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const Fr*)d_scalars, n, (Affine<F>*)d_packed); \
+        ZKG_CUDA(cudaGetLastError());                                                                               \
+        return ZKG_OK;                                                                                              \
+    }
+
+}  // namespace zkg

@@ -1,0 +1,800 @@
+// ntt.cu -- BN254 Fr transforms of the d_fft / d_ifft path and the PackedSharingParams maps.
+//
+// Replaces (reference file:line)
+//   fft1_in_place                     dist-primitives/src/dfft/mod.rs:178-208   (clients)
+//   king closure of fft2_with_rearrange dist-primitives/src/dfft/mod.rs:264-304 (king)
+//     = transpose + unpack_missing_shares (:265-274) + fft2_in_place (:210-237) + distribute_powers
+//       (:278-280) + fft_in_place_rearrange (:322-335) + pack / pack_vec (:287-302, utils/pack.rs:8-35)
+//   king closure of deg_red           dist-primitives/src/utils/deg_red.rs:103-111
+//   pack / det_pack / unpack / unpack2 secret-sharing/src/pss.rs:69-166
+//
+// fft1 closed form (checked against the literal loops in oracle/): with N = m/l, y = the share
+// vector read in bit-reversed order and w_N = gen^l,
+//      fft1(px)[k] = X[(k+1) mod N],   X = DFT_N(y; w_N).
+// The reference's "+1" twiddle convention is exactly that cyclic shift, so the kernel is an
+// ordinary bit-reversed-input / natural-output NTT whose final store is shifted by one slot.
+// Large N runs as a multi-pass four-step: every pass loads a tile into shared memory (limb-major,
+// bank-conflict free), multiplies by one on-the-fly inter-pass twiddle w^(klow * j) composed from a
+// two-level power table, and runs up to 10 radix-2 stages out of shared memory.
+//
+// fft2 closed form: the log2(l) stages only ever combine the l secrets of one share column k, and
+// send them to positions (k + q*m/l + 1) mod m; so the whole king pipeline is column-local up to
+// one permutation, which the first kernel applies while storing its results in pack order.
+#include "common.cuh"
+#include "fp.cuh"
+#include "host_fr.hpp"
+#include <deque>
+
+namespace zkg {
+
+using host::HFr;
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+    Fr r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(s), b = __ldg(s + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ Fr ld_fr_rw(const Fr* p) {
+    Fr r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4 a = s[0], b = s[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& r) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    d[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    d[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+struct FrArg { uint32_t v[8]; };       // Fr passed by value as a kernel argument
+static FrArg to_arg(const HFr& h) { FrArg a; memcpy(a.v, h.v, 32); return a; }
+__device__ __forceinline__ Fr from_arg(const FrArg& a) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = a.v[i];
+    return r;
+}
+
+// out[i] = base^i, i < count  (square-and-multiply per thread; count is a few thousand)
+__global__ void k_pow_table(FrArg base_, uint32_t count, Fr* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr base = from_arg(base_), acc = Fr::one();
+    for (int b = 31 - __clz(i | 1); b >= 0; --b) {
+        acc = fp_sqr(acc);
+        if ((i >> b) & 1) acc = fp_mul(acc, base);
+    }
+    st_fr(out + i, acc);
+}
+
+// Two-level power table of a root w: w^e = lo[e & (LO-1)] * hi[e >> LO_BITS]
+static constexpr int TW_LO_BITS = 12;
+static constexpr uint32_t TW_LO = 1u << TW_LO_BITS;
+struct PowTable { const Fr* lo; const Fr* hi; };
+__device__ __forceinline__ Fr pow_lookup(const PowTable& t, uint64_t e) {
+    Fr a = ld_fr(t.lo + (uint32_t)(e & (TW_LO - 1)));
+    uint64_t h = e >> TW_LO_BITS;
+    if (h) a = fp_mul(a, ld_fr(t.hi + h));
+    return a;
+}
+
+__device__ __forceinline__ uint32_t bitrev32(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+
+// ------------------------------------------------------------------------------------------
+// One NTT pass.  The transform index is split as  p = upper * 2^(s+b) + row * 2^s + klow; a block
+// owns one `upper`, CW consecutive klow ("columns") and all 2^b rows, and performs CW independent
+// size-2^b DFTs (bit-reversed rows in, natural rows out) after multiplying element (row, klow) by
+// rho^(klow * bitrev_b(row)), rho = w_N^(N / 2^(s+b)).
+// ------------------------------------------------------------------------------------------
+struct NttPass {
+    int logN, s, b, cw_log;
+    int first, last, shift;          // shift: store X[k] at (k-1) mod N (fft1 convention)
+    int has_scale;
+    FrArg scale;                     // pre-multiplier applied on the first pass (d_ifft's size_inv)
+};
+
+__global__ void __launch_bounds__(512)
+k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr* __restrict__ tw_small, PowTable tw,
+           const Fr* __restrict__ mask) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t T = 1u << P.b, CW = 1u << P.cw_log, E = T * CW;   // elements per block
+    uint32_t* S = smem;                       // 8 limb planes of E words
+    uint32_t* TWS = smem + 8 * E;             // 8 limb planes of T/2 words (small twiddles w_T^i)
+    const uint32_t cols_per_upper = (1u << P.s) >> P.cw_log;
+    const uint32_t upper = blockIdx.x / cols_per_upper;
+    const uint32_t klow0 = (blockIdx.x % cols_per_upper) << P.cw_log;
+    const size_t base = ((size_t)upper << (P.s + P.b)) + klow0;
+    const int rho_shift = P.logN - P.s - P.b;   // rho^e = w_N^(e << rho_shift)
+
+    for (uint32_t i = threadIdx.x; i < T / 2; i += blockDim.x) {
+        Fr t = ld_fr(tw_small + i);
+#pragma unroll
+        for (int l = 0; l < 8; ++l) TWS[l * (T / 2) + i] = t.v[l];
+    }
+    Fr scale = from_arg(P.scale);
+    for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
+        uint32_t col = idx & (CW - 1), row = idx >> P.cw_log;
+        Fr x = ld_fr(in + base + ((size_t)row << P.s) + col);
+        if (P.first && P.has_scale) x = fp_mul(x, scale);
+        if (!P.first) {
+            uint64_t e = (uint64_t)(klow0 + col) * bitrev32(row, P.b);
+            if (e) x = fp_mul(x, pow_lookup(tw, e << rho_shift));
+        }
+#pragma unroll
+        for (int l = 0; l < 8; ++l) S[l * E + idx] = x.v[l];
+    }
+    __syncthreads();
+
+    for (int sg = 0; sg < P.b; ++sg) {
+        const uint32_t half = 1u << sg;
+        for (uint32_t u = threadIdx.x; u < E / 2; u += blockDim.x) {
+            uint32_t col = u & (CW - 1), t = u >> P.cw_log;
+            uint32_t kin = t & (half - 1);
+            uint32_t i0 = (((t >> sg) << (sg + 1)) | kin) * CW + col;
+            uint32_t i1 = i0 + half * CW;
+            Fr x, y;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) { x.v[l] = S[l * E + i0]; y.v[l] = S[l * E + i1]; }
+            if (kin) {
+                Fr w;
+                uint32_t ti = kin << (P.b - 1 - sg);
+#pragma unroll
+                for (int l = 0; l < 8; ++l) w.v[l] = TWS[l * (T / 2) + ti];
+                y = fp_mul(y, w);
+            }
+            Fr a = fp_add(x, y), d = fp_sub(x, y);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) { S[l * E + i0] = a.v[l]; S[l * E + i1] = d.v[l]; }
+        }
+        __syncthreads();
+    }
+
+    const size_t N = (size_t)1 << P.logN;
+    for (uint32_t idx = threadIdx.x; idx < E; idx += blockDim.x) {
+        uint32_t col = idx & (CW - 1), row = idx >> P.cw_log;
+        Fr x;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) x.v[l] = S[l * E + idx];
+        size_t k = base + ((size_t)row << P.s) + col;
+        if (P.last && P.shift) k = (k + N - 1) & (N - 1);
+        if (P.last && mask) x = fp_add(x, ld_fr(mask + k));
+        st_fr(out + k, x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// King, kernel 1: per share column k: secrets = U * shares (unpack2 or Lagrange matrix), the
+// column-local fft2 butterflies, g^pos powers, and the store in *pack order*:
+//   S[c*l + j] = j-th secret of output column c.
+// mode 0: consecutive packing (pack_vec)          c = pos / l,          j = pos % l
+// mode 1: rearrange (bit-reverse + stride m/l)    p = bitrev_m(pos):    c = p % (m/l), j = p / (m/l)
+// mode 2: no fft2 at all (deg_red): S[k*l + j] = secrets[j]
+// mode 3: fft2 only, natural positions, input read directly from `direct` ([k*l + j])
+// ------------------------------------------------------------------------------------------
+template <int LL>
+__global__ void __launch_bounds__(256)
+k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restrict__ U, const Fr* __restrict__ direct,
+              size_t mbyl, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw, Fr* __restrict__ S) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= mbyl) return;
+    constexpr int LOGL = LL == 2 ? 1 : LL == 4 ? 2 : 3;
+    Fr v[LL];
+    if (direct) {
+#pragma unroll
+        for (int j = 0; j < LL; ++j) v[j] = ld_fr(direct + k * LL + j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < LL; ++j) v[j] = Fr::zero();
+        for (uint32_t r = 0; r < n_recv; ++r) {
+            Fr x = ld_fr(shares + (size_t)r * mbyl + k);
+#pragma unroll
+            for (int j = 0; j < LL; ++j) v[j] = fp_add(v[j], fp_mul(ld_fr(U + (size_t)j * n_recv + r), x));
+        }
+    }
+    if (mode == 2) {
+#pragma unroll
+        for (int j = 0; j < LL; ++j) st_fr(S + k * LL + j, v[j]);
+        return;
+    }
+    const size_t m = (size_t)1 << log_m;
+    // fft2: stage i = LOGL..1; before the stage there are C = m/2^i columns of E = 2^i entries.
+    // The entries descending from share column k live in columns kap_q = k + q*mbyl; we keep them as
+    // v[q*E + j] (q-th descendant column, j-th entry).
+    size_t C = mbyl;
+#pragma unroll
+    for (int i = LOGL; i >= 1; --i) {
+        const int E = 1 << i, Q = LL / E;            // Q descendant columns so far
+        Fr nv[LL];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            size_t kap = k + (size_t)q * mbyl;
+            Fr tw = pow_lookup(gen_tw, (((uint64_t)(kap + 1)) << (i - 1)) & (m - 1));
+#pragma unroll
+            for (int j = 0; j < E / 2; ++j) {
+                Fr x = v[q * E + 2 * j];
+                Fr y = fp_mul(v[q * E + 2 * j + 1], tw);
+                // sums stay in column kap, differences go to column kap + C = k + (q + Q)*mbyl
+                nv[q * (E / 2) + j] = fp_add(x, y);
+                nv[(q + Q) * (E / 2) + j] = fp_sub(x, y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < LL; ++j) v[j] = nv[j];
+        C <<= 1;
+    }
+    // now v[q] is the single entry of column k + q*mbyl; rotate_right(1): position = column + 1 mod m
+#pragma unroll
+    for (int q = 0; q < LL; ++q) {
+        size_t pos = (k + (size_t)q * mbyl + 1) & (m - 1);
+        Fr x = v[q];
+        if (has_g && pos) x = fp_mul(x, pow_lookup(g_tw, pos));
+        size_t dst;
+        if (mode == 1) {
+            size_t p = (size_t)(__brevll((unsigned long long)pos) >> (64 - log_m));
+            dst = (p & (mbyl - 1)) * LL + (p / mbyl);
+        } else {
+            dst = pos;        // mode 0: S[c*l + j] with c = pos / l, j = pos % l is S[pos]; mode 3 likewise
+        }
+        st_fr(S + dst, x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense map with the INPUT vector in registers (few inputs, many outputs): pack / det_pack.
+//   out(c, i) = sum_{j<K1} M[i][j] * in1(c, j) + sum_{j<K2} M[i][K1+j] * in2(c, j)
+// element (c, j) of an operand sits at ptr[c * cs + j * rs].
+// ------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+k_map_in_regs(const Fr* __restrict__ M, int rows, int k1, const Fr* __restrict__ in1, size_t in1_cs, size_t in1_rs,
+              const Fr* __restrict__ in2, size_t in2_cs, size_t in2_rs, int k2, Fr* __restrict__ out, size_t out_cs,
+              size_t out_rs, size_t cols) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    Fr x[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < k1) x[j] = ld_fr(in1 + c * in1_cs + (size_t)j * in1_rs);
+        else if (j < k1 + k2) x[j] = ld_fr(in2 + c * in2_cs + (size_t)(j - k1) * in2_rs);
+        else x[j] = Fr::zero();
+    }
+    const int kk = k1 + k2;             // row length of M is k1 + (declared k2 columns)
+    for (int i = 0; i < rows; ++i) {
+        Fr acc = Fr::zero();
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (j < kk) acc = fp_add(acc, fp_mul(ld_fr(M + (size_t)i * K + j), x[j]));
+        st_fr(out + c * out_cs + (size_t)i * out_rs, acc);
+    }
+}
+
+// Dense map with the OUTPUT accumulators in registers (many inputs, few outputs): unpack / unpack2.
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+k_map_acc_regs(const Fr* __restrict__ M, int k, const Fr* __restrict__ in, size_t in_cs, size_t in_rs,
+               Fr* __restrict__ out, size_t out_cs, size_t out_rs, size_t cols) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    Fr acc[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) acc[i] = Fr::zero();
+    for (int j = 0; j < k; ++j) {
+        Fr x = ld_fr(in + c * in_cs + (size_t)j * in_rs);
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) acc[i] = fp_add(acc[i], fp_mul(ld_fr(M + (size_t)i * k + j), x));
+    }
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) st_fr(out + c * out_cs + (size_t)i * out_rs, acc[i]);
+}
+
+// v[i] *= g^i
+__global__ void k_distribute_powers(Fr* __restrict__ v, size_t n, PowTable g_tw) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || i == 0) return;
+    st_fr(v + i, fp_mul(ld_fr_rw(v + i), pow_lookup(g_tw, i)));
+}
+// v[i] *= s * g^i  (ifft tail: size_inv * offset^-i)
+__global__ void k_scale_powers(Fr* __restrict__ v, size_t n, FrArg s_, int has_g, PowTable g_tw) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr f = from_arg(s_);
+    if (has_g && i) f = fp_mul(f, pow_lookup(g_tw, i));
+    st_fr(v + i, fp_mul(ld_fr_rw(v + i), f));
+}
+// out[bitrev(i)] = in[i]
+__global__ void k_bitrev(const Fr* __restrict__ in, Fr* __restrict__ out, int log_n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << log_n)) return;
+    size_t r = log_n ? (size_t)(__brevll((unsigned long long)i) >> (64 - log_n)) : 0;
+    st_fr(out + r, ld_fr(in + i));
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+static int ilog2(size_t x) { int r = 0; while (((size_t)1 << r) < x) ++r; return r; }
+static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+
+// carve scratch from ctx->small (tables, matrices)
+struct SmallAlloc {
+    zkg_ctx* ctx; size_t off = 0; size_t cap;
+    uint8_t* take(size_t bytes) { uint8_t* p = (uint8_t*)ctx->small.p + off; off = align_up(off + bytes, 256); return off <= cap ? p : nullptr; }
+};
+
+static int32_t build_pow_table(zkg_ctx* ctx, SmallAlloc& sa, const HFr& w, size_t max_exp_excl, PowTable* out) {
+    size_t hi_n = (max_exp_excl + TW_LO - 1) >> TW_LO_BITS;
+    if (hi_n == 0) hi_n = 1;
+    Fr* lo = (Fr*)sa.take(TW_LO * sizeof(Fr));
+    Fr* hi = (Fr*)sa.take(hi_n * sizeof(Fr));
+    ZKG_REQUIRE(lo && hi, "internal: small workspace exhausted");
+    k_pow_table<<<(TW_LO + 255) / 256, 256, 0, ctx->stream>>>(to_arg(w), TW_LO, lo);
+    HFr w_hi = host::h_pow(w, TW_LO);
+    k_pow_table<<<(unsigned)((hi_n + 255) / 256), 256, 0, ctx->stream>>>(to_arg(w_hi), (uint32_t)hi_n, hi);
+    ZKG_CUDA(cudaGetLastError());
+    out->lo = lo; out->hi = hi;
+    return ZKG_OK;
+}
+
+static size_t pow_table_bytes(size_t max_exp_excl) {
+    size_t hi_n = (max_exp_excl + TW_LO - 1) >> TW_LO_BITS;
+    if (hi_n == 0) hi_n = 1;
+    return align_up(TW_LO * sizeof(Fr), 256) + align_up(hi_n * sizeof(Fr), 256);
+}
+
+// In-order-output NTT of d_in (bit-reversed input order) with root w_N, into d_out.
+// shift = 1 stores X[k] at (k-1) mod N.  d_tmp: N-element scratch (used when > 2 passes or in == out).
+static int32_t ntt_bitrev_in(zkg_ctx* ctx, SmallAlloc& sa, const Fr* d_in, Fr* d_out, Fr* d_tmp, size_t N, const HFr& wN,
+                             int shift, const HFr* scale, const Fr* d_mask) {
+    const int logN = ilog2(N);
+    ZKG_REQUIRE(is_pow2(N) && logN <= 24 + 3, "ntt: size %zu unsupported", N);
+    int npass = (logN + 9) / 10;
+    if (npass == 0) npass = 1;
+    PowTable tw{nullptr, nullptr};
+    if (npass > 1) ZKG_TRY(build_pow_table(ctx, sa, wN, N, &tw));
+    int s = 0;
+    const Fr* src = d_in;
+    for (int q = 0; q < npass; ++q) {
+        int b = (logN - s + (npass - q) - 1) / (npass - q);      // spread the remaining bits evenly
+        int cw_log = 0;
+        if (q > 0) { cw_log = 11 - b; if (cw_log > s) cw_log = s; if (cw_log < 0) cw_log = 0; }
+        NttPass P;
+        P.logN = logN; P.s = s; P.b = b; P.cw_log = cw_log;
+        P.first = q == 0; P.last = q == npass - 1; P.shift = shift;
+        P.has_scale = scale != nullptr;
+        P.scale = to_arg(scale ? *scale : host::h_one());
+        // small twiddles: w_T^i, i < T/2, w_T = wN^(N/T)
+        size_t T = (size_t)1 << b;
+        Fr* tws = (Fr*)sa.take((T / 2 ? T / 2 : 1) * sizeof(Fr));
+        ZKG_REQUIRE(tws, "internal: small workspace exhausted");
+        HFr wT = host::h_pow(wN, N >> b);
+        if (T / 2) k_pow_table<<<(unsigned)((T / 2 + 255) / 256), 256, 0, ctx->stream>>>(to_arg(wT), (uint32_t)(T / 2), tws);
+        // destination: last pass -> d_out; otherwise the scratch (in place on scratch is safe: a
+        // block reads and writes the same index set when no shift is applied)
+        Fr* dst = P.last ? d_out : d_tmp;
+        size_t E = T << cw_log;
+        size_t shmem = (8 * E + 8 * (T / 2 ? T / 2 : 1)) * sizeof(uint32_t);
+        unsigned threads = (unsigned)(E / 2 < 32 ? 32 : (E / 2 > 512 ? 512 : E / 2));
+        unsigned blocks = (unsigned)(N / E);
+        ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        k_ntt_pass<<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, P.last ? d_mask : nullptr);
+        ZKG_CUDA(cudaGetLastError());
+        src = dst;
+        s += b;
+    }
+    return ZKG_OK;
+}
+
+static size_t ntt_small_bytes(size_t N) { return pow_table_bytes(N) + 4 * align_up(1024 * sizeof(Fr), 256); }
+
+// cached PSS matrices (host) per packing factor
+static std::mutex g_pss_mu;
+static host::PssMatrices g_pss[4];      // l = 2, 4, 8
+static const host::PssMatrices* pss_get(uint32_t l) {
+    int slot = l == 2 ? 0 : l == 4 ? 1 : l == 8 ? 2 : -1;
+    if (slot < 0) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pss_mu);
+    if (g_pss[slot].l != l) host::pss_matrices(l, &g_pss[slot]);
+    return &g_pss[slot];
+}
+
+static int32_t upload(zkg_ctx* ctx, SmallAlloc& sa, const std::vector<HFr>& m, const Fr** out) {
+    Fr* d = (Fr*)sa.take(m.size() * sizeof(Fr));
+    ZKG_REQUIRE(d, "internal: small workspace exhausted");
+    // the source vector lives in a cache or outlives the stream sync of the caller
+    ZKG_CUDA(cudaMemcpyAsync(d, m.data(), m.size() * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    *out = d;
+    return ZKG_OK;
+}
+
+// pad matrix rows from kk to K columns (k_map_in_regs indexes rows with stride K)
+static std::vector<HFr> pad_rows(const std::vector<HFr>& m, int rows, int kk, int K) {
+    std::vector<HFr> o((size_t)rows * K, host::h_zero());
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < kk; ++j) o[(size_t)i * K + j] = m[(size_t)i * kk + j];
+    return o;
+}
+
+static int32_t launch_pack(zkg_ctx* ctx, const Fr* dM, int K, int rows, int l, int t_used, const Fr* secrets, size_t s_cs,
+                           size_t s_rs, const Fr* rand, size_t r_cs, size_t r_rs, Fr* out, size_t o_cs, size_t o_rs,
+                           size_t cols) {
+    if (cols == 0) return ZKG_OK;
+    unsigned blocks = (unsigned)((cols + 255) / 256);
+#define LP(KK) k_map_in_regs<KK><<<blocks, 256, 0, ctx->stream>>>(dM, rows, l, secrets, s_cs, s_rs, rand, r_cs, r_rs, t_used, out, o_cs, o_rs, cols)
+    if (K == 4) LP(4); else if (K == 8) LP(8); else LP(16);
+#undef LP
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+static int32_t launch_unpack(zkg_ctx* ctx, const Fr* dM, int l, int k, const Fr* in, size_t i_cs, size_t i_rs, Fr* out,
+                             size_t o_cs, size_t o_rs, size_t cols) {
+    if (cols == 0) return ZKG_OK;
+    unsigned blocks = (unsigned)((cols + 255) / 256);
+    if (l == 2) k_map_acc_regs<2><<<blocks, 256, 0, ctx->stream>>>(dM, k, in, i_cs, i_rs, out, o_cs, o_rs, cols);
+    else if (l == 4) k_map_acc_regs<4><<<blocks, 256, 0, ctx->stream>>>(dM, k, in, i_cs, i_rs, out, o_cs, o_rs, cols);
+    else k_map_acc_regs<8><<<blocks, 256, 0, ctx->stream>>>(dM, k, in, i_cs, i_rs, out, o_cs, o_rs, cols);
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+// keeps host-side matrices alive until the stream has consumed the async upload
+struct HostKeep { std::deque<std::vector<HFr>> v; };   // deque: references stay valid across push_back
+
+// unpack matrix for the received party set (unpack2 if all present, Lagrange otherwise)
+static int32_t recv_matrix(uint32_t l, const uint32_t* parties, uint32_t n_recv, HostKeep& keep, const std::vector<HFr>** out) {
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    if (n_recv == pm->n) { *out = &pm->unpack2; return ZKG_OK; }
+    ZKG_REQUIRE(parties, "parties list required when shares are missing");
+    keep.v.emplace_back();
+    if (!host::pss_lagrange_matrix(l, parties, n_recv, &keep.v.back())) {
+        set_error("not enough shares to reconstruct: got %u of n = %u (need > %u distinct parties)", n_recv, pm->n,
+                  2 * (pm->t + pm->l - 1));
+        return ZKG_ERR_BAD_ARG;
+    }
+    *out = &keep.v.back();
+    return ZKG_OK;
+}
+
+// ---- king pipeline on device buffers ------------------------------------------------------
+// mode_fft: 1 = fft2 + powers + (re)packing (d_fft/d_ifft king), 0 = deg_red king
+static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* parties, uint32_t n_recv, size_t mbyl,
+                        uint32_t l, const HFr* gen, const HFr* g, int rearrange, const Fr* d_rand, Fr* d_out,
+                        int mode_fft, HostKeep& keep) {
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    ZKG_REQUIRE(is_pow2(mbyl) || !mode_fft, "king: m/l = %zu is not a power of two", mbyl);
+    if (mbyl == 0) return ZKG_OK;
+    const size_t m = mbyl * l;
+    const int log_m = ilog2(m);
+    ZKG_REQUIRE(!mode_fft || log_m <= 28, "king: m = %zu exceeds the 2-adicity of Fr", m);
+    const std::vector<HFr>* U;
+    ZKG_TRY(recv_matrix(l, parties, n_recv, keep, &U));
+    const int K = (int)(pm->l + pm->t) <= 4 ? 4 : (int)(pm->l + pm->t) <= 8 ? 8 : 16;
+    keep.v.push_back(pad_rows(pm->pack, pm->n, pm->l + pm->t, K));
+    const std::vector<HFr>& packK = keep.v.back();
+
+    size_t small_need = 2 * pow_table_bytes(m) + align_up(U->size() * 32, 256) + align_up(packK.size() * 32, 256) + 1024;
+    ZKG_TRY(ctx->small.reserve(small_need));
+    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    const Fr *dU, *dP;
+    ZKG_TRY(upload(ctx, sa, *U, &dU));
+    ZKG_TRY(upload(ctx, sa, packK, &dP));
+    PowTable gen_tw{nullptr, nullptr}, g_tw{nullptr, nullptr};
+    int has_g = 0;
+    if (mode_fft) {
+        ZKG_TRY(build_pow_table(ctx, sa, *gen, m, &gen_tw));
+        has_g = !(*g == host::h_one());
+        if (has_g) ZKG_TRY(build_pow_table(ctx, sa, *g, m, &g_tw));
+    }
+    ZKG_TRY(ctx->ws.reserve(m * sizeof(Fr)));
+    Fr* S = (Fr*)ctx->ws.p;
+    unsigned blocks = (unsigned)((mbyl + 255) / 256);
+    int mode = mode_fft ? (rearrange ? 1 : 0) : 2;
+#define KS(LLv) k_king_stage1<LLv><<<blocks, 256, 0, ctx->stream>>>(d_shares, n_recv, dU, nullptr, mbyl, log_m, mode, gen_tw, has_g, g_tw, S)
+    if (l == 2) KS(2); else if (l == 4) KS(4); else KS(8);
+#undef KS
+    ZKG_CUDA(cudaGetLastError());
+    // re-pack: column c takes secrets S[c*l..], rand[c*t..] -> party-major shares out[p*mbyl + c]
+    return launch_pack(ctx, dP, K, pm->n, pm->l, pm->t, S, pm->l, 1, d_rand, pm->t, 1, d_out, 1, mbyl, mbyl);
+}
+
+// gather host vectors (one per party) into a party-major device buffer
+static int32_t h2d_party_major(zkg_ctx* ctx, const uint64_t* const* by_party, uint32_t np, size_t len, Fr* d) {
+    for (uint32_t r = 0; r < np; ++r) {
+        ZKG_REQUIRE(by_party[r], "NULL share vector for index %u", r);
+        ZKG_CUDA(cudaMemcpyAsync(d + (size_t)r * len, by_party[r], len * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return ZKG_OK;
+}
+
+static int32_t king_host(int device, const uint64_t* const* shares_by_party, const uint32_t* parties, uint32_t n_recv,
+                         size_t mbyl, uint32_t l, const uint64_t* gen, const uint64_t* g, int rearrange,
+                         const uint64_t* rand, uint64_t* const* out_by_party, int mode_fft) {
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    ZKG_REQUIRE(shares_by_party && out_by_party && (mbyl == 0 || rand), "king: NULL argument");
+    ZKG_REQUIRE(n_recv >= 1 && n_recv <= pm->n, "king: n_recv = %u out of range", n_recv);
+    if (mbyl == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    size_t in_b = align_up((size_t)n_recv * mbyl * 32, 256), rand_b = align_up(mbyl * pm->t * 32, 256);
+    size_t out_b = (size_t)pm->n * mbyl * 32;
+    ZKG_TRY(ctx->io.reserve(in_b + rand_b + out_b));
+    Fr* d_in = (Fr*)ctx->io.p;
+    Fr* d_rand = (Fr*)((uint8_t*)ctx->io.p + in_b);
+    Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + in_b + rand_b);
+    ZKG_TRY(h2d_party_major(ctx, shares_by_party, n_recv, mbyl, d_in));
+    ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, mbyl * pm->t * 32, cudaMemcpyHostToDevice, ctx->stream));
+    HostKeep keep;
+    HFr hgen = mode_fft ? host::h_load(gen) : host::h_one(), hg = mode_fft ? host::h_load(g) : host::h_one();
+    ZKG_TRY(king_dev(ctx, d_in, parties, n_recv, mbyl, l, &hgen, &hg, rearrange, d_rand, d_out, mode_fft, keep));
+    for (uint32_t p = 0; p < pm->n; ++p) {
+        ZKG_REQUIRE(out_by_party[p], "NULL output vector for party %u", p);
+        ZKG_CUDA(cudaMemcpyAsync(out_by_party[p], d_out + (size_t)p * mbyl, mbyl * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+// ---- fft1 on a device buffer ----------------------------------------------------------------
+static int32_t fft1_dev(zkg_ctx* ctx, Fr* d_px, size_t mbyl, uint32_t l, const HFr& gen, const HFr* pre_scale,
+                        const Fr* d_mask) {
+    ZKG_REQUIRE(l >= 1 && is_pow2(l) && is_pow2(mbyl), "fft1: m/l = %zu and l = %u must be powers of two", mbyl, l);
+    ZKG_REQUIRE(ilog2(mbyl * l) <= 28, "fft1: m exceeds the 2-adicity of Fr");
+    ZKG_TRY(ctx->small.reserve(ntt_small_bytes(mbyl)));
+    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    ZKG_TRY(ctx->ws.reserve(mbyl * sizeof(Fr)));
+    Fr* tmp = (Fr*)ctx->ws.p;
+    HFr wN = host::h_pow(gen, l);
+    // Writing the result back into d_px is safe: with one pass a single block reads the whole
+    // vector before it stores; with several passes the last one reads the scratch, and pass 0 has
+    // already consumed d_px (stream order), so the shifted stores cannot race with any load.
+    return ntt_bitrev_in(ctx, sa, d_px, d_px, tmp, mbyl, wN, 1, pre_scale, d_mask);
+}
+
+}  // namespace zkg
+
+using namespace zkg;
+
+extern "C" {
+
+int32_t zkg_fft1_bn254_dev(zkg_ctx* ctx, uint64_t* d_px, size_t mbyl, uint32_t l, const uint64_t gen[4],
+                           const uint64_t* pre_scale, const uint64_t* d_in_mask) {
+    ZKG_REQUIRE(ctx && gen && (mbyl == 0 || d_px), "fft1: NULL argument");
+    if (mbyl == 0) return ZKG_OK;
+    DeviceGuard dg(ctx->device);
+    HFr hs;
+    if (pre_scale) hs = host::h_load(pre_scale);
+    return fft1_dev(ctx, (Fr*)d_px, mbyl, l, host::h_load(gen), pre_scale ? &hs : nullptr, (const Fr*)d_in_mask);
+}
+
+int32_t zkg_fft1_bn254(int32_t device, uint64_t* px, size_t mbyl, uint32_t l, const uint64_t gen[4],
+                       const uint64_t* pre_scale, const uint64_t* in_mask) {
+    ZKG_REQUIRE(gen && (mbyl == 0 || px), "fft1: NULL argument");
+    if (mbyl == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    size_t bytes = align_up(mbyl * 32, 256);
+    ZKG_TRY(ctx->io.reserve(2 * bytes));
+    Fr* d_px = (Fr*)ctx->io.p;
+    Fr* d_mask = (Fr*)((uint8_t*)ctx->io.p + bytes);
+    ZKG_CUDA(cudaMemcpyAsync(d_px, px, mbyl * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (in_mask) ZKG_CUDA(cudaMemcpyAsync(d_mask, in_mask, mbyl * 32, cudaMemcpyHostToDevice, ctx->stream));
+    HFr hs;
+    if (pre_scale) hs = host::h_load(pre_scale);
+    ZKG_TRY(fft1_dev(ctx, d_px, mbyl, l, host::h_load(gen), pre_scale ? &hs : nullptr, in_mask ? d_mask : nullptr));
+    ZKG_CUDA(cudaMemcpyAsync(px, d_px, mbyl * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+int32_t zkg_king_fft2_bn254(int32_t device, const uint64_t* const* shares_by_party, const uint32_t* parties,
+                            uint32_t n_recv, size_t mbyl, uint32_t l, const uint64_t gen[4], const uint64_t g[4],
+                            int32_t rearrange, const uint64_t* rand, uint64_t* const* out_by_party) {
+    ZKG_REQUIRE(gen && g, "king_fft2: NULL gen/g");
+    return king_host(device, shares_by_party, parties, n_recv, mbyl, l, gen, g, rearrange, rand, out_by_party, 1);
+}
+
+int32_t zkg_king_fft2_bn254_dev(zkg_ctx* ctx, const uint64_t* d_shares, const uint32_t* parties, uint32_t n_recv,
+                                size_t mbyl, uint32_t l, const uint64_t gen[4], const uint64_t g[4], int32_t rearrange,
+                                const uint64_t* d_rand, uint64_t* d_out) {
+    ZKG_REQUIRE(ctx && gen && g && (mbyl == 0 || (d_shares && d_rand && d_out)), "king_fft2: NULL argument");
+    DeviceGuard dg(ctx->device);
+    HostKeep keep;
+    HFr hgen = host::h_load(gen), hg = host::h_load(g);
+    ZKG_TRY(king_dev(ctx, (const Fr*)d_shares, parties, n_recv, mbyl, l, &hgen, &hg, rearrange, (const Fr*)d_rand, (Fr*)d_out, 1, keep));
+    // the async uploads read host matrices owned by `keep`: wait for them before it goes away
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+int32_t zkg_deg_red_king_bn254(int32_t device, const uint64_t* const* shares_by_party, const uint32_t* parties,
+                               uint32_t n_recv, size_t cols, uint32_t l, const uint64_t* rand,
+                               uint64_t* const* out_by_party) {
+    return king_host(device, shares_by_party, parties, n_recv, cols, l, nullptr, nullptr, 0, rand, out_by_party, 0);
+}
+
+int32_t zkg_deg_red_king_bn254_dev(zkg_ctx* ctx, const uint64_t* d_shares, const uint32_t* parties, uint32_t n_recv,
+                                   size_t cols, uint32_t l, const uint64_t* d_rand, uint64_t* d_out) {
+    ZKG_REQUIRE(ctx && (cols == 0 || (d_shares && d_rand && d_out)), "deg_red_king: NULL argument");
+    DeviceGuard dg(ctx->device);
+    HostKeep keep;
+    HFr one = host::h_one();
+    ZKG_TRY(king_dev(ctx, (const Fr*)d_shares, parties, n_recv, cols, l, &one, &one, 0, (const Fr*)d_rand, (Fr*)d_out, 0, keep));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+// ---- PSS, column-major batches ---------------------------------------------------------------
+static int32_t pss_host(int device, uint32_t l, int which, const uint64_t* in, const uint64_t* rand, uint64_t* out,
+                        size_t cols) {
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    ZKG_REQUIRE(cols == 0 || (in && out), "pss: NULL argument");
+    if (cols == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    const size_t n = pm->n, t = pm->t;
+    size_t in_elems = which == 0 ? cols * l : cols * n, out_elems = which == 0 ? cols * n : cols * l;
+    size_t in_b = align_up(in_elems * 32, 256), rand_b = align_up(cols * t * 32, 256);
+    ZKG_TRY(ctx->io.reserve(in_b + rand_b + out_elems * 32));
+    Fr* d_in = (Fr*)ctx->io.p;
+    Fr* d_rand = (Fr*)((uint8_t*)ctx->io.p + in_b);
+    Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + in_b + rand_b);
+    ZKG_CUDA(cudaMemcpyAsync(d_in, in, in_elems * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (which == 0 && rand) ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, cols * t * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(ctx->small.reserve(64 * 1024));
+    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    HostKeep keep;
+    const Fr* dM;
+    if (which == 0) {
+        const int K = (int)(l + t) <= 4 ? 4 : (int)(l + t) <= 8 ? 8 : 16;
+        keep.v.push_back(pad_rows(pm->pack, (int)n, (int)(l + t), K));
+        ZKG_TRY(upload(ctx, sa, keep.v.back(), &dM));
+        // det_pack (rand == NULL): the t padding entries are zero, so only the first l columns contribute
+        ZKG_TRY(launch_pack(ctx, dM, K, (int)n, (int)l, rand ? (int)t : 0, d_in, l, 1, d_rand, t, 1, d_out, n, 1, cols));
+    } else {
+        ZKG_TRY(upload(ctx, sa, which == 1 ? pm->unpack : pm->unpack2, &dM));
+        ZKG_TRY(launch_unpack(ctx, dM, (int)l, (int)n, d_in, n, 1, d_out, l, 1, cols));
+    }
+    ZKG_CUDA(cudaMemcpyAsync(out, d_out, out_elems * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+int32_t zkg_pss_pack_bn254_fr(int32_t device, uint32_t l, const uint64_t* secrets, const uint64_t* rand, uint64_t* shares, size_t cols) {
+    return pss_host(device, l, 0, secrets, rand, shares, cols);
+}
+int32_t zkg_pss_unpack_bn254_fr(int32_t device, uint32_t l, const uint64_t* shares, uint64_t* secrets, size_t cols) {
+    return pss_host(device, l, 1, shares, nullptr, secrets, cols);
+}
+int32_t zkg_pss_unpack2_bn254_fr(int32_t device, uint32_t l, const uint64_t* shares, uint64_t* secrets, size_t cols) {
+    return pss_host(device, l, 2, shares, nullptr, secrets, cols);
+}
+
+// ---- stand-alone pieces ----------------------------------------------------------------------
+int32_t zkg_fft2_bn254(int32_t device, uint64_t* s1, size_t m, uint32_t l, const uint64_t gen[4]) {
+    ZKG_REQUIRE(gen && (m == 0 || s1), "fft2: NULL argument");
+    ZKG_REQUIRE(l == 2 || l == 4 || l == 8, "packing factor l = %u unsupported (2, 4, 8)", l);
+    if (m == 0) return ZKG_OK;
+    ZKG_REQUIRE(is_pow2(m) && m >= l && ilog2(m) <= 28, "fft2: m = %zu must be a power of two in [l, 2^28]", m);
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    ZKG_TRY(ctx->io.reserve(2 * m * 32));
+    Fr* d_in = (Fr*)ctx->io.p;
+    Fr* d_out = d_in + m;
+    ZKG_CUDA(cudaMemcpyAsync(d_in, s1, m * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(ctx->small.reserve(pow_table_bytes(m) + 1024));
+    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    PowTable gen_tw, none{nullptr, nullptr};
+    ZKG_TRY(build_pow_table(ctx, sa, host::h_load(gen), m, &gen_tw));
+    size_t mbyl = m / l;
+    unsigned blocks = (unsigned)((mbyl + 255) / 256);
+    int log_m = ilog2(m);
+    if (l == 2) k_king_stage1<2><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, log_m, 3, gen_tw, 0, none, d_out);
+    else if (l == 4) k_king_stage1<4><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, log_m, 3, gen_tw, 0, none, d_out);
+    else k_king_stage1<8><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, log_m, 3, gen_tw, 0, none, d_out);
+    ZKG_CUDA(cudaGetLastError());
+    ZKG_CUDA(cudaMemcpyAsync(s1, d_out, m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+int32_t zkg_distribute_powers_bn254(int32_t device, uint64_t* v, size_t n, const uint64_t g[4]) {
+    ZKG_REQUIRE(g && (n == 0 || v), "distribute_powers: NULL argument");
+    if (n == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    ZKG_TRY(ctx->io.reserve(n * 32));
+    Fr* d = (Fr*)ctx->io.p;
+    ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(ctx->small.reserve(pow_table_bytes(n) + 1024));
+    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    PowTable tw;
+    ZKG_TRY(build_pow_table(ctx, sa, host::h_load(g), n, &tw));
+    k_distribute_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, n, tw);
+    ZKG_CUDA(cudaGetLastError());
+    ZKG_CUDA(cudaMemcpyAsync(v, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+int32_t zkg_bitrev_bn254(int32_t device, uint64_t* v, size_t n) {
+    ZKG_REQUIRE(n == 0 || v, "bitrev: NULL argument");
+    if (n <= 1) return ZKG_OK;
+    ZKG_REQUIRE(is_pow2(n), "bitrev: n = %zu is not a power of two", n);
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    ZKG_TRY(ctx->io.reserve(2 * n * 32));
+    Fr* d = (Fr*)ctx->io.p;
+    ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    k_bitrev<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, d + n, ilog2(n));
+    ZKG_CUDA(cudaGetLastError());
+    ZKG_CUDA(cudaMemcpyAsync(v, d + n, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+int32_t zkg_fr_fft_bn254(int32_t device, uint64_t* v, size_t n, const uint64_t* offset, int32_t inverse) {
+    ZKG_REQUIRE(n == 0 || v, "fr_fft: NULL argument");
+    if (n == 0) return ZKG_OK;
+    ZKG_REQUIRE(is_pow2(n) && ilog2(n) <= 27, "fr_fft: n = %zu must be a power of two <= 2^27", n);
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    ZKG_TRY(ctx->io.reserve(3 * n * 32));
+    Fr* d = (Fr*)ctx->io.p;
+    Fr* d_rev = d + n;
+    Fr* d_tmp = d + 2 * n;
+    ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(ctx->small.reserve(ntt_small_bytes(n) + pow_table_bytes(n) + 1024));
+    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    HFr w = host::h_root_of_unity(n), one = host::h_one();
+    HFr off = offset ? host::h_load(offset) : one;
+    bool coset = !(off == one);
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (!inverse) {
+        if (coset) {
+            PowTable tw;
+            ZKG_TRY(build_pow_table(ctx, sa, off, n, &tw));
+            k_distribute_powers<<<blocks, 256, 0, ctx->stream>>>(d, n, tw);
+        }
+        k_bitrev<<<blocks, 256, 0, ctx->stream>>>(d, d_rev, ilog2(n));
+        ZKG_TRY(ntt_bitrev_in(ctx, sa, d_rev, d, d_tmp, n, w, 0, nullptr, nullptr));
+    } else {
+        k_bitrev<<<blocks, 256, 0, ctx->stream>>>(d, d_rev, ilog2(n));
+        ZKG_TRY(ntt_bitrev_in(ctx, sa, d_rev, d, d_tmp, n, host::h_inv(w), 0, nullptr, nullptr));
+        HFr n_inv = host::h_inv(host::h_from_u64(n));
+        PowTable tw{nullptr, nullptr};
+        if (coset) ZKG_TRY(build_pow_table(ctx, sa, host::h_inv(off), n, &tw));
+        k_scale_powers<<<blocks, 256, 0, ctx->stream>>>(d, n, to_arg(n_inv), coset ? 1 : 0, tw);
+    }
+    ZKG_CUDA(cudaGetLastError());
+    ZKG_CUDA(cudaMemcpyAsync(v, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+}  // extern "C"
