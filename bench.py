@@ -1,0 +1,419 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the zk-SaaS hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 22]
+
+Metric (BASELINE.json): BN254 G1 MSM Mpts/s.  Workload: the per-party local MSM of d_msm
+(dist-primitives/src/dmsm/mod.rs:73) at 2^22 points per GPU ("Large BN254 G1 d_msm 2^22-2^24",
+BASELINE.json configs[3]); synthetic uniform scalars and bases with random discrete logs.  A step is
+one MSM.  With N GPUs every rank owns its own 2^22-point range of one N*2^22-point MSM (weak
+scaling); the partial sums are exchanged with one NCCL all-gather and added on the device.
+
+One JSON line is printed by rank 0; see README/DESIGN.md for the keys.  The d_fft leg (BASELINE
+configs[1], m = 2^16) and a 2^20-constraint d_fft are reported under "secondary".
+
+--impl reference times the CPU restatement of the reference's arkworks path (oracle/, kind "port":
+the Rust reference cannot be built in this image) on the host cores, same metric and unit.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+INT_PEAK_FALLBACK_TMACS = 18.39     # profiles/r01_intpipe_microbench.json: IMAD.WIDE issue rate, B200, 148 SMs
+HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    hbm, how = HBM_PEAK_FALLBACK_GBS, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            hbm, how = float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    imad, ihow = INT_PEAK_FALLBACK_TMACS, "measured (tools/microbench/intpipe.cu, profiles/r01_intpipe_microbench.json)"
+    return hbm, how, imad, ihow
+
+
+def ark_window(k):
+    """arkworks' own rule, used only to state the ALGORITHMIC work per point."""
+    lg = (k - 1).bit_length()
+    c = 3 if k < 32 else lg * 69 // 100 + 2
+    return c, (254 + c - 1) // c
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        clocks, reasons, smax, pmax = [], set(), None, 0.0
+        for r in self.rows:
+            try:
+                clocks.append(float(r[1])); smax = float(r[2]); pmax = max(pmax, float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        clocks.sort()
+        # "under load": upper half of the samples (the sampler also sees the idle gaps between steps)
+        load = clocks[len(clocks) // 2:] if clocks else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "power_w_max": pmax, "samples": len(clocks), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the arkworks path) -- reported beside the GPU number, never the target
+# ---------------------------------------------------------------------------------------------
+def cpu_msm_sample(log2n, reps, threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as ol
+    from oracle_lib import _p
+    lib = ol.oracle()
+    th = threads or min(lib.zko_max_threads(), os.cpu_count() or 1)
+    n = 1 << log2n
+    rng = np.random.default_rng(0x7A6B)
+    bases = np.zeros((n, 72), dtype=np.uint8)
+    lib.zko_g1_sequence(_p(ol.rand_fr(rng, 1)), _p(ol.rand_fr(rng, 1)), n, bases.ctypes.data, 72)
+    scalars = ol.rand_fr(rng, n)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        ol.o_g1_msm(bases, scalars, threads=th)
+        times.append(time.perf_counter() - t0)
+    return n, th, times
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port), all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    log2n = min(args.log2n, 20)
+    n, th, times = cpu_msm_sample(log2n, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    ms = 1e3 * sum(timed) / len(timed)
+    val = n / (ms * 1e-3) / 1e6
+    c, W = ark_window(n)
+    sample = f"G1 MSM of 2^{log2n} points per step (arkworks window rule c={c}, W={W}), {th} OpenMP threads over windows"
+    line = {
+        "impl": "reference", "metric": "BN254 G1 MSM Mpts/s", "value": round(val, 4), "unit": "Mpts/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs)",
+        "data": "synthetic",
+        "config": {"workload": f"d_msm local G1 MSM, BN254, 2^{args.log2n} points per GPU (bounded CPU sample 2^{log2n})",
+                   "curve": "BN254 G1", "l": 2},
+        "cpu_baseline": {"value": round(val, 4), "unit": "Mpts/s", "cores": th, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = C restatement of ark-ec 0.4.2 msm_bigint_wnaf (oracle/zkoracle.c); the Rust reference "
+                "cannot be built here (no cargo/rustc, arkworks crates un-vendored)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import zksaas_b200 as z
+    from zksaas_b200 import capi
+    from zksaas_b200.api import fr_image
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = z.lib()
+    # One explicit (non-default) stream for everything: the library launches on it, torch's events
+    # and NCCL collectives are recorded on it, so CUDA-event timings see the kernels they bracket.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx = capi.ctx_p()
+    capi.check(lib.zkg_ctx_create(local, C.c_void_p(stream.cuda_stream), C.byref(ctx)))
+
+    n = 1 << args.log2n
+    # ---- synthetic inputs, generated on the device: uniform scalars, bases = s_i * G ---------------
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x7A6B53616153 ^ (3 + rank))
+
+    def rand_fr_dev(k):
+        # uniform below 2^253 (< r): 253-bit uniform values used directly as Montgomery images
+        t = torch.randint(-2**63, 2**63 - 1, (k, 4), dtype=torch.int64, device=dev, generator=g)
+        t[:, 3] &= (1 << 61) - 1
+        return t
+
+    scalars = rand_fr_dev(n)
+    dlogs = rand_fr_dev(n)
+    bases = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    capi.check(lib.zkg_fixed_base_dev(ctx, 1, C.c_void_p(dlogs.data_ptr()), n, C.c_void_p(bases.data_ptr())))
+    torch.cuda.synchronize()
+    del dlogs
+    partial = torch.zeros(16, dtype=torch.int64, device=dev)           # XYZZ, 128 B
+    gathered = torch.zeros(16 * world, dtype=torch.int64, device=dev)
+    out_xyz = torch.zeros(12, dtype=torch.int64, device=dev)
+
+    def step_device():
+        if world == 1:
+            capi.check(lib.zkg_msm_bn254_g1_dev(ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(scalars.data_ptr()), n,
+                                                 C.c_void_p(out_xyz.data_ptr())))
+        else:
+            capi.check(lib.zkg_msm_bn254_partial_dev(ctx, 1, C.c_void_p(bases.data_ptr()), C.c_void_p(scalars.data_ptr()),
+                                                      n, C.c_void_p(partial.data_ptr())))
+            dist.all_gather_into_tensor(gathered, partial)
+            capi.check(lib.zkg_msm_combine_dev(ctx, 1, C.c_void_p(gathered.data_ptr()), world,
+                                                C.c_void_p(out_xyz.data_ptr())))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device time via CUDA events; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident leg ("value") ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = C.c_uint64(0)
+    lib.zkg_ctx_launch_count(ctx, C.byref(launches0))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_device, args.steps)
+    launches1 = C.c_uint64(0)
+    lib.zkg_ctx_launch_count(ctx, C.byref(launches1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = n * world / (ms_per_step * 1e-3) / 1e6
+    dev_result = out_xyz.cpu().numpy().copy()
+
+    # ---- dominant kernel (bucket accumulation) timed live with CUDA events on the launch stream -------
+    capi.check(lib.zkg_ctx_set_profiling(ctx, 1))
+    phase = [[], [], []]
+    for _ in range(max(3, min(args.steps, 10))):
+        if world == 1:
+            capi.check(lib.zkg_msm_bn254_g1_dev(ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(scalars.data_ptr()), n,
+                                                 C.c_void_p(out_xyz.data_ptr())))
+        else:
+            capi.check(lib.zkg_msm_bn254_partial_dev(ctx, 1, C.c_void_p(bases.data_ptr()), C.c_void_p(scalars.data_ptr()),
+                                                      n, C.c_void_p(partial.data_ptr())))
+        for ph in range(3):
+            f = C.c_float(0)
+            capi.check(lib.zkg_ctx_phase_ms(ctx, ph, C.byref(f)))
+            phase[ph].append(f.value)
+    capi.check(lib.zkg_ctx_set_profiling(ctx, 0))
+    acc_ms = sum(phase[1]) / len(phase[1])
+    sort_ms = sum(phase[0]) / len(phase[0])
+    red_ms = sum(phase[2]) / len(phase[2])
+
+    # ---- end-to-end leg: the reference-facing C-ABI call with HOST buffers ------------------------------
+    # arkworks Affine images (72 B/point) + Fr images in pinned host memory; every step copies them in.
+    h_bases = torch.zeros((n, 72), dtype=torch.uint8).pin_memory()
+    h_bases[:, :64] = bases.cpu()
+    h_scal = scalars.cpu().pin_memory()
+    h_out = torch.zeros(12, dtype=torch.int64).pin_memory()
+    xyzz_dev = torch.zeros(16, dtype=torch.int64, device=dev)
+    one_fq = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x
+                           for x in (0xd35d438dc58f0d9d, 0x0a78eb28f5c70b3d, 0x666ea36f7879462c, 0x0e0a77c19a07df2f)],
+                          dtype=torch.int64)
+    e2e_result = {}
+
+    def step_e2e():
+        capi.check(lib.zkg_msm_bn254_g1(local, C.c_void_p(h_bases.data_ptr()), 72, n, C.c_void_p(h_scal.data_ptr()), n,
+                                        C.c_void_p(h_out.data_ptr())))
+        if world > 1:
+            # the result is back on the host; combine the ranks' points with one more tiny exchange
+            xyzz = torch.zeros(16, dtype=torch.int64)
+            if bool((h_out[8:12] != 0).any()):
+                xyzz[0:8] = h_out[0:8]; xyzz[8:12] = one_fq; xyzz[12:16] = one_fq
+            xyzz_dev.copy_(xyzz)
+            dist.all_gather_into_tensor(gathered, xyzz_dev)
+            capi.check(lib.zkg_msm_combine_dev(ctx, 1, C.c_void_p(gathered.data_ptr()), world, C.c_void_p(out_xyz.data_ptr())))
+            e2e_result["xyz"] = out_xyz.cpu().numpy().copy()
+        else:
+            e2e_result["xyz"] = h_out.numpy().copy()
+
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = n * world * e2e_steps / e2e_s / 1e6
+    same = bool((e2e_result["xyz"] == dev_result).all())
+
+    # ---- secondary: d_fft pieces (configs[1]: m = 2^16; and the 2^20-constraint size), rank 0 only -------
+    secondary = {}
+    if rank == 0 and not args.no_secondary:
+        pp_l = 2
+        for lg in (16, 20):
+            m = 1 << lg
+            mbyl = m // pp_l
+            dom = z.Radix2EvaluationDomain.new(m)
+            px = rand_fr_dev(mbyl)
+            shares = rand_fr_dev(8 * mbyl)
+            rnd = rand_fr_dev(2 * mbyl)
+            outp = torch.empty((8 * mbyl, 4), dtype=torch.int64, device=dev)
+            gen = dom.group_gen()
+            gcos = z.Radix2EvaluationDomain.new(2 * m).element(1)
+
+            def f1():
+                capi.check(lib.zkg_fft1_bn254_dev(ctx, C.c_void_p(px.data_ptr()), mbyl, pp_l, gen.ctypes.data, None, None))
+
+            def fk():
+                capi.check(lib.zkg_king_fft2_bn254_dev(ctx, C.c_void_p(shares.data_ptr()), None, 8, mbyl, pp_l,
+                                                        gen.ctypes.data, gcos.ctypes.data, 1, C.c_void_p(rnd.data_ptr()),
+                                                        C.c_void_p(outp.data_ptr())))
+            for fn in (f1, fk):
+                for _ in range(3):
+                    fn()
+            t1 = timed(f1, 10) / 10
+            tk = timed(fk, 10) / 10
+            # e2e of the king call with host buffers (the reference-facing entry point)
+            hs = [np.ascontiguousarray(shares.cpu().numpy().view(np.uint64).reshape(8, mbyl, 4)[p]) for p in range(8)]
+            hr = rnd.cpu().numpy().view(np.uint64)
+            pp = z.PackedSharingParams.new(pp_l, device=local)
+            z.king_fft2(hs, list(range(8)), pp, gen, gcos, True, hr)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                z.king_fft2(hs, list(range(8)), pp, gen, gcos, True, hr)
+            tke = (time.perf_counter() - t0) / 3
+            secondary[f"d_fft_m2^{lg}"] = {
+                "fft1_ms": round(t1, 4), "king_ms": round(tk, 4),
+                "d_fft_elems_per_s": round(m / ((t1 + tk) * 1e-3), 1),
+                "king_e2e_host_ms": round(tke * 1e3, 3),
+                "king_hbm_gbs": round((256 + 32) * m / (tk * 1e-3) / 1e9, 1),
+                "fft1_hbm_gbs": round(64 * mbyl / (t1 * 1e-3) / 1e9, 1),
+            }
+            del px, shares, rnd, outp
+
+    if rank == 0:
+        hbm_peak, hbm_how, int_peak, int_how = measured_peaks()
+        c_ark, W_ark = ark_window(n)
+        macs_per_point = 11 * W_ark * 136                        # 11*W modmul x 136 limb-MACs
+        achieved = n * macs_per_point / (acc_ms * 1e-3) / 1e12
+        cpu_n, cpu_th, cpu_t = cpu_msm_sample(18, 3) if not args.no_cpu else (0, 0, [1.0])
+        cpu_val = cpu_n / min(cpu_t) / 1e6
+        line = {
+            "metric": "BN254 G1 MSM Mpts/s", "value": round(value, 2), "unit": "Mpts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (8x32-bit Montgomery limbs, IMAD.WIDE)", "data": "synthetic",
+            "config": {"workload": f"d_msm local G1 MSM (dist-primitives/src/dmsm/mod.rs:73), BN254, 2^{args.log2n} points per GPU",
+                       "points_per_gpu": n, "total_points": n * world, "curve": "BN254 G1", "l": 2,
+                       "window_bits": int(os.environ.get("ZKG_MSM_C", "0")) or "auto",
+                       "l2_policy": "inputs larger than L2 (bases 256 MiB + scalars 128 MiB per step at 2^22)",
+                       "multi_gpu": "point-range sharding; one NCCL all-gather of 128 B partial sums + device add"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_val, 2), "unit": "Mpts/s", "h2d_bytes_per_step": n * (72 + 32),
+                    "d2h_bytes_per_step": 96, "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3),
+                    "call": "zkg_msm_bn254_g1 (host pointers, pinned; arkworks 72-B affine images + Fr images)",
+                    "matches_device_leg": same},
+            "gpu_launches": int(launches1.value - launches0.value),
+            "roofline": {"bound": "int32 multiply-add pipe (IMAD.WIDE)", "kernel": "k_accumulate<Fq>",
+                         "achieved": round(achieved, 3), "peak": int_peak, "unit": "Tmac/s (32x32+64 limb-MACs)",
+                         "frac": round(achieved / int_peak, 4), "peak_source": int_how,
+                         "algorithmic_macs_per_point": macs_per_point, "kernel_ms": round(acc_ms, 4),
+                         "kernel_share_of_step": round(acc_ms / (acc_ms + sort_ms + red_ms), 4),
+                         "phase_ms": {"digits_sort": round(sort_ms, 4), "accumulate": round(acc_ms, 4),
+                                      "reduce_final": round(red_ms, 4)},
+                         "hbm": {"achieved_gbs": round(96 * n / (acc_ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
+                                 "frac": round(96 * n / (acc_ms * 1e-3) / 1e9 / hbm_peak, 4), "peak_source": hbm_how},
+                         "traffic": None},
+            "cpu_baseline": {"value": round(cpu_val, 4), "unit": "Mpts/s", "cores": cpu_th, "kind": "port",
+                             "sample": "G1 MSM of 2^18 points, best of 3, oracle/zkoracle.c (arkworks msm_bigint_wnaf restated), OpenMP over windows"},
+            "secondary": secondary,
+        }
+        print(json.dumps(line), flush=True)
+    lib.zkg_ctx_destroy(ctx)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=22)
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

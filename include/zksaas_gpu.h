@@ -54,6 +54,14 @@ int32_t zkg_ctx_create(int32_t device, void *stream, zkg_ctx **out);
 int32_t zkg_ctx_destroy(zkg_ctx *ctx);
 int32_t zkg_ctx_sync(zkg_ctx *ctx);
 void *zkg_ctx_stream(zkg_ctx *ctx);
+/* Instrumentation for benchmarks: number of kernels this context has launched so far; and, when
+ * profiling is enabled, the device time between phase boundaries of the LAST call on the context
+ * (MSM: phase 0 = digits + counting sort, 1 = bucket accumulation, 2 = bucket reduction + final;
+ * king pipeline: 0 = parameter tables, 1 = unpack + fft2 + powers, 2 = pack).  zkg_ctx_phase_ms
+ * synchronises the stream. */
+int32_t zkg_ctx_launch_count(zkg_ctx *ctx, uint64_t *count);
+int32_t zkg_ctx_set_profiling(zkg_ctx *ctx, int32_t enable);
+int32_t zkg_ctx_phase_ms(zkg_ctx *ctx, int32_t phase, float *ms);
 /* Frees the pooled contexts the host-pointer entry points create lazily. */
 int32_t zkg_shutdown(void);
 

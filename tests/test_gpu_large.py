@@ -1,0 +1,136 @@
+"""GPU parity at BASELINE sizes through size-independent properties (the oracle cannot run 2^22-point
+MSMs in seconds): bases are s_i * G with known discrete logs, so MSM(bases, a) must equal
+((sum_i a_i s_i) mod r) * G -- an O(k) field computation done by the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from oracle_lib import _p
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import zksaas_b200 as z
+    from zksaas_b200 import capi
+    ctx = capi.ctx_p()
+    capi.check(z.lib().zkg_ctx_create(0, None, C.byref(ctx)))
+    yield z, capi, torch, ctx
+    z.lib().zkg_ctx_destroy(ctx)
+
+
+def _rand_dev(torch, k, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    t = torch.randint(-2**63, 2**63 - 1, (k, 4), dtype=torch.int64, device="cuda", generator=g)
+    t[:, 3] &= (1 << 61) - 1
+    return t
+
+
+def _closed_form(o, a_img, s_img, g2=False):
+    n = a_img.shape[0]
+    prod = np.zeros_like(a_img)
+    o.zko_fr_mul(_p(a_img), _p(s_img), _p(prod), n)
+    tot = np.zeros(4, dtype=np.uint64)
+    o.zko_fr_sum(_p(prod), n, _p(tot))
+    if g2:
+        aff = np.zeros((1, 136), dtype=np.uint8)
+        o.zko_g2_fixed_base(_p(tot), 1, aff.ctypes.data, 136)
+        out = np.zeros(24, dtype=np.uint64)
+        one = ol.fr_np([1])
+        o.zko_g2_msm(aff.ctypes.data, 136, _p(one), 1, _p(out), 1, 0)
+        return out
+    aff = np.zeros((1, 72), dtype=np.uint8)
+    o.zko_g1_fixed_base(_p(tot), 1, aff.ctypes.data, 72)
+    return ol.o_g1_msm(aff, ol.fr_np([1]))
+
+
+@pytest.mark.parametrize("log2n", [14, 18, 20, 22])
+def test_msm_g1_closed_form(env, log2n):
+    z, capi, torch, ctx = env
+    o = ol.oracle()
+    n = 1 << log2n
+    a, s = _rand_dev(torch, n, 1000 + log2n), _rand_dev(torch, n, 2000 + log2n)
+    bases = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    out = torch.zeros(12, dtype=torch.int64, device="cuda")
+    lib = z.lib()
+    capi.check(lib.zkg_fixed_base_dev(ctx, 1, C.c_void_p(s.data_ptr()), n, C.c_void_p(bases.data_ptr())))
+    capi.check(lib.zkg_msm_bn254_g1_dev(ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(a.data_ptr()), n, C.c_void_p(out.data_ptr())))
+    capi.check(lib.zkg_ctx_sync(ctx))
+    got = out.cpu().numpy().view(np.uint64)
+    exp = _closed_form(o, a.cpu().numpy().view(np.uint64), s.cpu().numpy().view(np.uint64))
+    assert (got == exp).all()
+    if log2n == 14:
+        # the device generator itself vs the oracle's scalar multiplication, and the host-pointer path
+        hb = np.zeros((n, 72), dtype=np.uint8)
+        hb[:, :64] = bases.cpu().numpy()
+        ref = np.zeros((64, 72), dtype=np.uint8)
+        o.zko_g1_fixed_base(_p(np.ascontiguousarray(s.cpu().numpy().view(np.uint64)[:64])), 64, ref.ctypes.data, 72)
+        assert (hb[:64] == ref).all()
+        assert (z.msm_g1(hb, a.cpu().numpy().view(np.uint64)) == exp).all()
+
+
+@pytest.mark.parametrize("log2n", [12, 17])
+def test_msm_g2_closed_form(env, log2n):
+    z, capi, torch, ctx = env
+    o = ol.oracle()
+    n = 1 << log2n
+    a, s = _rand_dev(torch, n, 3000 + log2n), _rand_dev(torch, n, 4000 + log2n)
+    bases = torch.empty((n, 128), dtype=torch.uint8, device="cuda")
+    out = torch.zeros(24, dtype=torch.int64, device="cuda")
+    lib = z.lib()
+    capi.check(lib.zkg_fixed_base_dev(ctx, 2, C.c_void_p(s.data_ptr()), n, C.c_void_p(bases.data_ptr())))
+    capi.check(lib.zkg_msm_bn254_g2_dev(ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(a.data_ptr()), n, C.c_void_p(out.data_ptr())))
+    capi.check(lib.zkg_ctx_sync(ctx))
+    got = out.cpu().numpy().view(np.uint64)
+    exp = _closed_form(o, a.cpu().numpy().view(np.uint64), s.cpu().numpy().view(np.uint64), g2=True)
+    assert (got == exp).all()
+
+
+def test_msm_partials_combine_like_one_msm(env):
+    """Point-range sharding (multi-GPU path): partial XYZZ sums of two halves combine to the full MSM."""
+    z, capi, torch, ctx = env
+    n = 1 << 16
+    a, s = _rand_dev(torch, n, 7), _rand_dev(torch, n, 8)
+    bases = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    lib = z.lib()
+    capi.check(lib.zkg_fixed_base_dev(ctx, 1, C.c_void_p(s.data_ptr()), n, C.c_void_p(bases.data_ptr())))
+    full = torch.zeros(12, dtype=torch.int64, device="cuda")
+    capi.check(lib.zkg_msm_bn254_g1_dev(ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(a.data_ptr()), n, C.c_void_p(full.data_ptr())))
+    parts = torch.zeros((3, 16), dtype=torch.int64, device="cuda")
+    h = n // 2
+    capi.check(lib.zkg_msm_bn254_partial_dev(ctx, 1, C.c_void_p(bases.data_ptr()), C.c_void_p(a.data_ptr()), h, C.c_void_p(parts[0].data_ptr())))
+    capi.check(lib.zkg_msm_bn254_partial_dev(ctx, 1, C.c_void_p(bases[h:].data_ptr()), C.c_void_p(a[h:].data_ptr()), h, C.c_void_p(parts[1].data_ptr())))
+    capi.check(lib.zkg_msm_bn254_partial_dev(ctx, 1, C.c_void_p(bases.data_ptr()), C.c_void_p(a.data_ptr()), 0, C.c_void_p(parts[2].data_ptr())))
+    comb = torch.zeros(12, dtype=torch.int64, device="cuda")
+    capi.check(lib.zkg_msm_combine_dev(ctx, 1, C.c_void_p(parts.data_ptr()), 3, C.c_void_p(comb.data_ptr())))
+    capi.check(lib.zkg_ctx_sync(ctx))
+    assert bool((comb == full).all())
+
+
+@pytest.mark.parametrize("log2m", [16, 20])
+def test_d_fft_round_reconstructs_plain_fft(env, log2m):
+    """dfft/tests.rs:78-139 at BASELINE sizes: client fft1 on 8 GPUs' worth of shares + king pipeline,
+    then unpack == Radix2EvaluationDomain::fft of the clear vector (computed by the device plain FFT,
+    which test_gpu_core pins against the oracle)."""
+    z, capi, torch, ctx = env
+    l, m = 2, 1 << log2m
+    mbyl = m // l
+    rng = np.random.default_rng(log2m)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    x = ol.rand_fr(rng, m)
+    expect = dom.fft(x)
+    xr = z.fft_in_place_rearrange(x.copy())
+    # column i packs (xr[i], xr[i + m/l]) : dfft/tests.rs:29-39
+    secrets = np.ascontiguousarray(xr.reshape(l, mbyl, 4).transpose(1, 0, 2)).reshape(-1, 4)
+    shares = z.transpose(z.pack_vec(secrets, pp, ol.rand_fr(rng, mbyl * pp.t)))
+    masks = [z.FftMask.zero(mbyl) for _ in range(pp.n)]
+    out = z.d_fft(shares, masks, False, dom, pp, z.LocalTestNet(pp.n), ol.rand_fr(rng, mbyl * pp.t))
+    cols = np.stack(out, axis=1).reshape(-1, 4)           # column-major (mbyl x n)
+    got = pp.unpack(cols)
+    assert (got == expect).all()

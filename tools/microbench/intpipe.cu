@@ -26,6 +26,14 @@ __global__ void k_int(uint32_t* out, uint32_t a, uint32_t b, int iters) {
                 if (MODE == 2) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(x[c]));
                 if (MODE == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
                 if (MODE == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+                // 32x32+64 with carry-in/out (what ptxas turns into IMAD.WIDE.U32.X): 2 chains of 4 per step
+                if (MODE == 5 && (c & 3) == 0) {
+                    uint32_t* lo = reinterpret_cast<uint32_t*>(&w[c]);
+                    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[0]), "+r"(lo[1]) : "r"(a), "r"(x[c]));
+                    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[2]), "+r"(lo[3]) : "r"(a), "r"(x[c]));
+                    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[4]), "+r"(lo[5]) : "r"(a), "r"(x[c]));
+                    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[6]), "+r"(lo[7]) : "r"(a), "r"(x[c]));
+                }
             }
         }
     }
@@ -86,7 +94,7 @@ int main() {
     cudaMemset(d, 1, (size_t)blocks * threads * 64);
     int iters = 2000;
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d", prop.name, sms, prop.clockRate);
-    const char* names[5] = {"imad_lo", "imad_hi", "imad_wide", "iadd", "lop3"};
+    const char* names[6] = {"imad_lo", "imad_hi", "imad_wide", "iadd", "lop3", "imad_wide_carry"};
     double ops = (double)blocks * threads * iters * 8.0 * CHAINS;
     float ms;
     ms = time_ms([&] { k_int<0><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[0], ops / ms / 1e9);
@@ -94,6 +102,7 @@ int main() {
     ms = time_ms([&] { k_int<2><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[2], ops / ms / 1e9);
     ms = time_ms([&] { k_int<3><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[3], ops / ms / 1e9);
     ms = time_ms([&] { k_int<4><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[4], ops / ms / 1e9);
+    ms = time_ms([&] { k_int<5><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[5], ops / ms / 1e9);
     int mi = 400;
     for (int th : {128, 256, 512}) {
         int bl = sms * (2048 / th);

@@ -26,6 +26,9 @@ SIGNATURES = {
     "zkg_ctx_destroy": (C.c_int32, [ctx_p]),
     "zkg_ctx_sync": (C.c_int32, [ctx_p]),
     "zkg_ctx_stream": (C.c_void_p, [ctx_p]),
+    "zkg_ctx_launch_count": (C.c_int32, [ctx_p, u64p]),
+    "zkg_ctx_set_profiling": (C.c_int32, [ctx_p, C.c_int32]),
+    "zkg_ctx_phase_ms": (C.c_int32, [ctx_p, C.c_int32, C.POINTER(C.c_float)]),
     "zkg_shutdown": (C.c_int32, []),
     "zkg_msm_bn254_g1": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkg_msm_bn254_g2": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -44,6 +44,7 @@ static void ctx_free(zkg_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->ws.release(); c->io.release(); c->io2.release(); c->small.release();
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -113,6 +114,26 @@ int32_t zkg_ctx_sync(zkg_ctx* ctx) {
     return ZKG_OK;
 }
 void* zkg_ctx_stream(zkg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int32_t zkg_ctx_launch_count(zkg_ctx* ctx, uint64_t* count) {
+    ZKG_REQUIRE(ctx && count, "launch_count: NULL argument");
+    *count = ctx->launches;
+    return ZKG_OK;
+}
+int32_t zkg_ctx_set_profiling(zkg_ctx* ctx, int32_t enable) {
+    ZKG_REQUIRE(ctx, "ctx is NULL");
+    ctx->profile = enable != 0;
+    ctx->ev_count = 0;
+    return ZKG_OK;
+}
+int32_t zkg_ctx_phase_ms(zkg_ctx* ctx, int32_t phase, float* ms) {
+    ZKG_REQUIRE(ctx && ms, "phase_ms: NULL argument");
+    ZKG_REQUIRE(phase >= 0 && phase + 1 < ctx->ev_count, "phase %d was not recorded (profiling off, or no call yet)", phase);
+    DeviceGuard dg(ctx->device);
+    ZKG_CUDA(cudaEventSynchronize(ctx->ev[phase + 1]));
+    ZKG_CUDA(cudaEventElapsedTime(ms, ctx->ev[phase], ctx->ev[phase + 1]));
+    return ZKG_OK;
+}
 
 int32_t zkg_shutdown(void) {
     std::vector<zkg_ctx*> all;

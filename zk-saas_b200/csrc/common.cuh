@@ -64,6 +64,11 @@ struct zkg_ctx {
     void* pinned = nullptr;   // small pinned bounce buffer for results
     size_t pinned_bytes = 0;
     int sm_count = 0;
+    // instrumentation (bench.py): kernels launched so far, and optional per-phase CUDA events
+    uint64_t launches = 0;
+    bool profile = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last profiled call
+    int ev_count = 0;
 };
 
 namespace zkg {
@@ -84,5 +89,13 @@ struct DeviceGuard {
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// mark a phase boundary on the context's stream when profiling is enabled (no-op otherwise)
+static inline void phase_mark(zkg_ctx* ctx, int idx) {
+    if (!ctx->profile || idx >= 4) return;
+    if (!ctx->ev[idx]) cudaEventCreate(&ctx->ev[idx]);
+    cudaEventRecord(ctx->ev[idx], ctx->stream);
+    if (idx + 1 > ctx->ev_count) ctx->ev_count = idx + 1;
+}
 
 }  // namespace zkg

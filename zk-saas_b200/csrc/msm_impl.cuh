@@ -290,6 +290,7 @@ static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scala
     cudaStream_t st = ctx->stream;
     if (n == 0) {
         k_identity<F><<<1, 32, 0, st>>>(mode, d_out);
+        ctx->launches += 1;
         ZKG_CUDA(cudaGetLastError());
         return ZKG_OK;
     }
@@ -324,12 +325,16 @@ static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scala
     XYZZ<F>* Rb[2] = {(XYZZ<F>*)(ws + o_r0), (XYZZ<F>*)(ws + o_r1)};
     XYZZ<F>* Cb[2] = {(XYZZ<F>*)(ws + o_c0), (XYZZ<F>*)(ws + o_c1)};
 
+    phase_mark(ctx, 0);
     ZKG_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * slots, st));
     const int TB = 256;
     k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, c, W, nb, digits, counts);
     k_scan<<<W, 1024, 0, st>>>(counts, nb, cursor);
     k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), W), TB, 0, st>>>(digits, n, nb, cursor, sorted);
+    phase_mark(ctx, 1);
     k_accumulate<F><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(d_bases, sorted, cursor, counts, n, nb, W, buckets);
+    phase_mark(ctx, 2);
+    ctx->launches += 4;
 
     // multi-level bucket reduction
     const XYZZ<F>* Rin = buckets;
@@ -342,11 +347,14 @@ static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scala
         k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(Rin, Cin, n_in, L, log2_M, W, Rb[pp], Cb[pp], n_out);
         Rin = Rb[pp]; Cin = Cb[pp];
         pp ^= 1;
+        ctx->launches += 1;
         n_in = n_out;
         log2_M += 3;           // M *= L (L = 8)
         if (n_out == 1) break;
     }
     k_final<F><<<1, 32, 0, st>>>(Rin, Cin, c, W, mode, d_out);
+    ctx->launches += 1;
+    phase_mark(ctx, 3);
     ZKG_CUDA(cudaGetLastError());
     return ZKG_OK;
 }
@@ -356,6 +364,7 @@ static int32_t pack_bases(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t
     if (n == 0) return ZKG_OK;
     ZKG_REQUIRE(stride >= sizeof(Affine<F>) + 1, "base stride %zu too small", stride);
     k_pack_bases<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)d_ark, stride, n, (Affine<F>*)d_packed);
+    ctx->launches += 1;
     ZKG_CUDA(cudaGetLastError());
     return ZKG_OK;
 }
@@ -417,12 +426,14 @@ ZKG_MSM_DECLARE(g2)
     }                                                                                                               \
     int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out) {                         \
         k_combine<F><<<1, 32, 0, ctx->stream>>>((const XYZZ<F>*)d_parts, n, (F*)d_out);                             \
+        ctx->launches += 1;                                                                                         \
         ZKG_CUDA(cudaGetLastError());                                                                               \
         return ZKG_OK;                                                                                              \
     }                                                                                                               \
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed) {                     \
         if (n == 0) return ZKG_OK;                                                                                  \
         k_fixed_base<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const Fr*)d_scalars, n, (Affine<F>*)d_packed); \
+        ctx->launches += 1;                                                                                         \
         ZKG_CUDA(cudaGetLastError());                                                                               \
         return ZKG_OK;                                                                                              \
     }

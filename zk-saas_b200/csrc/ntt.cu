@@ -338,6 +338,7 @@ static int32_t build_pow_table(zkg_ctx* ctx, SmallAlloc& sa, const HFr& w, size_
     k_pow_table<<<(TW_LO + 255) / 256, 256, 0, ctx->stream>>>(to_arg(w), TW_LO, lo);
     HFr w_hi = host::h_pow(w, TW_LO);
     k_pow_table<<<(unsigned)((hi_n + 255) / 256), 256, 0, ctx->stream>>>(to_arg(w_hi), (uint32_t)hi_n, hi);
+    ctx->launches += 2;
     ZKG_CUDA(cudaGetLastError());
     out->lo = lo; out->hi = hi;
     return ZKG_OK;
@@ -357,6 +358,7 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, SmallAlloc& sa, const Fr* d_in, Fr* d
     ZKG_REQUIRE(is_pow2(N) && logN <= 24 + 3, "ntt: size %zu unsupported", N);
     int npass = (logN + 9) / 10;
     if (npass == 0) npass = 1;
+    phase_mark(ctx, 0);
     PowTable tw{nullptr, nullptr};
     if (npass > 1) ZKG_TRY(build_pow_table(ctx, sa, wN, N, &tw));
     int s = 0;
@@ -375,7 +377,7 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, SmallAlloc& sa, const Fr* d_in, Fr* d
         Fr* tws = (Fr*)sa.take((T / 2 ? T / 2 : 1) * sizeof(Fr));
         ZKG_REQUIRE(tws, "internal: small workspace exhausted");
         HFr wT = host::h_pow(wN, N >> b);
-        if (T / 2) k_pow_table<<<(unsigned)((T / 2 + 255) / 256), 256, 0, ctx->stream>>>(to_arg(wT), (uint32_t)(T / 2), tws);
+        if (T / 2) { k_pow_table<<<(unsigned)((T / 2 + 255) / 256), 256, 0, ctx->stream>>>(to_arg(wT), (uint32_t)(T / 2), tws); ctx->launches += 1; }
         // destination: last pass -> d_out; otherwise the scratch (in place on scratch is safe: a
         // block reads and writes the same index set when no shift is applied)
         Fr* dst = P.last ? d_out : d_tmp;
@@ -384,7 +386,10 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, SmallAlloc& sa, const Fr* d_in, Fr* d
         unsigned threads = (unsigned)(E / 2 < 32 ? 32 : (E / 2 > 512 ? 512 : E / 2));
         unsigned blocks = (unsigned)(N / E);
         ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        if (q == 0) phase_mark(ctx, 1);
         k_ntt_pass<<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, P.last ? d_mask : nullptr);
+        ctx->launches += 1;
+        if (P.last) phase_mark(ctx, 2);
         ZKG_CUDA(cudaGetLastError());
         src = dst;
         s += b;
@@ -430,6 +435,7 @@ static int32_t launch_pack(zkg_ctx* ctx, const Fr* dM, int K, int rows, int l, i
 #define LP(KK) k_map_in_regs<KK><<<blocks, 256, 0, ctx->stream>>>(dM, rows, l, secrets, s_cs, s_rs, rand, r_cs, r_rs, t_used, out, o_cs, o_rs, cols)
     if (K == 4) LP(4); else if (K == 8) LP(8); else LP(16);
 #undef LP
+    ctx->launches += 1;
     ZKG_CUDA(cudaGetLastError());
     return ZKG_OK;
 }
@@ -486,6 +492,7 @@ static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* partie
     ZKG_TRY(ctx->small.reserve(small_need));
     SmallAlloc sa{ctx, 0, ctx->small.bytes};
     const Fr *dU, *dP;
+    phase_mark(ctx, 0);
     ZKG_TRY(upload(ctx, sa, *U, &dU));
     ZKG_TRY(upload(ctx, sa, packK, &dP));
     PowTable gen_tw{nullptr, nullptr}, g_tw{nullptr, nullptr};
@@ -499,12 +506,17 @@ static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* partie
     Fr* S = (Fr*)ctx->ws.p;
     unsigned blocks = (unsigned)((mbyl + 255) / 256);
     int mode = mode_fft ? (rearrange ? 1 : 0) : 2;
+    phase_mark(ctx, 1);
 #define KS(LLv) k_king_stage1<LLv><<<blocks, 256, 0, ctx->stream>>>(d_shares, n_recv, dU, nullptr, mbyl, log_m, mode, gen_tw, has_g, g_tw, S)
     if (l == 2) KS(2); else if (l == 4) KS(4); else KS(8);
 #undef KS
+    ctx->launches += 1;
     ZKG_CUDA(cudaGetLastError());
+    phase_mark(ctx, 2);
     // re-pack: column c takes secrets S[c*l..], rand[c*t..] -> party-major shares out[p*mbyl + c]
-    return launch_pack(ctx, dP, K, pm->n, pm->l, pm->t, S, pm->l, 1, d_rand, pm->t, 1, d_out, 1, mbyl, mbyl);
+    ZKG_TRY(launch_pack(ctx, dP, K, pm->n, pm->l, pm->t, S, pm->l, 1, d_rand, pm->t, 1, d_out, 1, mbyl, mbyl));
+    phase_mark(ctx, 3);
+    return ZKG_OK;
 }
 
 // gather host vectors (one per party) into a party-major device buffer
