@@ -461,7 +461,10 @@ class Curve:
         if P is None:
             return True
         x, y = P
-        return y * y == x * x * x + self.b
+        lhs, rhs = y * y, x * x * x + self.b
+        if isinstance(lhs, Fq2):
+            return lhs == rhs
+        return (lhs - rhs) % Q_MOD == 0
 
     def neg(self, P):
         return None if P is None else (P[0], -P[1] if isinstance(P[1], Fq2) else (-P[1]) % Q_MOD)

@@ -1,0 +1,246 @@
+"""GPU: the reference's own protocol-level tests, re-stated against the CUDA path (BN254 Fr / G1):
+
+  dist-primitives/src/dfft/tests.rs      d_ifft_works, d_fft_works, d_ifftxd_fft_works, coset_d_ifftxd_fft_works
+  dist-primitives/src/utils/deg_red.rs   :142-191 (degree reduction of squared sharings, L = 4, with a dropout)
+  dist-primitives/examples/dmsm_test.rs  :13-53   (d_msm output unpacks to the plain MSM)
+  groth16/src/ext_wit.rs                 :411-538 circom_dummy_ext_witness (expected h = golden circom_ref)
+plus the committed golden fixtures (tests/golden) through the GPU entry points."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import oracle_lib as ol
+from oracle_lib import _p, pyref
+
+pytestmark = pytest.mark.gpu
+R = pyref.R_MOD
+
+
+@pytest.fixture(scope="module")
+def z():
+    import zksaas_b200
+    return zksaas_b200
+
+
+def strided_secrets(x, l):
+    """column i takes x[i + j*m/l], j < l  (dfft/tests.rs:29-39, groth16/src/qap.rs:103-113)"""
+    mbyl = x.shape[0] // l
+    return np.ascontiguousarray(x.reshape(l, mbyl, 4).transpose(1, 0, 2)).reshape(-1, 4)
+
+
+def unpack_all(z, pp, shares_by_party, two=False):
+    cols = np.ascontiguousarray(np.stack(shares_by_party, axis=1)).reshape(-1, 4)
+    return pp.unpack2(cols) if two else pp.unpack(cols)
+
+
+def sample_fft_mask(z, rng, rearrange, g, gen, m, pp):
+    mbyl = m // pp.l
+    return z.FftMask.sample(rearrange, g, gen, m, pp, ol.rand_fr(rng, m), ol.rand_fr(rng, mbyl * pp.t),
+                            ol.rand_fr(rng, mbyl * pp.t))
+
+
+def pack_rearranged(z, rng, pp, x):
+    xr = z.fft_in_place_rearrange(x.copy())
+    return z.transpose(z.pack_vec(strided_secrets(xr, pp.l), pp, ol.rand_fr(rng, xr.shape[0] // pp.l * pp.t)))
+
+
+@pytest.mark.parametrize("l,m", [(2, 8), (2, 1 << 10), (4, 64)])
+def test_d_ifft_works(z, l, m):
+    """dfft/tests.rs:20-79"""
+    from zksaas_b200 import api
+    rng = np.random.default_rng(m + l)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    evals = ol.rand_fr(rng, m)
+    coeffs = dom.ifft(evals)
+    shares = pack_rearranged(z, rng, pp, evals)
+    masks = sample_fft_mask(z, rng, False, api.fr_image(1), dom.group_gen_inv(), m, pp)
+    out = z.d_ifft(shares, masks, False, dom, api.fr_image(1), pp, z.LocalTestNet(pp.n), ol.rand_fr(rng, m // l * pp.t))
+    assert (unpack_all(z, pp, out) == coeffs).all()
+    o = ol.oracle()
+    exp = evals.copy()
+    o.zko_fr_fft(_p(exp), m, None, 1)
+    assert (coeffs == exp).all()
+
+
+@pytest.mark.parametrize("l,m", [(2, 8), (2, 1 << 10), (4, 64)])
+def test_d_fft_works(z, l, m):
+    """dfft/tests.rs:81-140"""
+    from zksaas_b200 import api
+    rng = np.random.default_rng(2 * m + l)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    coeffs = ol.rand_fr(rng, m)
+    evals = dom.fft(coeffs)
+    shares = pack_rearranged(z, rng, pp, coeffs)
+    masks = sample_fft_mask(z, rng, False, api.fr_image(1), dom.group_gen(), m, pp)
+    out = z.d_fft(shares, masks, False, dom, pp, z.LocalTestNet(pp.n), ol.rand_fr(rng, m // l * pp.t))
+    assert (unpack_all(z, pp, out) == evals).all()
+
+
+def test_d_ifft_then_d_fft_is_identity(z):
+    """dfft/tests.rs:142-220: ifft with rearrange=true feeds the fft directly."""
+    from zksaas_b200 import api
+    l, m = 2, 1 << 9
+    rng = np.random.default_rng(99)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    evals = ol.rand_fr(rng, m)
+    shares = pack_rearranged(z, rng, pp, evals)
+    one = api.fr_image(1)
+    m1 = sample_fft_mask(z, rng, True, one, dom.group_gen_inv(), m, pp)
+    m2 = sample_fft_mask(z, rng, False, one, dom.group_gen(), m, pp)
+    net = z.LocalTestNet(pp.n)
+    coeff_sh = z.d_ifft(shares, m1, True, dom, one, pp, net, ol.rand_fr(rng, m // l * pp.t))
+    eval_sh = z.d_fft(coeff_sh, m2, False, dom, pp, net, ol.rand_fr(rng, m // l * pp.t))
+    assert (unpack_all(z, pp, eval_sh) == evals).all()
+
+
+def test_coset_d_ifft_d_fft_chain(z):
+    """dfft/tests.rs:222-357: ifft (coset shift g on the way out) -> fft -> ifft (g^-1) -> fft."""
+    from zksaas_b200 import api
+    l, m = 2, 1 << 8
+    rng = np.random.default_rng(17)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    net = z.LocalTestNet(pp.n)
+    g = api.fr_image(5)
+    ginv = api.fr_image(pow(5, -1, R))
+    one = api.fr_image(1)
+    evals = ol.rand_fr(rng, m)
+    shares = pack_rearranged(z, rng, pp, evals)
+    rp = lambda: ol.rand_fr(rng, m // l * pp.t)
+    c1 = z.d_ifft(shares, sample_fft_mask(z, rng, True, g, dom.group_gen_inv(), m, pp), True, dom, g, pp, net, rp())
+    e1 = z.d_fft(c1, sample_fft_mask(z, rng, True, one, dom.group_gen(), m, pp), True, dom, pp, net, rp())
+    # e1 = evaluations over the coset g*H, re-arranged: compare with the plain coset FFT
+    coset_evals = dom.fft(dom.ifft(evals), offset=g)
+    got = unpack_all(z, pp, e1)                         # strided packing of the bit-reversed vector
+    mbyl = m // l
+    rev = np.ascontiguousarray(got.reshape(mbyl, l, 4).transpose(1, 0, 2)).reshape(-1, 4)
+    assert (z.fft_in_place_rearrange(rev.copy()) == coset_evals).all()
+    c2 = z.d_ifft(e1, sample_fft_mask(z, rng, True, ginv, dom.group_gen_inv(), m, pp), True, dom, ginv, pp, net, rp())
+    e2 = z.d_fft(c2, sample_fft_mask(z, rng, False, one, dom.group_gen(), m, pp), False, dom, pp, net, rp())
+    assert (unpack_all(z, pp, e2) == evals).all()
+
+
+@pytest.mark.parametrize("dropouts", [(), (15,)])
+def test_deg_red_squares(z, dropouts):
+    """utils/deg_red.rs:142-191, L = 4 (N = 16); lossy round drops the last party."""
+    from zksaas_b200 import api
+    l, num = 4, 64
+    rng = np.random.default_rng(5)
+    pp = z.PackedSharingParams.new(l)
+    secrets = ol.rand_fr(rng, num * l)
+    shares = z.transpose(z.pack_vec(secrets, pp, ol.rand_fr(rng, num * pp.t)))
+    sq = [api.fr_mul(s, s) for s in shares]
+    masks = z.DegRedMask.sample(pp, num, ol.rand_fr(rng, num * l), ol.rand_fr(rng, num * pp.t), ol.rand_fr(rng, num * pp.t))
+    out = z.deg_red(sq, masks, pp, z.LocalTestNet(pp.n, dropouts), ol.rand_fr(rng, num * pp.t))
+    assert (unpack_all(z, pp, out) == api.fr_mul(secrets, secrets)).all()       # degree is back to l+t-1
+
+
+def test_d_msm_matches_plain_msm(z):
+    """dmsm_test.rs:13-93 (BN254 G1, 2^10 public points, l = 2): config 1 of BASELINE.json."""
+    o = ol.oracle()
+    l, M = 2, 1 << 10
+    rng = np.random.default_rng(1010)
+    pp = z.PackedSharingParams.new(l)
+    y_pub = ol.rand_fr(rng, M)
+    dl = ol.rand_fr(rng, M)
+    x_pub = np.zeros((M, 72), dtype=np.uint8)
+    o.zko_g1_fixed_base(_p(dl), M, x_pub.ctypes.data, 72)
+    should_be = z.msm_g1(x_pub, y_pub)
+    assert (should_be == ol.o_g1_msm(x_pub, y_pub, threads=8)).all()
+    # pack the bases through their discrete logs (pack is linear: share_j of points = (share_j of dlogs) * G)
+    rand_x = ol.rand_fr(rng, M // l * pp.t)
+    dl_sh = z.transpose(z.pack_vec(dl, pp, rand_x))
+    x_shares = []
+    for p in range(pp.n):
+        aff = np.zeros((M // l, 72), dtype=np.uint8)
+        o.zko_g1_fixed_base(_p(dl_sh[p]), M // l, aff.ctypes.data, 72)
+        x_shares.append(aff)
+    y_shares = z.transpose(z.pack_vec(y_pub, pp, ol.rand_fr(rng, M // l * pp.t)))
+    masks = [z.MsmMask.zero() for _ in range(pp.n)]
+    out = z.d_msm(x_shares, y_shares, masks, pp, z.LocalTestNet(pp.n))
+    # every party ends with the same "repeated" sharing of the output: unpack2 -> result[0] == plain MSM
+    from zksaas_b200 import api
+    M2 = pp.unpack2_matrix()
+    res0 = api.group_lincomb(out, [M2[0][j] for j in range(pp.n)])
+    assert (res0 == should_be).all()
+
+
+def test_circom_h_dataflow_vs_golden(z):
+    """groth16/src/ext_wit.rs:104-181 + test :411-538 (a = b = (0..m), c = a*b, m = 2^10): the unpacked h
+    must equal circom_ref's h, committed as tests/golden/ext_wit.json."""
+    from zksaas_b200 import api
+    l, m = 2, 1 << 10
+    rng = np.random.default_rng(31)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    net = z.LocalTestNet(pp.n)
+    a = ol.fr_np(list(range(m)))
+    c = api.fr_mul(a, a)
+    root = z.Radix2EvaluationDomain.new(2 * m).element(1)
+    one = api.fr_image(1)
+    rp = lambda: ol.rand_fr(rng, m // l * pp.t)
+    sh = {k: pack_rearranged(z, rng, pp, v) for k, v in (("a", a), ("b", a), ("c", c))}            # QAP::pss
+    coeff = {k: z.d_ifft(sh[k], sample_fft_mask(z, rng, True, root, dom.group_gen_inv(), m, pp), True, dom, root, pp, net, rp())
+             for k in "abc"}                                                                       # :127-159
+    ev = {k: z.d_fft(coeff[k], sample_fft_mask(z, rng, False, one, dom.group_gen(), m, pp), False, dom, pp, net, rp())
+          for k in "abc"}                                                                          # :161-170
+    h = [api.fr_sub(api.fr_mul(ev["a"][p], ev["b"][p]), ev["c"][p]) for p in range(pp.n)]          # :173-177
+    num = m // l
+    dmask = z.DegRedMask.sample(pp, num, ol.rand_fr(rng, num * l), rp(), rp())
+    h_red = z.deg_red(h, dmask, pp, net, rp())                                                     # :179
+    got = unpack_all(z, pp, h_red, two=True)                                                       # test :532-535
+    exp = ol.fr_np(gu.ints(gu.load("ext_wit.json")[str(m)]["circom_h"]))
+    assert (got == exp).all()
+
+
+def test_gpu_vs_golden_fixtures(z):
+    from zksaas_b200 import api
+    g = gu.load("fields.json")
+    for name, p, field in (("fr", pyref.R_MOD, 0), ("fq", pyref.Q_MOD, 1)):
+        f = g[name]
+        A, B = ol.mont_np(gu.ints(f["a"]), p), ol.mont_np(gu.ints(f["b"]), p)
+        for op, key in ((0, "mul"), (1, "add"), (2, "sub")):
+            assert ol.np_ints(api._field_op(op, A, B, field), p) == gu.ints(f[key])
+    gg = gu.load("groups.json")
+    for case in gg["g1_msm"]:
+        got = z.msm_g1(gu.g1_from_dlogs(gu.ints(case["dlogs"])), ol.fr_np(gu.ints(case["scalars"])))
+        assert ol.g1_xyz_to_point(got) == gu.g1_point(case["result"])
+    for case in gg["g2_msm"]:
+        got = z.msm_g2(gu.g2_from_dlogs(gu.ints(case["dlogs"])), ol.fr_np(gu.ints(case["scalars"])))
+        assert ol.g2_xyz_to_point(got) == gu.g2_point(case["result"])
+    gen = np.zeros((1, 72), dtype=np.uint8)
+    gen[0] = np.frombuffer(pyref.g1_affine_image(pyref.G1_GEN), dtype=np.uint8)
+    for k, exp in gg["g1_multiples"].items():
+        assert ol.g1_xyz_to_point(z.msm_g1(gen, ol.fr_np([int(k, 16)]))) == gu.g1_point(exp)
+    ps = gu.load("pss.json")
+    for ls, f in ps.items():
+        pp = z.PackedSharingParams.new(int(ls))
+        sh = pp.pack(ol.fr_np(gu.ints(f["secrets"])), ol.fr_np(gu.ints(f["rand"])))
+        assert ol.np_fr(sh) == gu.ints(f["shares"])
+        assert ol.np_fr(pp.det_pack(ol.fr_np(gu.ints(f["secrets"])))) == gu.ints(f["det_shares"])
+        assert ol.np_fr(pp.unpack2(api.fr_mul(sh, sh))) == gu.ints(f["squared_shares_unpack2"])
+    df = gu.load("dfft.json")
+    for key, f in df.items():
+        l, m = int(key.split("_")[0][1:]), int(key.split("_")[1][1:])
+        pp = z.PackedSharingParams.new(l)
+        dom = z.Radix2EvaluationDomain.new(m)
+        assert ol.np_fr(dom.fft(ol.fr_np(list(range(m))))) == gu.ints(f["fft_x"])
+        fft1 = []
+        for p in range(pp.n):
+            v = ol.fr_np(gu.ints(f["party_shares"][p]))
+            z.fft1_in_place(v, pp, dom.group_gen())
+            assert ol.np_fr(v) == gu.ints(f["fft1"][p])
+            fft1.append(v)
+        rand = ol.fr_np(sum((gu.ints(r) for r in f["rand_king"]), []))
+        zeta = z.Radix2EvaluationDomain.new(2 * m).element(1)
+        for rearr in (0, 1):
+            for gname, gimg in (("one", api.fr_image(1)), ("zeta_2m", zeta)):
+                out = z.king_fft2(fft1, list(range(pp.n)), pp, dom.group_gen(), gimg, rearr, rand)
+                exp = f["king"][f"rearrange{rearr}_{gname}"]
+                for p in range(pp.n):
+                    assert ol.np_fr(out[p]) == gu.ints(exp[p])
+        s1 = ol.fr_np(gu.ints(f["fft2_in"]))
+        assert ol.np_fr(z.fft2_in_place(s1, pp, dom.group_gen())) == gu.ints(f["fft2_out"])

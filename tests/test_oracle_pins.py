@@ -1,0 +1,262 @@
+"""CPU: pins the C oracle (oracle/zkoracle.c) before anything trusts it.
+
+The reference cannot be run here (Rust, un-vendored arkworks) and holds no literal vectors for this
+path, so the pins are: (1) the BN254 constants and on-curve points that ARE in the reference tree,
+(2) the committed golden fixtures produced by the independent big-integer model oracle/pyref.py for
+the deterministic inputs of the reference's own tests, (3) the equalities those tests assert."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import oracle_lib as ol
+from oracle_lib import _p, pyref
+
+R, Q = pyref.R_MOD, pyref.Q_MOD
+
+
+@pytest.fixture(scope="module")
+def o():
+    return ol.oracle()
+
+
+def test_reference_tree_constants(o):
+    """fixtures/verifier.sol:52,216 (moduli), :26-37 (generators); fixtures/verification_key.json:5-51."""
+    assert Q == 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    assert R == 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    alpha1 = (20491192805390485299153009773594534940189261866228447918068658471970481763042,
+              9383485363053290200918347156157836566562967994039712273449902621266178545958)
+    beta2 = (pyref.Fq2(6375614351688725206403948262868962793625744043794305715222011528459656738731,
+                       4252822878758300859123897981450591353533073413197771768651442665752259397132),
+             pyref.Fq2(10505242626370262277552901082094356697409835680220590971873171140371331206856,
+                       21847035105528745403288232691147584728191162732299865338377159692350059136679))
+    delta2 = (pyref.Fq2(21086075896128623386704099092966653497087323138509663683018462960685844167040,
+                        4445819252396127360876514570383103865817685421921758980714409108431571569505),
+              pyref.Fq2(5869832979942504616594367432687964314626257558728420838411851172504272664862,
+                        690217893672263538725936186606040522546374712355023960948505364397173841096))
+    for P1 in (pyref.G1_GEN, alpha1):
+        assert pyref.G1.on_curve(P1)
+        assert o.zko_g1_on_curve(ol.g1_aff_np([P1]).ctypes.data) == 1
+    for P2 in (pyref.G2_GEN_PT, beta2, delta2):
+        assert pyref.G2.on_curve(P2)
+        assert o.zko_g2_on_curve(ol.g2_aff_np([P2]).ctypes.data) == 1
+    bad = ol.g1_aff_np([(1, 3)])
+    assert o.zko_g1_on_curve(bad.ctypes.data) == 0
+    # subgroup order: r * P = identity for the in-tree points
+    assert pyref.G1.mul(alpha1, R - 1) == pyref.G1.neg(alpha1)
+    assert pyref.G2.add(pyref.G2.mul(beta2, R - 1), beta2) is None
+
+
+def test_fields_vs_golden(o):
+    g = gu.load("fields.json")
+    for name, p, cv in (("fr", R, ol.fr_np), ("fq", Q, ol.fq_np)):
+        f = g[name]
+        a, b = gu.ints(f["a"]), gu.ints(f["b"])
+        A, B = cv(a), cv(b)
+        out = np.zeros_like(A)
+        for op in ("mul", "add", "sub"):
+            getattr(o, f"zko_{name}_{op}")(_p(A), _p(B), _p(out), len(a))
+            assert ol.np_ints(out, p) == gu.ints(f[op]), (name, op)
+        getattr(o, f"zko_{name}_inv")(_p(A), _p(out), len(a))
+        assert ol.np_ints(out, p) == gu.ints(f["inv"])
+    w = np.zeros(4, dtype=np.uint64)
+    for k, v in g["fr_roots_of_unity"].items():
+        o.zko_fr_root_of_unity(1 << int(k), _p(w))
+        assert ol.np_fr(w) == [int(v, 16)]
+
+
+def test_groups_vs_golden(o):
+    g = gu.load("groups.json")
+    gen = ol.g1_point_to_xyz(pyref.G1_GEN)
+    for k, exp in g["g1_multiples"].items():
+        out = np.zeros(12, dtype=np.uint64)
+        o.zko_g1_mul(_p(gen), _p(ol.fr_np([int(k, 16)])), _p(out))
+        assert ol.g1_xyz_to_point(out) == gu.g1_point(exp)
+    gen2 = ol.g2_point_to_xyz(pyref.G2_GEN_PT)
+    for k, exp in g["g2_multiples"].items():
+        out = np.zeros(24, dtype=np.uint64)
+        o.zko_g2_mul(_p(gen2), _p(ol.fr_np([int(k, 16)])), _p(out))
+        assert ol.g2_xyz_to_point(out) == gu.g2_point(exp)
+    for case in g["g1_msm"]:
+        bases = gu.g1_from_dlogs(gu.ints(case["dlogs"]))
+        sc = ol.fr_np(gu.ints(case["scalars"]))
+        for threads, c in ((1, 0), (4, 0), (2, 5), (1, 9)):
+            assert ol.g1_xyz_to_point(ol.o_g1_msm(bases, sc, threads, c)) == gu.g1_point(case["result"])
+    for case in g["g2_msm"]:
+        bases = gu.g2_from_dlogs(gu.ints(case["dlogs"]))
+        sc = ol.fr_np(gu.ints(case["scalars"]))
+        assert ol.g2_xyz_to_point(ol.o_g2_msm(bases, sc, 2, 0)) == gu.g2_point(case["result"])
+
+
+def test_msm_linearity_like_reference_test(o):
+    """dmsm/mod.rs:127-180 pack_unpack2_test: sum over parties of local MSMs on packed shares,
+    unpack2'ed, equals the plain MSM -- including identical bases with unit scalars (:144-147)."""
+    rng = random.Random(42)
+    l, M = 2, 16
+    pp = pyref.PackedSharingParams(l)
+    ops = pyref.group_ops(pyref.G1)
+    base = pyref.G1.mul(pyref.G1_GEN, rng.randrange(R))
+    gsec = [base] * M
+    fsec = [1] * M
+    expected = pyref.msm_naive(pyref.G1, gsec, fsec)
+    gsh = pyref.transpose([pp.pack(gsec[i:i + l], [pyref.G1.mul(pyref.G1_GEN, rng.randrange(R)) for _ in range(l)], ops)
+                           for i in range(0, M, l)])
+    fsh = pyref.transpose([pp.pack(fsec[i:i + l], [rng.randrange(R) for _ in range(l)]) for i in range(0, M, l)])
+    res = []
+    for i in range(pp.n):
+        out = ol.o_g1_msm(ol.g1_aff_np(gsh[i]), ol.fr_np(fsh[i]))
+        res.append(out)
+    u = np.zeros(12 * l, dtype=np.uint64)
+    o.zko_pss_unpack2_g1(l, _p(np.concatenate(res)), _p(u))
+    tot = np.zeros(12, dtype=np.uint64)
+    o.zko_g1_add(_p(u[:12].copy()), _p(u[12:].copy()), _p(tot))
+    assert ol.g1_xyz_to_point(tot) == expected
+
+
+def test_pss_vs_golden(o):
+    g = gu.load("pss.json")
+    for ls, f in g.items():
+        l = int(ls)
+        n = 4 * l
+        sec, rnd = ol.fr_np(gu.ints(f["secrets"])), ol.fr_np(gu.ints(f["rand"]))
+        out = np.zeros((n, 4), dtype=np.uint64)
+        o.zko_pss_pack_fr(l, _p(sec), _p(rnd), _p(out), 1)
+        assert ol.np_fr(out) == gu.ints(f["shares"])
+        o.zko_pss_pack_fr(l, _p(sec), None, _p(out), 1)
+        assert ol.np_fr(out) == gu.ints(f["det_shares"])
+        sh = gu.ints(f["shares"])
+        u = np.zeros((l, 4), dtype=np.uint64)
+        o.zko_pss_unpack_fr(l, _p(ol.fr_np(sh)), _p(u), 1)
+        assert ol.np_fr(u) == gu.ints(f["secrets"])
+        sq = [x * x % R for x in sh]
+        o.zko_pss_unpack2_fr(l, _p(ol.fr_np(sq)), _p(u), 1)
+        assert ol.np_fr(u) == gu.ints(f["squared_shares_unpack2"]) == [x * x % R for x in gu.ints(f["secrets"])]
+        par = (C.c_uint32 * (n - 1))(*range(n - 1))
+        assert o.zko_pss_lagrange_unpack_fr(l, _p(ol.fr_np(sq[:-1])), par, n - 1, _p(u), 1) == 0
+        assert ol.np_fr(u) == gu.ints(f["lagrange_missing_last"])
+        # the closed-form matrices the CUDA kernels apply
+        pp = pyref.PackedSharingParams(l)
+        assert [[hex(v) for v in row] for row in pp.pack_matrix()] == f["pack_matrix"]
+        assert [[hex(v) for v in row] for row in pp.unpack2_matrix()] == f["unpack2_matrix"]
+
+
+def test_dfft_vs_golden(o):
+    g = gu.load("dfft.json")
+    for key, f in g.items():
+        l, m = int(key.split("_")[0][1:]), int(key.split("_")[1][1:])
+        mbyl, n = m // l, 4 * l
+        dom = pyref.Radix2Domain(m)
+        gen = ol.fr_np([dom.group_gen])
+        x = ol.fr_np(list(range(m)))
+        v = x.copy(); o.zko_fr_fft(_p(v), m, None, 0)
+        assert ol.np_fr(v) == gu.ints(f["fft_x"])                         # local_dfft_test.rs:24
+        v = x.copy(); o.zko_fr_fft(_p(v), m, None, 1)
+        assert ol.np_fr(v) == gu.ints(f["ifft_x"])
+        fft1 = []
+        for p in range(n):
+            v = ol.fr_np(gu.ints(f["party_shares"][p]))
+            o.zko_fft1_in_place(_p(v), mbyl, l, _p(gen))
+            assert ol.np_fr(v) == gu.ints(f["fft1"][p])
+            fft1.append(v)
+        rand = ol.fr_np(sum((gu.ints(r) for r in f["rand_king"]), []))
+        zeta = pyref.Radix2Domain(2 * m).element(1)
+        par = (C.c_uint32 * n)(*range(n))
+        for rearr in (0, 1):
+            for gname, gval in (("one", 1), ("zeta_2m", zeta)):
+                outs = [np.zeros((mbyl, 4), dtype=np.uint64) for _ in range(n)]
+                assert o.zko_king_fft2(ol.ptr_array(fft1), par, n, mbyl, l, _p(gen), _p(ol.fr_np([gval])), rearr,
+                                       _p(rand), ol.ptr_array(outs)) == 0
+                exp = f["king"][f"rearrange{rearr}_{gname}"]
+                for p in range(n):
+                    assert ol.np_fr(outs[p]) == gu.ints(exp[p])
+        # d_fft_works (dfft/tests.rs:88-139): unpack of the king's output is fft(x)
+        outs = [np.zeros((mbyl, 4), dtype=np.uint64) for _ in range(n)]
+        o.zko_king_fft2(ol.ptr_array(fft1), par, n, mbyl, l, _p(gen), _p(ol.fr_np([1])), 0, _p(rand), ol.ptr_array(outs))
+        cols = np.ascontiguousarray(np.stack(outs, axis=1)).reshape(-1, 4)
+        u = np.zeros((m, 4), dtype=np.uint64)
+        o.zko_pss_unpack_fr(l, _p(cols), _p(u), mbyl)
+        assert ol.np_fr(u) == gu.ints(f["fft_x"])
+        s1 = ol.fr_np(gu.ints(f["fft2_in"]))
+        o.zko_fft2_in_place(_p(s1), m, l, _p(gen))
+        assert ol.np_fr(s1) == gu.ints(f["fft2_out"])
+
+
+def test_ext_wit_reference_pipelines_vs_golden(o):
+    """groth16/src/ext_wit.rs:204-285 with the tests' inputs a=b=(0..m), c=a*b (:302-310, :425-433)."""
+    g = gu.load("ext_wit.json")
+    for ms, f in g.items():
+        m = int(ms)
+        a = list(range(m)); c = [x * x % R for x in a]
+        root = ol.fr_np([pyref.Radix2Domain(2 * m).element(1)])
+
+        def coset_eval(vals):
+            v = ol.fr_np(vals)
+            o.zko_fr_fft(_p(v), m, None, 1)
+            o.zko_fr_distribute_powers(_p(v), m, _p(root))
+            o.zko_fr_fft(_p(v), m, None, 0)
+            return v
+        ae, ce = coset_eval(a), coset_eval(c)
+        ab = np.zeros_like(ae)
+        o.zko_fr_mul(_p(ae), _p(ae), _p(ab), m)
+        o.zko_fr_sub(_p(ab), _p(ce), _p(ab), m)
+        assert ol.np_fr(ab) == gu.ints(f["circom_h"])
+        # libsnark_ref
+        five = ol.fr_np([5])
+
+        def coset5(vals):
+            v = ol.fr_np(vals)
+            o.zko_fr_fft(_p(v), m, None, 1)
+            o.zko_fr_fft(_p(v), m, _p(five), 0)
+            return v
+        ae, ce = coset5(a), coset5(c)
+        o.zko_fr_mul(_p(ae), _p(ae), _p(ab), m)
+        o.zko_fr_sub(_p(ab), _p(ce), _p(ab), m)
+        vinv = ol.fr_np([pow((pow(5, m, R) - 1) % R, -1, R)] * m)
+        o.zko_fr_mul(_p(ab), _p(vinv), _p(ab), m)
+        o.zko_fr_fft(_p(ab), m, _p(five), 1)
+        assert ol.np_fr(ab) == gu.ints(f["libsnark_h"])
+
+
+def test_oracle_vs_bigint_model_random(o):
+    """Seeded cross-check of the C restatement against the big-integer model beyond the fixtures."""
+    rng = random.Random(2024)
+    for l, m in ((2, 16), (4, 64), (8, 64)):
+        pp = pyref.PackedSharingParams(l)
+        dom = pyref.Radix2Domain(m)
+        mbyl = m // l
+        px = [rng.randrange(R) for _ in range(mbyl)]
+        v = ol.fr_np(px)
+        o.zko_fft1_in_place(_p(v), mbyl, l, _p(ol.fr_np([dom.group_gen_inv])))
+        assert ol.np_fr(v) == pyref.fft1_in_place(px, pp, dom.group_gen_inv)
+        s1 = [rng.randrange(R) for _ in range(m)]
+        v = ol.fr_np(s1)
+        o.zko_fft2_in_place(_p(v), m, l, _p(ol.fr_np([dom.group_gen])))
+        assert ol.np_fr(v) == pyref.fft2_in_place(s1, pp, dom.group_gen)
+    # dropout path (pss.rs:210-221) with an arbitrary missing party
+    l = 2
+    pp = pyref.PackedSharingParams(l)
+    sec = [rng.randrange(R) for _ in range(l)]
+    sh = pp.pack(sec, [rng.randrange(R) for _ in range(l)])
+    sq = [x * x % R for x in sh]
+    parties = [0, 1, 2, 4, 5, 6, 7]
+    u = np.zeros((l, 4), dtype=np.uint64)
+    par = (C.c_uint32 * 7)(*parties)
+    assert o.zko_pss_lagrange_unpack_fr(l, _p(ol.fr_np([sq[p] for p in parties])), par, 7, _p(u), 1) == 0
+    assert ol.np_fr(u) == [x * x % R for x in sec]
+    # not enough shares -> error, like the debug_assert at pss.rs:185-188
+    par = (C.c_uint32 * 6)(*range(6))
+    assert o.zko_pss_lagrange_unpack_fr(l, _p(ol.fr_np(sq[:6])), par, 6, _p(u), 1) != 0
+
+
+def test_arkworks_window_rule_and_digits():
+    """ark-ec 0.4.2: c = ln_without_floats(n) + 2 and signed digits reconstruct the scalar."""
+    assert [pyref.ark_window_size(1 << k) for k in (4, 9, 19, 20, 22, 24)] == [3, 8, 15, 15, 17, 18]
+    rng = random.Random(3)
+    for c in (3, 8, 15, 17):
+        for _ in range(50):
+            s = rng.randrange(R)
+            d = pyref.make_digits(s, c)
+            assert sum(v << (c * i) for i, v in enumerate(d)) == s
+            assert all(-(1 << (c - 1)) <= v <= (1 << (c - 1)) for v in d[:-1])

@@ -390,6 +390,17 @@ class DegRedMask:
     def zero(num):
         return DegRedMask(np.zeros((num, 4), dtype=np.uint64), np.zeros((num, 4), dtype=np.uint64))
 
+    @staticmethod
+    def sample(pp: PackedSharingParams, num, mask_values, rand_in, rand_out):
+        """utils/deg_red.rs:40-66 over Fr with gen = 1: mask_values (num*l, 4) are the random draws,
+        rand_in / rand_out (num*t, 4) the packing randomness.  Returns the n parties' shares."""
+        mask_values = _fr_vec(mask_values)
+        assert mask_values.shape[0] == num * pp.l
+        neg = fr_sub(np.zeros_like(mask_values), mask_values, pp.device)
+        ins = transpose(pack_vec(mask_values, pp, rand_in))
+        outs = transpose(pack_vec(neg, pp, rand_out))
+        return [DegRedMask(i, o) for i, o in zip(ins, outs)]
+
 
 # ---- in-process stand-in for mpc-net's LocalTestNet -----------------------------------------------
 class LocalTestNet:
