@@ -136,18 +136,67 @@ static __global__ void k_scatter(const uint32_t* __restrict__ digits, size_t n, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Load balancing: order the (window,bucket) slots by descending population, so that the 32 lanes
+// of a warp walk buckets of (nearly) equal length and the longest buckets start first.  Counting
+// sort keyed by min(count, SIZE_KEYS-1); ~1 M slots, three tiny kernels.
+// ------------------------------------------------------------------------------------------
+static constexpr uint32_t SIZE_KEYS = 2048;
+
+static __global__ void k_size_hist(const uint32_t* __restrict__ counts, size_t slots, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[SIZE_KEYS];
+    for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots; t += (size_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[min(counts[t], SIZE_KEYS - 1)], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+// start[key] = number of slots with a larger key (descending order); one block of SIZE_KEYS/2 threads
+static __global__ void k_size_scan(const uint32_t* __restrict__ hist, uint32_t* __restrict__ start) {
+    __shared__ uint32_t v[SIZE_KEYS];
+    for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x) v[i] = hist[SIZE_KEYS - 1 - i];   // reversed
+    __syncthreads();
+    for (uint32_t off = 1; off < SIZE_KEYS; off <<= 1) {
+        uint32_t a[2];
+        for (int r = 0; r < 2; ++r) { uint32_t i = threadIdx.x + r * blockDim.x; a[r] = i >= off ? v[i - off] : 0; }
+        __syncthreads();
+        for (int r = 0; r < 2; ++r) { uint32_t i = threadIdx.x + r * blockDim.x; v[i] += a[r]; }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x)
+        start[SIZE_KEYS - 1 - i] = i ? v[i - 1] : 0;          // exclusive prefix in reversed (descending) order
+}
+static __global__ void k_size_scatter(const uint32_t* __restrict__ counts, size_t slots, uint32_t* __restrict__ start,
+                                      uint32_t* __restrict__ order) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = t < slots;
+    uint32_t key = valid ? min(counts[t], SIZE_KEYS - 1) : 0xffffffffu;
+    // warp-aggregated atomic: lanes with the same key reserve a contiguous range with one atomicAdd
+    uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (!valid) return;
+    int leader = __ffs(peers) - 1;
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t rank = __popc(peers & ((1u << lane) - 1));
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&start[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[base + rank] = (uint32_t)t;
+}
+
+// ------------------------------------------------------------------------------------------
 // bucket accumulation: one thread per (window, bucket)
 // ------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-             const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts, size_t n, uint32_t nb, int W,
-             XYZZ<F>* __restrict__ buckets) {
+             const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
+             const uint32_t* __restrict__ order, size_t n, uint32_t nb, int W, XYZZ<F>* __restrict__ buckets) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)W * nb) return;
-    // top window first: it is the one that can hold up to twice the points per bucket
-    uint32_t w = (uint32_t)(W - 1 - t / nb), b = (uint32_t)(t % nb);
-    size_t slot = (size_t)w * nb + b;
+    // slots in descending population order: neighbouring lanes get buckets of equal length
+    size_t slot = order[t];
+    uint32_t w = (uint32_t)(slot / nb);
     uint32_t end = cursor_end[slot], cnt = counts[slot];
     const uint32_t* idx = sorted + (size_t)w * n;
     XYZZ<F> acc = XYZZ<F>::inf();
@@ -310,6 +359,8 @@ static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scala
     size_t o_sorted = carve(sizeof(uint32_t) * W * n);
     size_t o_counts = carve(sizeof(uint32_t) * slots);
     size_t o_cursor = carve(sizeof(uint32_t) * slots);
+    size_t o_order = carve(sizeof(uint32_t) * slots);
+    size_t o_shist = carve(sizeof(uint32_t) * 2 * SIZE_KEYS);
     size_t o_buckets = carve(sizeof(XYZZ<F>) * slots);
     size_t o_r0 = carve(sizeof(XYZZ<F>) * W * n1);
     size_t o_c0 = carve(sizeof(XYZZ<F>) * W * n1);
@@ -321,20 +372,31 @@ static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scala
     uint32_t* sorted = (uint32_t*)(ws + o_sorted);
     uint32_t* counts = (uint32_t*)(ws + o_counts);
     uint32_t* cursor = (uint32_t*)(ws + o_cursor);
+    uint32_t* order = (uint32_t*)(ws + o_order);
+    uint32_t* shist = (uint32_t*)(ws + o_shist);
+    uint32_t* sstart = shist + SIZE_KEYS;
     XYZZ<F>* buckets = (XYZZ<F>*)(ws + o_buckets);
     XYZZ<F>* Rb[2] = {(XYZZ<F>*)(ws + o_r0), (XYZZ<F>*)(ws + o_r1)};
     XYZZ<F>* Cb[2] = {(XYZZ<F>*)(ws + o_c0), (XYZZ<F>*)(ws + o_c1)};
 
     phase_mark(ctx, 0);
     ZKG_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * slots, st));
+    ZKG_CUDA(cudaMemsetAsync(shist, 0, sizeof(uint32_t) * SIZE_KEYS, st));
     const int TB = 256;
     k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, c, W, nb, digits, counts);
     k_scan<<<W, 1024, 0, st>>>(counts, nb, cursor);
     k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), W), TB, 0, st>>>(digits, n, nb, cursor, sorted);
+    {
+        unsigned hb = (unsigned)((slots + 1023) / 1024);
+        if (hb > 592) hb = 592;
+        k_size_hist<<<hb, 256, 0, st>>>(counts, slots, shist);
+        k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(shist, sstart);
+        k_size_scatter<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(counts, slots, sstart, order);
+    }
     phase_mark(ctx, 1);
-    k_accumulate<F><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(d_bases, sorted, cursor, counts, n, nb, W, buckets);
+    k_accumulate<F><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(d_bases, sorted, cursor, counts, order, n, nb, W, buckets);
     phase_mark(ctx, 2);
-    ctx->launches += 4;
+    ctx->launches += 7;
 
     // multi-level bucket reduction
     const XYZZ<F>* Rin = buckets;
