@@ -128,3 +128,11 @@ extern "C" void emu_fq2_sqr(const uint64_t* a, uint64_t* o, size_t n) {
 extern "C" void emu_fq2_inv(const uint64_t* a, uint64_t* o, size_t n) {
     for (size_t i = 0; i < n; ++i) stf(o + 8 * i, f_inv(ldf<Fq2>(a + 8 * i)));
 }
+
+// the carry-free radix-2^29 schedule (experiment kept in fp.cuh): must agree bit for bit
+extern "C" void emu_fr_mul_r29(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
+    for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_mul_r29(ld<Fr>(a + 4 * i), ld<Fr>(b + 4 * i)));
+}
+extern "C" void emu_fq_mul_r29(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
+    for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_mul_r29(ld<Fq>(a + 4 * i), ld<Fq>(b + 4 * i)));
+}

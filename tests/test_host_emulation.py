@@ -50,7 +50,7 @@ def test_montgomery_limb_schedule(emu, fld, p):
     A, B = raw(a), raw(b)
     O = np.zeros_like(A)
     rinv = pow(1 << 256, -1, p)
-    for op, f in (("mul", lambda x, y: x * y * rinv % p), ("add", lambda x, y: (x + y) % p), ("sub", lambda x, y: (x - y) % p)):
+    for op, f in (("mul", lambda x, y: x * y * rinv % p), ("mul_r29", lambda x, y: x * y * rinv % p), ("add", lambda x, y: (x + y) % p), ("sub", lambda x, y: (x - y) % p)):
         fn = getattr(emu, f"emu_{fld}_{op}")
         fn.argtypes = [u64p, u64p, u64p, C.c_size_t]
         fn(_p(A), _p(B), _p(O), len(a))

@@ -26,6 +26,8 @@ __global__ void k_int(uint32_t* out, uint32_t a, uint32_t b, int iters) {
                 if (MODE == 2) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(x[c]));
                 if (MODE == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
                 if (MODE == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+                // 3-input adds that cannot be strength-reduced (each chain mixes its two neighbours)
+                if (MODE == 6) asm volatile("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, %0, t; }" : "+r"(x[c]) : "r"(x[(c + 1) % CHAINS]), "r"(x[(c + 3) % CHAINS]));
                 // 32x32+64 with carry-in/out (what ptxas turns into IMAD.WIDE.U32.X): 2 chains of 4 per step
                 if (MODE == 5 && (c & 3) == 0) {
                     uint32_t* lo = reinterpret_cast<uint32_t*>(&w[c]);
@@ -43,7 +45,7 @@ __global__ void k_int(uint32_t* out, uint32_t a, uint32_t b, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <class F, int ILP>
+template <class F, int ILP, int VARIANT>
 __global__ void k_modmul(F* io, int iters) {
     int tid = blockIdx.x * blockDim.x + threadIdx.x;
     F x[ILP], y = io[tid];
@@ -51,7 +53,7 @@ __global__ void k_modmul(F* io, int iters) {
     for (int c = 0; c < ILP; ++c) { x[c] = y; x[c].v[0] ^= c; }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int c = 0; c < ILP; ++c) x[c] = fp_mul(x[c], y);
+        for (int c = 0; c < ILP; ++c) x[c] = VARIANT == 0 ? fp_mul_r29(x[c], y) : fp_mul(x[c], y);
     }
     F s = x[0];
 #pragma unroll
@@ -94,7 +96,7 @@ int main() {
     cudaMemset(d, 1, (size_t)blocks * threads * 64);
     int iters = 2000;
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d", prop.name, sms, prop.clockRate);
-    const char* names[6] = {"imad_lo", "imad_hi", "imad_wide", "iadd", "lop3", "imad_wide_carry"};
+    const char* names[7] = {"imad_lo", "imad_hi", "imad_wide", "iadd", "lop3", "imad_wide_carry", "iadd3_mixed"};
     double ops = (double)blocks * threads * iters * 8.0 * CHAINS;
     float ms;
     ms = time_ms([&] { k_int<0><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[0], ops / ms / 1e9);
@@ -103,13 +105,14 @@ int main() {
     ms = time_ms([&] { k_int<3><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[3], ops / ms / 1e9);
     ms = time_ms([&] { k_int<4><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[4], ops / ms / 1e9);
     ms = time_ms([&] { k_int<5><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[5], ops / ms / 1e9);
+    ms = time_ms([&] { k_int<6><<<blocks, threads>>>(d, 3, 5, iters); }); printf(", \"%s_Tops\": %.3f", names[6], ops / ms / 1e9);
     int mi = 400;
     for (int th : {128, 256, 512}) {
         int bl = sms * (2048 / th);
         double mm = (double)bl * th * mi;
-        ms = time_ms([&] { k_modmul<Fq, 1><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul_ilp1_t%d_G\": %.2f", th, mm / ms / 1e6);
-        ms = time_ms([&] { k_modmul<Fq, 2><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul_ilp2_t%d_G\": %.2f", th, 2 * mm / ms / 1e6);
-        ms = time_ms([&] { k_modmul<Fq, 4><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul_ilp4_t%d_G\": %.2f", th, 4 * mm / ms / 1e6);
+        ms = time_ms([&] { k_modmul<Fq, 1, 0><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul29_ilp1_t%d_G\": %.2f", th, mm / ms / 1e6);
+        ms = time_ms([&] { k_modmul<Fq, 2, 0><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul29_ilp2_t%d_G\": %.2f", th, 2 * mm / ms / 1e6);
+        ms = time_ms([&] { k_modmul<Fq, 1, 1><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul_cios_ilp1_t%d_G\": %.2f", th, mm / ms / 1e6);
     }
     {
         int th = 256, bl = sms * 8;

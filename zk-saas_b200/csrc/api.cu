@@ -45,6 +45,8 @@ static void ctx_free(zkg_ctx* c) {
     c->ws.release(); c->io.release(); c->io2.release(); c->small.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < c->copy_ev_count; ++i) cudaEventDestroy(c->copy_ev[i]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -68,6 +70,16 @@ int32_t ctx_pinned(zkg_ctx* ctx, size_t bytes) {
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
     ZKG_CUDA(cudaMallocHost(&ctx->pinned, bytes));
     ctx->pinned_bytes = bytes;
+    return ZKG_OK;
+}
+
+int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events) {
+    if (!ctx->copy_stream) ZKG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (n_events > 16) n_events = 16;
+    while (ctx->copy_ev_count < n_events) {
+        ZKG_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[ctx->copy_ev_count], cudaEventDisableTiming));
+        ctx->copy_ev_count += 1;
+    }
     return ZKG_OK;
 }
 

@@ -64,6 +64,10 @@ struct zkg_ctx {
     void* pinned = nullptr;   // small pinned bounce buffer for results
     size_t pinned_bytes = 0;
     int sm_count = 0;
+    // second stream + events for overlapping H2D copies with compute in host-pointer entry points
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[16] = {};
+    int copy_ev_count = 0;
     // instrumentation (bench.py): kernels launched so far, and optional per-phase CUDA events
     uint64_t launches = 0;
     bool profile = false;
@@ -81,6 +85,7 @@ struct PooledCtx {
 };
 
 int32_t ctx_pinned(zkg_ctx* ctx, size_t bytes);
+int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events);
 
 struct DeviceGuard {
     int prev = -1;

@@ -93,12 +93,16 @@ ZKG_D void madc_wide_cc_from(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b,
 // --------------------------------------------------------------------------------------------
 struct FrParams {
     static constexpr uint32_t INV = BN254_FR_INV;
+    static constexpr uint32_t INV29 = BN254_FR_INV29;
+    ZKG_HD static constexpr uint32_t mod29(int i) { return BN254_FR_MOD29_L(i); }
     ZKG_HD static constexpr uint32_t mod(int i) { return BN254_FR_MOD_L(i); }
     ZKG_HD static constexpr uint32_t one(int i) { return BN254_FR_R_L(i); }
     ZKG_HD static constexpr uint32_t r2(int i) { return BN254_FR_R2_L(i); }
 };
 struct FqParams {
     static constexpr uint32_t INV = BN254_FQ_INV;
+    static constexpr uint32_t INV29 = BN254_FQ_INV29;
+    ZKG_HD static constexpr uint32_t mod29(int i) { return BN254_FQ_MOD29_L(i); }
     ZKG_HD static constexpr uint32_t mod(int i) { return BN254_FQ_MOD_L(i); }
     ZKG_HD static constexpr uint32_t one(int i) { return BN254_FQ_R_L(i); }
     ZKG_HD static constexpr uint32_t r2(int i) { return BN254_FQ_R2_L(i); }
@@ -240,7 +244,9 @@ ZKG_D void mont_row(uint32_t* x, uint32_t* y, const uint32_t* a, uint32_t bi) {
     y[7] = addc(y[7], 0);
 }
 
-// r = a * b * 2^-256 mod p, fully reduced
+// r = a * b * 2^-256 mod p, fully reduced -- carry-chain (CIOS) schedule: 128 IMAD.WIDE.U32.X.
+// This is the production multiplier: 67 G products/s on B200 (tools/microbench/intpipe.cu), i.e.
+// the rate of the half-speed carry-propagating wide MAD it is made of.
 template <class P>
 ZKG_D Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     uint32_t even[8], odd[8];
@@ -257,6 +263,108 @@ ZKG_D Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #pragma unroll
     for (int i = 1; i < 7; ++i) r.v[i] = addc_cc(even[i], odd[i + 1]);
     r.v[7] = addc(even[7], 0);
+    final_sub<P>(r.v);
+    return r;
+}
+
+
+// --------------------------------------------------------------------------------------------
+// EXPERIMENT (not used by the kernels; kept with its measurement because it decides the design):
+// carry-free multiplier.  IMAD.WIDE.U32 without carry issues at 18.4e12/s on B200 and its carry-
+// propagating form at 9.0e12/s, so in principle an unsaturated radix-2^29 product (162 carry-free
+// MADs) should beat the CIOS schedule (128 half-rate MADs).  It does not: ptxas de-fuses every
+// `mad.wide` accumulate into IMAD.WIDE(+RZ) + IADD3/IADD3.X trees, the re-slicing adds ~150 ALU
+// instructions, and the MAD and ALU pipes do not overlap well enough (tools/microbench/coissue.cu:
+// IMAD.WIDE + LOP3 co-issue collapses to 5.9e12 pairs/s).  Measured: 40 G products/s vs 67 G/s for
+// CIOS (profiles/r01_intpipe_microbench.json).  The product is formed on
+// an UNSATURATED radix-2^29 view of the operands: 9 limbs of 29 bits, 58-bit partial products, and
+// every column of the product (<= 18 terms + carry < 2^63) accumulates in one 64-bit register pair
+// with plain wide MADs -- no carry flags anywhere.  Montgomery reduction is interleaved column by
+// column (product scanning).  Eight columns retire 29 bits each and the ninth retires 24 bits, 256
+// in total, so the result is a*b*2^-256 mod p: bit-identical to the CIOS schedule above and to
+// arkworks.  The 8x32 <-> 9x29 re-slicing is funnel shifts on the (otherwise idle) ALU pipe.
+// --------------------------------------------------------------------------------------------
+static constexpr uint32_t MASK29 = (1u << 29) - 1;
+
+ZKG_D uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+#ifdef ZKG_HOST_EMU
+    return c + (uint64_t)a * b;
+#else
+    uint64_t d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+#endif
+}
+// bits [lo, lo+32) of the 256-bit value v (8 x u32), zero above bit 255
+ZKG_D uint32_t bits32_at(const uint32_t* v, int lo) {
+    int w = lo >> 5, s = lo & 31;
+    uint32_t a = w < 8 ? v[w] : 0u, b = w + 1 < 8 ? v[w + 1] : 0u;
+#ifdef ZKG_HOST_EMU
+    return s ? (a >> s) | (b << (32 - s)) : a;
+#else
+    return __funnelshift_r(a, b, s);
+#endif
+}
+// 8 x 32-bit limbs -> 9 x 29-bit limbs (value < 2^256, so the top limb has 24 bits)
+ZKG_D void split29(const uint32_t* v, uint32_t* x) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = bits32_at(v, 29 * i) & MASK29;
+}
+
+template <class P>
+ZKG_D Fp<P> fp_mul_r29(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t x[9], y[9], m[9], u[10];
+    split29(a.v, x);
+    split29(b.v, y);
+    uint64_t carry = 0;
+    // columns 0..8: accumulate a*b and m*p, pick m[k] so that the column's low bits cancel
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i <= k; ++i) c = mad_wide(x[i], y[k - i], c);
+        uint64_t d = carry;
+#pragma unroll
+        for (int i = 0; i < k; ++i) d = mad_wide(m[i], P::mod29(k - i), d);
+        d += c;
+        if (k < 8) {
+            m[k] = ((uint32_t)d * P::INV29) & MASK29;
+            d = mad_wide(m[k], P::mod29(0), d);          // low 29 bits are now zero
+            carry = d >> 29;
+        } else {
+            m[8] = ((uint32_t)d * P::INV29) & ((1u << 24) - 1);
+            d = mad_wide(m[8], P::mod29(0), d);          // low 24 bits are now zero: 8*29 + 24 = 256 retired
+            u[0] = (uint32_t)d & MASK29;
+            carry = d >> 29;
+        }
+    }
+    // columns 9..16
+#pragma unroll
+    for (int k = 9; k < 17; ++k) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = k - 8; i <= 8; ++i) c = mad_wide(x[i], y[k - i], c);
+        uint64_t d = carry;
+#pragma unroll
+        for (int i = k - 8; i <= 8; ++i) d = mad_wide(m[i], P::mod29(k - i), d);
+        d += c;
+        u[k - 8] = (uint32_t)d & MASK29;
+        carry = d >> 29;
+    }
+    u[9] = (uint32_t)carry;
+    // result = (sum_j u[j] 2^(29 j)) >> 24, re-sliced into 8 x 32 bits; it is < 2p < 2^255
+    Fp<P> r;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        // bits [32w + 24, 32w + 56) of U
+        int lo = 32 * w + 24;
+        int j = lo / 29, s = lo % 29;                    // starts inside limb j at bit s
+        uint64_t t = (uint64_t)u[j] >> s;
+        int have = 29 - s;
+        if (j + 1 < 10) { t |= (uint64_t)u[j + 1] << have; have += 29; }
+        if (have < 32 && j + 2 < 10) t |= (uint64_t)u[j + 2] << have;
+        r.v[w] = (uint32_t)t;
+    }
     final_sub<P>(r.v);
     return r;
 }

@@ -191,7 +191,8 @@ template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
-             const uint32_t* __restrict__ order, size_t n, uint32_t nb, int W, XYZZ<F>* __restrict__ buckets) {
+             const uint32_t* __restrict__ order, size_t n, uint32_t nb, int W, int accumulate_into,
+             XYZZ<F>* __restrict__ buckets) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)W * nb) return;
     // slots in descending population order: neighbouring lanes get buckets of equal length
@@ -199,7 +200,8 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
     uint32_t w = (uint32_t)(slot / nb);
     uint32_t end = cursor_end[slot], cnt = counts[slot];
     const uint32_t* idx = sorted + (size_t)w * n;
-    XYZZ<F> acc = XYZZ<F>::inf();
+    if (accumulate_into && cnt == 0) return;                 // nothing new for this bucket in this chunk
+    XYZZ<F> acc = accumulate_into ? load_vec_rw(buckets + slot) : XYZZ<F>::inf();
     for (uint32_t k = end - cnt; k < end; ++k) {
         uint32_t e = idx[k];
         Affine<F> p = load_vec(bases + (e & 0x7fffffffu));
@@ -334,91 +336,133 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+// The pipeline is split in three host-side steps so that the host-pointer entry point can feed it
+// point-range CHUNKS while the next chunk is still crossing PCIe:
+//   msm_plan    window size, workspace carve-up (digit/sort arrays sized for ONE chunk)
+//   msm_chunk   digits -> counting sort -> size ordering -> bucket accumulation INTO the bucket array
+//   msm_finish  bucket reduction + Horner + normalisation
 template <class F>
-static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, F* d_out, int mode) {
+struct MsmPlan {
+    size_t n_total = 0, chunk_cap = 0;
+    int c = 0, W = 0;
+    uint32_t nb = 0, n1 = 0;
+    size_t slots = 0;
+    uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *cursor = nullptr, *order = nullptr, *shist = nullptr;
+    XYZZ<F>* buckets = nullptr;
+    XYZZ<F>* Rb[2] = {nullptr, nullptr};
+    XYZZ<F>* Cb[2] = {nullptr, nullptr};
+    int chunks_done = 0;
+};
+static constexpr uint32_t MSM_REDUCE_L = 8;
+
+template <class F>
+static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<F>* pl) {
+    ZKG_REQUIRE(n_total < ((size_t)1 << 31), "msm: n = %zu exceeds 2^31-1", n_total);
+    pl->n_total = n_total;
+    pl->chunk_cap = chunk_cap;
+    int c = env_int("ZKG_MSM_C", 0);
+    if (c < 2 || c > 22) c = msm_pick_c(n_total);
+    pl->c = c;
+    pl->W = msm_num_windows(c);
+    pl->nb = 1u << (c - 1);
+    pl->slots = (size_t)pl->W * pl->nb;
+    pl->n1 = (pl->nb + MSM_REDUCE_L - 1) / MSM_REDUCE_L;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_digits = carve(sizeof(uint32_t) * pl->W * chunk_cap);
+    size_t o_sorted = carve(sizeof(uint32_t) * pl->W * chunk_cap);
+    size_t o_counts = carve(sizeof(uint32_t) * pl->slots);
+    size_t o_cursor = carve(sizeof(uint32_t) * pl->slots);
+    size_t o_order = carve(sizeof(uint32_t) * pl->slots);
+    size_t o_shist = carve(sizeof(uint32_t) * 2 * SIZE_KEYS);
+    size_t o_buckets = carve(sizeof(XYZZ<F>) * pl->slots);
+    size_t o_r0 = carve(sizeof(XYZZ<F>) * pl->W * pl->n1);
+    size_t o_c0 = carve(sizeof(XYZZ<F>) * pl->W * pl->n1);
+    size_t o_r1 = carve(sizeof(XYZZ<F>) * pl->W * pl->n1);
+    size_t o_c1 = carve(sizeof(XYZZ<F>) * pl->W * pl->n1);
+    ZKG_TRY(ctx->ws.reserve(off));
+    uint8_t* ws = (uint8_t*)ctx->ws.p;
+    pl->digits = (uint32_t*)(ws + o_digits);
+    pl->sorted = (uint32_t*)(ws + o_sorted);
+    pl->counts = (uint32_t*)(ws + o_counts);
+    pl->cursor = (uint32_t*)(ws + o_cursor);
+    pl->order = (uint32_t*)(ws + o_order);
+    pl->shist = (uint32_t*)(ws + o_shist);
+    pl->buckets = (XYZZ<F>*)(ws + o_buckets);
+    pl->Rb[0] = (XYZZ<F>*)(ws + o_r0); pl->Rb[1] = (XYZZ<F>*)(ws + o_r1);
+    pl->Cb[0] = (XYZZ<F>*)(ws + o_c0); pl->Cb[1] = (XYZZ<F>*)(ws + o_c1);
+    pl->chunks_done = 0;
+    return ZKG_OK;
+}
+
+// accumulate `n` points (n <= chunk_cap) into the plan's buckets
+template <class F>
+static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n) {
+    if (n == 0) return ZKG_OK;
     cudaStream_t st = ctx->stream;
-    if (n == 0) {
+    const int TB = 256;
+    const bool first = pl->chunks_done == 0;
+    if (first) phase_mark(ctx, 0);
+    ZKG_CUDA(cudaMemsetAsync(pl->counts, 0, sizeof(uint32_t) * pl->slots, st));
+    ZKG_CUDA(cudaMemsetAsync(pl->shist, 0, sizeof(uint32_t) * SIZE_KEYS, st));
+    k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, pl->c, pl->W, pl->nb, pl->digits, pl->counts);
+    k_scan<<<pl->W, 1024, 0, st>>>(pl->counts, pl->nb, pl->cursor);
+    k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), pl->W), TB, 0, st>>>(pl->digits, n, pl->nb, pl->cursor, pl->sorted);
+    unsigned hb = (unsigned)((pl->slots + 1023) / 1024);
+    if (hb > 592) hb = 592;
+    uint32_t* sstart = pl->shist + SIZE_KEYS;
+    k_size_hist<<<hb, 256, 0, st>>>(pl->counts, pl->slots, pl->shist);
+    k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(pl->shist, sstart);
+    k_size_scatter<<<(unsigned)((pl->slots + 255) / 256), 256, 0, st>>>(pl->counts, pl->slots, sstart, pl->order);
+    if (first) phase_mark(ctx, 1);
+    k_accumulate<F><<<(unsigned)((pl->slots + 127) / 128), 128, 0, st>>>(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order,
+                                                                       n, pl->nb, pl->W, first ? 0 : 1, pl->buckets);
+    if (first) phase_mark(ctx, 2);
+    ctx->launches += 7;
+    pl->chunks_done += 1;
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+template <class F>
+static int32_t msm_finish(zkg_ctx* ctx, MsmPlan<F>* pl, F* d_out, int mode) {
+    cudaStream_t st = ctx->stream;
+    if (pl->chunks_done == 0) {
         k_identity<F><<<1, 32, 0, st>>>(mode, d_out);
         ctx->launches += 1;
         ZKG_CUDA(cudaGetLastError());
         return ZKG_OK;
     }
-    ZKG_REQUIRE(n < ((size_t)1 << 31), "msm: n = %zu exceeds 2^31-1", n);
-    int c = env_int("ZKG_MSM_C", 0);
-    if (c < 2 || c > 22) c = msm_pick_c(n);
-    const int W = msm_num_windows(c);
-    const uint32_t nb = 1u << (c - 1);
-    const uint32_t L = 8;
-    const size_t slots = (size_t)W * nb;
-    const uint32_t n1 = (nb + L - 1) / L;
-
-    // workspace carve-up
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_digits = carve(sizeof(uint32_t) * W * n);
-    size_t o_sorted = carve(sizeof(uint32_t) * W * n);
-    size_t o_counts = carve(sizeof(uint32_t) * slots);
-    size_t o_cursor = carve(sizeof(uint32_t) * slots);
-    size_t o_order = carve(sizeof(uint32_t) * slots);
-    size_t o_shist = carve(sizeof(uint32_t) * 2 * SIZE_KEYS);
-    size_t o_buckets = carve(sizeof(XYZZ<F>) * slots);
-    size_t o_r0 = carve(sizeof(XYZZ<F>) * W * n1);
-    size_t o_c0 = carve(sizeof(XYZZ<F>) * W * n1);
-    size_t o_r1 = carve(sizeof(XYZZ<F>) * W * n1);
-    size_t o_c1 = carve(sizeof(XYZZ<F>) * W * n1);
-    ZKG_TRY(ctx->ws.reserve(off));
-    uint8_t* ws = (uint8_t*)ctx->ws.p;
-    uint32_t* digits = (uint32_t*)(ws + o_digits);
-    uint32_t* sorted = (uint32_t*)(ws + o_sorted);
-    uint32_t* counts = (uint32_t*)(ws + o_counts);
-    uint32_t* cursor = (uint32_t*)(ws + o_cursor);
-    uint32_t* order = (uint32_t*)(ws + o_order);
-    uint32_t* shist = (uint32_t*)(ws + o_shist);
-    uint32_t* sstart = shist + SIZE_KEYS;
-    XYZZ<F>* buckets = (XYZZ<F>*)(ws + o_buckets);
-    XYZZ<F>* Rb[2] = {(XYZZ<F>*)(ws + o_r0), (XYZZ<F>*)(ws + o_r1)};
-    XYZZ<F>* Cb[2] = {(XYZZ<F>*)(ws + o_c0), (XYZZ<F>*)(ws + o_c1)};
-
-    phase_mark(ctx, 0);
-    ZKG_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * slots, st));
-    ZKG_CUDA(cudaMemsetAsync(shist, 0, sizeof(uint32_t) * SIZE_KEYS, st));
-    const int TB = 256;
-    k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, c, W, nb, digits, counts);
-    k_scan<<<W, 1024, 0, st>>>(counts, nb, cursor);
-    k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), W), TB, 0, st>>>(digits, n, nb, cursor, sorted);
-    {
-        unsigned hb = (unsigned)((slots + 1023) / 1024);
-        if (hb > 592) hb = 592;
-        k_size_hist<<<hb, 256, 0, st>>>(counts, slots, shist);
-        k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(shist, sstart);
-        k_size_scatter<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(counts, slots, sstart, order);
-    }
-    phase_mark(ctx, 1);
-    k_accumulate<F><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(d_bases, sorted, cursor, counts, order, n, nb, W, buckets);
-    phase_mark(ctx, 2);
-    ctx->launches += 7;
-
-    // multi-level bucket reduction
-    const XYZZ<F>* Rin = buckets;
+    const XYZZ<F>* Rin = pl->buckets;
     const XYZZ<F>* Cin = nullptr;
-    uint32_t n_in = nb;
+    uint32_t n_in = pl->nb;
     int log2_M = 0, pp = 0;
     while (true) {
-        uint32_t n_out = (n_in + L - 1) / L;
-        size_t th = (size_t)W * n_out;
-        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(Rin, Cin, n_in, L, log2_M, W, Rb[pp], Cb[pp], n_out);
-        Rin = Rb[pp]; Cin = Cb[pp];
+        uint32_t n_out = (n_in + MSM_REDUCE_L - 1) / MSM_REDUCE_L;
+        size_t th = (size_t)pl->W * n_out;
+        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(Rin, Cin, n_in, MSM_REDUCE_L, log2_M, pl->W, pl->Rb[pp], pl->Cb[pp], n_out);
+        Rin = pl->Rb[pp]; Cin = pl->Cb[pp];
         pp ^= 1;
         ctx->launches += 1;
         n_in = n_out;
         log2_M += 3;           // M *= L (L = 8)
         if (n_out == 1) break;
     }
-    k_final<F><<<1, 32, 0, st>>>(Rin, Cin, c, W, mode, d_out);
+    k_final<F><<<1, 32, 0, st>>>(Rin, Cin, pl->c, pl->W, mode, d_out);
     ctx->launches += 1;
     phase_mark(ctx, 3);
     ZKG_CUDA(cudaGetLastError());
     return ZKG_OK;
+}
+
+template <class F>
+static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, F* d_out, int mode) {
+    MsmPlan<F> pl;
+    if (n) {
+        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl));
+        ZKG_TRY(msm_chunk<F>(ctx, &pl, d_bases, d_scalars, n));
+    }
+    return msm_finish<F>(ctx, &pl, d_out, mode);
 }
 
 template <class F>
@@ -431,7 +475,9 @@ static int32_t pack_bases(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t
     return ZKG_OK;
 }
 
-// blocking host-pointer MSM (both curves)
+// blocking host-pointer MSM (both curves).  Large inputs are fed in point-range chunks: the H2D
+// copy of chunk j+1 (copy stream) overlaps digits/sort/accumulate of chunk j (compute stream), so
+// the PCIe transfer of the 72+32 B/point inputs hides behind the bucket accumulation.
 template <class F>
 static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,
                         size_t n_scalars, uint64_t* out_xyz) {
@@ -441,28 +487,49 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
     }
     ZKG_REQUIRE(out_xyz != nullptr, "msm: out is NULL");
     ZKG_REQUIRE(n_bases == 0 || (bases && scalars), "msm: NULL input");
+    ZKG_REQUIRE(n_bases == 0 || stride >= sizeof(Affine<F>) + 1, "base stride %zu too small", stride);
     PooledCtx pc;
     ZKG_TRY(pc.acquire(device));
     zkg_ctx* ctx = pc.ctx;
     DeviceGuard dg(ctx->device);
-    size_t n = n_bases;
+    const size_t n = n_bases;
+    int K = env_int("ZKG_MSM_CHUNKS", 0);
+    if (K <= 0) K = n >= ((size_t)1 << 20) ? 4 : (n >= ((size_t)1 << 17) ? 2 : 1);
+    if (K > 16) K = 16;
+    const size_t chunk = (n + K - 1) / (K ? K : 1);
     size_t ark_bytes = align_up(n * stride, 256), sc_bytes = align_up(n * 32, 256), pk_bytes = align_up(n * sizeof(Affine<F>), 256);
     ZKG_TRY(ctx->io.reserve(ark_bytes + sc_bytes + pk_bytes + 256));
     uint8_t* d_ark = (uint8_t*)ctx->io.p;
     uint8_t* d_sc = d_ark + ark_bytes;
     uint8_t* d_pk = d_sc + sc_bytes;
     F* d_out = (F*)(d_pk + pk_bytes);
+    MsmPlan<F> pl;
     if (n) {
-        ZKG_CUDA(cudaMemcpyAsync(d_sc, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-        ZKG_CUDA(cudaMemcpyAsync(d_ark, bases, n * stride, cudaMemcpyHostToDevice, ctx->stream));
-        ZKG_TRY(pack_bases<F>(ctx, d_ark, stride, n, d_pk));
+        ZKG_TRY(msm_plan<F>(ctx, n, chunk, &pl));
+        ZKG_TRY(ctx_copy_stream(ctx, K));
+        // order the copy stream after whatever the compute stream last did with these buffers
+        ZKG_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+        ZKG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+        for (int j = 0; j < K; ++j) {
+            size_t lo = (size_t)j * chunk, hi = lo + chunk < n ? lo + chunk : n;
+            if (lo >= hi) break;
+            ZKG_CUDA(cudaMemcpyAsync(d_sc + lo * 32, (const uint8_t*)scalars + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ZKG_CUDA(cudaMemcpyAsync(d_ark + lo * stride, (const uint8_t*)bases + lo * stride, (hi - lo) * stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ZKG_CUDA(cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
+        }
+        for (int j = 0; j < K; ++j) {
+            size_t lo = (size_t)j * chunk, hi = lo + chunk < n ? lo + chunk : n;
+            if (lo >= hi) break;
+            ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[j], 0));
+            ZKG_TRY(pack_bases<F>(ctx, d_ark + lo * stride, stride, hi - lo, d_pk + lo * sizeof(Affine<F>)));
+            ZKG_TRY(msm_chunk<F>(ctx, &pl, (const Affine<F>*)d_pk + lo, (const Fr*)d_sc + lo, hi - lo));
+        }
     }
-    ZKG_TRY(msm_run<F>(ctx, (const Affine<F>*)d_pk, (const Fr*)d_sc, n, d_out, 0));
+    ZKG_TRY(msm_finish<F>(ctx, &pl, d_out, 0));
     ZKG_CUDA(cudaMemcpyAsync(out_xyz, d_out, 3 * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }
-
 
 // per-curve entry points, instantiated in msm_g1.cu (F = Fq) and msm_g2.cu (F = Fq2)
 #define ZKG_MSM_DECLARE(G)                                                                                          \
