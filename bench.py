@@ -27,7 +27,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-INT_PEAK_FALLBACK_TMACS = 18.39     # profiles/r01_intpipe_microbench.json: IMAD.WIDE issue rate, B200, 148 SMs
+INT_PEAK_TIMAD = 18.51              # profiles/r01_intpipe_microbench.json: 32-bit IMAD issue rate, B200, 148 SMs @1965 MHz
+MODMUL_PEAK_G = 67.3                # same file: this repo's Montgomery multiplier in isolation (G products/s)
+ACC_TRAFFIC_BYTES = 7.109e9         # profiles/r01_ncu_k_accumulate_v1.json: dram read+write of one k_accumulate launch at 2^22
 HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
 
 
@@ -38,7 +40,7 @@ def measured_peaks():
             hbm, how = float(json.load(fh)["hbm_gbs"]), "measured"
     except Exception:
         pass
-    imad, ihow = INT_PEAK_FALLBACK_TMACS, "measured (tools/microbench/intpipe.cu, profiles/r01_intpipe_microbench.json)"
+    imad, ihow = INT_PEAK_TIMAD, "measured (tools/microbench/intpipe.cu -> profiles/r01_intpipe_microbench.json)"
     return hbm, how, imad, ihow
 
 
@@ -211,22 +213,23 @@ def run_ours(args):
             capi.check(lib.zkg_msm_combine_dev(ctx, 1, C.c_void_p(gathered.data_ptr()), world,
                                                 C.c_void_p(out_xyz.data_ptr())))
 
-    def barrier():
-        if world > 1:
+    def barrier(collective=True):
+        if world > 1 and collective:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """K steps bracketed by barrier + synchronize; device time via CUDA events; max over ranks."""
-        barrier()
+    def timed(fn, steps, collective=True):
+        """K steps bracketed by barrier + synchronize; device time via CUDA events; max over ranks.
+        collective=False: rank-local timing (the secondary legs run on rank 0 only)."""
+        barrier(collective)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
+        barrier(collective)
         ms = e0.elapsed_time(e1)
-        if world > 1:
+        if world > 1 and collective:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
@@ -335,8 +338,8 @@ def run_ours(args):
             for fn in (f1, fk):
                 for _ in range(3):
                     fn()
-            t1 = timed(f1, 10) / 10
-            tk = timed(fk, 10) / 10
+            t1 = timed(f1, 10, collective=False) / 10
+            tk = timed(fk, 10, collective=False) / 10
             # e2e of the king call with host buffers (the reference-facing entry point)
             hs = [np.ascontiguousarray(shares.cpu().numpy().view(np.uint64).reshape(8, mbyl, 4)[p]) for p in range(8)]
             hr = rnd.cpu().numpy().view(np.uint64)
@@ -358,8 +361,11 @@ def run_ours(args):
     if rank == 0:
         hbm_peak, hbm_how, int_peak, int_how = measured_peaks()
         c_ark, W_ark = ark_window(n)
-        macs_per_point = 11 * W_ark * 136                        # 11*W modmul x 136 limb-MACs
-        achieved = n * macs_per_point / (acc_ms * 1e-3) / 1e12
+        imad_per_point = 11 * W_ark * 272                        # 11*W modmul x 272 IMAD-class instructions
+        achieved = n * imad_per_point / (acc_ms * 1e-3) / 1e12
+        my_c = int(os.environ.get("ZKG_MSM_C", "0")) or {20: 16, 21: 17, 22: 17, 23: 20, 24: 20}.get(args.log2n, 17)
+        my_W = 254 // my_c + 1
+        modmul_rate = n * my_W * 10 / (acc_ms * 1e-3) / 1e9      # products the kernel actually executes (XYZZ mixed add = 10)
         cpu_n, cpu_th, cpu_t = cpu_msm_sample(18, 3) if not args.no_cpu else (0, 0, [1.0])
         cpu_val = cpu_n / min(cpu_t) / 1e6
         line = {
@@ -378,21 +384,28 @@ def run_ours(args):
                     "call": "zkg_msm_bn254_g1 (host pointers, pinned; arkworks 72-B affine images + Fr images)",
                     "matches_device_leg": same},
             "gpu_launches": int(launches1.value - launches0.value),
-            "roofline": {"bound": "int32 multiply-add pipe (IMAD.WIDE)", "kernel": "k_accumulate<Fq>",
-                         "achieved": round(achieved, 3), "peak": int_peak, "unit": "Tmac/s (32x32+64 limb-MACs)",
+            "roofline": {"bound": "int (fmaheavy integer multiply-add pipe; not hbm, not tensor)", "kernel": "k_accumulate<Fq>",
+                         "achieved": round(achieved, 3), "peak": int_peak, "unit": "TIMAD/s",
                          "frac": round(achieved / int_peak, 4), "peak_source": int_how,
-                         "algorithmic_macs_per_point": macs_per_point, "kernel_ms": round(acc_ms, 4),
+                         "algorithmic_imad_per_point": imad_per_point,
+                         "note": "SURVEY 8(d) formula k*11*W*272/T with arkworks' W; frac can exceed 1 because the XYZZ mixed "
+                                 "add needs 10 products where arkworks' Jacobian madd needs 11",
+                         "executed_modmul_G_per_s": round(modmul_rate, 2), "modmul_peak_G_per_s": MODMUL_PEAK_G,
+                         "modmul_frac": round(modmul_rate / MODMUL_PEAK_G, 4), "kernel_ms": round(acc_ms, 4),
                          "kernel_share_of_step": round(acc_ms / (acc_ms + sort_ms + red_ms), 4),
                          "phase_ms": {"digits_sort": round(sort_ms, 4), "accumulate": round(acc_ms, 4),
                                       "reduce_final": round(red_ms, 4)},
                          "hbm": {"achieved_gbs": round(96 * n / (acc_ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
                                  "frac": round(96 * n / (acc_ms * 1e-3) / 1e9 / hbm_peak, 4), "peak_source": hbm_how},
-                         "traffic": None},
+                         "traffic": ACC_TRAFFIC_BYTES if args.log2n == 22 else None,
+                         "traffic_note": "ncu dram bytes per launch; 17x the 96 B/point because Pippenger re-reads every base once per window (15 x 64 B) -- 0.73 TB/s, 11% of HBM peak, not the bound"},
             "cpu_baseline": {"value": round(cpu_val, 4), "unit": "Mpts/s", "cores": cpu_th, "kind": "port",
                              "sample": "G1 MSM of 2^18 points, best of 3, oracle/zkoracle.c (arkworks msm_bigint_wnaf restated), OpenMP over windows"},
             "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
     lib.zkg_ctx_destroy(ctx)
     if world > 1:
         dist.destroy_process_group()

@@ -21,6 +21,9 @@ template <class P> ZKG_D Fp<P> f_add(const Fp<P>& a, const Fp<P>& b) { return fp
 template <class P> ZKG_D Fp<P> f_sub(const Fp<P>& a, const Fp<P>& b) { return fp_sub(a, b); }
 template <class P> ZKG_D Fp<P> f_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
 template <class P> ZKG_D Fp<P> f_sqr(const Fp<P>& a) { return fp_sqr(a); }
+// (an out-of-line shared multiplier body was tried for the cold formulas: slower, 2.89 vs 2.67 ms tail)
+template <class P> ZKG_D Fp<P> f_mul_hot(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
+template <class P> ZKG_D Fp<P> f_sqr_hot(const Fp<P>& a) { return fp_mul(a, a); }
 template <class P> ZKG_D Fp<P> f_dbl(const Fp<P>& a) { return fp_dbl(a); }
 template <class P> ZKG_D Fp<P> f_neg(const Fp<P>& a) { return fp_neg(a); }
 template <class P> ZKG_D Fp<P> f_inv(const Fp<P>& a) { return fp_inv(a); }
@@ -55,6 +58,8 @@ ZKG_NI Fq2 f_sqr(const Fq2& a) {
     r.c1 = fp_dbl(m);
     return r;
 }
+ZKG_D Fq2 f_mul_hot(const Fq2& a, const Fq2& b) { return f_mul(a, b); }
+ZKG_D Fq2 f_sqr_hot(const Fq2& a) { return f_sqr(a); }
 ZKG_NI Fq2 f_inv(const Fq2& a) {
     Fq n = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
     Fq2 r;
@@ -126,8 +131,8 @@ ZKG_D void xyzz_madd(XYZZ<F>& acc, const Affine<F>& p_in, bool neg) {
     Affine<F> p = p_in;
     if (neg) p.y = f_neg(p.y);
     if (acc.is_inf()) { acc.x = p.x; acc.y = p.y; acc.zz = F::one(); acc.zzz = F::one(); return; }
-    F u2 = f_mul(p.x, acc.zz);
-    F s2 = f_mul(p.y, acc.zzz);
+    F u2 = f_mul_hot(p.x, acc.zz);
+    F s2 = f_mul_hot(p.y, acc.zzz);
     F pp_ = f_sub(u2, acc.x);
     F r = f_sub(s2, acc.y);
     if (pp_.is_zero()) {
@@ -135,14 +140,14 @@ ZKG_D void xyzz_madd(XYZZ<F>& acc, const Affine<F>& p_in, bool neg) {
         else acc = XYZZ<F>::inf();                     // P == -Q
         return;
     }
-    F pp = f_sqr(pp_);
-    F ppp = f_mul(pp_, pp);
-    F q = f_mul(acc.x, pp);
-    F x3 = f_sub(f_sub(f_sub(f_sqr(r), ppp), q), q);
-    acc.y = f_sub(f_mul(r, f_sub(q, x3)), f_mul(acc.y, ppp));
+    F pp = f_sqr_hot(pp_);
+    F ppp = f_mul_hot(pp_, pp);
+    F q = f_mul_hot(acc.x, pp);
+    F x3 = f_sub(f_sub(f_sub(f_sqr_hot(r), ppp), q), q);
+    acc.y = f_sub(f_mul_hot(r, f_sub(q, x3)), f_mul_hot(acc.y, ppp));
     acc.x = x3;
-    acc.zz = f_mul(acc.zz, pp);
-    acc.zzz = f_mul(acc.zzz, ppp);
+    acc.zz = f_mul_hot(acc.zz, pp);
+    acc.zzz = f_mul_hot(acc.zzz, ppp);
 }
 
 // a += b      (add-2008-s: 12M + 2S)
@@ -192,6 +197,14 @@ ZKG_NI XYZZ<F> xyzz_mul_small(const XYZZ<F>& p, uint32_t k) {
     }
     return acc;
 }
+
+
+// (Round-1 experiment, removed: "quad-cooperative" add/double with four lanes evaluating the
+// independent products of a formula level and width-4 shuffles between levels.  A lone warp runs
+// this code at ~6.3 cycles per instruction (ncu: 3.2 wait + 1.5 branch-resolving stalls per issue),
+// so the select/shuffle overhead of ~250 instructions per level cost as much as the products it
+// saved: k_final 1.55 ms vs 1.37 ms single-lane.)
+
 
 typedef Affine<Fq> G1Affine;
 typedef Affine<Fq2> G2Affine;

@@ -15,14 +15,28 @@ static constexpr uint32_t MSM_DIGIT_NONE = 0xffffffffu;
 // final carry of the signed recoding is absorbed without an extra window.
 ZKG_HD int msm_num_windows(int c) { return MSM_SCALAR_BITS / c + 1; }
 
-// window size for n points: balances n*W mixed adds against W*2^(c-1) bucket-reduction adds
+// Window size for n points.  Cost model (field multiplications): n*W mixed adds of 10 plus
+// W*2^(c-1) buckets reduced with two 14-multiplication adds each.  The TOP window only holds the
+// r = 254 - (W-1)c leftover bits, so its points fall into just 2^r buckets; one thread walks one
+// bucket, so a small r serialises n/2^r additions on a handful of threads (measured: c = 18 at
+// n = 2^22 has r = 2 and takes 7 s instead of 10 ms).  Window sizes whose top buckets would hold
+// more than 1024 points are therefore excluded.
 ZKG_HD int msm_pick_c(size_t n) {
     int lg = 0;
     while (((size_t)1 << lg) < n) ++lg;
-    int c = lg - 5;
-    if (c < 5) c = 5;
-    if (c > 20) c = 20;
-    return c;
+    int best = 0, fallback = 5, fallback_used = -1;
+    double best_cost = 0;
+    for (int c = 5; c <= 20; ++c) {
+        if (c > lg + 1 && c > 5) break;
+        int W = msm_num_windows(c);
+        int r = MSM_SCALAR_BITS - (W - 1) * c;             // bits in the top window (1..c-1)
+        int used = r < c - 1 ? r : c - 1;                  // log2 of the top window's populated buckets
+        if (used > fallback_used) { fallback = c; fallback_used = used; }
+        if ((n >> used) > 1024) continue;
+        double cost = (double)n * W * 10.0 + (double)W * (double)((size_t)1 << (c - 1)) * 28.0;
+        if (best == 0 || cost < best_cost) { best = c; best_cost = cost; }
+    }
+    return best ? best : fallback;      // huge n: no window meets the bound, take the best-filled top window
 }
 
 // c-bit window `w` of a canonical 256-bit scalar held as 8 x u32
