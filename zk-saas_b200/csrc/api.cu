@@ -44,6 +44,7 @@ static void ctx_free(zkg_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->ws.release(); c->io.release(); c->io2.release(); c->small.release();
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto& e : c->cache) cudaFree(e.p);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < c->copy_ev_count; ++i) cudaEventDestroy(c->copy_ev[i]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -70,6 +71,34 @@ int32_t ctx_pinned(zkg_ctx* ctx, size_t bytes) {
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
     ZKG_CUDA(cudaMallocHost(&ctx->pinned, bytes));
     ctx->pinned_bytes = bytes;
+    return ZKG_OK;
+}
+
+static void fnv2(const void* key, size_t n, uint64_t* h1, uint64_t* h2) {
+    const uint8_t* b = (const uint8_t*)key;
+    uint64_t a = 0xcbf29ce484222325ULL, c = 0x9e3779b97f4a7c15ULL;
+    for (size_t i = 0; i < n; ++i) {
+        a = (a ^ b[i]) * 0x100000001b3ULL;
+        c = (c + b[i] + 0x632be59bd9b4e019ULL) * 0xff51afd7ed558ccdULL;
+        c ^= c >> 29;
+    }
+    *h1 = a; *h2 = c;
+}
+
+int32_t ctx_cache_get(zkg_ctx* ctx, const void* key, size_t key_bytes, size_t bytes, void** out, bool* fresh) {
+    uint64_t h1, h2;
+    fnv2(key, key_bytes, &h1, &h2);
+    for (auto& e : ctx->cache)
+        if (e.h1 == h1 && e.h2 == h2 && e.bytes == bytes) { *out = e.p; *fresh = false; return ZKG_OK; }
+    if (ctx->cache.size() >= 256) {          // bounded: drop everything once nothing in flight can still read it
+        ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (auto& e : ctx->cache) cudaFree(e.p);
+        ctx->cache.clear();
+    }
+    void* p = nullptr;
+    ZKG_CUDA(cudaMalloc(&p, bytes ? bytes : 256));
+    ctx->cache.push_back({h1, h2, bytes, p});
+    *out = p; *fresh = true;
     return ZKG_OK;
 }
 

@@ -64,6 +64,9 @@ struct zkg_ctx {
     void* pinned = nullptr;   // small pinned bounce buffer for results
     size_t pinned_bytes = 0;
     int sm_count = 0;
+    // persistent device-side parameter cache (twiddle/power tables, PSS matrices), keyed by content
+    struct CacheEnt { uint64_t h1, h2; size_t bytes; void* p; };
+    std::vector<CacheEnt> cache;
     // second stream + events for overlapping H2D copies with compute in host-pointer entry points
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev[16] = {};
@@ -86,6 +89,9 @@ struct PooledCtx {
 
 int32_t ctx_pinned(zkg_ctx* ctx, size_t bytes);
 int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events);
+// Look up (or reserve) a persistent device block for the parameter identified by `key`.
+// *fresh = true means the caller must fill it (on ctx->stream) before use.
+int32_t ctx_cache_get(zkg_ctx* ctx, const void* key, size_t key_bytes, size_t bytes, void** out, bool* fresh);
 
 struct DeviceGuard {
     int prev = -1;

@@ -323,31 +323,36 @@ __global__ void k_bitrev(const Fr* __restrict__ in, Fr* __restrict__ out, int lo
 static int ilog2(size_t x) { int r = 0; while (((size_t)1 << r) < x) ++r; return r; }
 static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 
-// carve scratch from ctx->small (tables, matrices)
-struct SmallAlloc {
-    zkg_ctx* ctx; size_t off = 0; size_t cap;
-    uint8_t* take(size_t bytes) { uint8_t* p = (uint8_t*)ctx->small.p + off; off = align_up(off + bytes, 256); return off <= cap ? p : nullptr; }
-};
+// Parameter tables live in the context's persistent cache (keyed by their defining values), so a
+// prover that keeps calling d_fft / d_ifft with the same domain builds them once.
+struct SmallAlloc { zkg_ctx* ctx; };      // (kept as a handle type: tables come from ctx_cache_get)
 
-static int32_t build_pow_table(zkg_ctx* ctx, SmallAlloc& sa, const HFr& w, size_t max_exp_excl, PowTable* out) {
-    size_t hi_n = (max_exp_excl + TW_LO - 1) >> TW_LO_BITS;
-    if (hi_n == 0) hi_n = 1;
-    Fr* lo = (Fr*)sa.take(TW_LO * sizeof(Fr));
-    Fr* hi = (Fr*)sa.take(hi_n * sizeof(Fr));
-    ZKG_REQUIRE(lo && hi, "internal: small workspace exhausted");
-    k_pow_table<<<(TW_LO + 255) / 256, 256, 0, ctx->stream>>>(to_arg(w), TW_LO, lo);
-    HFr w_hi = host::h_pow(w, TW_LO);
-    k_pow_table<<<(unsigned)((hi_n + 255) / 256), 256, 0, ctx->stream>>>(to_arg(w_hi), (uint32_t)hi_n, hi);
-    ctx->launches += 2;
-    ZKG_CUDA(cudaGetLastError());
-    out->lo = lo; out->hi = hi;
+struct PowKey { char tag[8]; uint64_t w[4]; uint64_t count; };
+
+// out[i] = w^i, i < count, cached
+static int32_t cached_pow_seq(zkg_ctx* ctx, const char* tag, const HFr& w, size_t count, const Fr** out) {
+    PowKey k;
+    memset(&k, 0, sizeof k);
+    strncpy(k.tag, tag, sizeof k.tag - 1);
+    memcpy(k.w, w.v, 32);
+    k.count = count;
+    void* p; bool fresh;
+    ZKG_TRY(ctx_cache_get(ctx, &k, sizeof k, (count ? count : 1) * sizeof(Fr), &p, &fresh));
+    if (fresh && count) {
+        k_pow_table<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(to_arg(w), (uint32_t)count, (Fr*)p);
+        ctx->launches += 1;
+        ZKG_CUDA(cudaGetLastError());
+    }
+    *out = (const Fr*)p;
     return ZKG_OK;
 }
 
-static size_t pow_table_bytes(size_t max_exp_excl) {
+static int32_t build_pow_table(zkg_ctx* ctx, SmallAlloc&, const HFr& w, size_t max_exp_excl, PowTable* out) {
     size_t hi_n = (max_exp_excl + TW_LO - 1) >> TW_LO_BITS;
     if (hi_n == 0) hi_n = 1;
-    return align_up(TW_LO * sizeof(Fr), 256) + align_up(hi_n * sizeof(Fr), 256);
+    ZKG_TRY(cached_pow_seq(ctx, "pow_lo", w, TW_LO, &out->lo));
+    ZKG_TRY(cached_pow_seq(ctx, "pow_hi", host::h_pow(w, TW_LO), hi_n, &out->hi));
+    return ZKG_OK;
 }
 
 // In-order-output NTT of d_in (bit-reversed input order) with root w_N, into d_out.
@@ -374,10 +379,9 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, SmallAlloc& sa, const Fr* d_in, Fr* d
         P.scale = to_arg(scale ? *scale : host::h_one());
         // small twiddles: w_T^i, i < T/2, w_T = wN^(N/T)
         size_t T = (size_t)1 << b;
-        Fr* tws = (Fr*)sa.take((T / 2 ? T / 2 : 1) * sizeof(Fr));
-        ZKG_REQUIRE(tws, "internal: small workspace exhausted");
+        const Fr* tws;
         HFr wT = host::h_pow(wN, N >> b);
-        if (T / 2) { k_pow_table<<<(unsigned)((T / 2 + 255) / 256), 256, 0, ctx->stream>>>(to_arg(wT), (uint32_t)(T / 2), tws); ctx->launches += 1; }
+        ZKG_TRY(cached_pow_seq(ctx, "tw_small", wT, T / 2, &tws));
         // destination: last pass -> d_out; otherwise the scratch (in place on scratch is safe: a
         // block reads and writes the same index set when no shift is applied)
         Fr* dst = P.last ? d_out : d_tmp;
@@ -397,7 +401,6 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, SmallAlloc& sa, const Fr* d_in, Fr* d
     return ZKG_OK;
 }
 
-static size_t ntt_small_bytes(size_t N) { return pow_table_bytes(N) + 4 * align_up(1024 * sizeof(Fr), 256); }
 
 // cached PSS matrices (host) per packing factor
 static std::mutex g_pss_mu;
@@ -410,12 +413,12 @@ static const host::PssMatrices* pss_get(uint32_t l) {
     return &g_pss[slot];
 }
 
-static int32_t upload(zkg_ctx* ctx, SmallAlloc& sa, const std::vector<HFr>& m, const Fr** out) {
-    Fr* d = (Fr*)sa.take(m.size() * sizeof(Fr));
-    ZKG_REQUIRE(d, "internal: small workspace exhausted");
-    // the source vector lives in a cache or outlives the stream sync of the caller
-    ZKG_CUDA(cudaMemcpyAsync(d, m.data(), m.size() * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    *out = d;
+static int32_t upload(zkg_ctx* ctx, SmallAlloc&, const std::vector<HFr>& m, const Fr** out) {
+    void* p; bool fresh;
+    ZKG_TRY(ctx_cache_get(ctx, m.data(), m.size() * sizeof(HFr), m.size() * sizeof(Fr), &p, &fresh));
+    // blocking copy, once per distinct matrix: the source may be a temporary
+    if (fresh && !m.empty()) ZKG_CUDA(cudaMemcpy(p, m.data(), m.size() * sizeof(Fr), cudaMemcpyHostToDevice));
+    *out = (const Fr*)p;
     return ZKG_OK;
 }
 
@@ -488,9 +491,7 @@ static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* partie
     keep.v.push_back(pad_rows(pm->pack, pm->n, pm->l + pm->t, K));
     const std::vector<HFr>& packK = keep.v.back();
 
-    size_t small_need = 2 * pow_table_bytes(m) + align_up(U->size() * 32, 256) + align_up(packK.size() * 32, 256) + 1024;
-    ZKG_TRY(ctx->small.reserve(small_need));
-    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    SmallAlloc sa{ctx};
     const Fr *dU, *dP;
     phase_mark(ctx, 0);
     ZKG_TRY(upload(ctx, sa, *U, &dU));
@@ -564,8 +565,7 @@ static int32_t fft1_dev(zkg_ctx* ctx, Fr* d_px, size_t mbyl, uint32_t l, const H
                         const Fr* d_mask) {
     ZKG_REQUIRE(l >= 1 && is_pow2(l) && is_pow2(mbyl), "fft1: m/l = %zu and l = %u must be powers of two", mbyl, l);
     ZKG_REQUIRE(ilog2(mbyl * l) <= 28, "fft1: m exceeds the 2-adicity of Fr");
-    ZKG_TRY(ctx->small.reserve(ntt_small_bytes(mbyl)));
-    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    SmallAlloc sa{ctx};
     ZKG_TRY(ctx->ws.reserve(mbyl * sizeof(Fr)));
     Fr* tmp = (Fr*)ctx->ws.p;
     HFr wN = host::h_pow(gen, l);
@@ -670,8 +670,7 @@ static int32_t pss_host(int device, uint32_t l, int which, const uint64_t* in, c
     Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + in_b + rand_b);
     ZKG_CUDA(cudaMemcpyAsync(d_in, in, in_elems * 32, cudaMemcpyHostToDevice, ctx->stream));
     if (which == 0 && rand) ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, cols * t * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKG_TRY(ctx->small.reserve(64 * 1024));
-    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    SmallAlloc sa{ctx};
     HostKeep keep;
     const Fr* dM;
     if (which == 0) {
@@ -713,8 +712,7 @@ int32_t zkg_fft2_bn254(int32_t device, uint64_t* s1, size_t m, uint32_t l, const
     Fr* d_in = (Fr*)ctx->io.p;
     Fr* d_out = d_in + m;
     ZKG_CUDA(cudaMemcpyAsync(d_in, s1, m * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKG_TRY(ctx->small.reserve(pow_table_bytes(m) + 1024));
-    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    SmallAlloc sa{ctx};
     PowTable gen_tw, none{nullptr, nullptr};
     ZKG_TRY(build_pow_table(ctx, sa, host::h_load(gen), m, &gen_tw));
     size_t mbyl = m / l;
@@ -739,8 +737,7 @@ int32_t zkg_distribute_powers_bn254(int32_t device, uint64_t* v, size_t n, const
     ZKG_TRY(ctx->io.reserve(n * 32));
     Fr* d = (Fr*)ctx->io.p;
     ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKG_TRY(ctx->small.reserve(pow_table_bytes(n) + 1024));
-    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    SmallAlloc sa{ctx};
     PowTable tw;
     ZKG_TRY(build_pow_table(ctx, sa, host::h_load(g), n, &tw));
     k_distribute_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, n, tw);
@@ -781,8 +778,7 @@ int32_t zkg_fr_fft_bn254(int32_t device, uint64_t* v, size_t n, const uint64_t* 
     Fr* d_rev = d + n;
     Fr* d_tmp = d + 2 * n;
     ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKG_TRY(ctx->small.reserve(ntt_small_bytes(n) + pow_table_bytes(n) + 1024));
-    SmallAlloc sa{ctx, 0, ctx->small.bytes};
+    SmallAlloc sa{ctx};
     HFr w = host::h_root_of_unity(n), one = host::h_one();
     HFr off = offset ? host::h_load(offset) : one;
     bool coset = !(off == one);
