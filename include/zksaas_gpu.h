@@ -124,6 +124,18 @@ int32_t zkg_king_fft2_bn254_dev(zkg_ctx *ctx, const uint64_t *d_shares, const ui
                                 size_t mbyl, uint32_t l, const uint64_t gen[4], const uint64_t g[4],
                                 int32_t rearrange, const uint64_t *d_rand, uint64_t *d_out);
 
+/* Column-range halves of the same pipeline, for sharding ONE king over the GPUs of a box.
+ * Stage 1 takes the share columns [col0, col0+cols) (d_shares_local: n_recv x cols, party-major) and
+ * scatters unpack -> fft2 -> g^i into the FULL-size buffer d_S_full (m = mbyl*l elements in pack order,
+ * zeroed by the caller): every slot is written by exactly one rank, so a sum reduce-scatter over the
+ * ranks (one NCCL collective) hands each rank the contiguous slice of its own output columns.  Stage 2
+ * packs `cols` output columns: d_S_local (cols*l), d_rand_local (cols*t) -> d_out_local (n x cols). */
+int32_t zkg_king_stage1_bn254_dev(zkg_ctx *ctx, const uint64_t *d_shares_local, const uint32_t *parties,
+                                  uint32_t n_recv, size_t col0, size_t cols, size_t mbyl, uint32_t l,
+                                  const uint64_t gen[4], const uint64_t g[4], int32_t rearrange, uint64_t *d_S_full);
+int32_t zkg_king_stage2_bn254_dev(zkg_ctx *ctx, const uint64_t *d_S_local, const uint64_t *d_rand_local, size_t cols,
+                                  uint32_t l, uint64_t *d_out_local);
+
 /* ---- king closure of deg_red: dist-primitives/src/utils/deg_red.rs:103-111 ------------------ */
 int32_t zkg_deg_red_king_bn254(int32_t device, const uint64_t *const *shares_by_party, const uint32_t *parties,
                                uint32_t n_recv, size_t cols, uint32_t l, const uint64_t *rand,

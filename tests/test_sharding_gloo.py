@@ -80,3 +80,87 @@ def test_sharded_msm_world2_gloo(n):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded king pipeline: host logic (column ranges + ONE sum reduce-scatter) with the big-integer
+# model standing in for the two CUDA stages
+# ------------------------------------------------------------------------------------------------
+def _king_worker(rank, world, port, l, m, rearrange, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+    import oracle_lib as ol
+    from oracle_lib import pyref
+    from zksaas_b200.sharding import king_sharded
+    R = pyref.R_MOD
+    rng = random.Random(77)                                  # same inputs on every rank
+    pp = pyref.PackedSharingParams(l)
+    dom = pyref.Radix2Domain(m)
+    mbyl = m // l
+    gen, g = dom.group_gen, pyref.Radix2Domain(2 * m).element(1)
+    cols = [pp.pack([rng.randrange(R) for _ in range(l)], [rng.randrange(R) for _ in range(l)]) for _ in range(mbyl)]
+    shares = pyref.transpose([[v * v % R for v in c] for c in cols])          # party-major, degree 2(l+t)-2
+    rand = [[rng.randrange(R) for _ in range(pp.t)] for _ in range(mbyl)]
+    expect = pyref.king_fft2(shares, list(range(pp.n)), pp, gen, g, rearrange, rand)
+    log_m = m.bit_length() - 1
+
+    def brev(x):
+        return int(format(x, f"0{log_m}b")[::-1], 2)
+
+    def stage1(lo, hi):
+        """what k_king_stage1 computes for columns [lo, hi): column-local fft2 closed form, pack-order scatter"""
+        S = [0] * m
+        for k in range(lo, hi):
+            ent = {k: pp.unpack2([shares[p][k] for p in range(pp.n)])}
+            C, E = mbyl, l
+            for i in range(l.bit_length() - 1, 0, -1):
+                new = {}
+                for kap, e in ent.items():
+                    tw = pow(gen, (1 << (i - 1)) * (kap + 1), R)
+                    new[kap] = [(e[2 * j] + e[2 * j + 1] * tw) % R for j in range(E // 2)]
+                    new[kap + C] = [(e[2 * j] - e[2 * j + 1] * tw) % R for j in range(E // 2)]
+                ent, C, E = new, C * 2, E // 2
+            for kap, e in ent.items():
+                pos = (kap + 1) % m
+                v = e[0] * pow(g, pos, R) % R
+                if rearrange:
+                    p = brev(pos)
+                    S[(p % mbyl) * l + p // mbyl] = v
+                else:
+                    S[pos] = v
+        return torch.from_numpy(ol.fr_np(S).view(np.int64).copy())
+
+    def reduce_scatter(S):
+        # gloo has no reduce_scatter_tensor: all_reduce + slice has the same semantics
+        t = S.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t[rank * (m // world):(rank + 1) * (m // world)]
+
+    def stage2(lo, hi, S_r):
+        vals = ol.np_fr(S_r.numpy().view(np.uint64))
+        out = [pp.pack(vals[c * l:(c + 1) * l], rand[lo + c]) for c in range(hi - lo)]
+        return pyref.transpose(out)
+
+    got = king_sharded(mbyl, world, rank, stage1, reduce_scatter, stage2)
+    lo, hi = rank * (mbyl // world), (rank + 1) * (mbyl // world)
+    ok = all(got[p] == expect[p][lo:hi] for p in range(pp.n))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("l,m,rearrange", [(2, 32, 0), (2, 32, 1), (4, 64, 1)])
+def test_sharded_king_world2_gloo(l, m, rearrange):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + l + m + rearrange
+    procs = [ctx.Process(target=_king_worker, args=(r, 2, port, l, m, rearrange, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -182,19 +182,23 @@ k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr*
 template <int LL>
 __global__ void __launch_bounds__(256)
 k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restrict__ U, const Fr* __restrict__ direct,
-              size_t mbyl, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw, Fr* __restrict__ S) {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= mbyl) return;
+              size_t mbyl, size_t col0, size_t cols, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw,
+              Fr* __restrict__ S) {
+    // this launch owns the share columns [col0, col0 + cols) of the mbyl columns (cols == mbyl unsharded);
+    // inputs are indexed locally (kk), twiddles and destinations by the global column k
+    size_t kk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= cols) return;
+    const size_t k = col0 + kk;
     constexpr int LOGL = LL == 2 ? 1 : LL == 4 ? 2 : 3;
     Fr v[LL];
     if (direct) {
 #pragma unroll
-        for (int j = 0; j < LL; ++j) v[j] = ld_fr(direct + k * LL + j);
+        for (int j = 0; j < LL; ++j) v[j] = ld_fr(direct + kk * LL + j);
     } else {
 #pragma unroll
         for (int j = 0; j < LL; ++j) v[j] = Fr::zero();
         for (uint32_t r = 0; r < n_recv; ++r) {
-            Fr x = ld_fr(shares + (size_t)r * mbyl + k);
+            Fr x = ld_fr(shares + (size_t)r * cols + kk);
 #pragma unroll
             for (int j = 0; j < LL; ++j) v[j] = fp_add(v[j], fp_mul(ld_fr(U + (size_t)j * n_recv + r), x));
         }
@@ -475,27 +479,24 @@ static int32_t recv_matrix(uint32_t l, const uint32_t* parties, uint32_t n_recv,
 
 // ---- king pipeline on device buffers ------------------------------------------------------
 // mode_fft: 1 = fft2 + powers + (re)packing (d_fft/d_ifft king), 0 = deg_red king
-static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* parties, uint32_t n_recv, size_t mbyl,
-                        uint32_t l, const HFr* gen, const HFr* g, int rearrange, const Fr* d_rand, Fr* d_out,
-                        int mode_fft, HostKeep& keep) {
+// stage 1 on the share columns [col0, col0+cols): unpack (+ fft2 + powers) and scatter into S (pack order)
+static int32_t king_stage1(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* parties, uint32_t n_recv, size_t mbyl,
+                           size_t col0, size_t cols, uint32_t l, const HFr* gen, const HFr* g, int rearrange,
+                           int mode_fft, Fr* S, HostKeep& keep) {
     const host::PssMatrices* pm = pss_get(l);
     ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
     ZKG_REQUIRE(is_pow2(mbyl) || !mode_fft, "king: m/l = %zu is not a power of two", mbyl);
-    if (mbyl == 0) return ZKG_OK;
+    ZKG_REQUIRE(col0 + cols <= mbyl, "king: column range [%zu, %zu) outside 0..%zu", col0, col0 + cols, mbyl);
+    if (cols == 0) return ZKG_OK;
     const size_t m = mbyl * l;
     const int log_m = ilog2(m);
     ZKG_REQUIRE(!mode_fft || log_m <= 28, "king: m = %zu exceeds the 2-adicity of Fr", m);
     const std::vector<HFr>* U;
     ZKG_TRY(recv_matrix(l, parties, n_recv, keep, &U));
-    const int K = (int)(pm->l + pm->t) <= 4 ? 4 : (int)(pm->l + pm->t) <= 8 ? 8 : 16;
-    keep.v.push_back(pad_rows(pm->pack, pm->n, pm->l + pm->t, K));
-    const std::vector<HFr>& packK = keep.v.back();
-
     SmallAlloc sa{ctx};
-    const Fr *dU, *dP;
+    const Fr* dU;
     phase_mark(ctx, 0);
     ZKG_TRY(upload(ctx, sa, *U, &dU));
-    ZKG_TRY(upload(ctx, sa, packK, &dP));
     PowTable gen_tw{nullptr, nullptr}, g_tw{nullptr, nullptr};
     int has_g = 0;
     if (mode_fft) {
@@ -503,21 +504,43 @@ static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* partie
         has_g = !(*g == host::h_one());
         if (has_g) ZKG_TRY(build_pow_table(ctx, sa, *g, m, &g_tw));
     }
-    ZKG_TRY(ctx->ws.reserve(m * sizeof(Fr)));
-    Fr* S = (Fr*)ctx->ws.p;
-    unsigned blocks = (unsigned)((mbyl + 255) / 256);
+    unsigned blocks = (unsigned)((cols + 255) / 256);
     int mode = mode_fft ? (rearrange ? 1 : 0) : 2;
     phase_mark(ctx, 1);
-#define KS(LLv) k_king_stage1<LLv><<<blocks, 256, 0, ctx->stream>>>(d_shares, n_recv, dU, nullptr, mbyl, log_m, mode, gen_tw, has_g, g_tw, S)
+#define KS(LLv) k_king_stage1<LLv><<<blocks, 256, 0, ctx->stream>>>(d_shares, n_recv, dU, nullptr, mbyl, col0, cols, log_m, mode, gen_tw, has_g, g_tw, S)
     if (l == 2) KS(2); else if (l == 4) KS(4); else KS(8);
 #undef KS
     ctx->launches += 1;
     ZKG_CUDA(cudaGetLastError());
     phase_mark(ctx, 2);
-    // re-pack: column c takes secrets S[c*l..], rand[c*t..] -> party-major shares out[p*mbyl + c]
-    ZKG_TRY(launch_pack(ctx, dP, K, pm->n, pm->l, pm->t, S, pm->l, 1, d_rand, pm->t, 1, d_out, 1, mbyl, mbyl));
+    return ZKG_OK;
+}
+
+// stage 2 on `cols` output columns: secrets S[c*l..] + rand[c*t..] -> party-major shares out[p*cols + c]
+static int32_t king_stage2(zkg_ctx* ctx, const Fr* S, const Fr* d_rand, size_t cols, uint32_t l, Fr* d_out, HostKeep& keep) {
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    if (cols == 0) return ZKG_OK;
+    const int K = (int)(pm->l + pm->t) <= 4 ? 4 : (int)(pm->l + pm->t) <= 8 ? 8 : 16;
+    keep.v.push_back(pad_rows(pm->pack, pm->n, pm->l + pm->t, K));
+    SmallAlloc sa{ctx};
+    const Fr* dP;
+    ZKG_TRY(upload(ctx, sa, keep.v.back(), &dP));
+    ZKG_TRY(launch_pack(ctx, dP, K, pm->n, pm->l, pm->t, S, pm->l, 1, d_rand, pm->t, 1, d_out, 1, cols, cols));
     phase_mark(ctx, 3);
     return ZKG_OK;
+}
+
+// ---- king pipeline on device buffers ------------------------------------------------------
+// mode_fft: 1 = fft2 + powers + (re)packing (d_fft/d_ifft king), 0 = deg_red king
+static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* parties, uint32_t n_recv, size_t mbyl,
+                        uint32_t l, const HFr* gen, const HFr* g, int rearrange, const Fr* d_rand, Fr* d_out,
+                        int mode_fft, HostKeep& keep) {
+    if (mbyl == 0) return ZKG_OK;
+    ZKG_TRY(ctx->ws.reserve(mbyl * l * sizeof(Fr)));
+    Fr* S = (Fr*)ctx->ws.p;
+    ZKG_TRY(king_stage1(ctx, d_shares, parties, n_recv, mbyl, 0, mbyl, l, gen, g, rearrange, mode_fft, S, keep));
+    return king_stage2(ctx, S, d_rand, mbyl, l, d_out, keep);
 }
 
 // gather host vectors (one per party) into a party-major device buffer
@@ -633,6 +656,25 @@ int32_t zkg_king_fft2_bn254_dev(zkg_ctx* ctx, const uint64_t* d_shares, const ui
     return ZKG_OK;
 }
 
+int32_t zkg_king_stage1_bn254_dev(zkg_ctx* ctx, const uint64_t* d_shares_local, const uint32_t* parties, uint32_t n_recv,
+                                  size_t col0, size_t cols, size_t mbyl, uint32_t l, const uint64_t gen[4],
+                                  const uint64_t g[4], int32_t rearrange, uint64_t* d_S_full) {
+    ZKG_REQUIRE(ctx && gen && g && (cols == 0 || (d_shares_local && d_S_full)), "king_stage1: NULL argument");
+    DeviceGuard dg(ctx->device);
+    HostKeep keep;
+    HFr hgen = host::h_load(gen), hg = host::h_load(g);
+    return king_stage1(ctx, (const Fr*)d_shares_local, parties, n_recv, mbyl, col0, cols, l, &hgen, &hg, rearrange, 1,
+                       (Fr*)d_S_full, keep);
+}
+
+int32_t zkg_king_stage2_bn254_dev(zkg_ctx* ctx, const uint64_t* d_S_local, const uint64_t* d_rand_local, size_t cols,
+                                  uint32_t l, uint64_t* d_out_local) {
+    ZKG_REQUIRE(ctx && (cols == 0 || (d_S_local && d_rand_local && d_out_local)), "king_stage2: NULL argument");
+    DeviceGuard dg(ctx->device);
+    HostKeep keep;
+    return king_stage2(ctx, (const Fr*)d_S_local, (const Fr*)d_rand_local, cols, l, (Fr*)d_out_local, keep);
+}
+
 int32_t zkg_deg_red_king_bn254(int32_t device, const uint64_t* const* shares_by_party, const uint32_t* parties,
                                uint32_t n_recv, size_t cols, uint32_t l, const uint64_t* rand,
                                uint64_t* const* out_by_party) {
@@ -718,9 +760,9 @@ int32_t zkg_fft2_bn254(int32_t device, uint64_t* s1, size_t m, uint32_t l, const
     size_t mbyl = m / l;
     unsigned blocks = (unsigned)((mbyl + 255) / 256);
     int log_m = ilog2(m);
-    if (l == 2) k_king_stage1<2><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, log_m, 3, gen_tw, 0, none, d_out);
-    else if (l == 4) k_king_stage1<4><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, log_m, 3, gen_tw, 0, none, d_out);
-    else k_king_stage1<8><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, log_m, 3, gen_tw, 0, none, d_out);
+    if (l == 2) k_king_stage1<2><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, d_out);
+    else if (l == 4) k_king_stage1<4><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, d_out);
+    else k_king_stage1<8><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, d_out);
     ZKG_CUDA(cudaGetLastError());
     ZKG_CUDA(cudaMemcpyAsync(s1, d_out, m * 32, cudaMemcpyDeviceToHost, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -41,3 +41,53 @@ def sharded_msm(n_total: int, world: int, rank: int, partial_fn, all_gather_fn, 
     if len(parts) != world:
         raise RuntimeError("all_gather returned %d partials for world size %d" % (len(parts), world))
     return combine_fn(parts)
+
+
+def king_sharded(mbyl: int, world: int, rank: int, stage1_fn, reduce_scatter_fn, stage2_fn):
+    """One king pipeline (dist-primitives/src/dfft/mod.rs:264-304) sharded by share columns.
+
+    stage1_fn(lo, hi)      -> FULL-size S (m x 4 int64 words, pack order), zero except the slots this
+                              rank's columns [lo, hi) produce (unpack -> fft2 -> g^i);
+    reduce_scatter_fn(S)   -> this rank's contiguous slice of the element-wise SUM over ranks.  Every slot
+                              is written by exactly one rank, so the 64-bit lane sums never carry: the one
+                              collective of the pipeline *is* the rotate / bit-reverse / stride permutation;
+    stage2_fn(lo, hi, S_r) -> the rank's output columns [lo, hi) (pack), party-major.
+    """
+    if mbyl % world:
+        raise ValueError("king_sharded: m/l must be divisible by the number of ranks")
+    lo, hi = shard_range(mbyl, world, rank)
+    return stage2_fn(lo, hi, reduce_scatter_fn(stage1_fn(lo, hi)))
+
+
+def king_fft2_sharded_cuda(ctx, lib, torch, dist, shares_local, mbyl, l, gen, g, rearrange, rand_local, rank, world):
+    """CUDA + NCCL instantiation of king_sharded.  shares_local: (n, cols, 4) int64 device tensor holding
+    this rank's columns of every party's vector; rand_local: (cols*t, 4).  Returns (n, cols, 4)."""
+    import ctypes as C
+    from .capi import check
+    n = shares_local.shape[0]
+    cols = shares_local.shape[1]
+    m = mbyl * l
+    dev = shares_local.device
+
+    def stage1(lo, hi):
+        S = torch.zeros((m, 4), dtype=torch.int64, device=dev)
+        check(lib.zkg_king_stage1_bn254_dev(ctx, C.c_void_p(shares_local.data_ptr()), None, n, lo, hi - lo, mbyl, l,
+                                            gen.ctypes.data, g.ctypes.data, 1 if rearrange else 0,
+                                            C.c_void_p(S.data_ptr())))
+        return S
+
+    def reduce_scatter(S):
+        out = torch.empty((m // world, 4), dtype=torch.int64, device=dev)
+        if world == 1:
+            out.copy_(S)
+        else:
+            dist.reduce_scatter_tensor(out, S, op=dist.ReduceOp.SUM)
+        return out
+
+    def stage2(lo, hi, S_r):
+        out = torch.empty((n, cols, 4), dtype=torch.int64, device=dev)
+        check(lib.zkg_king_stage2_bn254_dev(ctx, C.c_void_p(S_r.data_ptr()), C.c_void_p(rand_local.data_ptr()), hi - lo, l,
+                                            C.c_void_p(out.data_ptr())))
+        return out
+
+    return king_sharded(mbyl, world, rank, stage1, reduce_scatter, stage2)
