@@ -49,7 +49,9 @@ int32_t zkg_version(void);
 int32_t zkg_device_count(int32_t *count);
 const char *zkg_last_error(void);
 /* Context = device ordinal + stream + grow-only device workspace.  `stream` may be an existing
- * cudaStream_t (e.g. torch's current stream) or NULL to let the library create one. */
+ * cudaStream_t (e.g. torch's current stream; pass cudaStreamLegacy = (void*)1 for the default
+ * stream) or NULL to let the library create its own non-blocking stream -- in which case the caller
+ * must order its own work against zkg_ctx_sync(). */
 int32_t zkg_ctx_create(int32_t device, void *stream, zkg_ctx **out);
 int32_t zkg_ctx_destroy(zkg_ctx *ctx);
 int32_t zkg_ctx_sync(zkg_ctx *ctx);
@@ -74,11 +76,19 @@ int32_t zkg_msm_bn254_g2(int32_t device, const void *bases, size_t base_stride, 
                          const uint64_t *scalars, size_t n_scalars, uint64_t out_xyz[24]);
 
 /* Device-resident CRS shares (the bases of groth16/src/proving_key.rs:15-45 are static across
- * proofs): upload + repack once, then run MSMs against the handle.  group: 1 = G1, 2 = G2. */
+ * proofs).  Registration uploads the bases once and PREPARES them: the table holds every window
+ * shift 2^(c*w) * P_i (W = 254/c + 1 affine copies per base, e.g. 13 x 256 MiB for 2^22 G1 points --
+ * sized for the B200's 180 GB).  MSMs against the handle then need a single bucket set and no
+ * Horner over windows: ~1.4x faster at 2^22 points and ~2x at 2^19.  group: 1 = G1, 2 = G2. */
 int32_t zkg_bases_register(int32_t device, int32_t group, const void *bases, size_t base_stride, size_t n,
                            uint64_t *handle);
+/* same, from packed device bases (zkg_pack_bases_dev / zkg_fixed_base_dev output); asynchronous on ctx */
+int32_t zkg_bases_register_dev(zkg_ctx *ctx, int32_t group, const void *d_bases_packed, size_t n, uint64_t *handle);
 int32_t zkg_bases_release(uint64_t handle);
 int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t *scalars, size_t n_scalars, uint64_t *out_xyz);
+/* device scalars / device result; partial != 0 leaves the XYZZ partial sum (see zkg_msm_combine_dev) */
+int32_t zkg_msm_bn254_registered_dev(zkg_ctx *ctx, uint64_t handle, const uint64_t *d_scalars, size_t n_scalars,
+                                     uint64_t *d_out, int32_t partial);
 
 /* Device-pointer MSM.  d_bases: packed affine (x,y) Montgomery, 64 B (G1) / 128 B (G2) per point,
  * infinity encoded as (0,0) -- produce it with zkg_pack_bases_dev.  d_scalars: n x 32 B.

@@ -153,7 +153,11 @@ def test_msm_registered_bases(z):
     from zksaas_b200 import capi
     rng = random.Random(9)
     _, bases = _g1_points(rng, 128)
-    S = ol.fr_np([rng.randrange(R) for _ in range(128)])
+    sc = [rng.randrange(R) for _ in range(128)]
+    sc[0], sc[1], sc[2] = 0, 1, R - 1
+    bases[3] = np.frombuffer(pyref.g1_affine_image(None), dtype=np.uint8)
+    bases[5] = bases[4]; sc[5] = sc[4]
+    S = ol.fr_np(sc)
     h = C.c_uint64(0)
     capi.check(z.lib().zkg_bases_register(0, 1, bases.ctypes.data, 72, 128, C.byref(h)))
     out = np.zeros(12, dtype=np.uint64)

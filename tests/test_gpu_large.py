@@ -18,7 +18,9 @@ def env():
     import zksaas_b200 as z
     from zksaas_b200 import capi
     ctx = capi.ctx_p()
-    capi.check(z.lib().zkg_ctx_create(0, None, C.byref(ctx)))
+    # cudaStreamLegacy (handle 1): the library's kernels are then ordered with torch's default-stream
+    # work (random fills, slice assignments) instead of racing it on a private non-blocking stream
+    capi.check(z.lib().zkg_ctx_create(0, C.c_void_p(1), C.byref(ctx)))
     yield z, capi, torch, ctx
     z.lib().zkg_ctx_destroy(ctx)
 
@@ -134,3 +136,41 @@ def test_d_fft_round_reconstructs_plain_fft(env, log2m):
     cols = np.stack(out, axis=1).reshape(-1, 4)           # column-major (mbyl x n)
     got = pp.unpack(cols)
     assert (got == expect).all()
+
+
+@pytest.mark.parametrize("group,log2n", [(1, 10), (1, 15), (1, 19), (1, 22), (2, 13)])
+def test_msm_registered_dev_closed_form(env, group, log2n):
+    """Prepared bases (window-shifted table, merged buckets, no Horner) give the same group element."""
+    z, capi, torch, ctx = env
+    o = ol.oracle()
+    n = 1 << log2n
+    a, s = _rand_dev(torch, n, 5000 + log2n), _rand_dev(torch, n, 6000 + log2n)
+    a[0] = 0                                              # a zero scalar
+    a[1, :] = torch.tensor([-1, -1, -1, (1 << 61) - 1])   # all window bits set (carries ripple to the top window)
+    pk = 64 if group == 1 else 128
+    bases = torch.empty((n, pk), dtype=torch.uint8, device="cuda")
+    lib = z.lib()
+    capi.check(lib.zkg_fixed_base_dev(ctx, group, C.c_void_p(s.data_ptr()), n, C.c_void_p(bases.data_ptr())))
+    bases[5] = 0                                          # an infinity base
+    s_h = s.cpu().numpy().view(np.uint64).copy()
+    s_h[5] = 0
+    h = C.c_uint64(0)
+    capi.check(lib.zkg_bases_register_dev(ctx, group, C.c_void_p(bases.data_ptr()), n, C.byref(h)))
+    out = torch.zeros(12 * group, dtype=torch.int64, device="cuda")
+    capi.check(lib.zkg_msm_bn254_registered_dev(ctx, h.value, C.c_void_p(a.data_ptr()), n, C.c_void_p(out.data_ptr()), 0))
+    plain = torch.zeros(12 * group, dtype=torch.int64, device="cuda")
+    fn = lib.zkg_msm_bn254_g1_dev if group == 1 else lib.zkg_msm_bn254_g2_dev
+    capi.check(fn(ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(a.data_ptr()), n, C.c_void_p(plain.data_ptr())))
+    capi.check(lib.zkg_ctx_sync(ctx))
+    exp = _closed_form(o, a.cpu().numpy().view(np.uint64).copy(), s_h, g2=(group == 2))
+    assert (out.cpu().numpy().view(np.uint64) == exp).all()
+    assert bool((plain == out).all())
+    # partial (XYZZ) output combines to the same point
+    part = torch.zeros(16 * group, dtype=torch.int64, device="cuda")
+    comb = torch.zeros(12 * group, dtype=torch.int64, device="cuda")
+    capi.check(lib.zkg_msm_bn254_registered_dev(ctx, h.value, C.c_void_p(a.data_ptr()), n, C.c_void_p(part.data_ptr()), 1))
+    capi.check(lib.zkg_msm_combine_dev(ctx, group, C.c_void_p(part.data_ptr()), 1, C.c_void_p(comb.data_ptr())))
+    capi.check(lib.zkg_ctx_sync(ctx))
+    assert bool((comb == out).all())
+    assert lib.zkg_msm_bn254_registered_dev(ctx, h.value, C.c_void_p(a.data_ptr()), n - 1, C.c_void_p(out.data_ptr()), 0) == capi.ZKG_ERR_LEN_MISMATCH
+    capi.check(lib.zkg_bases_release(h.value))

@@ -33,7 +33,9 @@ SIGNATURES = {
     "zkg_msm_bn254_g1": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkg_msm_bn254_g2": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkg_bases_register": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, u64p]),
+    "zkg_bases_register_dev": (C.c_int32, [ctx_p, C.c_int32, C.c_void_p, C.c_size_t, u64p]),
     "zkg_bases_release": (C.c_int32, [C.c_uint64]),
+    "zkg_msm_bn254_registered_dev": (C.c_int32, [ctx_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32]),
     "zkg_msm_bn254_registered": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkg_pack_bases_dev": (C.c_int32, [ctx_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "zkg_msm_bn254_g1_dev": (C.c_int32, [ctx_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -21,7 +21,8 @@ template <class P> ZKG_D Fp<P> f_add(const Fp<P>& a, const Fp<P>& b) { return fp
 template <class P> ZKG_D Fp<P> f_sub(const Fp<P>& a, const Fp<P>& b) { return fp_sub(a, b); }
 template <class P> ZKG_D Fp<P> f_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
 template <class P> ZKG_D Fp<P> f_sqr(const Fp<P>& a) { return fp_sqr(a); }
-// (an out-of-line shared multiplier body was tried for the cold formulas: slower, 2.89 vs 2.67 ms tail)
+// (tried for the cold formulas: an out-of-line shared multiplier body -- slower, 2.89 vs 2.67 ms tail;
+//  the flag-free fp_mul_r29 so that ptxas may interleave independent products -- slower, 2.47 vs 1.35 ms)
 template <class P> ZKG_D Fp<P> f_mul_hot(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
 template <class P> ZKG_D Fp<P> f_sqr_hot(const Fp<P>& a) { return fp_mul(a, a); }
 template <class P> ZKG_D Fp<P> f_dbl(const Fp<P>& a) { return fp_dbl(a); }

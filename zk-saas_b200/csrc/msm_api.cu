@@ -9,11 +9,15 @@ namespace zkg {
     int32_t msm_host_##G(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,     \
                          size_t n_scalars, uint64_t* out_xyz);                                                      \
     int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out);                          \
-    int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);
+    int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);                      \
+    int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table);                         \
+    int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode);
 ZKG_MSM_DECLARE(g1)
 ZKG_MSM_DECLARE(g2)
 
-struct BaseSet { int device; int group; size_t n; void* d_packed; };
+// device-resident CRS share: table[w*n + i] = 2^(c*w) * P_i (packed affine), W = 254/c + 1 window shifts
+struct BaseSet { int device; int group; size_t n; int c; void* d_table; };
+int msm_pick_c_merged_host(size_t n);
 static std::mutex g_bases_mu;
 static std::vector<BaseSet*> g_bases;   // handle = index + 1
 static inline size_t packed_bytes(int group) { return group == 1 ? 64 : 128; }
@@ -71,6 +75,36 @@ int32_t zkg_fixed_base_dev(zkg_ctx* ctx, int32_t group, const uint64_t* d_scalar
     return group == 1 ? fixed_base_g1(ctx, d_scalars, n, d_bases_packed) : fixed_base_g2(ctx, d_scalars, n, d_bases_packed);
 }
 
+static int32_t base_set_create(zkg_ctx* ctx, int32_t group, const void* d_packed, size_t n, uint64_t* handle) {
+    BaseSet* bs = new BaseSet{ctx->device, group, n, 0, nullptr};
+    if (n) {
+        bs->c = msm_pick_c_merged_host(n);
+        int env_c = getenv("ZKG_MSM_PREP_C") ? atoi(getenv("ZKG_MSM_PREP_C")) : 0;
+        if (env_c >= 4 && env_c <= 23) bs->c = env_c;
+        const int W = 254 / bs->c + 1;
+        size_t bytes = n * (size_t)W * packed_bytes(group);
+        cudaError_t e = cudaMalloc(&bs->d_table, bytes);
+        if (e != cudaSuccess) {
+            delete bs;
+            set_error("bases_register: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            return ZKG_ERR_OOM;
+        }
+        int32_t rc = group == 1 ? prepare_g1(ctx, d_packed, n, bs->c, bs->d_table) : prepare_g2(ctx, d_packed, n, bs->c, bs->d_table);
+        if (rc != ZKG_OK) { cudaFree(bs->d_table); delete bs; return rc; }
+    }
+    std::lock_guard<std::mutex> lk(g_bases_mu);
+    g_bases.push_back(bs);
+    *handle = g_bases.size();
+    return ZKG_OK;
+}
+
+static int32_t base_set_get(uint64_t handle, BaseSet* out) {
+    std::lock_guard<std::mutex> lk(g_bases_mu);
+    ZKG_REQUIRE(handle >= 1 && handle <= g_bases.size() && g_bases[handle - 1], "bad bases handle %llu", (unsigned long long)handle);
+    *out = *g_bases[handle - 1];
+    return ZKG_OK;
+}
+
 int32_t zkg_bases_register(int32_t device, int32_t group, const void* bases, size_t base_stride, size_t n,
                            uint64_t* handle) {
     ZKG_REQUIRE(handle && (group == 1 || group == 2) && (n == 0 || bases), "bases_register: bad argument");
@@ -78,29 +112,23 @@ int32_t zkg_bases_register(int32_t device, int32_t group, const void* bases, siz
     ZKG_TRY(pc.acquire(device));
     zkg_ctx* ctx = pc.ctx;
     DeviceGuard dg(ctx->device);
-    BaseSet* bs = new BaseSet{ctx->device, group, n, nullptr};
+    size_t ark_bytes = align_up(n * base_stride, 256);
+    ZKG_TRY(ctx->io.reserve(ark_bytes + n * packed_bytes(group) + 256));
+    uint8_t* d_ark = (uint8_t*)ctx->io.p;
+    uint8_t* d_pk = d_ark + ark_bytes;
     if (n) {
-        cudaError_t e = cudaMalloc(&bs->d_packed, n * packed_bytes(group));
-        if (e != cudaSuccess) {
-            delete bs;
-            set_error("bases_register: cudaMalloc(%zu) failed: %s", n * packed_bytes(group), cudaGetErrorString(e));
-            return ZKG_ERR_OOM;
-        }
-        int32_t rc = ctx->io.reserve(n * base_stride);
-        if (rc == ZKG_OK) {
-            cudaError_t e2 = cudaMemcpyAsync(ctx->io.p, bases, n * base_stride, cudaMemcpyHostToDevice, ctx->stream);
-            if (e2 != cudaSuccess) { set_error("bases_register: H2D failed: %s", cudaGetErrorString(e2)); rc = ZKG_ERR_CUDA; }
-        }
-        if (rc == ZKG_OK)
-            rc = group == 1 ? pack_bases_g1(ctx, ctx->io.p, base_stride, n, bs->d_packed)
-                            : pack_bases_g2(ctx, ctx->io.p, base_stride, n, bs->d_packed);
-        if (rc == ZKG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("bases_register: sync failed"); rc = ZKG_ERR_CUDA; }
-        if (rc != ZKG_OK) { cudaFree(bs->d_packed); delete bs; return rc; }
+        ZKG_CUDA(cudaMemcpyAsync(d_ark, bases, n * base_stride, cudaMemcpyHostToDevice, ctx->stream));
+        ZKG_TRY(group == 1 ? pack_bases_g1(ctx, d_ark, base_stride, n, d_pk) : pack_bases_g2(ctx, d_ark, base_stride, n, d_pk));
     }
-    std::lock_guard<std::mutex> lk(g_bases_mu);
-    g_bases.push_back(bs);
-    *handle = g_bases.size();
+    ZKG_TRY(base_set_create(ctx, group, d_pk, n, handle));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
+}
+
+int32_t zkg_bases_register_dev(zkg_ctx* ctx, int32_t group, const void* d_bases_packed, size_t n, uint64_t* handle) {
+    ZKG_REQUIRE(ctx && handle && (group == 1 || group == 2) && (n == 0 || d_bases_packed), "bases_register_dev: bad argument");
+    DeviceGuard dg(ctx->device);
+    return base_set_create(ctx, group, d_bases_packed, n, handle);
 }
 
 int32_t zkg_bases_release(uint64_t handle) {
@@ -109,18 +137,30 @@ int32_t zkg_bases_release(uint64_t handle) {
     BaseSet* bs = g_bases[handle - 1];
     g_bases[handle - 1] = nullptr;
     DeviceGuard dg(bs->device);
-    if (bs->d_packed) cudaFree(bs->d_packed);
+    cudaDeviceSynchronize();
+    if (bs->d_table) cudaFree(bs->d_table);
     delete bs;
     return ZKG_OK;
 }
 
+int32_t zkg_msm_bn254_registered_dev(zkg_ctx* ctx, uint64_t handle, const uint64_t* d_scalars, size_t n_scalars,
+                                     uint64_t* d_out, int32_t partial) {
+    ZKG_REQUIRE(ctx && d_out, "msm_registered_dev: NULL argument");
+    BaseSet bs;
+    ZKG_TRY(base_set_get(handle, &bs));
+    ZKG_REQUIRE(bs.device == ctx->device, "msm_registered_dev: bases live on device %d, context on %d", bs.device, ctx->device);
+    if (bs.n != n_scalars) {
+        set_error("msm: bases.len() = %zu, scalars.len() = %zu", bs.n, n_scalars);
+        return ZKG_ERR_LEN_MISMATCH;
+    }
+    DeviceGuard dg(ctx->device);
+    return bs.group == 1 ? msm_run_prepared_g1(ctx, bs.d_table, bs.c, d_scalars, n_scalars, d_out, partial ? 1 : 0)
+                         : msm_run_prepared_g2(ctx, bs.d_table, bs.c, d_scalars, n_scalars, d_out, partial ? 1 : 0);
+}
+
 int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t* scalars, size_t n_scalars, uint64_t* out_xyz) {
     BaseSet bs;
-    {
-        std::lock_guard<std::mutex> lk(g_bases_mu);
-        ZKG_REQUIRE(handle >= 1 && handle <= g_bases.size() && g_bases[handle - 1], "msm_registered: bad handle");
-        bs = *g_bases[handle - 1];
-    }
+    ZKG_TRY(base_set_get(handle, &bs));
     if (bs.n != n_scalars) {
         set_error("msm: bases.len() = %zu, scalars.len() = %zu", bs.n, n_scalars);
         return ZKG_ERR_LEN_MISMATCH;
@@ -135,8 +175,8 @@ int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t* scalars, size_
     uint8_t* d_sc = (uint8_t*)ctx->io.p;
     void* d_out = d_sc + sc_bytes;
     if (n_scalars) ZKG_CUDA(cudaMemcpyAsync(d_sc, scalars, n_scalars * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKG_TRY(bs.group == 1 ? msm_run_g1(ctx, bs.d_packed, (const uint64_t*)d_sc, n_scalars, d_out, 0)
-                          : msm_run_g2(ctx, bs.d_packed, (const uint64_t*)d_sc, n_scalars, d_out, 0));
+    ZKG_TRY(bs.group == 1 ? msm_run_prepared_g1(ctx, bs.d_table, bs.c, (const uint64_t*)d_sc, n_scalars, d_out, 0)
+                          : msm_run_prepared_g2(ctx, bs.d_table, bs.c, (const uint64_t*)d_sc, n_scalars, d_out, 0));
     ZKG_CUDA(cudaMemcpyAsync(out_xyz, d_out, bs.group == 1 ? 96 : 192, cudaMemcpyDeviceToHost, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;

@@ -33,10 +33,34 @@ ZKG_HD int msm_pick_c(size_t n) {
         int used = r < c - 1 ? r : c - 1;                  // log2 of the top window's populated buckets
         if (used > fallback_used) { fallback = c; fallback_used = used; }
         if ((n >> used) > 1024) continue;
-        double cost = (double)n * W * 10.0 + (double)W * (double)((size_t)1 << (c - 1)) * 28.0;
+        double cost = (double)n * W * 10.0 + (double)W * (double)((size_t)1 << (c - 1)) * 28.0 + (double)((c - 1 + 2) / 3) * 13e6;
         if (best == 0 || cost < best_cost) { best = c; best_cost = cost; }
     }
     return best ? best : fallback;      // huge n: no window meets the bound, take the best-filled top window
+}
+
+// Window size when the bases come with precomputed window shifts 2^(cw) * P (static CRS shares):
+// all windows then share ONE set of 2^(c-1) buckets, the bucket reduction shrinks W-fold and the
+// Horner over windows disappears, so much larger windows pay off.  The top window's 2^r buckets
+// still receive n extra points, hence the same fill constraint.
+ZKG_HD int msm_pick_c_merged(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << lg) < n) ++lg;
+    int best = 0, fallback = 8, fallback_used = -1;
+    double best_cost = 0;
+    for (int c = 8; c <= 23; ++c) {
+        if (c > lg + 4 && c > 8) break;
+        int W = msm_num_windows(c);
+        int r = MSM_SCALAR_BITS - (W - 1) * c;
+        int used = r < c - 1 ? r : c - 1;
+        if (used > fallback_used) { fallback = c; fallback_used = used; }
+        if ((n >> used) > 1024) continue;
+        // + the latency of the reduction levels: each of the ceil((c-1)/3) launches is a chain of ~24
+        //   dependent group additions (~0.2 ms, i.e. the time of ~13 M multiplications at full rate)
+        double cost = (double)n * W * 10.0 + (double)((size_t)1 << (c - 1)) * 28.0 + (double)((c - 1 + 2) / 3) * 13e6;
+        if (best == 0 || cost < best_cost) { best = c; best_cost = cost; }
+    }
+    return best ? best : fallback;
 }
 
 // c-bit window `w` of a canonical 256-bit scalar held as 8 x u32

@@ -77,7 +77,7 @@ __global__ void k_pack_bases(const uint8_t* __restrict__ ark, size_t stride, siz
 // ------------------------------------------------------------------------------------------
 // scalars -> signed digits + histogram
 // ------------------------------------------------------------------------------------------
-static __global__ void k_digits(const Fr* __restrict__ scalars, size_t n, int c, int W, uint32_t nb,
+static __global__ void k_digits(const Fr* __restrict__ scalars, size_t n, int c, int W, uint32_t bstride,
                          uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -96,43 +96,87 @@ static __global__ void k_digits(const Fr* __restrict__ scalars, size_t n, int c,
         uint32_t d = MSM_DIGIT_NONE;
         if (coef != 0) {
             d = (coef - 1) | (neg << 31);
-            atomicAdd(&counts[(size_t)w * nb + (coef - 1)], 1u);
+            atomicAdd(&counts[(size_t)w * bstride + (coef - 1)], 1u);      // bstride = 0: windows share the buckets
         }
         digits[(size_t)w * n + i] = d;
     }
 }
 
-// exclusive scan of counts inside each window (one block per window)
-static __global__ void k_scan(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t* __restrict__ cursor) {
-    __shared__ uint32_t part[1024];
-    const uint32_t* in = counts + (size_t)blockIdx.x * nb;
-    uint32_t* out = cursor + (size_t)blockIdx.x * nb;
-    uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
-    uint32_t lo = threadIdx.x * per, hi = min(lo + per, nb);
+// Exclusive scan of the bucket counts inside each window, in three small launches so that a merged
+// plan (ONE window of up to 2^22 buckets) does not serialise on a single block:
+//   k_scan_partial  per (window, tile of SCAN_TILE counts): tile total
+//   k_scan_tiles    per window: exclusive scan of its tile totals (one block; <= 2^22/4096 = 1024 tiles)
+//   k_scan_final    per (window, tile): exclusive scan inside the tile + tile offset
+static constexpr uint32_t SCAN_TILE = 4096;      // counts per tile; 256 threads x 16 consecutive counts
+static constexpr uint32_t SCAN_PER_THREAD = 16;
+
+static __global__ void k_scan_partial(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t tiles, uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t red[256];
+    const uint32_t w = blockIdx.y, tile = blockIdx.x;
+    const uint32_t* in = counts + (size_t)w * nb;
+    uint32_t lo = tile * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
     uint32_t s = 0;
-    for (uint32_t k = lo; k < hi; ++k) s += in[k];
-    part[threadIdx.x] = s;
+#pragma unroll
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; ++k) s += lo + k < nb ? in[lo + k] : 0u;
+    red[threadIdx.x] = s;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the per-thread partial sums
-    for (uint32_t off = 1; off < blockDim.x; off <<= 1) {
-        uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
+    for (uint32_t off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
         __syncthreads();
     }
-    uint32_t base = threadIdx.x == 0 ? 0 : part[threadIdx.x - 1];
-    for (uint32_t k = lo; k < hi; ++k) { out[k] = base; base += in[k]; }
+    if (threadIdx.x == 0) tile_sum[(size_t)w * tiles + tile] = red[0];
+}
+static __global__ void k_scan_tiles(uint32_t* __restrict__ tile_sum, uint32_t tiles) {
+    __shared__ uint32_t part[1024];
+    uint32_t* v = tile_sum + (size_t)blockIdx.x * tiles;
+    uint32_t x = threadIdx.x < tiles ? v[threadIdx.x] : 0u;
+    part[threadIdx.x] = x;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t a = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += a;
+        __syncthreads();
+    }
+    if (threadIdx.x < tiles) v[threadIdx.x] = part[threadIdx.x] - x;      // exclusive
+}
+static __global__ void k_scan_final(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t tiles,
+                                    const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t part[256];
+    const uint32_t w = blockIdx.y, tile = blockIdx.x;
+    const uint32_t* in = counts + (size_t)w * nb;
+    uint32_t* out = cursor + (size_t)w * nb;
+    uint32_t lo = tile * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t c[SCAN_PER_THREAD], s = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; ++k) { c[k] = lo + k < nb ? in[lo + k] : 0u; s += c[k]; }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t off = 1; off < 256; off <<= 1) {
+        uint32_t a = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += a;
+        __syncthreads();
+    }
+    uint32_t base = tile_off[(size_t)w * tiles + tile] + part[threadIdx.x] - s;
+#pragma unroll
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; ++k) {
+        if (lo + k < nb) out[lo + k] = base;
+        base += c[k];
+    }
 }
 
-static __global__ void k_scatter(const uint32_t* __restrict__ digits, size_t n, uint32_t nb, uint32_t* __restrict__ cursor,
-                          uint32_t* __restrict__ sorted) {
+// bstride / sstride / ioff = (nb, n, 0) for per-window buckets, (0, 0, n_total) for merged windows, where the
+// sorted entry indexes the window-shifted base table (w * n_total + point)
+static __global__ void k_scatter(const uint32_t* __restrict__ digits, size_t n, uint32_t bstride, size_t sstride, size_t ioff,
+                          size_t point0, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t w = blockIdx.y;
     if (i >= n) return;
     uint32_t d = digits[(size_t)w * n + i];
     if (d == MSM_DIGIT_NONE) return;
-    uint32_t pos = atomicAdd(&cursor[(size_t)w * nb + (d & 0x7fffffffu)], 1u);
-    sorted[(size_t)w * n + pos] = (uint32_t)i | (d & 0x80000000u);
+    uint32_t pos = atomicAdd(&cursor[(size_t)w * bstride + (d & 0x7fffffffu)], 1u);
+    sorted[(size_t)w * sstride + pos] = (uint32_t)(point0 + i + (size_t)w * ioff) | (d & 0x80000000u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -191,7 +235,7 @@ template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
-             const uint32_t* __restrict__ order, size_t n, uint32_t nb, int W, int accumulate_into,
+             const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
              XYZZ<F>* __restrict__ buckets) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)W * nb) return;
@@ -199,7 +243,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
     size_t slot = order[t];
     uint32_t w = (uint32_t)(slot / nb);
     uint32_t end = cursor_end[slot], cnt = counts[slot];
-    const uint32_t* idx = sorted + (size_t)w * n;
+    const uint32_t* idx = sorted + (size_t)w * sstride;
     if (accumulate_into && cnt == 0) return;                 // nothing new for this bucket in this chunk
     XYZZ<F> acc = accumulate_into ? load_vec_rw(buckets + slot) : XYZZ<F>::inf();
     for (uint32_t k = end - cnt; k < end; ++k) {
@@ -344,9 +388,11 @@ static int env_int(const char* name, int dflt) {
 template <class F>
 struct MsmPlan {
     size_t n_total = 0, chunk_cap = 0;
-    int c = 0, W = 0;
+    int c = 0, W = 0;          // scalar windows
+    int Wb = 0;                // bucket sets: W (one per window) or 1 (merged: bases carry the window shifts)
+    bool merged = false;
     uint32_t nb = 0, n1 = 0;
-    size_t slots = 0;
+    size_t slots = 0;          // Wb * nb
     uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *cursor = nullptr, *order = nullptr, *shist = nullptr;
     XYZZ<F>* buckets = nullptr;
     XYZZ<F>* Rb[2] = {nullptr, nullptr};
@@ -356,16 +402,22 @@ struct MsmPlan {
 static constexpr uint32_t MSM_REDUCE_L = 8;
 
 template <class F>
-static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<F>* pl) {
+static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<F>* pl, int merged_c = 0) {
     ZKG_REQUIRE(n_total < ((size_t)1 << 31), "msm: n = %zu exceeds 2^31-1", n_total);
     pl->n_total = n_total;
     pl->chunk_cap = chunk_cap;
-    int c = env_int("ZKG_MSM_C", 0);
-    if (c < 2 || c > 22) c = msm_pick_c(n_total);
+    int c = merged_c;
+    if (!merged_c) {
+        c = env_int("ZKG_MSM_C", 0);
+        if (c < 2 || c > 22) c = msm_pick_c(n_total);
+    }
     pl->c = c;
     pl->W = msm_num_windows(c);
+    pl->merged = merged_c != 0;
+    pl->Wb = pl->merged ? 1 : pl->W;
+    ZKG_REQUIRE(!pl->merged || n_total * (size_t)pl->W < ((size_t)1 << 31), "msm: n*W exceeds 2^31-1");
     pl->nb = 1u << (c - 1);
-    pl->slots = (size_t)pl->W * pl->nb;
+    pl->slots = (size_t)pl->Wb * pl->nb;
     pl->n1 = (pl->nb + MSM_REDUCE_L - 1) / MSM_REDUCE_L;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -374,12 +426,14 @@ static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<
     size_t o_counts = carve(sizeof(uint32_t) * pl->slots);
     size_t o_cursor = carve(sizeof(uint32_t) * pl->slots);
     size_t o_order = carve(sizeof(uint32_t) * pl->slots);
-    size_t o_shist = carve(sizeof(uint32_t) * 2 * SIZE_KEYS);
+    const uint32_t scan_tiles = (pl->nb + SCAN_TILE - 1) / SCAN_TILE;
+    ZKG_REQUIRE(scan_tiles <= 1024, "msm: window of %d bits too large", c);
+    size_t o_shist = carve(sizeof(uint32_t) * (2 * SIZE_KEYS + (size_t)pl->Wb * scan_tiles));
     size_t o_buckets = carve(sizeof(XYZZ<F>) * pl->slots);
-    size_t o_r0 = carve(sizeof(XYZZ<F>) * pl->W * pl->n1);
-    size_t o_c0 = carve(sizeof(XYZZ<F>) * pl->W * pl->n1);
-    size_t o_r1 = carve(sizeof(XYZZ<F>) * pl->W * pl->n1);
-    size_t o_c1 = carve(sizeof(XYZZ<F>) * pl->W * pl->n1);
+    size_t o_r0 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
+    size_t o_c0 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
+    size_t o_r1 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
+    size_t o_c1 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
     ZKG_TRY(ctx->ws.reserve(off));
     uint8_t* ws = (uint8_t*)ctx->ws.p;
     pl->digits = (uint32_t*)(ws + o_digits);
@@ -395,9 +449,10 @@ static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<
     return ZKG_OK;
 }
 
-// accumulate `n` points (n <= chunk_cap) into the plan's buckets
+// accumulate `n` points (n <= chunk_cap) into the plan's buckets.  Merged plans pass the whole
+// window-shifted table as d_bases and the chunk's first point index as point0.
 template <class F>
-static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n) {
+static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, size_t point0 = 0) {
     if (n == 0) return ZKG_OK;
     cudaStream_t st = ctx->stream;
     const int TB = 256;
@@ -405,9 +460,17 @@ static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases,
     if (first) phase_mark(ctx, 0);
     ZKG_CUDA(cudaMemsetAsync(pl->counts, 0, sizeof(uint32_t) * pl->slots, st));
     ZKG_CUDA(cudaMemsetAsync(pl->shist, 0, sizeof(uint32_t) * SIZE_KEYS, st));
-    k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, pl->c, pl->W, pl->nb, pl->digits, pl->counts);
-    k_scan<<<pl->W, 1024, 0, st>>>(pl->counts, pl->nb, pl->cursor);
-    k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), pl->W), TB, 0, st>>>(pl->digits, n, pl->nb, pl->cursor, pl->sorted);
+    const uint32_t bstride = pl->merged ? 0u : pl->nb;
+    const size_t sstride = pl->merged ? 0 : n, ioff = pl->merged ? pl->n_total : 0;
+    k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, pl->c, pl->W, bstride, pl->digits, pl->counts);
+    {
+        const uint32_t tiles = (pl->nb + SCAN_TILE - 1) / SCAN_TILE;      // <= 1024 (nb <= 2^22)
+        uint32_t* tile_sum = pl->shist + 2 * SIZE_KEYS;
+        k_scan_partial<<<dim3(tiles, pl->Wb), 256, 0, st>>>(pl->counts, pl->nb, tiles, tile_sum);
+        k_scan_tiles<<<pl->Wb, 1024, 0, st>>>(tile_sum, tiles);
+        k_scan_final<<<dim3(tiles, pl->Wb), 256, 0, st>>>(pl->counts, pl->nb, tiles, tile_sum, pl->cursor);
+    }
+    k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), pl->W), TB, 0, st>>>(pl->digits, n, bstride, sstride, ioff, point0, pl->cursor, pl->sorted);
     unsigned hb = (unsigned)((pl->slots + 1023) / 1024);
     if (hb > 592) hb = 592;
     uint32_t* sstart = pl->shist + SIZE_KEYS;
@@ -416,9 +479,9 @@ static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases,
     k_size_scatter<<<(unsigned)((pl->slots + 255) / 256), 256, 0, st>>>(pl->counts, pl->slots, sstart, pl->order);
     if (first) phase_mark(ctx, 1);
     k_accumulate<F><<<(unsigned)((pl->slots + 127) / 128), 128, 0, st>>>(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order,
-                                                                       n, pl->nb, pl->W, first ? 0 : 1, pl->buckets);
+                                                                       sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
     if (first) phase_mark(ctx, 2);
-    ctx->launches += 7;
+    ctx->launches += 9;
     pl->chunks_done += 1;
     ZKG_CUDA(cudaGetLastError());
     return ZKG_OK;
@@ -439,8 +502,8 @@ static int32_t msm_finish(zkg_ctx* ctx, MsmPlan<F>* pl, F* d_out, int mode) {
     int log2_M = 0, pp = 0;
     while (true) {
         uint32_t n_out = (n_in + MSM_REDUCE_L - 1) / MSM_REDUCE_L;
-        size_t th = (size_t)pl->W * n_out;
-        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(Rin, Cin, n_in, MSM_REDUCE_L, log2_M, pl->W, pl->Rb[pp], pl->Cb[pp], n_out);
+        size_t th = (size_t)pl->Wb * n_out;
+        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(Rin, Cin, n_in, MSM_REDUCE_L, log2_M, pl->Wb, pl->Rb[pp], pl->Cb[pp], n_out);
         Rin = pl->Rb[pp]; Cin = pl->Cb[pp];
         pp ^= 1;
         ctx->launches += 1;
@@ -448,7 +511,7 @@ static int32_t msm_finish(zkg_ctx* ctx, MsmPlan<F>* pl, F* d_out, int mode) {
         log2_M += 3;           // M *= L (L = 8)
         if (n_out == 1) break;
     }
-    k_final<F><<<1, 32, 0, st>>>(Rin, Cin, pl->c, pl->W, mode, d_out);
+    k_final<F><<<1, 32, 0, st>>>(Rin, Cin, pl->merged ? 0 : pl->c, pl->Wb, mode, d_out);
     ctx->launches += 1;
     phase_mark(ctx, 3);
     ZKG_CUDA(cudaGetLastError());
@@ -461,6 +524,45 @@ static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scala
     if (n) {
         ZKG_TRY(msm_plan<F>(ctx, n, n, &pl));
         ZKG_TRY(msm_chunk<F>(ctx, &pl, d_bases, d_scalars, n));
+    }
+    return msm_finish<F>(ctx, &pl, d_out, mode);
+}
+
+// ------------------------------------------------------------------------------------------
+// Prepared bases (static CRS shares): table[w*n + i] = 2^(c*w) * P_i in packed affine form.
+// One thread per point walks the windows: c doublings, one inversion per stored copy.  One-time
+// cost (~7 k multiplications per point); it buys MSMs with a single bucket set and no Horner tail.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_prepare_bases(const Affine<F>* __restrict__ bases, size_t n, int c, int W, Affine<F>* __restrict__ table) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = load_vec(bases + i);
+    store_vec(table + i, p);
+    XYZZ<F> acc = XYZZ<F>::from_affine(p);
+    for (int w = 1; w < W; ++w) {
+        for (int d = 0; d < c; ++d) xyzz_dbl(acc);
+        store_vec(table + (size_t)w * n + i, xyzz_to_affine(acc));
+    }
+}
+
+template <class F>
+static int32_t msm_prepare(zkg_ctx* ctx, const Affine<F>* d_bases, size_t n, int c, Affine<F>* d_table) {
+    if (n == 0) return ZKG_OK;
+    k_prepare_bases<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_bases, n, c, msm_num_windows(c), d_table);
+    ctx->launches += 1;
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+// MSM against a prepared table (n points, window size c fixed at preparation time)
+template <class F>
+static int32_t msm_run_prepared(zkg_ctx* ctx, const Affine<F>* d_table, int c, const Fr* d_scalars, size_t n, F* d_out, int mode) {
+    MsmPlan<F> pl;
+    if (n) {
+        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl, c));
+        ZKG_TRY(msm_chunk<F>(ctx, &pl, d_table, d_scalars, n, 0));
     }
     return msm_finish<F>(ctx, &pl, d_out, mode);
 }
@@ -555,7 +657,9 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
     int32_t msm_host_##G(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,     \
                          size_t n_scalars, uint64_t* out_xyz);                                                      \
     int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out);                          \
-    int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);
+    int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);                      \
+    int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table);                         \
+    int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode);
 ZKG_MSM_DECLARE(g1)
 ZKG_MSM_DECLARE(g2)
 
@@ -575,6 +679,12 @@ ZKG_MSM_DECLARE(g2)
         ctx->launches += 1;                                                                                         \
         ZKG_CUDA(cudaGetLastError());                                                                               \
         return ZKG_OK;                                                                                              \
+    }                                                                                                               \
+    int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table) {                        \
+        return msm_prepare<F>(ctx, (const Affine<F>*)d_bases, n, c, (Affine<F>*)d_table);                           \
+    }                                                                                                               \
+    int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode) { \
+        return msm_run_prepared<F>(ctx, (const Affine<F>*)d_table, c, (const Fr*)d_scalars, n, (F*)d_out, mode);    \
     }                                                                                                               \
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed) {                     \
         if (n == 0) return ZKG_OK;                                                                                  \
