@@ -11,7 +11,8 @@ namespace zkg {
     int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out);                          \
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);                      \
     int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table);                         \
-    int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode);
+    int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode); \
+    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out);
 ZKG_MSM_DECLARE(g1)
 ZKG_MSM_DECLARE(g2)
 
@@ -171,12 +172,10 @@ int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t* scalars, size_
     zkg_ctx* ctx = pc.ctx;
     DeviceGuard dg(ctx->device);
     size_t sc_bytes = align_up(n_scalars * 32, 256);
-    ZKG_TRY(ctx->io.reserve(sc_bytes + 256));
-    uint8_t* d_sc = (uint8_t*)ctx->io.p;
-    void* d_out = d_sc + sc_bytes;
-    if (n_scalars) ZKG_CUDA(cudaMemcpyAsync(d_sc, scalars, n_scalars * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKG_TRY(bs.group == 1 ? msm_run_prepared_g1(ctx, bs.d_table, bs.c, (const uint64_t*)d_sc, n_scalars, d_out, 0)
-                          : msm_run_prepared_g2(ctx, bs.d_table, bs.c, (const uint64_t*)d_sc, n_scalars, d_out, 0));
+    ZKG_TRY(ctx->io.reserve(sc_bytes + 512));
+    void* d_out = (uint8_t*)ctx->io.p + sc_bytes;
+    ZKG_TRY(bs.group == 1 ? msm_run_prepared_host_g1(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out)
+                          : msm_run_prepared_host_g2(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out));
     ZKG_CUDA(cudaMemcpyAsync(out_xyz, d_out, bs.group == 1 ? 96 : 192, cudaMemcpyDeviceToHost, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;

@@ -567,6 +567,37 @@ static int32_t msm_run_prepared(zkg_ctx* ctx, const Affine<F>* d_table, int c, c
     return msm_finish<F>(ctx, &pl, d_out, mode);
 }
 
+// Registered bases + HOST scalars: the scalars cross PCIe in quarters on the copy stream while the
+// previous quarter is being sorted and accumulated (merged plans take any point range of the table).
+template <class F>
+static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int c, const uint64_t* h_scalars, size_t n,
+                                     F* d_out) {
+    MsmPlan<F> pl;
+    if (n) {
+        const int K = n >= ((size_t)1 << 18) ? 4 : 1;
+        const size_t chunk = (n + K - 1) / K;
+        ZKG_TRY(ctx->io.reserve(align_up(n * 32, 256) + 512));
+        uint8_t* d_sc = (uint8_t*)ctx->io.p;
+        ZKG_TRY(msm_plan<F>(ctx, n, chunk, &pl, c));
+        ZKG_TRY(ctx_copy_stream(ctx, K));
+        ZKG_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+        ZKG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+        for (int j = 0; j < K; ++j) {
+            size_t lo = (size_t)j * chunk, hi = lo + chunk < n ? lo + chunk : n;
+            if (lo >= hi) break;
+            ZKG_CUDA(cudaMemcpyAsync(d_sc + lo * 32, (const uint8_t*)h_scalars + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ZKG_CUDA(cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
+        }
+        for (int j = 0; j < K; ++j) {
+            size_t lo = (size_t)j * chunk, hi = lo + chunk < n ? lo + chunk : n;
+            if (lo >= hi) break;
+            ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[j], 0));
+            ZKG_TRY(msm_chunk<F>(ctx, &pl, d_table, (const Fr*)d_sc + lo, hi - lo, lo));
+        }
+    }
+    return msm_finish<F>(ctx, &pl, d_out, 0);
+}
+
 template <class F>
 static int32_t pack_bases(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t n, void* d_packed) {
     if (n == 0) return ZKG_OK;
@@ -659,7 +690,8 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
     int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out);                          \
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);                      \
     int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table);                         \
-    int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode);
+    int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode); \
+    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out);
 ZKG_MSM_DECLARE(g1)
 ZKG_MSM_DECLARE(g2)
 
@@ -685,6 +717,9 @@ ZKG_MSM_DECLARE(g2)
     }                                                                                                               \
     int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode) { \
         return msm_run_prepared<F>(ctx, (const Affine<F>*)d_table, c, (const Fr*)d_scalars, n, (F*)d_out, mode);    \
+    }                                                                                                               \
+    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out) { \
+        return msm_run_prepared_host<F>(ctx, (const Affine<F>*)d_table, c, h_scalars, n, (F*)d_out);                \
     }                                                                                                               \
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed) {                     \
         if (n == 0) return ZKG_OK;                                                                                  \
