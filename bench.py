@@ -292,6 +292,37 @@ def run_ours(args):
     value = n * world / (ms_per_step * 1e-3) / 1e6
     dev_result = out_xyz.cpu().numpy().copy()
 
+    # ---- same workload with two MSMs in flight (two contexts / streams): the latency-bound tail of one
+    #      (bucket reduction) overlaps the bucket accumulation of the next -- how a prover that issues its
+    #      d_msm calls concurrently (prove.rs:227 try_join!) drives the library.  Reported beside `value`.
+    two_stream_ms = None
+    if world == 1:
+        st2 = torch.cuda.Stream(device=dev)
+        ctx2 = capi.ctx_p()
+        capi.check(lib.zkg_ctx_create(local, C.c_void_p(st2.cuda_stream), C.byref(ctx2)))
+        out2 = torch.zeros(12, dtype=torch.int64, device=dev)
+        st2.wait_stream(stream)
+
+        def run_pair_steps(k):
+            for i in range(k):
+                if i % 2 == 0:
+                    capi.check(lib.zkg_msm_bn254_registered_dev(ctx, handle.value, C.c_void_p(scalars.data_ptr()), n, C.c_void_p(out_xyz.data_ptr()), 0))
+                else:
+                    capi.check(lib.zkg_msm_bn254_registered_dev(ctx2, handle.value, C.c_void_p(scalars.data_ptr()), n, C.c_void_p(out2.data_ptr()), 0))
+            stream.wait_stream(st2)
+        run_pair_steps(4)
+        torch.cuda.synchronize()
+        k2 = max(4, args.steps)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st2.wait_stream(stream)
+        e0.record()
+        run_pair_steps(k2)
+        e1.record()
+        torch.cuda.synchronize()
+        two_stream_ms = e0.elapsed_time(e1) / k2
+        two_stream_same = bool((out2.cpu().numpy() == dev_result).all())
+        lib.zkg_ctx_destroy(ctx2)
+
     # ---- dominant kernel (bucket accumulation) timed live with CUDA events on the launch stream -------
     capi.check(lib.zkg_ctx_set_profiling(ctx, 1))
     phase = [[], [], []]
@@ -457,6 +488,91 @@ def run_ours(args):
                                                "elems_per_s": round(mbyl_ * l_ / (tks * 1e-3), 1),
                                                "collective": "one NCCL reduce_scatter (sum) of the pack-order buffer"}
 
+    # ---- secondary: emulated distributed Groth16 prove (BASELINE configs[4]: 2^20 constraints, l = 2, n = 8 parties) ----
+    # Dataflow of groth16/examples/sha256.rs:32-129 with synthetic CRS shares (PackedProvingKeyShare::rand sizes,
+    # groth16/src/proving_key.rs:125-176): per party circom_h = 3 d_ifft + 3 d_fft + deg_red (ext_wit.rs:104-181) then
+    # 5 d_msm (prove.rs:52,106,154,209,219).  Parties are dealt round-robin to the ranks; the king closures run on rank 0.
+    # Device-resident, network excluded; correctness of this dataflow is pinned in tests/test_gpu_protocol.py.
+    if not args.no_secondary and not args.no_prove:
+        lg_m, l_ = 20, 2
+        m_ = 1 << lg_m
+        mbyl_ = m_ // l_
+        dom_ = z.Radix2EvaluationDomain.new(m_)
+        gen_i, gen_f, sinv = dom_.group_gen_inv(), dom_.group_gen(), dom_.size_inv()
+        zeta = z.Radix2EvaluationDomain.new(2 * m_).element(1)
+        one_ = fr_image(1)
+        my_parties = [p for p in range(8) if p % world == rank]
+        hs = {}
+        for name, grp, cnt in (("S", 1, mbyl_), ("H", 1, mbyl_), ("W", 1, mbyl_), ("U", 1, 2 * mbyl_), ("V", 2, mbyl_)):
+            bb = torch.empty((cnt, 64 * grp), dtype=torch.uint8, device=dev)
+            capi.check(lib.zkg_fixed_base_dev(ctx, grp, C.c_void_p(rand_fr_dev(cnt).data_ptr()), cnt, C.c_void_p(bb.data_ptr())))
+            hh = C.c_uint64(0)
+            capi.check(lib.zkg_bases_register_dev(ctx, grp, C.c_void_p(bb.data_ptr()), cnt, C.byref(hh)))
+            torch.cuda.synchronize()
+            hs[name] = (hh, grp, cnt)
+            del bb
+        va, vb, vc = rand_fr_dev(mbyl_), rand_fr_dev(mbyl_), rand_fr_dev(mbyl_)
+        mask = rand_fr_dev(mbyl_)
+        hbuf = rand_fr_dev(2 * mbyl_)
+        kin = rand_fr_dev(8 * mbyl_)
+        kout = torch.empty((8 * mbyl_, 4), dtype=torch.int64, device=dev)
+        krand = rand_fr_dev(2 * mbyl_)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        # The 5 MSMs of a party (and the parties themselves) are independent: in the reference they are
+        # concurrent tokio tasks (prove.rs:227 try_join!, multi.rs:320-325), i.e. concurrent C-ABI calls on
+        # pooled contexts.  Here: 4 contexts on 4 streams, so one MSM's latency-bound tail overlaps the
+        # bucket accumulation of the next.
+        n_lanes = 4
+        lanes = []
+        for _i in range(n_lanes):
+            st_ = torch.cuda.Stream(device=dev)
+            cx_ = capi.ctx_p()
+            capi.check(lib.zkg_ctx_create(local, C.c_void_p(st_.cuda_stream), C.byref(cx_)))
+            lanes.append((st_, cx_, torch.zeros(24, dtype=torch.int64, device=dev)))
+
+        def prove_round():
+            for _p in my_parties:                                   # clients: 3 x d_ifft first halves
+                for v in (va, vb, vc):
+                    capi.check(lib.zkg_fft1_bn254_dev(ctx, P(v), mbyl_, l_, gen_i.ctypes.data, sinv.ctypes.data, P(mask)))
+            if rank == 0:                                           # king: 3 x (unpack2, fft2, powers, rearranged pack)
+                for _ in range(3):
+                    capi.check(lib.zkg_king_fft2_bn254_dev(ctx, P(kin), None, 8, mbyl_, l_, gen_i.ctypes.data, zeta.ctypes.data, 1, P(krand), P(kout)))
+            for _p in my_parties:                                   # clients: 3 x d_fft first halves
+                for v in (va, vb, vc):
+                    capi.check(lib.zkg_fft1_bn254_dev(ctx, P(v), mbyl_, l_, gen_f.ctypes.data, None, P(mask)))
+            if rank == 0:
+                for _ in range(3):
+                    capi.check(lib.zkg_king_fft2_bn254_dev(ctx, P(kin), None, 8, mbyl_, l_, gen_f.ctypes.data, one_.ctypes.data, 0, P(krand), P(kout)))
+            for _p in my_parties:                                   # h = a*b - c on shares, then deg_red
+                capi.check(lib.zkg_field_op_dev(ctx, 0, 0, P(va), P(vb), P(hbuf), mbyl_))
+                capi.check(lib.zkg_field_op_dev(ctx, 0, 2, P(hbuf), P(vc), P(hbuf), mbyl_))
+            if rank == 0:
+                capi.check(lib.zkg_deg_red_king_bn254_dev(ctx, P(kin), None, 8, mbyl_, l_, P(krand), P(kout)))
+            for st_, _, _ in lanes:                                 # 5 d_msm local MSMs against the registered CRS shares
+                st_.wait_stream(stream)
+            k_ = 0
+            for _p in my_parties:
+                for name, sc in (("V", va), ("U", hbuf), ("S", va), ("H", va), ("W", vb)):
+                    hh, grp, cnt = hs[name]
+                    st_, cx_, mo_ = lanes[k_ % n_lanes]
+                    k_ += 1
+                    capi.check(lib.zkg_msm_bn254_registered_dev(cx_, hh.value, P(sc), cnt, P(mo_), 0))
+            for st_, _, _ in lanes:
+                stream.wait_stream(st_)
+        prove_round()
+        t_prove = timed(prove_round, 3) / 3
+        for hh, _, _ in hs.values():
+            lib.zkg_bases_release(hh.value)
+        for _, cx_, _ in lanes:
+            lib.zkg_ctx_destroy(cx_)
+        if rank == 0:
+            secondary["groth16_prove_emulated_m2^20"] = {
+                "prove_sec": round(t_prove * 1e-3, 5), "parties": 8, "ranks": world, "l": 2,
+                "msm_streams": n_lanes,
+                "what": "6 client fft1 + 5 registered MSMs (S,H,W: 2^19 G1; U: 2^20 G1; V: 2^19 G2) per party, 6 king d_fft "
+                        "closures + 1 deg_red king on rank 0; device-resident, network and pairing check excluded"}
+        del va, vb, vc, mask, hbuf, kin, kout, krand
+
     if rank == 0:
         hbm_peak, hbm_how, int_peak, int_how = measured_peaks()
         c_ark, W_ark = ark_window(n)
@@ -488,6 +604,9 @@ def run_ours(args):
                     "matches_device_leg": same,
                     "registered_bases_ms_per_step": round(e2e_reg_ms, 3) if e2e_reg_ms else None,
                     "registered_bases_Mpts_per_s": round(n / (e2e_reg_ms * 1e-3) / 1e6, 2) if e2e_reg_ms else None},
+            "value_two_streams": {"Mpts_per_s": round(n / (two_stream_ms * 1e-3) / 1e6, 2), "ms_per_step": round(two_stream_ms, 4),
+                                  "what": "same K registered MSMs alternating over two contexts/streams (tail of one overlaps "
+                                          "accumulation of the next)", "matches": two_stream_same} if two_stream_ms else None,
             "value_unprepared": {"Mpts_per_s": round(n / (unprepared_ms * 1e-3) / 1e6, 2), "ms_per_step": round(unprepared_ms, 4),
                                  "what": "same MSM through zkg_msm_bn254_g1_dev (no prepared table)",
                                  "matches": unprepared_same} if unprepared_ms else None,
@@ -528,6 +647,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=22)
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prove", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -177,6 +177,9 @@ int32_t zkg_fr_fft_bn254(int32_t device, uint64_t *v, size_t n, const uint64_t *
  * 2 sub; field: 0 Fr, 1 Fq) ---- */
 int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t *a, const uint64_t *b, uint64_t *out,
                      size_t n);
+/* device form; also the share-wise h = a*b - c of groth16/src/ext_wit.rs:82-86,173-177 and the mask adds */
+int32_t zkg_field_op_dev(zkg_ctx *ctx, int32_t field, int32_t op, const uint64_t *d_a, const uint64_t *d_b,
+                         uint64_t *d_out, size_t n);
 
 #ifdef __cplusplus
 }

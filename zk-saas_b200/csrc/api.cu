@@ -186,6 +186,18 @@ int32_t zkg_shutdown(void) {
     return ZKG_OK;
 }
 
+int32_t zkg_field_op_dev(zkg_ctx* ctx, int32_t field, int32_t op, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n) {
+    ZKG_REQUIRE(ctx && (field == 0 || field == 1) && op >= 0 && op <= 2 && (n == 0 || (d_a && d_b && d_out)), "field_op_dev: bad argument");
+    if (n == 0) return ZKG_OK;
+    DeviceGuard dg(ctx->device);
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (field == 0) k_field_op<Fr><<<blocks, 256, 0, ctx->stream>>>(op, (const Fr*)d_a, (const Fr*)d_b, (Fr*)d_out, n);
+    else k_field_op<Fq><<<blocks, 256, 0, ctx->stream>>>(op, (const Fq*)d_a, (const Fq*)d_b, (Fq*)d_out, n);
+    ctx->launches += 1;
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
 int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
     ZKG_REQUIRE((field == 0 || field == 1) && op >= 0 && op <= 2 && (n == 0 || (a && b && out)), "field_op: bad argument");
     if (n == 0) return ZKG_OK;
