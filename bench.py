@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 INT_PEAK_TIMAD = 18.51              # profiles/r01_intpipe_microbench.json: 32-bit IMAD issue rate, B200, 148 SMs @1965 MHz
 MODMUL_PEAK_G = 67.3                # same file: this repo's Montgomery multiplier in isolation (G products/s)
-ACC_TRAFFIC_BYTES = 7.109e9         # profiles/r01_ncu_k_accumulate_v1.json: dram read+write of one k_accumulate launch at 2^22
+ACC_TRAFFIC_BYTES = 7.329e9         # profiles/r01_ncu_k_accumulate.json: dram read+write of one k_accumulate launch at 2^22 (prepared path)
 HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
 
 
