@@ -291,6 +291,71 @@ k_reduce_lvl(const XYZZ<F>* __restrict__ R_in, const XYZZ<F>* __restrict__ Cs_in
     store_vec(Cs_out + t, cs);
 }
 
+// ------------------------------------------------------------------------------------------
+// Log-depth continuation of the bucket reduction.  After level 0 every window holds n1 = nb/8 pairs
+// (R_u, A_u) and needs   sum_u A_u + 8 * sum_u u * R_u   (+ sum_u R_u).  Writing u in binary,
+//   sum_u u R_u = sum_j 2^j m_j,   m_j = sum of the R_u whose index has bit j set,
+// and the masked sums obey a butterfly: merging two sibling nodes of 2^(b-1) entries into one of 2^b,
+//   total = total_lo + total_hi,  sumA = sumA_lo + sumA_hi,  m_j = m_j_lo + m_j_hi (j < b-1),  m_(b-1) = total_hi.
+// All (b+1) additions of all merges of a level are independent: k_merge_lvl runs them one per thread,
+// so a level costs ONE group-addition latency instead of the 24 of a running-sum level, and the total
+// work stays ~2 additions per entry.  k_bits_final then scales m_j by 2^(j+3) in parallel lanes and
+// tree-sums them.  (7 levels x ~0.2 ms -> ~0.35 ms at 2^19 buckets.)
+// Node layout at level b >= 1: (b+2) consecutive XYZZ values [total, sumA, m_0 .. m_(b-1)].
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_merge_lvl(const XYZZ<F>* __restrict__ in, const XYZZ<F>* __restrict__ in_R0, const XYZZ<F>* __restrict__ in_A0,
+            XYZZ<F>* __restrict__ out, int b, uint32_t n_prev, int Wb) {
+    const uint32_t n_new = n_prev >> 1, slots = (uint32_t)b + 2;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)Wb * n_new * slots) return;
+    uint32_t v = (uint32_t)(t % slots);
+    size_t node = t / slots;                               // w * n_new + q
+    uint32_t w = (uint32_t)(node / n_new), q = (uint32_t)(node % n_new);
+    size_t lo = (size_t)w * n_prev + 2 * (size_t)q, hi = lo + 1;
+    XYZZ<F> r;
+    if (b == 1) {                                          // children are level-0 entries (R_u, A_u)
+        if (v == 0) { r = load_vec_rw(in_R0 + lo); xyzz_add(r, load_vec_rw(in_R0 + hi)); }
+        else if (v == 1) { r = load_vec_rw(in_A0 + lo); xyzz_add(r, load_vec_rw(in_A0 + hi)); }
+        else r = load_vec_rw(in_R0 + hi);                  // m_0 = total of the odd child
+    } else {
+        const uint32_t ps = (uint32_t)b + 1;               // slots per child node
+        if (v == slots - 1) r = load_vec_rw(in + hi * ps); // m_(b-1) = total_hi
+        else { r = load_vec_rw(in + lo * ps + v); xyzz_add(r, load_vec_rw(in + hi * ps + v)); }
+    }
+    store_vec(out + t, r);
+}
+
+// One block of 32 threads per window: S_w = sumA + 8 * sum_j 2^j m_j + total.  Lane j owns m_j.
+template <class F>
+__global__ void __launch_bounds__(32)
+k_bits_final(const XYZZ<F>* __restrict__ nodes, const XYZZ<F>* __restrict__ R0, const XYZZ<F>* __restrict__ A0, int B,
+             XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ Z_out) {
+    __shared__ XYZZ<F> sh[32];
+    const uint32_t w = blockIdx.x, lane = threadIdx.x;
+    XYZZ<F> x = XYZZ<F>::inf();
+    if (B == 0) {                                          // a single level-0 entry: u = 0 has weight 0
+        if (lane == 0) { x = load_vec_rw(A0 + w); xyzz_add(x, load_vec_rw(R0 + w)); }
+    } else {
+        const XYZZ<F>* nd = nodes + (size_t)w * (B + 2);
+        if ((int)lane < B) {
+            x = load_vec_rw(nd + 2 + lane);
+            for (uint32_t d = 0; d < lane + 3; ++d) xyzz_dbl(x);          // 8 * 2^j
+        } else if ((int)lane == B) {
+            x = load_vec_rw(nd);                           // total
+            xyzz_add(x, load_vec_rw(nd + 1));              // + sumA
+        }
+    }
+    sh[lane] = x;
+    __syncthreads();
+    for (uint32_t off = 16; off > 0; off >>= 1) {
+        if (lane < off) { XYZZ<F> a = sh[lane]; xyzz_add(a, sh[lane + off]); sh[lane] = a; }
+        __syncthreads();
+    }
+    if (lane == 0) { store_vec(S_out + w, sh[0]); store_vec(Z_out + w, XYZZ<F>::inf()); }
+}
+
 // Horner over the window sums + normalisation.  mode 0: Jacobian image (x, y, 1) / (1, 1, 0);
 // mode 1: raw XYZZ partial (for multi-GPU combination).
 template <class F>
@@ -496,21 +561,34 @@ static int32_t msm_finish(zkg_ctx* ctx, MsmPlan<F>* pl, F* d_out, int mode) {
         ZKG_CUDA(cudaGetLastError());
         return ZKG_OK;
     }
-    const XYZZ<F>* Rin = pl->buckets;
-    const XYZZ<F>* Cin = nullptr;
-    uint32_t n_in = pl->nb;
-    int log2_M = 0, pp = 0;
-    while (true) {
-        uint32_t n_out = (n_in + MSM_REDUCE_L - 1) / MSM_REDUCE_L;
-        size_t th = (size_t)pl->Wb * n_out;
-        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(Rin, Cin, n_in, MSM_REDUCE_L, log2_M, pl->Wb, pl->Rb[pp], pl->Cb[pp], n_out);
-        Rin = pl->Rb[pp]; Cin = pl->Cb[pp];
-        pp ^= 1;
+    // level 0: running sums over segments of 8 buckets (throughput-bound: two adds per bucket)
+    const uint32_t n1 = pl->n1;
+    {
+        size_t th = (size_t)pl->Wb * n1;
+        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(pl->buckets, nullptr, pl->nb, MSM_REDUCE_L, 0, pl->Wb, pl->Rb[0], pl->Cb[0], n1);
         ctx->launches += 1;
-        n_in = n_out;
-        log2_M += 3;           // M *= L (L = 8)
-        if (n_out == 1) break;
     }
+    // log-depth butterfly over the n1 segment results (n1 is a power of two); ping-pong between the
+    // two halves of the reduction scratch (each half = 2 * Wb * n1 values, enough for every level)
+    int B = 0;
+    while (((uint32_t)1 << B) < n1) ++B;
+    XYZZ<F>* buf[2] = {pl->Rb[1], pl->Rb[0]};              // level 1 -> second half, level 2 -> first half (level-0 data is dead by then)
+    const XYZZ<F>* cur = nullptr;
+    uint32_t n_prev = n1;
+    for (int lvl = 1; lvl <= B; ++lvl) {
+        XYZZ<F>* dst = buf[(lvl - 1) & 1];
+        size_t th = (size_t)pl->Wb * (n_prev >> 1) * (lvl + 2);
+        k_merge_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(cur, pl->Rb[0], pl->Cb[0], dst, lvl, n_prev, pl->Wb);
+        ctx->launches += 1;
+        cur = dst;
+        n_prev >>= 1;
+    }
+    XYZZ<F>* S_arr = B == 0 ? pl->Rb[1] : buf[B & 1];       // the buffer the last level did not write
+    XYZZ<F>* Z_arr = S_arr + pl->Wb;
+    k_bits_final<F><<<pl->Wb, 32, 0, st>>>(cur, pl->Rb[0], pl->Cb[0], B, S_arr, Z_arr);
+    ctx->launches += 1;
+    const XYZZ<F>* Rin = S_arr;
+    const XYZZ<F>* Cin = Z_arr;
     k_final<F><<<1, 32, 0, st>>>(Rin, Cin, pl->merged ? 0 : pl->c, pl->Wb, mode, d_out);
     ctx->launches += 1;
     phase_mark(ctx, 3);
