@@ -244,3 +244,52 @@ def test_gpu_vs_golden_fixtures(z):
                     assert ol.np_fr(out[p]) == gu.ints(exp[p])
         s1 = ol.fr_np(gu.ints(f["fft2_in"]))
         assert ol.np_fr(z.fft2_in_place(s1, pp, dom.group_gen())) == gu.ints(f["fft2_out"])
+
+
+def test_concurrent_calls_from_threads(z):
+    """The C ABI must be re-entrant: LocalTestNet polls up to n party tasks from different OS threads
+    (mpc-net/src/multi.rs:320-325).  8 threads issue MSM / fft1 / king / pack calls at once (ctypes
+    releases the GIL) and every result must equal the single-threaded one."""
+    import threading
+    from zksaas_b200 import api
+    o = ol.oracle()
+    l, mbyl = 2, 1 << 11
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(mbyl * l)
+    rng = np.random.default_rng(4242)
+    jobs = []
+    for t in range(8):
+        n = 700 + 37 * t
+        dl = ol.rand_fr(rng, n)
+        bases = np.zeros((n, 72), dtype=np.uint8)
+        o.zko_g1_fixed_base(_p(dl), n, bases.ctypes.data, 72)
+        jobs.append({"bases": bases, "scalars": ol.rand_fr(rng, n), "px": ol.rand_fr(rng, mbyl),
+                     "shares": [ol.rand_fr(rng, mbyl) for _ in range(pp.n)], "rand": ol.rand_fr(rng, mbyl * pp.t),
+                     "sec": ol.rand_fr(rng, 64 * l)})
+
+    def work(j):
+        return (z.msm_g1(j["bases"], j["scalars"]),
+                z.fft1_in_place(j["px"].copy(), pp, dom.group_gen()),
+                z.king_fft2(j["shares"], list(range(pp.n)), pp, dom.group_gen(), api.fr_image(5), True, j["rand"]),
+                pp.pack(j["sec"], j["rand"][:64 * pp.t]))
+
+    expect = [work(j) for j in jobs]
+    got = [None] * len(jobs)
+    errs = []
+
+    def run(i):
+        try:
+            for _ in range(3):
+                got[i] = work(jobs[i])
+        except Exception as e:          # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for e, g in zip(expect, got):
+        assert (e[0] == g[0]).all() and (e[1] == g[1]).all() and (e[3] == g[3]).all()
+        assert all((a == b).all() for a, b in zip(e[2], g[2]))
