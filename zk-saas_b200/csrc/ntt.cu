@@ -280,6 +280,38 @@ k_map_in_regs(const Fr* __restrict__ M, int rows, int k1, const Fr* __restrict__
     }
 }
 
+// pack for the reference's one real configuration (l = t = 2, n = 8; pss.rs:14 "(2, 2, 8) - currently
+// implemented") as the transforms it is defined by -- size-4 inverse DFT on the coset g<zeta_4>, size-8
+// DFT on <zeta_8> of the zero-padded coefficients -- instead of the dense 8 x 4 matrix: 10 field
+// products per column instead of 32.  Same canonical results (the map is the same linear map).
+// cst[0] = zeta_4^-1, cst[1..4] = g^-d / 4 (d = 0..3), cst[5] = zeta_4, cst[6..8] = zeta_8^1..3
+struct Pack2Consts { FrArg c[9]; };
+__global__ void __launch_bounds__(256)
+k_pack_l2(Pack2Consts K, const Fr* __restrict__ secrets, size_t s_cs, size_t s_rs, const Fr* __restrict__ rand, size_t r_cs,
+          size_t r_rs, int has_rand, Fr* __restrict__ out, size_t out_cs, size_t out_rs, size_t cols) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    Fr v0 = ld_fr(secrets + c * s_cs), v1 = ld_fr(secrets + c * s_cs + s_rs);
+    Fr v2 = has_rand ? ld_fr(rand + c * r_cs) : Fr::zero(), v3 = has_rand ? ld_fr(rand + c * r_cs + r_rs) : Fr::zero();
+    // inverse DFT_4 (root zeta_4^-1), then coefficient d scaled by g^-d / 4
+    Fr a0 = fp_add(v0, v2), a1 = fp_sub(v0, v2), b0 = fp_add(v1, v3);
+    Fr b1 = fp_mul(fp_sub(v1, v3), from_arg(K.c[0]));
+    Fr c0 = fp_mul(fp_add(a0, b0), from_arg(K.c[1]));
+    Fr c1 = fp_mul(fp_add(a1, b1), from_arg(K.c[2]));
+    Fr c2 = fp_mul(fp_sub(a0, b0), from_arg(K.c[3]));
+    Fr c3 = fp_mul(fp_sub(a1, b1), from_arg(K.c[4]));
+    // DFT_8 of (c0, c1, c2, c3, 0, 0, 0, 0): s_j = E_(j mod 4) + zeta_8^j O_(j mod 4)
+    Fr t2 = fp_mul(c2, from_arg(K.c[5])), t3 = fp_mul(c3, from_arg(K.c[5]));
+    Fr E[4] = {fp_add(c0, c2), fp_add(c0, t2), fp_sub(c0, c2), fp_sub(c0, t2)};
+    Fr O[4] = {fp_add(c1, c3), fp_add(c1, t3), fp_sub(c1, c3), fp_sub(c1, t3)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        Fr o = k == 0 ? O[0] : fp_mul(O[k], from_arg(K.c[5 + k]));
+        st_fr(out + c * out_cs + (size_t)k * out_rs, fp_add(E[k], o));
+        st_fr(out + c * out_cs + (size_t)(k + 4) * out_rs, fp_sub(E[k], o));
+    }
+}
+
 // Dense map with the OUTPUT accumulators in registers (many inputs, few outputs): unpack / unpack2.
 template <int ROWS>
 __global__ void __launch_bounds__(256)
@@ -434,11 +466,33 @@ static std::vector<HFr> pad_rows(const std::vector<HFr>& m, int rows, int kk, in
     return o;
 }
 
+static Pack2Consts pack2_consts() {
+    using namespace host;
+    HFr g = h_load(BN254_FR_GENERATOR_MONT_64), z4 = h_root_of_unity(4), z8 = h_root_of_unity(8);
+    HFr ginv = h_inv(g), quarter = h_inv(h_from_u64(4));
+    Pack2Consts K;
+    K.c[0] = to_arg(h_inv(z4));
+    HFr sc = quarter;
+    for (int d = 0; d < 4; ++d) { K.c[1 + d] = to_arg(sc); sc = h_mul(sc, ginv); }
+    K.c[5] = to_arg(z4);                 // == zeta_8^2
+    K.c[6] = to_arg(z8);
+    K.c[7] = to_arg(z4);
+    K.c[8] = to_arg(h_mul(z8, z4));
+    return K;
+}
+
 static int32_t launch_pack(zkg_ctx* ctx, const Fr* dM, int K, int rows, int l, int t_used, const Fr* secrets, size_t s_cs,
                            size_t s_rs, const Fr* rand, size_t r_cs, size_t r_rs, Fr* out, size_t o_cs, size_t o_rs,
                            size_t cols) {
     if (cols == 0) return ZKG_OK;
     unsigned blocks = (unsigned)((cols + 255) / 256);
+    if (l == 2 && rows == 8 && !getenv("ZKG_PACK_DENSE")) {
+        static const Pack2Consts P2 = pack2_consts();
+        k_pack_l2<<<blocks, 256, 0, ctx->stream>>>(P2, secrets, s_cs, s_rs, rand, r_cs, r_rs, t_used ? 1 : 0, out, o_cs, o_rs, cols);
+        ctx->launches += 1;
+        ZKG_CUDA(cudaGetLastError());
+        return ZKG_OK;
+    }
 #define LP(KK) k_map_in_regs<KK><<<blocks, 256, 0, ctx->stream>>>(dM, rows, l, secrets, s_cs, s_rs, rand, r_cs, r_rs, t_used, out, o_cs, o_rs, cols)
     if (K == 4) LP(4); else if (K == 8) LP(8); else LP(16);
 #undef LP
