@@ -153,6 +153,15 @@ int32_t zkg_deg_red_king_bn254(int32_t device, const uint64_t *const *shares_by_
 int32_t zkg_deg_red_king_bn254_dev(zkg_ctx *ctx, const uint64_t *d_shares, const uint32_t *parties, uint32_t n_recv,
                                    size_t cols, uint32_t l, const uint64_t *d_rand, uint64_t *d_out);
 
+/* ---- king closure of d_pp (SURVEY.md 8f "next", rank 1): dist-primitives/src/dpp/mod.rs:41-76 ----
+ * shares_by_party[r]: 2*cols elements (the party's num shares followed by its den shares).  The king
+ * unpacks both halves, divides (batch inversion), takes the running product over all cols*l secrets
+ * and re-packs with the supplied randomness.  A zero denominator returns ZKG_ERR_BAD_ARG (the
+ * reference's `.inverse().unwrap()` panics). */
+int32_t zkg_dpp_king_bn254(int32_t device, const uint64_t *const *shares_by_party, const uint32_t *parties,
+                           uint32_t n_recv, size_t cols, uint32_t l, const uint64_t *rand,
+                           uint64_t *const *out_by_party);
+
 /* ---- PackedSharingParams transforms over Fr, batched over `cols` columns -------------------
  * secret-sharing/src/pss.rs: pack :90-122 (rand != NULL), det_pack :69-87 (rand == NULL),
  * unpack :125-138, unpack2 :141-166.  Column-major contiguous: column c reads secrets[c*l..],

@@ -418,6 +418,20 @@ def deg_red_king(shares_by_party, parties, pp, rand):
     return transpose(out)
 
 
+def dpp_king(shares_by_party, parties, pp, rand, p=R_MOD):
+    """King closure of d_pp, dist-primitives/src/dpp/mod.rs:41-76 (shares: num columns then den columns)."""
+    cols2 = len(shares_by_party[0])
+    numden = []
+    for col in transpose(shares_by_party):
+        numden += pp.unpack_missing_shares(col, parties)
+    half = len(numden) // 2
+    q = [numden[i] * finv(numden[i + half], p) % p for i in range(half)]
+    for i in range(1, half):
+        q[i] = q[i] * q[i - 1] % p
+    assert cols2 % 2 == 0
+    return transpose(pack_vec(q, pp, rand))
+
+
 # ----------------------------------------------------------------------------------------
 # Fq2 and curve arithmetic (affine, big-int; None = point at infinity)
 # ----------------------------------------------------------------------------------------

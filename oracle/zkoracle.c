@@ -830,3 +830,34 @@ API void zko_fr_sum(const uint64_t *a, size_t n, uint64_t *o) {
     for (size_t i = 0; i < n; ++i) fr_add(acc, acc, a + 4 * i);
     fr_set(o, acc);
 }
+
+/* King closure of d_pp: dist-primitives/src/dpp/mod.rs:41-76.  shares_by_party[r] = the 2*cols-element
+ * vector (num shares then den shares) received from parties[r]; rand = cols x t packing randomness;
+ * out_by_party[p] = cols elements.  Returns -2 if a denominator is zero (the reference unwraps). */
+API int zko_dpp_king(const uint64_t *const *shares_by_party, const uint32_t *parties, uint32_t n_recv, size_t cols,
+                     uint32_t l, const uint64_t *rand, uint64_t *const *out_by_party) {
+    pss_t pp;
+    pss_new(&pp, l);
+    if (pp.n > 32) return -1;
+    size_t m = cols * pp.l;
+    uint64_t *numden = (uint64_t *)malloc(2 * m * 32);
+    uint64_t col[32 * 4], tmp[32 * 4];
+    for (size_t i = 0; i < 2 * cols; ++i) {                       /* transpose + unpack, :44-53 */
+        for (uint32_t r = 0; r < n_recv; ++r) memcpy(col + 4 * r, shares_by_party[r] + 4 * i, 32);
+        if (pss_unpack_missing_shares(&pp, col, parties, n_recv, tmp, &FR_OPS)) { free(numden); return -1; }
+        memcpy(numden + 4 * i * pp.l, tmp, pp.l * 32);
+    }
+    for (size_t i = 0; i < m; ++i) {                              /* :55-58 */
+        uint64_t den[4];
+        if (fr_is_zero(numden + 4 * (i + m))) { free(numden); return -2; }
+        fr_inv(den, numden + 4 * (i + m));
+        fr_mul(numden + 4 * i, numden + 4 * i, den);
+    }
+    for (size_t i = 1; i < m; ++i) fr_mul(numden + 4 * i, numden + 4 * i, numden + 4 * (i - 1));   /* :62-66 */
+    for (size_t i = 0; i < cols; ++i) {                           /* pack_vec + transpose, :71-76 */
+        pss_pack(&pp, numden + 4 * i * pp.l, rand + i * pp.t * 4, col, &FR_OPS);
+        for (size_t p = 0; p < pp.n; ++p) memcpy(out_by_party[p] + 4 * i, col + 4 * p, 32);
+    }
+    free(numden);
+    return 0;
+}

@@ -72,6 +72,8 @@ def oracle():
         lib.zko_king_fft2.restype = C.c_int
         lib.zko_deg_red_king.argtypes = [pp, C.POINTER(C.c_uint32), C.c_uint32, C.c_size_t, C.c_uint32, u64p, pp]
         lib.zko_deg_red_king.restype = C.c_int
+        lib.zko_dpp_king.argtypes = [pp, C.POINTER(C.c_uint32), C.c_uint32, C.c_size_t, C.c_uint32, u64p, pp]
+        lib.zko_dpp_king.restype = C.c_int
         _LIB = lib
     return _LIB
 

@@ -293,3 +293,44 @@ def test_concurrent_calls_from_threads(z):
     for e, g in zip(expect, got):
         assert (e[0] == g[0]).all() and (e[1] == g[1]).all() and (e[3] == g[3]).all()
         assert all((a == b).all() for a, b in zip(e[2], g[2]))
+
+
+@pytest.mark.parametrize("l,cols", [(2, 16), (2, 5000), (4, 333)])
+def test_dpp_king_vs_oracle(z, l, cols):
+    """king closure of d_pp (dpp/mod.rs:41-76) vs the literal oracle loop."""
+    import ctypes as C
+    o = ol.oracle()
+    rng = np.random.default_rng(cols + l)
+    pp = z.PackedSharingParams.new(l)
+    num, den = ol.rand_fr(rng, cols * l), ol.rand_fr(rng, cols * l)
+    ns = z.transpose(z.pack_vec(num, pp, ol.rand_fr(rng, cols * pp.t)))
+    ds = z.transpose(z.pack_vec(den, pp, ol.rand_fr(rng, cols * pp.t)))
+    shares = [np.concatenate([ns[p], ds[p]]) for p in range(pp.n)]
+    rand = ol.rand_fr(rng, cols * pp.t)
+    exp = [np.zeros((cols, 4), dtype=np.uint64) for _ in range(pp.n)]
+    par = (C.c_uint32 * pp.n)(*range(pp.n))
+    assert o.zko_dpp_king(ol.ptr_array(shares), par, pp.n, cols, l, _p(rand), ol.ptr_array(exp)) == 0
+    got = z.dpp_king(shares, list(range(pp.n)), pp, rand)
+    for p in range(pp.n):
+        assert (got[p] == exp[p]).all()
+    # a zero denominator is an error, as in the reference (inverse().unwrap())
+    den[7] = 0
+    ds = z.transpose(z.pack_vec(den, pp, ol.rand_fr(rng, cols * pp.t)))
+    shares = [np.concatenate([ns[p], ds[p]]) for p in range(pp.n)]
+    with pytest.raises(z.ZkgError):
+        z.dpp_king(shares, list(range(pp.n)), pp, rand)
+
+
+def test_d_pp_example(z):
+    """dist-primitives/examples/dpp_test.rs: num = den = (1..m) => every partial product is one."""
+    from zksaas_b200 import api
+    l, m = 2, 1 << 5
+    rng = np.random.default_rng(55)
+    pp = z.PackedSharingParams.new(l)
+    x = ol.fr_np(list(range(1, m + 1)))
+    px = z.transpose(z.pack_vec(x, pp, ol.rand_fr(rng, m // l * pp.t)))
+    num = m // l
+    masks = z.DegRedMask.sample(pp, num, ol.rand_fr(rng, num * l), ol.rand_fr(rng, num * pp.t), ol.rand_fr(rng, num * pp.t))
+    out = z.d_pp(px, px, masks, pp, z.LocalTestNet(pp.n), ol.rand_fr(rng, num * pp.t), ol.rand_fr(rng, num * pp.t))
+    got = unpack_all(z, pp, out)
+    assert (got == ol.fr_np([1] * m)).all()

@@ -260,3 +260,32 @@ def test_arkworks_window_rule_and_digits():
             d = pyref.make_digits(s, c)
             assert sum(v << (c * i) for i, v in enumerate(d)) == s
             assert all(-(1 << (c - 1)) <= v <= (1 << (c - 1)) for v in d[:-1])
+
+
+def test_dpp_king_c_vs_bigint_model(o):
+    """dist-primitives/src/dpp/mod.rs:41-76; also the example's invariant (dpp_test.rs: x/x partial products = 1)."""
+    rng = random.Random(31)
+    for l, cols in ((2, 8), (4, 4)):
+        pp = pyref.PackedSharingParams(l)
+        m = cols * l
+        num = [rng.randrange(1, R) for _ in range(m)]
+        den = [rng.randrange(1, R) for _ in range(m)]
+        rnd = lambda: [[rng.randrange(R) for _ in range(pp.t)] for _ in range(cols)]
+        ns = pyref.transpose(pyref.pack_vec(num, pp, rnd()))
+        ds = pyref.transpose(pyref.pack_vec(den, pp, rnd()))
+        shares = [ns[p] + ds[p] for p in range(pp.n)]
+        rand = rnd()
+        exp = pyref.dpp_king(shares, list(range(pp.n)), pp, rand)
+        acc, ref = 1, []
+        for a, b in zip(num, den):
+            acc = acc * a * pow(b, -1, R) % R
+            ref.append(acc)
+        assert [v for col in pyref.transpose(exp) for v in pp.unpack(col)] == ref
+        ins = [ol.fr_np(s) for s in shares]
+        outs = [np.zeros((cols, 4), dtype=np.uint64) for _ in range(pp.n)]
+        par = (C.c_uint32 * pp.n)(*range(pp.n))
+        assert o.zko_dpp_king(ol.ptr_array(ins), par, pp.n, cols, l, _p(ol.fr_np(sum(rand, []))), ol.ptr_array(outs)) == 0
+        assert [ol.np_fr(x) for x in outs] == exp
+        ins[0][cols] = 0                           # a den share column that unpacks to a zero secret is unlikely; zero ALL den
+        zero_den = [np.concatenate([ins[p][:cols], np.zeros((cols, 4), dtype=np.uint64)]) for p in range(pp.n)]
+        assert o.zko_dpp_king(ol.ptr_array(zero_den), par, pp.n, cols, l, _p(ol.fr_np(sum(rand, []))), ol.ptr_array(outs)) == -2

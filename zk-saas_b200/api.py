@@ -309,6 +309,18 @@ def deg_red_king(shares, parties, pp: PackedSharingParams, rand_points):
     return outs
 
 
+def dpp_king(shares, parties, pp: PackedSharingParams, rand_points):
+    """King closure of d_pp, dpp/mod.rs:41-76.  shares[r]: (2*cols, 4) = num shares then den shares."""
+    shares = [_fr_vec(s) for s in shares]
+    cols = shares[0].shape[0] // 2
+    rand_points = _fr_vec(rand_points, "rand_points")
+    outs = [np.empty((cols, 4), dtype=np.uint64) for _ in range(pp.n)]
+    par = (C.c_uint32 * len(parties))(*parties)
+    check(lib().zkg_dpp_king_bn254(pp.device, _ptr_array(shares), par, len(shares), cols, pp.l,
+                                   _ptr(rand_points), _ptr_array(outs)))
+    return outs
+
+
 def _field_op(op, a, b, field=0, device=0):
     a, b = _fr_vec(a), _fr_vec(b)
     out = np.empty_like(a)
@@ -453,6 +465,14 @@ def deg_red(x_shares, masks, pp, net, rand_points):
     recv, parties = net.received(sent)
     out = deg_red_king(recv, parties, pp, rand_points)
     return [fr_add(out[p], masks[p].out_mask, pp.device) for p in range(net.n_parties())]
+
+
+def d_pp(num_shares, den_shares, masks, pp, net, rand_king, rand_degred):
+    """dpp/mod.rs:15-87 for all parties at once (the dummy randomness s = 1 of :24-25 included)."""
+    sent = [np.concatenate([_fr_vec(num_shares[p]), _fr_vec(den_shares[p])]) for p in range(net.n_parties())]
+    recv, parties = net.received(sent)
+    out = dpp_king(recv, parties, pp, rand_king)
+    return deg_red(out, masks, pp, net, rand_degred)        # :86
 
 
 def d_msm(bases_by_party, scalars_by_party, masks, pp, net, g2=False, device_of_party=None):

@@ -354,6 +354,77 @@ __global__ void k_bitrev(const Fr* __restrict__ in, Fr* __restrict__ out, int lo
 }
 
 // ------------------------------------------------------------------------------------------
+// d_pp king closure pieces (dist-primitives/src/dpp/mod.rs:55-66): q[i] = num[i] / den[i] with a
+// chunked Montgomery batch inversion, then the inclusive prefix PRODUCT of q as a three-kernel scan.
+// ------------------------------------------------------------------------------------------
+static constexpr uint32_t DPP_CHUNK = 32;     // elements per thread
+
+// q[i] = num[i] * den[i]^-1 over one chunk per thread; scratch holds the running products.  A zero
+// denominator (the reference's `.inverse().unwrap()` panics) raises *err.
+__global__ void __launch_bounds__(128)
+k_dpp_divide(Fr* __restrict__ num, const Fr* __restrict__ den, Fr* __restrict__ scratch, size_t m, int* __restrict__ err) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * DPP_CHUNK, hi = lo + DPP_CHUNK < m ? lo + DPP_CHUNK : m;
+    if (lo >= m) return;
+    Fr run = Fr::one();
+    for (size_t i = lo; i < hi; ++i) {
+        Fr d = ld_fr(den + i);
+        if (d.is_zero()) { atomicExch(err, 1); d = Fr::one(); }
+        st_fr(scratch + i, run);                 // product of den[lo..i)
+        run = fp_mul(run, d);
+    }
+    Fr inv = fp_inv(run);                        // one inversion per chunk
+    for (size_t i = hi; i-- > lo;) {
+        Fr d = ld_fr(den + i);
+        if (d.is_zero()) d = Fr::one();
+        Fr di = fp_mul(inv, ld_fr_rw(scratch + i));      // den[i]^-1
+        inv = fp_mul(inv, d);
+        st_fr(num + i, fp_mul(ld_fr_rw(num + i), di));
+    }
+}
+// phase 1: in-place inclusive product inside each chunk, chunk total to tot[t]
+__global__ void __launch_bounds__(128)
+k_dpp_scan_local(Fr* __restrict__ q, size_t m, Fr* __restrict__ tot) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * DPP_CHUNK, hi = lo + DPP_CHUNK < m ? lo + DPP_CHUNK : m;
+    if (lo >= m) return;
+    Fr run = ld_fr_rw(q + lo);
+    for (size_t i = lo + 1; i < hi; ++i) { run = fp_mul(run, ld_fr_rw(q + i)); st_fr(q + i, run); }
+    st_fr(tot + t, run);
+}
+// phase 2: exclusive prefix product of the chunk totals, one block (sequential over tiles of 1024)
+__global__ void __launch_bounds__(1024)
+k_dpp_scan_totals(Fr* __restrict__ tot, size_t n) {
+    __shared__ Fr sh[1024];
+    Fr carry = Fr::one();
+    for (size_t base = 0; base < n; base += 1024) {
+        size_t i = base + threadIdx.x;
+        Fr x = i < n ? ld_fr_rw(tot + i) : Fr::one();
+        sh[threadIdx.x] = x;
+        __syncthreads();
+        for (uint32_t off = 1; off < 1024; off <<= 1) {
+            Fr a = threadIdx.x >= off ? sh[threadIdx.x - off] : Fr::one();
+            __syncthreads();
+            if (threadIdx.x >= off) sh[threadIdx.x] = fp_mul(sh[threadIdx.x], a);
+            __syncthreads();
+        }
+        Fr incl = sh[threadIdx.x];
+        Fr excl = threadIdx.x ? sh[threadIdx.x - 1] : Fr::one();
+        if (i < n) st_fr(tot + i, fp_mul(carry, excl));
+        carry = fp_mul(carry, sh[1023]);
+        (void)incl;
+        __syncthreads();
+    }
+}
+// phase 3: multiply every element of chunk t by the product of all earlier chunks
+__global__ void __launch_bounds__(256)
+k_dpp_scan_apply(Fr* __restrict__ q, size_t m, const Fr* __restrict__ tot) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m || i < DPP_CHUNK) return;
+    st_fr(q + i, fp_mul(ld_fr_rw(q + i), ld_fr(tot + i / DPP_CHUNK)));
+}
+
+// ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
 static int ilog2(size_t x) { int r = 0; while (((size_t)1 << r) < x) ++r; return r; }
@@ -727,6 +798,56 @@ int32_t zkg_king_stage2_bn254_dev(zkg_ctx* ctx, const uint64_t* d_S_local, const
     DeviceGuard dg(ctx->device);
     HostKeep keep;
     return king_stage2(ctx, (const Fr*)d_S_local, (const Fr*)d_rand_local, cols, l, (Fr*)d_out_local, keep);
+}
+
+int32_t zkg_dpp_king_bn254(int32_t device, const uint64_t* const* shares_by_party, const uint32_t* parties, uint32_t n_recv,
+                           size_t cols, uint32_t l, const uint64_t* rand, uint64_t* const* out_by_party) {
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    ZKG_REQUIRE(shares_by_party && out_by_party && (cols == 0 || rand), "dpp_king: NULL argument");
+    ZKG_REQUIRE(n_recv >= 1 && n_recv <= pm->n, "dpp_king: n_recv = %u out of range", n_recv);
+    if (cols == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    const size_t m = cols * l, n_chunks = (m + DPP_CHUNK - 1) / DPP_CHUNK;
+    size_t in_b = align_up((size_t)n_recv * 2 * cols * 32, 256), rand_b = align_up(cols * pm->t * 32, 256);
+    size_t out_b = align_up((size_t)pm->n * cols * 32, 256);
+    ZKG_TRY(ctx->io.reserve(in_b + rand_b + out_b + 256));
+    Fr* d_in = (Fr*)ctx->io.p;
+    Fr* d_rand = (Fr*)((uint8_t*)ctx->io.p + in_b);
+    Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + in_b + rand_b);
+    int* d_err = (int*)((uint8_t*)ctx->io.p + in_b + rand_b + out_b);
+    // workspace: numden secrets (2m) | scratch (m) | chunk totals
+    ZKG_TRY(ctx->ws.reserve((3 * m + n_chunks + 8) * sizeof(Fr)));
+    Fr* S = (Fr*)ctx->ws.p;
+    Fr* scratch = S + 2 * m;
+    Fr* tot = scratch + m;
+    ZKG_TRY(h2d_party_major(ctx, shares_by_party, n_recv, 2 * cols, d_in));
+    ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, cols * pm->t * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+    HostKeep keep;
+    HFr one = host::h_one();
+    // unpack all 2*cols columns (num columns, then den columns): dpp/mod.rs:44-53
+    ZKG_TRY(king_stage1(ctx, d_in, parties, n_recv, 2 * cols, 0, 2 * cols, l, &one, &one, 0, 0, S, keep));
+    unsigned cb = (unsigned)((n_chunks + 127) / 128);
+    k_dpp_divide<<<cb, 128, 0, ctx->stream>>>(S, S + m, scratch, m, d_err);                 // :55-58
+    k_dpp_scan_local<<<cb, 128, 0, ctx->stream>>>(S, m, tot);                               // :62-66
+    k_dpp_scan_totals<<<1, 1024, 0, ctx->stream>>>(tot, n_chunks);
+    k_dpp_scan_apply<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(S, m, tot);
+    ctx->launches += 4;
+    ZKG_CUDA(cudaGetLastError());
+    ZKG_TRY(king_stage2(ctx, S, d_rand, cols, l, d_out, keep));                             // pack_vec, :71
+    int h_err = 0;
+    ZKG_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    for (uint32_t p = 0; p < pm->n; ++p) {
+        ZKG_REQUIRE(out_by_party[p], "NULL output vector for party %u", p);
+        ZKG_CUDA(cudaMemcpyAsync(out_by_party[p], d_out + (size_t)p * cols, cols * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZKG_REQUIRE(h_err == 0, "dpp_king: a denominator is zero (the reference's inverse().unwrap() would panic)");
+    return ZKG_OK;
 }
 
 int32_t zkg_deg_red_king_bn254(int32_t device, const uint64_t* const* shares_by_party, const uint32_t* parties,
