@@ -182,6 +182,12 @@ int32_t zkg_bitrev_bn254(int32_t device, uint64_t *v, size_t n);
  * the plain transforms of groth16/src/ext_wit.rs:204-285 and the reconstruction side of the tests. */
 int32_t zkg_fr_fft_bn254(int32_t device, uint64_t *v, size_t n, const uint64_t *offset, int32_t inverse);
 
+/* ---- wire format: ark-serialize compressed Fr = 32 LE bytes of the canonical
+ * value (the payload of mpc-net/src/ser_net.rs:25,40,112,119 frames after the u64 length prefix).
+ * from_wire fails with ZKG_ERR_BAD_ARG if an element is >= r, as arkworks' deserializer does. */
+int32_t zkg_fr_from_wire_bn254(int32_t device, const void *wire, uint64_t *out_mont, size_t n);
+int32_t zkg_fr_to_wire_bn254(int32_t device, const uint64_t *in_mont, void *wire, size_t n);
+
 /* ---- element-wise helpers used by kernel unit tests (out[i] = a[i] op b[i]; op: 0 mul, 1 add,
  * 2 sub; field: 0 Fr, 1 Fq) ---- */
 int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t *a, const uint64_t *b, uint64_t *out,

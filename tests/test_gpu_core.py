@@ -346,3 +346,19 @@ def test_domain_fft_ifft_coset(z, o, n):
             got = dom.ifft(v, off) if inv else dom.fft(v, off)
             assert (got == exp).all(), (off is not None, inv)
     assert (dom.ifft(dom.fft(v)) == v).all()
+
+
+def test_fr_wire_format_roundtrip(z):
+    """ark-serialize compressed Fr (32 LE bytes, canonical) <-> Montgomery images; >= r is rejected."""
+    from zksaas_b200 import capi
+    rng = random.Random(6)
+    vals = [0, 1, R - 1, 1 << 253] + [rng.randrange(R) for _ in range(1000)]
+    wire = raw_np(vals)                                   # canonical little-endian limbs == the 32 wire bytes
+    mont = np.zeros_like(wire)
+    capi.check(z.lib().zkg_fr_from_wire_bn254(0, wire.ctypes.data, mont.ctypes.data, len(vals)))
+    assert (mont == ol.fr_np(vals)).all()
+    back = np.zeros_like(wire)
+    capi.check(z.lib().zkg_fr_to_wire_bn254(0, mont.ctypes.data, back.ctypes.data, len(vals)))
+    assert (back == wire).all()
+    bad = raw_np([5, R, 7])
+    assert z.lib().zkg_fr_from_wire_bn254(0, bad.ctypes.data, mont.ctypes.data, 3) == capi.ZKG_ERR_BAD_ARG

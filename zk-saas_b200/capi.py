@@ -62,6 +62,8 @@ SIGNATURES = {
     "zkg_distribute_powers_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkg_bitrev_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t]),
     "zkg_fr_fft_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32]),
+    "zkg_fr_from_wire_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zkg_fr_to_wire_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zkg_field_op_dev": (C.c_int32, [ctx_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zkg_field_op": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }

@@ -102,6 +102,28 @@ int32_t ctx_cache_get(zkg_ctx* ctx, const void* key, size_t key_bytes, size_t by
     return ZKG_OK;
 }
 
+// ark-serialize (compressed) form of Fr: 32 little-endian bytes of the CANONICAL value.
+// dir 0: wire -> Montgomery image (values >= r are invalid: arkworks' deserializer rejects them); dir 1: back.
+__global__ void k_fr_wire(int dir, const Fr* __restrict__ in, Fr* __restrict__ out, size_t n, int* __restrict__ err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = in[i];
+    if (dir == 0) {
+        // x < r ?  (compare from the top limb)
+        bool lt = false, eq = true;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            uint32_t m = FrParams::mod(k);
+            if (eq && x.v[k] < m) { lt = true; eq = false; }
+            else if (eq && x.v[k] > m) { eq = false; }
+        }
+        if (!lt) { atomicExch(err, 1); return; }
+        out[i] = fp_to_mont(x);
+    } else {
+        out[i] = fp_from_mont(x);
+    }
+}
+
 int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events) {
     if (!ctx->copy_stream) ZKG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (n_events > 16) n_events = 16;
@@ -185,6 +207,33 @@ int32_t zkg_shutdown(void) {
     for (zkg_ctx* c : all) ctx_free(c);
     return ZKG_OK;
 }
+
+static int32_t fr_wire(int32_t device, int dir, const void* in, void* out, size_t n) {
+    ZKG_REQUIRE(n == 0 || (in && out), "fr wire conversion: NULL argument");
+    if (n == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    size_t bytes = align_up(n * 32, 256);
+    ZKG_TRY(ctx->io.reserve(2 * bytes + 256));
+    uint8_t* d = (uint8_t*)ctx->io.p;
+    int* d_err = (int*)(d + 2 * bytes);
+    ZKG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+    ZKG_CUDA(cudaMemcpyAsync(d, in, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    k_fr_wire<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dir, (const Fr*)d, (Fr*)(d + bytes), n, d_err);
+    ctx->launches += 1;
+    ZKG_CUDA(cudaGetLastError());
+    int h_err = 0;
+    ZKG_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaMemcpyAsync(out, d + bytes, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZKG_REQUIRE(h_err == 0, "fr_from_wire: an element is not below the field modulus");
+    return ZKG_OK;
+}
+
+int32_t zkg_fr_from_wire_bn254(int32_t device, const void* wire, uint64_t* out_mont, size_t n) { return fr_wire(device, 0, wire, out_mont, n); }
+int32_t zkg_fr_to_wire_bn254(int32_t device, const uint64_t* in_mont, void* wire, size_t n) { return fr_wire(device, 1, in_mont, wire, n); }
 
 int32_t zkg_field_op_dev(zkg_ctx* ctx, int32_t field, int32_t op, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n) {
     ZKG_REQUIRE(ctx && (field == 0 || field == 1) && op >= 0 && op <= 2 && (n == 0 || (d_a && d_b && d_out)), "field_op_dev: bad argument");
