@@ -488,6 +488,58 @@ def run_ours(args):
                                                "elems_per_s": round(mbyl_ * l_ / (tks * 1e-3), 1),
                                                "collective": "one NCCL reduce_scatter (sum) of the pack-order buffer"}
 
+    # ---- secondary: the SURVEY 8(f) rows built so far, through their host-pointer entry points (PCIe included) ----
+    if rank == 0 and not args.no_secondary:
+        from zksaas_b200 import api as zapi
+        rngn = np.random.default_rng(9)
+
+        def np_fr(k):
+            a = rngn.integers(0, 2**64, size=(k, 4), dtype=np.uint64)
+            a[:, 3] &= np.uint64((1 << 61) - 1)
+            return a
+        widened = {}
+        pp2 = z.PackedSharingParams.new(2, device=local)
+        cols = 1 << 17                                              # d_pp over m = 2^18 secrets
+        shares_pp = [np_fr(2 * cols) for _ in range(8)]
+        rnd_pp = np_fr(cols * 2)
+        z.dpp_king(shares_pp, list(range(8)), pp2, rnd_pp)
+        t0 = time.perf_counter()
+        z.dpp_king(shares_pp, list(range(8)), pp2, rnd_pp)
+        t_dpp = time.perf_counter() - t0
+        widened["dpp_king_m2^18_host_ms"] = round(t_dpp * 1e3, 3)
+        ncrs = 1 << 14                                              # CRS query of 2^14 G1 points -> 8 x 2^13 share points
+        crs = np.zeros((ncrs, 72), dtype=np.uint8)
+        crs[:, :64] = bases[:ncrs].cpu().numpy()
+        zapi.crs_det_pack(crs, pp2)
+        t0 = time.perf_counter()
+        zapi.crs_det_pack(crs, pp2)
+        t_crs = time.perf_counter() - t0
+        widened["crs_det_pack_g1_2^14_host_ms"] = round(t_crs * 1e3, 3)
+        widened["crs_det_pack_g1_points_per_s"] = round(ncrs / t_crs, 1)
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as ol
+            from oracle_lib import _p
+            o = ol.oracle()
+            ccols = 1 << 12
+            outs_ = [np.zeros((ccols, 4), dtype=np.uint64) for _ in range(8)]
+            sh_ = [np.ascontiguousarray(np.concatenate([x[:ccols], x[cols:cols + ccols]])) for x in shares_pp]
+            par_ = (C.c_uint32 * 8)(*range(8))
+            t0 = time.perf_counter()
+            o.zko_dpp_king(ol.ptr_array(sh_), par_, 8, ccols, 2, _p(rnd_pp), ol.ptr_array(outs_))
+            widened["cpu_dpp_king_ms_scaled_to_m2^18"] = round((time.perf_counter() - t0) * 1e3 * cols / ccols, 1)
+            sec_ = np.zeros((2, 12), dtype=np.uint64)
+            one_q = np.array([0xd35d438dc58f0d9d, 0x0a78eb28f5c70b3d, 0x666ea36f7879462c, 0x0e0a77c19a07df2f], dtype=np.uint64)
+            for k_ in range(2):
+                sec_[k_, 0:8] = crs[k_, :64].view(np.uint64)
+                sec_[k_, 8:12] = one_q
+            exp_ = np.zeros(8 * 12, dtype=np.uint64)
+            t0 = time.perf_counter()
+            for _ in range(8):
+                o.zko_pss_pack_g1(2, _p(sec_.reshape(-1)), None, _p(exp_))
+            widened["cpu_crs_det_pack_g1_points_per_s"] = round(16 / (time.perf_counter() - t0), 1)
+        secondary["survey_8f_rows"] = widened
+
     # ---- secondary: emulated distributed Groth16 prove (BASELINE configs[4]: 2^20 constraints, l = 2, n = 8 parties) ----
     # Dataflow of groth16/examples/sha256.rs:32-129 with synthetic CRS shares (PackedProvingKeyShare::rand sizes,
     # groth16/src/proving_key.rs:125-176): per party circom_h = 3 d_ifft + 3 d_fft + deg_red (ext_wit.rs:104-181) then

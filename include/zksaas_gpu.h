@@ -90,6 +90,13 @@ int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t *scalars, size_
 int32_t zkg_msm_bn254_registered_dev(zkg_ctx *ctx, uint64_t handle, const uint64_t *d_scalars, size_t n_scalars,
                                      uint64_t *d_out, int32_t partial);
 
+/* CRS share pre-processing: `pp.det_pack::<G>(chunk)` for every l-chunk of a proving-key
+ * query, then the per-party affine shares -- groth16/src/proving_key.rs:72-104 (pack_from_arkworks_proving_key),
+ * secret-sharing/src/pss.rs:69-87.  bases: n = chunks*l arkworks Affine images; out_by_party[i] (i < 4l):
+ * `chunks` Affine images, i.e. party i's `s` / `u` / `w` / `h` (G1) or `v` (G2) vector. */
+int32_t zkg_crs_det_pack_bn254(int32_t device, int32_t group, const void *bases, size_t base_stride, size_t n,
+                               uint32_t l, void *const *out_by_party, size_t out_stride);
+
 /* Device-pointer MSM.  d_bases: packed affine (x,y) Montgomery, 64 B (G1) / 128 B (G2) per point,
  * infinity encoded as (0,0) -- produce it with zkg_pack_bases_dev.  d_scalars: n x 32 B.
  * d_out_xyz: 96 B / 192 B on the device. */

@@ -334,3 +334,41 @@ def test_d_pp_example(z):
     out = z.d_pp(px, px, masks, pp, z.LocalTestNet(pp.n), ol.rand_fr(rng, num * pp.t), ol.rand_fr(rng, num * pp.t))
     got = unpack_all(z, pp, out)
     assert (got == ol.fr_np([1] * m)).all()
+
+
+@pytest.mark.parametrize("l,g2", [(2, False), (4, False), (2, True)])
+def test_crs_det_pack_group_vs_oracle(z, l, g2):
+    """det_pack over group elements per l-chunk (groth16/src/proving_key.rs:72-104) vs the oracle's
+    literal FFT-over-points det_pack (secret-sharing/src/pss.rs:69-87), incl. an infinity element."""
+    from zksaas_b200 import api
+    o = ol.oracle()
+    rng = np.random.default_rng(l * 10 + g2)
+    pp = z.PackedSharingParams.new(l)
+    chunks = 6
+    n = chunks * l
+    stride, words = (136, 24) if g2 else (72, 12)
+    bases = np.zeros((n, stride), dtype=np.uint8)
+    (o.zko_g2_fixed_base if g2 else o.zko_g1_fixed_base)(_p(ol.rand_fr(rng, n)), n, bases.ctypes.data, stride)
+    bases[3] = 0
+    bases[3, stride - 8] = 1                                   # infinity
+    got = api.crs_det_pack(bases, pp, g2)
+    half = (stride - 8) // 2
+    for j in range(chunks):
+        sec = np.zeros((l, words), dtype=np.uint64)
+        for k in range(l):
+            img = bases[j * l + k]
+            if img[stride - 8]:
+                pt = None
+            elif g2:
+                f = lambda b: int.from_bytes(bytes(b), "little") * pow(1 << 256, -1, pyref.Q_MOD) % pyref.Q_MOD
+                pt = (pyref.Fq2(f(img[0:32]), f(img[32:64])), pyref.Fq2(f(img[64:96]), f(img[96:128])))
+            else:
+                f = lambda b: int.from_bytes(bytes(b), "little") * pow(1 << 256, -1, pyref.Q_MOD) % pyref.Q_MOD
+                pt = (f(img[0:32]), f(img[32:64]))
+            sec[k] = ol.g2_point_to_xyz(pt) if g2 else ol.g1_point_to_xyz(pt)
+        exp = np.zeros(pp.n * words, dtype=np.uint64)
+        (o.zko_pss_pack_g2 if g2 else o.zko_pss_pack_g1)(l, _p(sec.reshape(-1)), None, _p(exp))
+        for i in range(pp.n):
+            e = exp[i * words:(i + 1) * words]
+            want = api._xyz_to_affine_images([e], g2)[0]
+            assert (got[i][j] == want).all(), (j, i)

@@ -214,6 +214,19 @@ def msm_g2(bases, scalars, device=0):
     return _msm(lib().zkg_msm_bn254_g2, 24, 136, bases, scalars, device)
 
 
+def crs_det_pack(bases, pp: "PackedSharingParams", g2=False):
+    """pack_from_arkworks_proving_key's inner step (groth16/src/proving_key.rs:72-104): det_pack every l-chunk of a
+    CRS query over group elements; returns the n parties' affine share vectors ((chunks, 72|136) uint8 each)."""
+    stride = 136 if g2 else 72
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    assert bases.ndim == 2 and bases.shape[1] == stride and bases.shape[0] % pp.l == 0
+    chunks = bases.shape[0] // pp.l
+    outs = [np.zeros((chunks, stride), dtype=np.uint8) for _ in range(pp.n)]
+    arr = (C.c_void_p * pp.n)(*[o.ctypes.data for o in outs])
+    check(lib().zkg_crs_det_pack_bn254(pp.device, 2 if g2 else 1, _ptr(bases), stride, bases.shape[0], pp.l, arr, stride))
+    return outs
+
+
 def _xyz_to_affine_images(points, g2=False):
     """normalised Jacobian images -> arkworks Affine images (for feeding results back as bases)."""
     w = 8 if g2 else 4

@@ -32,6 +32,8 @@ SIGNATURES = {
     "zkg_shutdown": (C.c_int32, []),
     "zkg_msm_bn254_g1": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkg_msm_bn254_g2": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "zkg_crs_det_pack_bn254": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32,
+                                            C.POINTER(C.c_void_p), C.c_size_t]),
     "zkg_bases_register": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, u64p]),
     "zkg_bases_register_dev": (C.c_int32, [ctx_p, C.c_int32, C.c_void_p, C.c_size_t, u64p]),
     "zkg_bases_release": (C.c_int32, [C.c_uint64]),

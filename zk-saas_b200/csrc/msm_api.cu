@@ -1,6 +1,7 @@
 // msm_api.cu -- C-ABI entry points of the MSM path (dispatch over G1/G2 + device-resident CRS registry).
 // Declarations and reference citations: include/zksaas_gpu.h.
 #include "common.cuh"
+#include "host_fr.hpp"
 
 namespace zkg {
 #define ZKG_MSM_DECLARE(G)                                                                                          \
@@ -12,7 +13,9 @@ namespace zkg {
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);                      \
     int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table);                         \
     int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode); \
-    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out);
+    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out); \
+    int32_t crs_det_pack_##G(int device, const void* bases, size_t stride, size_t n, int l, int n_parties,          \
+                             const uint32_t* h_scal, void* const* out_by_party, size_t out_stride);
 ZKG_MSM_DECLARE(g1)
 ZKG_MSM_DECLARE(g2)
 
@@ -104,6 +107,26 @@ static int32_t base_set_get(uint64_t handle, BaseSet* out) {
     ZKG_REQUIRE(handle >= 1 && handle <= g_bases.size() && g_bases[handle - 1], "bad bases handle %llu", (unsigned long long)handle);
     *out = *g_bases[handle - 1];
     return ZKG_OK;
+}
+
+int32_t zkg_crs_det_pack_bn254(int32_t device, int32_t group, const void* bases, size_t base_stride, size_t n, uint32_t l,
+                               void* const* out_by_party, size_t out_stride) {
+    ZKG_REQUIRE((group == 1 || group == 2) && out_by_party && (n == 0 || bases), "crs_det_pack: bad argument");
+    ZKG_REQUIRE(l == 2 || l == 4 || l == 8, "packing factor l = %u unsupported (2, 4, 8)", l);
+    host::PssMatrices pm;
+    host::pss_matrices(l, &pm);
+    // det_pack pads with zeros, so only the first l columns of the n x (l+t) pack matrix matter; the
+    // kernel wants canonical (non-Montgomery) scalars
+    std::vector<uint32_t> scal((size_t)pm.n * l * 8);
+    host::HFr raw_one = host::h_zero();
+    raw_one.v[0] = 1;
+    for (uint32_t i = 0; i < pm.n; ++i)
+        for (uint32_t k = 0; k < l; ++k) {
+            host::HFr c = host::h_mul(pm.pack[(size_t)i * (pm.l + pm.t) + k], raw_one);
+            memcpy(&scal[((size_t)i * l + k) * 8], c.v, 32);
+        }
+    return group == 1 ? crs_det_pack_g1(device, bases, base_stride, n, (int)l, (int)pm.n, scal.data(), out_by_party, out_stride)
+                      : crs_det_pack_g2(device, bases, base_stride, n, (int)l, (int)pm.n, scal.data(), out_by_party, out_stride);
 }
 
 int32_t zkg_bases_register(int32_t device, int32_t group, const void* bases, size_t base_stride, size_t n,

@@ -677,6 +677,83 @@ static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int
 }
 
 template <class F>
+static int32_t pack_bases(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t n, void* d_packed);
+
+// ------------------------------------------------------------------------------------------
+// CRS share pre-processing: PackedSharingParams::det_pack over GROUP elements,
+// as pack_from_arkworks_proving_key does for every l-chunk of the proving key
+// (groth16/src/proving_key.rs:72-104, secret-sharing/src/pss.rs:69-87).  det_pack is the linear map
+// share_i = sum_{k<l} M[i][k] * P_k with M the first l columns of the pack matrix, so one thread per
+// (chunk, party) runs an interleaved double-and-add over the l canonical 254-bit scalars and
+// normalises -- the result is the same group element arkworks' FFT-over-points computes.
+// scal: n_parties x l canonical scalars (8 x u32 each).  out[i * chunks + j] = party i's share of chunk j.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_det_pack_group(const Affine<F>* __restrict__ bases, size_t chunks, int l, int n_parties, const uint32_t* __restrict__ scal,
+                 Affine<F>* __restrict__ out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks * (size_t)n_parties) return;
+    size_t j = t % chunks;
+    int i = (int)(t / chunks);
+    const uint32_t* sc = scal + (size_t)i * l * 8;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int b = 253; b >= 0; --b) {
+        xyzz_dbl(acc);
+        for (int k = 0; k < l; ++k)
+            if ((sc[k * 8 + (b >> 5)] >> (b & 31)) & 1) xyzz_madd(acc, load_vec(bases + j * l + k), false);
+    }
+    store_vec(out + t, xyzz_to_affine(acc));
+}
+
+// packed (x, y) -> arkworks Affine image (coordinates, infinity flag, zero padding up to `stride`)
+template <class F>
+__global__ void k_unpack_bases(const Affine<F>* __restrict__ in, size_t n, uint8_t* __restrict__ ark, size_t stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> a = load_vec_rw(in + i);
+    uint8_t* p = ark + i * stride;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(&a);
+    for (size_t k = 0; k < sizeof(Affine<F>); ++k) p[k] = src[k];
+    p[sizeof(Affine<F>)] = a.is_inf() ? 1 : 0;
+    for (size_t k = sizeof(Affine<F>) + 1; k < stride; ++k) p[k] = 0;
+}
+
+// host-pointer entry: bases (n = chunks*l arkworks images) -> n_parties share vectors of `chunks` images
+template <class F>
+static int32_t crs_det_pack_host(int device, const void* bases, size_t stride, size_t n, int l, int n_parties,
+                                 const uint32_t* h_scal, void* const* out_by_party, size_t out_stride) {
+    ZKG_REQUIRE(stride >= sizeof(Affine<F>) + 1 && out_stride >= sizeof(Affine<F>) + 1, "crs_det_pack: stride too small");
+    ZKG_REQUIRE(l > 0 && n % (size_t)l == 0, "crs_det_pack: %zu bases is not a multiple of l = %d", n, l);
+    if (n == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    const size_t chunks = n / l, outs = chunks * (size_t)n_parties;
+    size_t ark_b = align_up(n * stride, 256), pk_b = align_up(n * sizeof(Affine<F>), 256), sc_b = align_up((size_t)n_parties * l * 32, 256);
+    size_t o_pk = align_up(outs * sizeof(Affine<F>), 256), o_ark = align_up(outs * out_stride, 256);
+    ZKG_TRY(ctx->io.reserve(ark_b + pk_b + sc_b + o_pk + o_ark));
+    uint8_t* d = (uint8_t*)ctx->io.p;
+    uint8_t *d_ark = d, *d_pk = d + ark_b, *d_sc = d_pk + pk_b, *d_opk = d_sc + sc_b, *d_oark = d_opk + o_pk;
+    ZKG_CUDA(cudaMemcpyAsync(d_ark, bases, n * stride, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_CUDA(cudaMemcpyAsync(d_sc, h_scal, (size_t)n_parties * l * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(pack_bases<F>(ctx, d_ark, stride, n, d_pk));
+    k_det_pack_group<F><<<(unsigned)((outs + 127) / 128), 128, 0, ctx->stream>>>((const Affine<F>*)d_pk, chunks, l, n_parties,
+                                                                              (const uint32_t*)d_sc, (Affine<F>*)d_opk);
+    k_unpack_bases<F><<<(unsigned)((outs + 255) / 256), 256, 0, ctx->stream>>>((const Affine<F>*)d_opk, outs, d_oark, out_stride);
+    ctx->launches += 2;
+    ZKG_CUDA(cudaGetLastError());
+    for (int i = 0; i < n_parties; ++i) {
+        ZKG_REQUIRE(out_by_party[i], "crs_det_pack: NULL output for party %d", i);
+        ZKG_CUDA(cudaMemcpyAsync(out_by_party[i], d_oark + (size_t)i * chunks * out_stride, chunks * out_stride,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+template <class F>
 static int32_t pack_bases(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t n, void* d_packed) {
     if (n == 0) return ZKG_OK;
     ZKG_REQUIRE(stride >= sizeof(Affine<F>) + 1, "base stride %zu too small", stride);
@@ -769,7 +846,9 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);                      \
     int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table);                         \
     int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode); \
-    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out);
+    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out); \
+    int32_t crs_det_pack_##G(int device, const void* bases, size_t stride, size_t n, int l, int n_parties,          \
+                             const uint32_t* h_scal, void* const* out_by_party, size_t out_stride);
 ZKG_MSM_DECLARE(g1)
 ZKG_MSM_DECLARE(g2)
 
@@ -798,6 +877,10 @@ ZKG_MSM_DECLARE(g2)
     }                                                                                                               \
     int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out) { \
         return msm_run_prepared_host<F>(ctx, (const Affine<F>*)d_table, c, h_scalars, n, (F*)d_out);                \
+    }                                                                                                               \
+    int32_t crs_det_pack_##G(int device, const void* bases, size_t stride, size_t n, int l, int n_parties,          \
+                             const uint32_t* h_scal, void* const* out_by_party, size_t out_stride) {                \
+        return crs_det_pack_host<F>(device, bases, stride, n, l, n_parties, h_scal, out_by_party, out_stride);      \
     }                                                                                                               \
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed) {                     \
         if (n == 0) return ZKG_OK;                                                                                  \
