@@ -42,8 +42,7 @@ static void ctx_free(zkg_ctx* c) {
     if (!c) return;
     DeviceGuard dg(c->device);
     cudaStreamSynchronize(c->stream);
-    c->ws.release(); c->io.release(); c->io2.release(); c->small.release();
-    if (c->pinned) cudaFreeHost(c->pinned);
+    c->ws.release(); c->io.release();
     for (auto& e : c->cache) cudaFree(e.p);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < c->copy_ev_count; ++i) cudaEventDestroy(c->copy_ev[i]);
@@ -64,14 +63,6 @@ PooledCtx::~PooledCtx() {
     if (!ctx) return;
     std::lock_guard<std::mutex> lk(g_pool_mu);
     g_pool.push_back(ctx);
-}
-
-int32_t ctx_pinned(zkg_ctx* ctx, size_t bytes) {
-    if (bytes <= ctx->pinned_bytes) return ZKG_OK;
-    if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
-    ZKG_CUDA(cudaMallocHost(&ctx->pinned, bytes));
-    ctx->pinned_bytes = bytes;
-    return ZKG_OK;
 }
 
 static void fnv2(const void* key, size_t n, uint64_t* h1, uint64_t* h2) {

@@ -59,10 +59,6 @@ struct zkg_ctx {
     bool own_stream = false;
     zkg::DevBuf ws;        // kernel workspace (digits, sorted indices, buckets, NTT scratch ...)
     zkg::DevBuf io;        // staging for host-pointer entry points
-    zkg::DevBuf io2;
-    zkg::DevBuf small;     // twiddle tables / matrices / results
-    void* pinned = nullptr;   // small pinned bounce buffer for results
-    size_t pinned_bytes = 0;
     int sm_count = 0;
     // persistent device-side parameter cache (twiddle/power tables, PSS matrices), keyed by content
     struct CacheEnt { uint64_t h1, h2; size_t bytes; void* p; };
@@ -87,7 +83,6 @@ struct PooledCtx {
     ~PooledCtx();
 };
 
-int32_t ctx_pinned(zkg_ctx* ctx, size_t bytes);
 int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events);
 // Look up (or reserve) a persistent device block for the parameter identified by `key`.
 // *fresh = true means the caller must fill it (on ctx->stream) before use.

@@ -188,18 +188,6 @@ ZKG_NI Affine<F> xyzz_to_affine(const XYZZ<F>& a) {
     return r;
 }
 
-// k * p for a small non-negative integer k (bucket-segment offsets); double-and-add, MSB first
-template <class F>
-ZKG_NI XYZZ<F> xyzz_mul_small(const XYZZ<F>& p, uint32_t k) {
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (int b = 31; b >= 0; --b) {
-        xyzz_dbl(acc);
-        if ((k >> b) & 1) xyzz_add(acc, p);
-    }
-    return acc;
-}
-
-
 // (Round-1 experiment, removed: "quad-cooperative" add/double with four lanes evaluating the
 // independent products of a formula level and width-4 shuffles between levels.  A lone warp runs
 // this code at ~6.3 cycles per instruction (ncu: 3.2 wait + 1.5 branch-resolving stalls per issue),

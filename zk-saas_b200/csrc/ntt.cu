@@ -408,11 +408,9 @@ k_dpp_scan_totals(Fr* __restrict__ tot, size_t n) {
             if (threadIdx.x >= off) sh[threadIdx.x] = fp_mul(sh[threadIdx.x], a);
             __syncthreads();
         }
-        Fr incl = sh[threadIdx.x];
         Fr excl = threadIdx.x ? sh[threadIdx.x - 1] : Fr::one();
         if (i < n) st_fr(tot + i, fp_mul(carry, excl));
         carry = fp_mul(carry, sh[1023]);
-        (void)incl;
         __syncthreads();
     }
 }
@@ -432,8 +430,6 @@ static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 
 // Parameter tables live in the context's persistent cache (keyed by their defining values), so a
 // prover that keeps calling d_fft / d_ifft with the same domain builds them once.
-struct SmallAlloc { zkg_ctx* ctx; };      // (kept as a handle type: tables come from ctx_cache_get)
-
 struct PowKey { char tag[8]; uint64_t w[4]; uint64_t count; };
 
 // out[i] = w^i, i < count, cached
@@ -454,7 +450,7 @@ static int32_t cached_pow_seq(zkg_ctx* ctx, const char* tag, const HFr& w, size_
     return ZKG_OK;
 }
 
-static int32_t build_pow_table(zkg_ctx* ctx, SmallAlloc&, const HFr& w, size_t max_exp_excl, PowTable* out) {
+static int32_t build_pow_table(zkg_ctx* ctx, const HFr& w, size_t max_exp_excl, PowTable* out) {
     size_t hi_n = (max_exp_excl + TW_LO - 1) >> TW_LO_BITS;
     if (hi_n == 0) hi_n = 1;
     ZKG_TRY(cached_pow_seq(ctx, "pow_lo", w, TW_LO, &out->lo));
@@ -464,7 +460,7 @@ static int32_t build_pow_table(zkg_ctx* ctx, SmallAlloc&, const HFr& w, size_t m
 
 // In-order-output NTT of d_in (bit-reversed input order) with root w_N, into d_out.
 // shift = 1 stores X[k] at (k-1) mod N.  d_tmp: N-element scratch (used when > 2 passes or in == out).
-static int32_t ntt_bitrev_in(zkg_ctx* ctx, SmallAlloc& sa, const Fr* d_in, Fr* d_out, Fr* d_tmp, size_t N, const HFr& wN,
+static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp, size_t N, const HFr& wN,
                              int shift, const HFr* scale, const Fr* d_mask) {
     const int logN = ilog2(N);
     ZKG_REQUIRE(is_pow2(N) && logN <= 24 + 3, "ntt: size %zu unsupported", N);
@@ -472,7 +468,7 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, SmallAlloc& sa, const Fr* d_in, Fr* d
     if (npass == 0) npass = 1;
     phase_mark(ctx, 0);
     PowTable tw{nullptr, nullptr};
-    if (npass > 1) ZKG_TRY(build_pow_table(ctx, sa, wN, N, &tw));
+    if (npass > 1) ZKG_TRY(build_pow_table(ctx, wN, N, &tw));
     int s = 0;
     const Fr* src = d_in;
     for (int q = 0; q < npass; ++q) {
@@ -520,7 +516,7 @@ static const host::PssMatrices* pss_get(uint32_t l) {
     return &g_pss[slot];
 }
 
-static int32_t upload(zkg_ctx* ctx, SmallAlloc&, const std::vector<HFr>& m, const Fr** out) {
+static int32_t upload(zkg_ctx* ctx, const std::vector<HFr>& m, const Fr** out) {
     void* p; bool fresh;
     ZKG_TRY(ctx_cache_get(ctx, m.data(), m.size() * sizeof(HFr), m.size() * sizeof(Fr), &p, &fresh));
     // blocking copy, once per distinct matrix: the source may be a temporary
@@ -618,16 +614,15 @@ static int32_t king_stage1(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* par
     ZKG_REQUIRE(!mode_fft || log_m <= 28, "king: m = %zu exceeds the 2-adicity of Fr", m);
     const std::vector<HFr>* U;
     ZKG_TRY(recv_matrix(l, parties, n_recv, keep, &U));
-    SmallAlloc sa{ctx};
     const Fr* dU;
     phase_mark(ctx, 0);
-    ZKG_TRY(upload(ctx, sa, *U, &dU));
+    ZKG_TRY(upload(ctx, *U, &dU));
     PowTable gen_tw{nullptr, nullptr}, g_tw{nullptr, nullptr};
     int has_g = 0;
     if (mode_fft) {
-        ZKG_TRY(build_pow_table(ctx, sa, *gen, m, &gen_tw));
+        ZKG_TRY(build_pow_table(ctx, *gen, m, &gen_tw));
         has_g = !(*g == host::h_one());
-        if (has_g) ZKG_TRY(build_pow_table(ctx, sa, *g, m, &g_tw));
+        if (has_g) ZKG_TRY(build_pow_table(ctx, *g, m, &g_tw));
     }
     unsigned blocks = (unsigned)((cols + 255) / 256);
     int mode = mode_fft ? (rearrange ? 1 : 0) : 2;
@@ -648,9 +643,8 @@ static int32_t king_stage2(zkg_ctx* ctx, const Fr* S, const Fr* d_rand, size_t c
     if (cols == 0) return ZKG_OK;
     const int K = (int)(pm->l + pm->t) <= 4 ? 4 : (int)(pm->l + pm->t) <= 8 ? 8 : 16;
     keep.v.push_back(pad_rows(pm->pack, pm->n, pm->l + pm->t, K));
-    SmallAlloc sa{ctx};
     const Fr* dP;
-    ZKG_TRY(upload(ctx, sa, keep.v.back(), &dP));
+    ZKG_TRY(upload(ctx, keep.v.back(), &dP));
     ZKG_TRY(launch_pack(ctx, dP, K, pm->n, pm->l, pm->t, S, pm->l, 1, d_rand, pm->t, 1, d_out, 1, cols, cols));
     phase_mark(ctx, 3);
     return ZKG_OK;
@@ -713,14 +707,13 @@ static int32_t fft1_dev(zkg_ctx* ctx, Fr* d_px, size_t mbyl, uint32_t l, const H
                         const Fr* d_mask) {
     ZKG_REQUIRE(l >= 1 && is_pow2(l) && is_pow2(mbyl), "fft1: m/l = %zu and l = %u must be powers of two", mbyl, l);
     ZKG_REQUIRE(ilog2(mbyl * l) <= 28, "fft1: m exceeds the 2-adicity of Fr");
-    SmallAlloc sa{ctx};
     ZKG_TRY(ctx->ws.reserve(mbyl * sizeof(Fr)));
     Fr* tmp = (Fr*)ctx->ws.p;
     HFr wN = host::h_pow(gen, l);
     // Writing the result back into d_px is safe: with one pass a single block reads the whole
     // vector before it stores; with several passes the last one reads the scratch, and pass 0 has
     // already consumed d_px (stream order), so the shifted stores cannot race with any load.
-    return ntt_bitrev_in(ctx, sa, d_px, d_px, tmp, mbyl, wN, 1, pre_scale, d_mask);
+    return ntt_bitrev_in(ctx, d_px, d_px, tmp, mbyl, wN, 1, pre_scale, d_mask);
 }
 
 }  // namespace zkg
@@ -887,17 +880,16 @@ static int32_t pss_host(int device, uint32_t l, int which, const uint64_t* in, c
     Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + in_b + rand_b);
     ZKG_CUDA(cudaMemcpyAsync(d_in, in, in_elems * 32, cudaMemcpyHostToDevice, ctx->stream));
     if (which == 0 && rand) ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, cols * t * 32, cudaMemcpyHostToDevice, ctx->stream));
-    SmallAlloc sa{ctx};
     HostKeep keep;
     const Fr* dM;
     if (which == 0) {
         const int K = (int)(l + t) <= 4 ? 4 : (int)(l + t) <= 8 ? 8 : 16;
         keep.v.push_back(pad_rows(pm->pack, (int)n, (int)(l + t), K));
-        ZKG_TRY(upload(ctx, sa, keep.v.back(), &dM));
+        ZKG_TRY(upload(ctx, keep.v.back(), &dM));
         // det_pack (rand == NULL): the t padding entries are zero, so only the first l columns contribute
         ZKG_TRY(launch_pack(ctx, dM, K, (int)n, (int)l, rand ? (int)t : 0, d_in, l, 1, d_rand, t, 1, d_out, n, 1, cols));
     } else {
-        ZKG_TRY(upload(ctx, sa, which == 1 ? pm->unpack : pm->unpack2, &dM));
+        ZKG_TRY(upload(ctx, which == 1 ? pm->unpack : pm->unpack2, &dM));
         ZKG_TRY(launch_unpack(ctx, dM, (int)l, (int)n, d_in, n, 1, d_out, l, 1, cols));
     }
     ZKG_CUDA(cudaMemcpyAsync(out, d_out, out_elems * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -929,9 +921,8 @@ int32_t zkg_fft2_bn254(int32_t device, uint64_t* s1, size_t m, uint32_t l, const
     Fr* d_in = (Fr*)ctx->io.p;
     Fr* d_out = d_in + m;
     ZKG_CUDA(cudaMemcpyAsync(d_in, s1, m * 32, cudaMemcpyHostToDevice, ctx->stream));
-    SmallAlloc sa{ctx};
     PowTable gen_tw, none{nullptr, nullptr};
-    ZKG_TRY(build_pow_table(ctx, sa, host::h_load(gen), m, &gen_tw));
+    ZKG_TRY(build_pow_table(ctx, host::h_load(gen), m, &gen_tw));
     size_t mbyl = m / l;
     unsigned blocks = (unsigned)((mbyl + 255) / 256);
     int log_m = ilog2(m);
@@ -954,9 +945,8 @@ int32_t zkg_distribute_powers_bn254(int32_t device, uint64_t* v, size_t n, const
     ZKG_TRY(ctx->io.reserve(n * 32));
     Fr* d = (Fr*)ctx->io.p;
     ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    SmallAlloc sa{ctx};
     PowTable tw;
-    ZKG_TRY(build_pow_table(ctx, sa, host::h_load(g), n, &tw));
+    ZKG_TRY(build_pow_table(ctx, host::h_load(g), n, &tw));
     k_distribute_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, n, tw);
     ZKG_CUDA(cudaGetLastError());
     ZKG_CUDA(cudaMemcpyAsync(v, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -995,7 +985,6 @@ int32_t zkg_fr_fft_bn254(int32_t device, uint64_t* v, size_t n, const uint64_t* 
     Fr* d_rev = d + n;
     Fr* d_tmp = d + 2 * n;
     ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    SmallAlloc sa{ctx};
     HFr w = host::h_root_of_unity(n), one = host::h_one();
     HFr off = offset ? host::h_load(offset) : one;
     bool coset = !(off == one);
@@ -1003,17 +992,17 @@ int32_t zkg_fr_fft_bn254(int32_t device, uint64_t* v, size_t n, const uint64_t* 
     if (!inverse) {
         if (coset) {
             PowTable tw;
-            ZKG_TRY(build_pow_table(ctx, sa, off, n, &tw));
+            ZKG_TRY(build_pow_table(ctx, off, n, &tw));
             k_distribute_powers<<<blocks, 256, 0, ctx->stream>>>(d, n, tw);
         }
         k_bitrev<<<blocks, 256, 0, ctx->stream>>>(d, d_rev, ilog2(n));
-        ZKG_TRY(ntt_bitrev_in(ctx, sa, d_rev, d, d_tmp, n, w, 0, nullptr, nullptr));
+        ZKG_TRY(ntt_bitrev_in(ctx, d_rev, d, d_tmp, n, w, 0, nullptr, nullptr));
     } else {
         k_bitrev<<<blocks, 256, 0, ctx->stream>>>(d, d_rev, ilog2(n));
-        ZKG_TRY(ntt_bitrev_in(ctx, sa, d_rev, d, d_tmp, n, host::h_inv(w), 0, nullptr, nullptr));
+        ZKG_TRY(ntt_bitrev_in(ctx, d_rev, d, d_tmp, n, host::h_inv(w), 0, nullptr, nullptr));
         HFr n_inv = host::h_inv(host::h_from_u64(n));
         PowTable tw{nullptr, nullptr};
-        if (coset) ZKG_TRY(build_pow_table(ctx, sa, host::h_inv(off), n, &tw));
+        if (coset) ZKG_TRY(build_pow_table(ctx, host::h_inv(off), n, &tw));
         k_scale_powers<<<blocks, 256, 0, ctx->stream>>>(d, n, to_arg(n_inv), coset ? 1 : 0, tw);
     }
     ZKG_CUDA(cudaGetLastError());
