@@ -474,7 +474,12 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp,
     for (int q = 0; q < npass; ++q) {
         int b = (logN - s + (npass - q) - 1) / (npass - q);      // spread the remaining bits evenly
         int cw_log = 0;
-        if (q > 0) { cw_log = 11 - b; if (cw_log > s) cw_log = s; if (cw_log < 0) cw_log = 0; }
+        if (q > 0) {
+            cw_log = 11 - b; if (cw_log > s) cw_log = s; if (cw_log < 0) cw_log = 0;
+            // small transforms: prefer more, narrower tiles (>= 4 columns = 128-byte rows) so that the
+            // pass spreads over the 148 SMs instead of a dozen fat blocks
+            while (cw_log > 2 && (N >> (b + cw_log)) < 296) --cw_log;
+        }
         NttPass P;
         P.logN = logN; P.s = s; P.b = b; P.cw_log = cw_log;
         P.first = q == 0; P.last = q == npass - 1; P.shift = shift;
