@@ -167,6 +167,53 @@ def test_msm_registered_bases(z):
     capi.check(z.lib().zkg_bases_release(h.value))
 
 
+def _skewed_scalars(rng, n, kind):
+    if kind == "all_equal":
+        return [rng.randrange(R)] * n
+    if kind == "all_one":
+        return [1] * n
+    if kind == "all_minus_one":
+        return [R - 1] * n
+    if kind == "tiny":                       # witness-like: booleans and small integers, a few full-size values
+        return [rng.choice([0, 1, 1, 2, 3, R - 1, rng.randrange(1 << 16)]) if rng.random() < 0.95 else rng.randrange(R)
+                for _ in range(n)]
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "all_one", "all_minus_one", "tiny"])
+@pytest.mark.parametrize("chunks", [0, 3])
+def test_msm_g1_skewed_scalars(z, kind, chunks, monkeypatch):
+    """Skewed digit distributions put thousands of points into one bucket (block-cooperative
+    k_accumulate_heavy); also through the chunked path, where heavy buckets accumulate across chunks."""
+    rng = random.Random(hash(kind) & 0xffff)
+    n = 1 << 14
+    _, bases = _g1_points(rng, n)
+    S = ol.fr_np(_skewed_scalars(rng, n, kind))
+    if chunks:
+        monkeypatch.setenv("ZKG_MSM_CHUNKS", str(chunks))
+    assert (z.msm_g1(bases, S) == ol.o_g1_msm(bases, S, threads=8)).all()
+
+
+def test_msm_skewed_registered_and_g2(z):
+    from zksaas_b200 import capi
+    rng = random.Random(4242)
+    n = 1 << 13
+    _, bases = _g1_points(rng, n)
+    h = C.c_uint64(0)
+    capi.check(z.lib().zkg_bases_register(0, 1, bases.ctypes.data, 72, n, C.byref(h)))
+    out = np.zeros(12, dtype=np.uint64)
+    for kind in ("all_equal", "tiny"):
+        S = ol.fr_np(_skewed_scalars(rng, n, kind))
+        capi.check(z.lib().zkg_msm_bn254_registered(h.value, S.ctypes.data, n, out.ctypes.data))
+        assert (out == ol.o_g1_msm(bases, S, threads=8)).all()
+    capi.check(z.lib().zkg_bases_release(h.value))
+    n2 = 1 << 12
+    _, b2 = _g2_points(rng, n2)
+    for kind in ("all_equal", "tiny"):
+        S = ol.fr_np(_skewed_scalars(rng, n2, kind))
+        assert (z.msm_g2(b2, S) == ol.o_g2_msm(b2, S, threads=8)).all()
+
+
 # ------------------------------------------------------------------------------------------------
 # fft1 (K4)
 # ------------------------------------------------------------------------------------------------

@@ -76,6 +76,39 @@ def test_msm_g1_closed_form(env, log2n):
         assert (z.msm_g1(hb, a.cpu().numpy().view(np.uint64)) == exp).all()
 
 
+@pytest.mark.parametrize("kind", ["witness_like", "all_equal"])
+def test_msm_g1_skewed_closed_form_2p20(env, kind):
+    """Groth16 witnesses are mostly booleans / small values: 2^20 points whose scalars pile into a
+    handful of buckets must stay exact AND must not serialise on one thread per bucket."""
+    import time
+    z, capi, torch, ctx = env
+    o = ol.oracle()
+    n = 1 << 20
+    a, s = _rand_dev(torch, n, 91), _rand_dev(torch, n, 92)
+    one = torch.from_numpy(ol.fr_np([1]).view(np.int64)).cuda()
+    if kind == "witness_like":
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        u = torch.rand(n, device="cuda", generator=g)
+        a[u < 0.6] = one
+        a[u < 0.3] = 0
+    else:
+        a[:] = a[0].clone()
+    bases = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    out = torch.zeros(12, dtype=torch.int64, device="cuda")
+    lib = z.lib()
+    capi.check(lib.zkg_fixed_base_dev(ctx, 1, C.c_void_p(s.data_ptr()), n, C.c_void_p(bases.data_ptr())))
+    capi.check(lib.zkg_ctx_sync(ctx))
+    t0 = time.perf_counter()
+    capi.check(lib.zkg_msm_bn254_g1_dev(ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(a.data_ptr()), n, C.c_void_p(out.data_ptr())))
+    capi.check(lib.zkg_ctx_sync(ctx))
+    dt = time.perf_counter() - t0
+    got = out.cpu().numpy().view(np.uint64)
+    exp = _closed_form(o, a.cpu().numpy().view(np.uint64), s.cpu().numpy().view(np.uint64))
+    assert (got == exp).all()
+    print(f"skewed {kind}: {dt * 1e3:.1f} ms")
+    assert dt < 1.0, f"skewed MSM took {dt:.2f} s"
+
+
 @pytest.mark.parametrize("log2n", [12, 17])
 def test_msm_g2_closed_form(env, log2n):
     z, capi, torch, ctx = env

@@ -245,6 +245,10 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
     uint32_t end = cursor_end[slot], cnt = counts[slot];
     const uint32_t* idx = sorted + (size_t)w * sstride;
     if (accumulate_into && cnt == 0) return;                 // nothing new for this bucket in this chunk
+    if (cnt >= SIZE_KEYS - 1) {                              // heavy bucket: left to k_accumulate_heavy
+        if (!accumulate_into) store_vec(buckets + slot, XYZZ<F>::inf());
+        return;
+    }
     XYZZ<F> acc = accumulate_into ? load_vec_rw(buckets + slot) : XYZZ<F>::inf();
     for (uint32_t k = end - cnt; k < end; ++k) {
         uint32_t e = idx[k];
@@ -252,6 +256,74 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
         xyzz_madd(acc, p, (e >> 31) != 0);
     }
     store_vec(buckets + slot, acc);
+}
+
+// Skewed scalar distributions (many equal scalars, boolean witnesses, structured inputs) put thousands
+// of points into one bucket; one thread per bucket would serialise them.  Buckets with at least
+// SIZE_KEYS-1 points are the first hist[SIZE_KEYS-1] entries of `order`: blocks (x = heavy bucket,
+// y = part) stride over a slice of the bucket, fold their 128 partial sums in shared memory and add
+// the block sum into the bucket under a per-bucket spin lock (the holder never waits on anything,
+// so the lock cannot deadlock).  Uniform scalars never reach the threshold (the window rule keeps
+// the mean population near 2^7), so this launch is normally a few thousand empty blocks.
+static constexpr uint32_t HEAVY_LOCKS = 1024;      // lock words, hashed by slot
+static constexpr uint32_t HEAVY_PARTS = 32;        // gridDim.y
+static constexpr uint32_t HEAVY_PART_MIN = 4096;   // points per part before a bucket is split further
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_accumulate_heavy(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                   const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
+                   const uint32_t* __restrict__ order, const uint32_t* __restrict__ size_hist,
+                   uint32_t* __restrict__ locks, size_t sstride, uint32_t nb, XYZZ<F>* buckets) {
+    __shared__ __align__(16) unsigned char raw[128 * sizeof(XYZZ<F>)];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(raw);
+    const uint32_t n_heavy = size_hist[SIZE_KEYS - 1];
+    const uint32_t tid = threadIdx.x, part = blockIdx.y;
+    for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        size_t slot = order[h];
+        uint32_t w = (uint32_t)(slot / nb);
+        uint32_t end = cursor_end[slot], cnt = counts[slot];
+        uint32_t parts = (cnt + HEAVY_PART_MIN - 1) / HEAVY_PART_MIN;
+        if (parts > HEAVY_PARTS) parts = HEAVY_PARTS;
+        if (part >= parts) continue;                                   // uniform over the block
+        const uint32_t lo = end - cnt + (uint32_t)(((uint64_t)cnt * part) / parts);
+        const uint32_t hi = end - cnt + (uint32_t)(((uint64_t)cnt * (part + 1)) / parts);
+        const uint32_t* idx = sorted + (size_t)w * sstride;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = lo + tid; k < hi; k += 128) {
+            uint32_t e = idx[k];
+            Affine<F> p = load_vec(bases + (e & 0x7fffffffu));
+            xyzz_madd(acc, p, (e >> 31) != 0);
+        }
+        sh[tid] = acc;
+        __syncthreads();
+        for (uint32_t s = 64; s > 0; s >>= 1) {
+            if (tid < s) { XYZZ<F> a = sh[tid]; xyzz_add(a, sh[tid + s]); sh[tid] = a; }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            uint32_t* lock = locks + (slot & (HEAVY_LOCKS - 1));
+            while (atomicCAS(lock, 0u, 1u) != 0u) __nanosleep(200);
+            __threadfence();
+            XYZZ<F> b;
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(buckets + slot);
+                uint4* dst = reinterpret_cast<uint4*>(&b);
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 16); ++i) dst[i] = __ldcg(src + i);     // L2: other SMs update it
+            }
+            xyzz_add(b, sh[0]);
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(&b);
+                uint4* dst = reinterpret_cast<uint4*>(buckets + slot);
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 16); ++i) __stcg(dst + i, src[i]);
+            }
+            __threadfence();
+            atomicExch(lock, 0u);
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -493,7 +565,7 @@ static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<
     size_t o_order = carve(sizeof(uint32_t) * pl->slots);
     const uint32_t scan_tiles = (pl->nb + SCAN_TILE - 1) / SCAN_TILE;
     ZKG_REQUIRE(scan_tiles <= 1024, "msm: window of %d bits too large", c);
-    size_t o_shist = carve(sizeof(uint32_t) * (2 * SIZE_KEYS + (size_t)pl->Wb * scan_tiles));
+    size_t o_shist = carve(sizeof(uint32_t) * (2 * SIZE_KEYS + HEAVY_LOCKS + (size_t)pl->Wb * scan_tiles));   // hist | locks | start | scan tiles
     size_t o_buckets = carve(sizeof(XYZZ<F>) * pl->slots);
     size_t o_r0 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
     size_t o_c0 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
@@ -524,13 +596,13 @@ static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases,
     const bool first = pl->chunks_done == 0;
     if (first) phase_mark(ctx, 0);
     ZKG_CUDA(cudaMemsetAsync(pl->counts, 0, sizeof(uint32_t) * pl->slots, st));
-    ZKG_CUDA(cudaMemsetAsync(pl->shist, 0, sizeof(uint32_t) * SIZE_KEYS, st));
+    ZKG_CUDA(cudaMemsetAsync(pl->shist, 0, sizeof(uint32_t) * (SIZE_KEYS + HEAVY_LOCKS), st));
     const uint32_t bstride = pl->merged ? 0u : pl->nb;
     const size_t sstride = pl->merged ? 0 : n, ioff = pl->merged ? pl->n_total : 0;
     k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, pl->c, pl->W, bstride, pl->digits, pl->counts);
     {
         const uint32_t tiles = (pl->nb + SCAN_TILE - 1) / SCAN_TILE;      // <= 1024 (nb <= 2^22)
-        uint32_t* tile_sum = pl->shist + 2 * SIZE_KEYS;
+        uint32_t* tile_sum = pl->shist + 2 * SIZE_KEYS + HEAVY_LOCKS;
         k_scan_partial<<<dim3(tiles, pl->Wb), 256, 0, st>>>(pl->counts, pl->nb, tiles, tile_sum);
         k_scan_tiles<<<pl->Wb, 1024, 0, st>>>(tile_sum, tiles);
         k_scan_final<<<dim3(tiles, pl->Wb), 256, 0, st>>>(pl->counts, pl->nb, tiles, tile_sum, pl->cursor);
@@ -538,13 +610,23 @@ static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases,
     k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), pl->W), TB, 0, st>>>(pl->digits, n, bstride, sstride, ioff, point0, pl->cursor, pl->sorted);
     unsigned hb = (unsigned)((pl->slots + 1023) / 1024);
     if (hb > 592) hb = 592;
-    uint32_t* sstart = pl->shist + SIZE_KEYS;
+    uint32_t* sstart = pl->shist + SIZE_KEYS + HEAVY_LOCKS;
     k_size_hist<<<hb, 256, 0, st>>>(pl->counts, pl->slots, pl->shist);
     k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(pl->shist, sstart);
     k_size_scatter<<<(unsigned)((pl->slots + 255) / 256), 256, 0, st>>>(pl->counts, pl->slots, sstart, pl->order);
     if (first) phase_mark(ctx, 1);
     k_accumulate<F><<<(unsigned)((pl->slots + 127) / 128), 128, 0, st>>>(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order,
                                                                        sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
+    {
+        size_t max_heavy = (n * (size_t)pl->W) / (SIZE_KEYS - 1);
+        if (max_heavy > pl->slots) max_heavy = pl->slots;
+        if (max_heavy > 0) {
+            unsigned hg = (unsigned)(max_heavy < 74 ? max_heavy : 74);
+            k_accumulate_heavy<F><<<dim3(hg, HEAVY_PARTS), 128, 0, st>>>(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order, pl->shist,
+                                                                       pl->shist + SIZE_KEYS, sstride, pl->nb, pl->buckets);
+            ctx->launches += 1;
+        }
+    }
     if (first) phase_mark(ctx, 2);
     ctx->launches += 9;
     pl->chunks_done += 1;
