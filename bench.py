@@ -402,7 +402,7 @@ def run_ours(args):
     secondary = {}
     if rank == 0 and not args.no_secondary:
         pp_l = 2
-        for lg in (16, 20):
+        for lg in (16, 20, 24):
             m = 1 << lg
             mbyl = m // pp_l
             dom = z.Radix2EvaluationDomain.new(m)
@@ -425,6 +425,15 @@ def run_ours(args):
                     fn()
             t1 = timed(f1, 10, collective=False) / 10
             tk = timed(fk, 10, collective=False) / 10
+            if lg > 20:                      # top of the north_star range: device-resident figures only
+                secondary[f"d_fft_m2^{lg}"] = {
+                    "fft1_ms": round(t1, 4), "king_ms": round(tk, 4),
+                    "d_fft_elems_per_s": round(m / ((t1 + tk) * 1e-3), 1),
+                    "king_hbm_gbs": round((256 + 32) * m / (tk * 1e-3) / 1e9, 1),
+                    "fft1_hbm_gbs": round(64 * mbyl / (t1 * 1e-3) / 1e9, 1),
+                }
+                del px, shares, rnd, outp
+                continue
             # e2e of the king call with host buffers (the reference-facing entry point)
             hs = [np.ascontiguousarray(shares.cpu().numpy().view(np.uint64).reshape(8, mbyl, 4)[p]) for p in range(8)]
             hr = rnd.cpu().numpy().view(np.uint64)
@@ -467,6 +476,29 @@ def run_ours(args):
         tg1 = timed(fg1, 5, collective=False) / 5
         secondary["msm_g1_2^20"] = {"ms": round(tg1, 3), "Mpts_per_s": round(n1 / (tg1 * 1e-3) / 1e6, 2)}
         del a2, s2, b2, a1
+        # top of the north_star range: 2^24 points on one GPU (generic path and registered bases)
+        n24 = 1 << 24
+        a24, s24 = rand_fr_dev(n24), rand_fr_dev(n24)
+        b24 = torch.empty((n24, 64), dtype=torch.uint8, device=dev)
+        capi.check(lib.zkg_fixed_base_dev(ctx, 1, C.c_void_p(s24.data_ptr()), n24, C.c_void_p(b24.data_ptr())))
+        del s24
+        h24 = C.c_uint64(0)
+        capi.check(lib.zkg_bases_register_dev(ctx, 1, C.c_void_p(b24.data_ptr()), n24, C.byref(h24)))
+        o24 = torch.zeros((2, 12), dtype=torch.int64, device=dev)
+
+        def fg24():
+            capi.check(lib.zkg_msm_bn254_g1_dev(ctx, C.c_void_p(b24.data_ptr()), C.c_void_p(a24.data_ptr()), n24, C.c_void_p(o24[0].data_ptr())))
+
+        def fr24():
+            capi.check(lib.zkg_msm_bn254_registered_dev(ctx, h24.value, C.c_void_p(a24.data_ptr()), n24, C.c_void_p(o24[1].data_ptr()), 0))
+        fg24(); fr24()
+        tg24 = timed(fg24, 3, collective=False) / 3
+        tr24 = timed(fr24, 3, collective=False) / 3
+        secondary["msm_g1_2^24"] = {"generic_ms": round(tg24, 3), "generic_Mpts_per_s": round(n24 / (tg24 * 1e-3) / 1e6, 2),
+                                    "registered_ms": round(tr24, 3), "registered_Mpts_per_s": round(n24 / (tr24 * 1e-3) / 1e6, 2),
+                                    "paths_agree": bool((o24[0] == o24[1]).all())}
+        capi.check(lib.zkg_bases_release(h24.value))
+        del a24, b24
 
     # ---- secondary: ONE king pipeline (m = 2^20) sharded over all ranks: stage 1 -> reduce-scatter -> stage 2 ----
     if world > 1 and not args.no_secondary:

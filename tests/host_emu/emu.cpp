@@ -79,7 +79,7 @@ static void emu_msm(const uint64_t* bases_packed, const uint64_t* scalars_mont, 
                     if (k != lo) xyzz_add(acc, run);
                     if (!Cin.empty()) xyzz_add(cs, Cin[(size_t)w * n_in + k]);
                 }
-                for (int d = 0; d < log2_M; ++d) xyzz_dbl(acc);
+                xyzz_dbl_k(acc, log2_M);
                 xyzz_add(cs, acc);
                 Rout[(size_t)w * n_out + u] = run;
                 Cout[(size_t)w * n_out + u] = cs;
@@ -91,7 +91,7 @@ static void emu_msm(const uint64_t* bases_packed, const uint64_t* scalars_mont, 
     }
     XYZZ<F> acc = XYZZ<F>::inf();
     for (int w = W - 1; w >= 0; --w) {
-        for (int d = 0; d < c; ++d) xyzz_dbl(acc);
+        xyzz_dbl_k(acc, c);
         XYZZ<F> s = Rin[w];
         xyzz_add(s, Cin[w]);
         xyzz_add(acc, s);

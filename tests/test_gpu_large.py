@@ -51,7 +51,7 @@ def _closed_form(o, a_img, s_img, g2=False):
     return ol.o_g1_msm(aff, ol.fr_np([1]))
 
 
-@pytest.mark.parametrize("log2n", [14, 18, 20, 22])
+@pytest.mark.parametrize("log2n", [14, 18, 20, 22, 24])
 def test_msm_g1_closed_form(env, log2n):
     z, capi, torch, ctx = env
     o = ol.oracle()
@@ -147,7 +147,7 @@ def test_msm_partials_combine_like_one_msm(env):
     assert bool((comb == full).all())
 
 
-@pytest.mark.parametrize("log2m", [16, 20])
+@pytest.mark.parametrize("log2m", [16, 20, 22])
 def test_d_fft_round_reconstructs_plain_fft(env, log2m):
     """dfft/tests.rs:78-139 at BASELINE sizes: client fft1 on 8 GPUs' worth of shares + king pipeline,
     then unpack == Radix2EvaluationDomain::fft of the clear vector (computed by the device plain FFT,
@@ -171,7 +171,7 @@ def test_d_fft_round_reconstructs_plain_fft(env, log2m):
     assert (got == expect).all()
 
 
-@pytest.mark.parametrize("group,log2n", [(1, 10), (1, 15), (1, 19), (1, 22), (2, 13)])
+@pytest.mark.parametrize("group,log2n", [(1, 10), (1, 15), (1, 19), (1, 22), (1, 24), (2, 13)])
 def test_msm_registered_dev_closed_form(env, group, log2n):
     """Prepared bases (window-shifted table, merged buckets, no Horner) give the same group element."""
     z, capi, torch, ctx = env

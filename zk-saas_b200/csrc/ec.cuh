@@ -125,6 +125,34 @@ ZKG_NI void xyzz_dbl(XYZZ<F>& a) {
     a.zzz = f_mul(w, a.zzz);
 }
 
+// a = 2^k * a through Jacobian coordinates (dbl-2009-l, a = 0: 2M + 5S per doubling against 6M + 4S
+// for XYZZ).  Used by the serial Horner tail of the MSM, whose c*(W-1) dependent doublings are pure
+// latency.  XYZZ -> Jacobian without inversion: scale by lambda = zz, i.e. (zz^2 X, zz^3 Y, zzz).
+template <class F>
+ZKG_NI void xyzz_dbl_k(XYZZ<F>& a, int k) {
+    if (a.is_inf() || k <= 0) return;
+    F t = f_sqr(a.zz);
+    F X = f_mul(a.x, t);
+    F Y = f_mul(a.y, f_mul(t, a.zz));
+    F Z = a.zzz;
+    for (int i = 0; i < k; ++i) {
+        F A = f_sqr(X);
+        F B = f_sqr(Y);
+        F C = f_sqr(B);
+        F D = f_dbl(f_sub(f_sub(f_sqr(f_add(X, B)), A), C));
+        F E = f_add(f_dbl(A), A);
+        F X3 = f_sub(f_sub(f_sqr(E), D), D);
+        F C8 = f_dbl(f_dbl(f_dbl(C)));
+        Z = f_dbl(f_mul(Y, Z));
+        Y = f_sub(f_mul(E, f_sub(D, X3)), C8);
+        X = X3;
+    }
+    a.x = X;
+    a.y = Y;
+    a.zz = f_sqr(Z);
+    a.zzz = f_mul(a.zz, Z);
+}
+
 // acc += (neg ? -p : p), p affine      (madd-2008-s: 8M + 2S)
 template <class F>
 ZKG_D void xyzz_madd(XYZZ<F>& acc, const Affine<F>& p_in, bool neg) {

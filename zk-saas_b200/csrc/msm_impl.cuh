@@ -357,7 +357,7 @@ k_reduce_lvl(const XYZZ<F>* __restrict__ R_in, const XYZZ<F>* __restrict__ Cs_in
             xyzz_add(cs, cc);
         }
     }
-    for (int d = 0; d < log2_M; ++d) xyzz_dbl(acc);
+    xyzz_dbl_k(acc, log2_M);
     xyzz_add(cs, acc);
     store_vec(R_out + t, run);
     store_vec(Cs_out + t, cs);
@@ -413,7 +413,7 @@ k_bits_final(const XYZZ<F>* __restrict__ nodes, const XYZZ<F>* __restrict__ R0, 
         const XYZZ<F>* nd = nodes + (size_t)w * (B + 2);
         if ((int)lane < B) {
             x = load_vec_rw(nd + 2 + lane);
-            for (uint32_t d = 0; d < lane + 3; ++d) xyzz_dbl(x);          // 8 * 2^j
+            xyzz_dbl_k(x, (int)lane + 3);                                  // 8 * 2^j
         } else if ((int)lane == B) {
             x = load_vec_rw(nd);                           // total
             xyzz_add(x, load_vec_rw(nd + 1));              // + sumA
@@ -436,7 +436,7 @@ __global__ void k_final(const XYZZ<F>* __restrict__ R, const XYZZ<F>* __restrict
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     XYZZ<F> acc = XYZZ<F>::inf();
     for (int w = W - 1; w >= 0; --w) {
-        for (int d = 0; d < c; ++d) xyzz_dbl(acc);
+        xyzz_dbl_k(acc, c);
         XYZZ<F> s = load_vec_rw(R + w);
         XYZZ<F> cs = load_vec_rw(Cs + w);
         xyzz_add(s, cs);
@@ -702,7 +702,7 @@ k_prepare_bases(const Affine<F>* __restrict__ bases, size_t n, int c, int W, Aff
     store_vec(table + i, p);
     XYZZ<F> acc = XYZZ<F>::from_affine(p);
     for (int w = 1; w < W; ++w) {
-        for (int d = 0; d < c; ++d) xyzz_dbl(acc);
+        xyzz_dbl_k(acc, c);
         store_vec(table + (size_t)w * n + i, xyzz_to_affine(acc));
     }
 }
