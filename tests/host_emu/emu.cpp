@@ -29,6 +29,9 @@ static void st(uint64_t* p, const F& a) { memcpy(p, a.v, 32); }
     extern "C" void emu_##NAME##_inv(const uint64_t* a, uint64_t* o, size_t n) {                   \
         for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_inv(ld<F>(a + 4 * i)));                    \
     }                                                                                              \
+    extern "C" void emu_##NAME##_inv_fermat(const uint64_t* a, uint64_t* o, size_t n) {            \
+        for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_inv_fermat(ld<F>(a + 4 * i)));             \
+    }                                                                                              \
     extern "C" void emu_##NAME##_from_mont(const uint64_t* a, uint64_t* o, size_t n) {             \
         for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_from_mont(ld<F>(a + 4 * i)));              \
     }                                                                                              \

@@ -58,9 +58,17 @@ def test_montgomery_limb_schedule(emu, fld, p):
     fn = getattr(emu, f"emu_{fld}_neg"); fn.argtypes = [u64p, u64p, C.c_size_t]
     fn(_p(A), _p(O), len(a))
     assert unraw(O) == [(-x) % p for x in a]
+    # binary-Euclid inversion (production) and the Fermat ladder, on random values and the edge set
+    inv_in = a[:3000] + edge + [3, 4, p - 3, (p + 1) // 2, 1 << 255 & (p - 1), pow(1 << 256, 1, p), pow(1 << 256, 2, p)]
+    IA = raw(inv_in)
+    IO = np.zeros_like(IA)
+    expect = [pow(x * rinv % p, -1, p) * (1 << 256) % p if x else 0 for x in inv_in]
     fn = getattr(emu, f"emu_{fld}_inv"); fn.argtypes = [u64p, u64p, C.c_size_t]
-    fn(_p(A[:40]), _p(O), 40)
-    assert unraw(O[:40]) == [pow(x * rinv % p, -1, p) * (1 << 256) % p if x else 0 for x in a[:40]]
+    fn(_p(IA), _p(IO), len(inv_in))
+    assert unraw(IO) == expect
+    fn = getattr(emu, f"emu_{fld}_inv_fermat"); fn.argtypes = [u64p, u64p, C.c_size_t]
+    fn(_p(IA[:60]), _p(IO), 60)
+    assert unraw(IO[:60]) == expect[:60]
     fn = getattr(emu, f"emu_{fld}_from_mont"); fn.argtypes = [u64p, u64p, C.c_size_t]
     fn(_p(A), _p(O), len(a))
     assert unraw(O) == [x * rinv % p for x in a]

@@ -394,14 +394,97 @@ ZKG_NI Fp<P> fp_pow(const Fp<P>& a, const uint32_t* e, int nlimbs) {
     return acc;
 }
 
-// Fermat inversion a^(p-2); 0 -> 0
+// Fermat inversion a^(p-2); 0 -> 0.  Uniform control flow (384 multiplications): kept as the
+// cross-check of fp_inv below in the host-emulation tests.
 template <class P>
-ZKG_NI Fp<P> fp_inv(const Fp<P>& a) {
+ZKG_NI Fp<P> fp_inv_fermat(const Fp<P>& a) {
     uint32_t e[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) e[i] = P::mod(i);
     e[0] -= 2;   // both moduli are odd and > 2: low limb does not borrow
     return fp_pow(a, e, 8);
+}
+
+// 256-bit helpers for the binary inversion (plain C++: add/sub/shift chains, no multiplier)
+ZKG_HD bool big_lt(const uint32_t* a, const uint32_t* b) {
+    bool lt = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) lt = a[i] < b[i] || (a[i] == b[i] && lt);     // most significant limb decides last
+    return lt;
+}
+ZKG_HD void big_sub(uint32_t* a, const uint32_t* b) {          // a -= b   (a >= b)
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint64_t d = (uint64_t)a[i] - b[i] - br;
+        a[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+}
+template <class P>
+ZKG_HD void big_add_p(uint32_t* a) {                            // a += p   (a < p < 2^254: no carry out)
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        c += (uint64_t)a[i] + P::mod(i);
+        a[i] = (uint32_t)c;
+        c >>= 32;
+    }
+}
+ZKG_HD void big_shr1(uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[7] >>= 1;
+}
+ZKG_HD bool big_is_one(const uint32_t* a) {
+    uint32_t o = a[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) o |= a[i];
+    return o == 0;
+}
+
+// Inversion by the binary extended Euclidean algorithm (HAC 14.61 with both cofactors kept mod p):
+// ~2*254 halving/subtraction steps of 8-limb add/shift chains, about a tenth of the instructions of
+// the Fermat ladder.  The callers are the normalisations at the end of an MSM (one lone thread,
+// where the ladder's 384 dependent multiplications cost ~0.15 ms) and the per-point to-affine of the
+// table/CRS preparation kernels.  Data-dependent control flow; the result is the unique canonical
+// inverse either way.  0 -> 0.
+template <class P>
+ZKG_NI Fp<P> fp_inv(const Fp<P>& a) {
+    if (a.is_zero()) return a;
+    uint32_t u[8], v[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { u[i] = a.v[i]; v[i] = P::mod(i); b[i] = 0; c[i] = 0; }
+    b[0] = 1;
+    // invariants:  b * A == u,  c * A == v   (mod p),  A = the integer held in a (= a_std * R)
+    while (!big_is_one(u) && !big_is_one(v)) {
+        while ((u[0] & 1u) == 0) {
+            big_shr1(u);
+            if (b[0] & 1u) big_add_p<P>(b);
+            big_shr1(b);
+        }
+        while ((v[0] & 1u) == 0) {
+            big_shr1(v);
+            if (c[0] & 1u) big_add_p<P>(c);
+            big_shr1(c);
+        }
+        if (!big_lt(u, v)) {
+            big_sub(u, v);
+            if (big_lt(b, c)) big_add_p<P>(b);
+            big_sub(b, c);
+        } else {
+            big_sub(v, u);
+            if (big_lt(c, b)) big_add_p<P>(c);
+            big_sub(c, b);
+        }
+    }
+    Fp<P> r;
+    const bool from_b = big_is_one(u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = from_b ? b[i] : c[i];
+    // r = A^-1 = a_std^-1 * R^-1 ;  two Montgomery products by R^2 give a_std^-1 * R
+    r = fp_mul(r, Fp<P>::r2());
+    return fp_mul(r, Fp<P>::r2());
 }
 
 typedef Fp<FrParams> Fr;
