@@ -520,6 +520,24 @@ def run_ours(args):
                                                "elems_per_s": round(mbyl_ * l_ / (tks * 1e-3), 1),
                                                "collective": "one NCCL reduce_scatter (sum) of the pack-order buffer"}
 
+    # ---- secondary: ONE fft1 lane (m = 2^24, l = 2) sharded over all ranks: inner NTT -> all-to-all -> outer DFT ----
+    if world > 1 and not args.no_secondary and (world & (world - 1)) == 0:
+        from zksaas_b200 import sharding
+        l_, mbyl_ = 2, 1 << 23
+        gen_ = z.Radix2EvaluationDomain.new(mbyl_ * l_).group_gen()
+        blk_ = rand_fr_dev(mbyl_ // world)
+
+        def ffs():
+            sharding.fft1_sharded_cuda(ctx, lib, torch, dist, blk_, mbyl_, l_, gen_, rank, world)
+        for _ in range(3):
+            ffs()
+        tfs = timed(ffs, 10) / 10
+        if rank == 0:
+            secondary["fft1_sharded_m2^24"] = {"ms": round(tfs, 4), "ranks": world,
+                                               "share_elems_per_s": round(mbyl_ / (tfs * 1e-3), 1),
+                                               "collective": "one NCCL all_to_all_single of the twiddled inner transforms (m/l x 32 B in total)"}
+        del blk_
+
     # ---- secondary: the SURVEY 8(f) rows built so far, through their host-pointer entry points (PCIe included) ----
     if rank == 0 and not args.no_secondary:
         from zksaas_b200 import api as zapi

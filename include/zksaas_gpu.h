@@ -127,6 +127,18 @@ int32_t zkg_fft1_bn254(int32_t device, uint64_t *px, size_t mbyl, uint32_t l, co
 int32_t zkg_fft1_bn254_dev(zkg_ctx *ctx, uint64_t *d_px, size_t mbyl, uint32_t l, const uint64_t gen[4],
                            const uint64_t *pre_scale, const uint64_t *d_in_mask);
 
+/* fft1 of ONE lane sharded over the GPUs of a box (north_star "four-step with an NCCL
+ * all-to-all transpose").  Rank g holds the contiguous block px[g*block_len, (g+1)*block_len) of the
+ * lane (block_len = (m/l)/n_ranks).  shard_local transforms the block in place into the send
+ * buffer (inner size-block_len transform + twiddles; chunk d of it goes to rank d); after the
+ * all-to-all, shard_outer turns the n_ranks x cols receive buffer (chunk g from rank g) into
+ * out[k1*cols + j] = X[(first_col + j) + block_len*k1], where fft1_in_place(px)[k] = X[(k+1) mod (m/l)]
+ * (dfft/mod.rs:178-208) and first_col = rank * cols.  All sizes are powers of two. */
+int32_t zkg_fft1_shard_local_bn254_dev(zkg_ctx *ctx, uint64_t *d_block, size_t block_len, uint32_t l, uint32_t n_ranks,
+                                       uint32_t rank, const uint64_t gen[4], const uint64_t *pre_scale);
+int32_t zkg_fft1_shard_outer_bn254_dev(zkg_ctx *ctx, const uint64_t *d_recv, size_t cols, size_t block_len, uint32_t l,
+                                       uint32_t n_ranks, const uint64_t gen[4], uint64_t *d_out);
+
 /* ---- king closure of fft2_with_rearrange: dist-primitives/src/dfft/mod.rs:264-304 -----------
  * shares_by_party[r]: the mbyl-element vector received from party parties[r] (r < n_recv; n_recv
  * == n = 4l uses unpack2, fewer uses the Lagrange matrix of pss.rs:170-207).  rand: mbyl x t

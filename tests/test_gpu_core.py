@@ -217,6 +217,40 @@ def test_msm_skewed_registered_and_g2(z):
 # ------------------------------------------------------------------------------------------------
 # fft1 (K4)
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("l,mbyl,world", [(2, 16, 1), (2, 16, 2), (2, 64, 4), (2, 1 << 13, 8), (4, 1 << 16, 4), (2, 1 << 20, 8)])
+def test_fft1_sharded_steps_on_one_gpu(z, l, mbyl, world):
+    """The two CUDA steps of the rank-sharded fft1 with the all-to-all emulated by slicing on one device:
+    together they must reproduce the single-GPU fft1 (which the next test pins against the literal loops)."""
+    import torch
+    from zksaas_b200 import capi, sharding
+    lib = z.lib()
+    ctx = capi.ctx_p()
+    capi.check(lib.zkg_ctx_create(0, C.c_void_p(1), C.byref(ctx)))
+    try:
+        g = torch.Generator(device="cuda"); g.manual_seed(mbyl + world)
+        px = torch.randint(-2**63, 2**63 - 1, (mbyl, 4), dtype=torch.int64, device="cuda", generator=g)
+        px[:, 3] &= (1 << 61) - 1
+        gen = z.Radix2EvaluationDomain.new(mbyl * l).group_gen()
+        full = px.clone()
+        capi.check(lib.zkg_fft1_bn254_dev(ctx, C.c_void_p(full.data_ptr()), mbyl, l, gen.ctypes.data, None, None))
+        n2, cnt = mbyl // world, mbyl // world // world
+        sends = []
+        for r in range(world):
+            blk = px[r * n2:(r + 1) * n2].clone()
+            capi.check(lib.zkg_fft1_shard_local_bn254_dev(ctx, C.c_void_p(blk.data_ptr()), n2, l, world, r, gen.ctypes.data, None))
+            sends.append(blk)
+        for r in range(world):
+            recv = torch.cat([sends[src][r * cnt:(r + 1) * cnt] for src in range(world)]).contiguous()
+            out = torch.empty((world * cnt, 4), dtype=torch.int64, device="cuda")
+            capi.check(lib.zkg_fft1_shard_outer_bn254_dev(ctx, C.c_void_p(recv.data_ptr()), cnt, n2, l, world, gen.ctypes.data,
+                                                          C.c_void_p(out.data_ptr())))
+            capi.check(lib.zkg_ctx_sync(ctx))
+            idx = torch.from_numpy(sharding.fft1_sharded_index(mbyl, world, r)).cuda()
+            assert bool((out == full[idx]).all()), r
+    finally:
+        lib.zkg_ctx_destroy(ctx)
+
+
 @pytest.mark.parametrize("l,mbyl", [(2, 1), (2, 2), (2, 4), (2, 8), (2, 512), (2, 1024), (2, 2048), (2, 1 << 15),
                                     (4, 16), (4, 1 << 11), (8, 1 << 12), (2, 1 << 17)])
 def test_fft1_vs_literal_oracle(z, o, l, mbyl):

@@ -1,6 +1,7 @@
 """GPU, >= 2 devices: the NCCL paths (one process per GPU) against the single-GPU results.
   - one king pipeline sharded by share columns: stage 1 -> ONE sum reduce-scatter -> stage 2
   - one large MSM sharded by point range: partial sums -> all-gather -> combine
+  - one fft1 lane sharded by contiguous blocks: inner transforms -> ONE all-to-all -> outer DFT
 Skipped on single-GPU boxes; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
 import ctypes as C
 import os
@@ -58,6 +59,19 @@ def _worker(rank, world, port, q):
         got = sharding.king_fft2_sharded_cuda(ctx, lib, torch, dist, loc, mbyl, l, gen, g, rearr, rloc, rank, world)
         torch.cuda.synchronize()
         ok[f"king_l{l}_r{rearr}"] = bool((got == full[:, lo:hi, :]).all())
+
+    # ---- sharded fft1 (four-step, ONE all-to-all) vs the single-GPU fft1 ----
+    for l, mbyl in ((2, 1 << 14), (2, 1 << 21), (8, 1 << 6)):
+        gen = z.Radix2EvaluationDomain.new(mbyl * l).group_gen()
+        px = rand_fr(mbyl, 31 + l)
+        full = px.clone()
+        capi.check(lib.zkg_fft1_bn254_dev(ctx, C.c_void_p(full.data_ptr()), mbyl, l, gen.ctypes.data, None, None))
+        n2 = mbyl // world
+        blk = px[rank * n2:(rank + 1) * n2].clone()
+        got = sharding.fft1_sharded_cuda(ctx, lib, torch, dist, blk, mbyl, l, gen, rank, world)
+        idx = torch.from_numpy(sharding.fft1_sharded_index(mbyl, world, rank)).to(dev)
+        torch.cuda.synchronize()
+        ok[f"fft1_l{l}_n{mbyl}"] = bool((got.reshape(-1, 4) == full[idx]).all())
 
     # ---- sharded MSM vs the single-GPU MSM ----
     npts = 1 << 14

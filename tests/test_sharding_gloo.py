@@ -164,3 +164,74 @@ def test_sharded_king_world2_gloo(l, m, rearrange):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded fft1: host logic (block ownership, ONE all-to-all, output index map) with big-integer
+# stand-ins for the two CUDA steps, against the literal fft1_in_place of the oracle
+# ------------------------------------------------------------------------------------------------
+def _fft1_worker(rank, world, port, l, m, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+    import oracle_lib as ol
+    from oracle_lib import pyref
+    from zksaas_b200.sharding import fft1_sharded, fft1_sharded_index
+    R = pyref.R_MOD
+    rng = random.Random(5)                                   # same lane on every rank
+    pp = pyref.PackedSharingParams(l)
+    gen = pyref.Radix2Domain(m).group_gen
+    mbyl = m // l
+    px = [rng.randrange(R) for _ in range(mbyl)]
+    expect = pyref.fft1_in_place(px, pp, gen)
+    n2, cnt = mbyl // world, mbyl // world // world
+    w = pow(gen, l, R)
+    lg_w, lg_n2 = world.bit_length() - 1, n2.bit_length() - 1
+
+    def brev(x, bits):
+        return int(format(x, f"0{bits}b")[::-1], 2) if bits else 0
+
+    def local():
+        blk = px[rank * n2:(rank + 1) * n2]
+        i1 = brev(rank, lg_w)
+        wi = pow(w, world, R)
+        inner = [sum(blk[brev(i2, lg_n2)] * pow(wi, i2 * k2, R) for i2 in range(n2)) % R for k2 in range(n2)]
+        return torch.from_numpy(ol.fr_np([v * pow(w, i1 * k2, R) % R for k2, v in enumerate(inner)]).view(np.int64).copy())
+
+    def all_to_all(send):
+        # gloo stand-in with all_to_all_single semantics: chunk g of the result is chunk `rank` of rank g's buffer
+        bufs = [torch.zeros_like(send) for _ in range(world)]
+        dist.all_gather(bufs, send)
+        return torch.cat([b[rank * cnt:(rank + 1) * cnt] for b in bufs])
+
+    def outer(recv):
+        v = ol.np_fr(recv.numpy().view(np.uint64))
+        wg = pow(w, n2, R)
+        return [[sum(v[g * cnt + j] * pow(wg, brev(g, lg_w) * k1, R) for g in range(world)) % R for j in range(cnt)]
+                for k1 in range(world)]
+
+    got = fft1_sharded(mbyl, world, rank, local, all_to_all, outer)
+    idx = fft1_sharded_index(mbyl, world, rank)
+    flat = [x for row in got for x in row]
+    ok = len(idx) == len(flat) and all(expect[int(k)] == x for k, x in zip(idx, flat))
+    q.put((rank, ok, sorted(int(k) for k in idx)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("l,m", [(2, 32), (4, 64), (2, 8)])
+def test_sharded_fft1_world2_gloo(l, m):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + l + m
+    procs = [ctx.Process(target=_fft1_worker, args=(r, 2, port, l, m, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted((r, ok) for r, ok, _ in res) == [(0, True), (1, True)]
+    # the two ranks' index sets partition the lane
+    assert sorted(res[0][2] + res[1][2]) == list(range(m // l))

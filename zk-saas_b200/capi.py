@@ -47,6 +47,10 @@ SIGNATURES = {
     "zkg_fixed_base_dev": (C.c_int32, [ctx_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkg_fft1_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zkg_fft1_bn254_dev": (C.c_int32, [ctx_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zkg_fft1_shard_local_bn254_dev": (C.c_int32, [ctx_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                    C.c_void_p, C.c_void_p]),
+    "zkg_fft1_shard_outer_bn254_dev": (C.c_int32, [ctx_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32,
+                                                    C.c_void_p, C.c_void_p]),
     "zkg_king_fft2_bn254": (C.c_int32, [C.c_int32, pp_u64, u32p, C.c_uint32, C.c_size_t, C.c_uint32, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, pp_u64]),
     "zkg_king_fft2_bn254_dev": (C.c_int32, [ctx_p, C.c_void_p, u32p, C.c_uint32, C.c_size_t, C.c_uint32, C.c_void_p,

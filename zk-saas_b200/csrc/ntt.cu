@@ -345,6 +345,27 @@ __global__ void k_scale_powers(Fr* __restrict__ v, size_t n, FrArg s_, int has_g
     if (has_g && i) f = fp_mul(f, pow_lookup(g_tw, i));
     st_fr(v + i, fp_mul(ld_fr_rw(v + i), f));
 }
+// Outer step of the rank-sharded fft1 (four-step with G = number of ranks as the short dimension):
+// recv[g][j] = w^(i1*k2) * Inner_i1[k2] from rank g (i1 = bitrev_G(g), k2 = first_col + j);
+// out[k1][j] = X[k2 + N2*k1] = sum_i1 wG^(i1*k1) * recv[bitrev_G(i1)][j],  wG = w^(N2) of order G.
+__global__ void __launch_bounds__(256)
+k_fft1_shard_outer(const Fr* __restrict__ recv, size_t cnt, int G, int logG, const Fr* __restrict__ wG_pows,
+                   Fr* __restrict__ out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cnt) return;
+    for (int k1 = 0; k1 < G; ++k1) {
+        Fr acc = Fr::zero();
+        for (int g = 0; g < G; ++g) {
+            int i1 = (int)bitrev32((uint32_t)g, logG);
+            int e = (i1 * k1) & (G - 1);
+            Fr v = ld_fr(recv + (size_t)g * cnt + j);
+            if (e) v = fp_mul(v, ld_fr(wG_pows + e));
+            acc = fp_add(acc, v);
+        }
+        st_fr(out + (size_t)k1 * cnt + j, acc);
+    }
+}
+
 // out[bitrev(i)] = in[i]
 __global__ void k_bitrev(const Fr* __restrict__ in, Fr* __restrict__ out, int log_n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -721,6 +742,43 @@ static int32_t fft1_dev(zkg_ctx* ctx, Fr* d_px, size_t mbyl, uint32_t l, const H
     return ntt_bitrev_in(ctx, d_px, d_px, tmp, mbyl, wN, 1, pre_scale, d_mask);
 }
 
+// ---- fft1 of one lane sharded over G ranks (four-step with one all-to-all) ----------
+// X = DFT_N(bitrev_N(px)) with root w = gen^l (fft1(px)[k] = X[(k+1) mod N]).  Write the transform
+// index as i = i1 + G*i2: bitrev_N(i) = bitrev_G(i1)*N2 + bitrev_N2(i2), so rank g's contiguous block
+// IS the bit-reversed input of the inner size-N2 transform number i1 = bitrev_G(g):
+//   local :  Inner_i1 = DFT_N2(bitrev(block), root w^G);  T_i1[k2] = w^(i1*k2) * Inner_i1[k2]
+//   all-to-all over k2 ranges (rank d receives columns [d*N2/G, (d+1)*N2/G) of every T_i1)
+//   outer :  X[k2 + N2*k1] = sum_i1 (w^N2)^(i1*k1) * T_i1[k2]          (G-point DFT per column)
+static int32_t fft1_shard_local(zkg_ctx* ctx, Fr* d_block, size_t N2, uint32_t l, uint32_t G, uint32_t rank,
+                                const HFr& gen, const HFr* pre_scale) {
+    ZKG_REQUIRE(is_pow2(G) && is_pow2(N2) && is_pow2(l) && rank < G, "fft1_shard: block %zu, l %u, ranks %u must be powers of two", N2, l, G);
+    ZKG_REQUIRE(ilog2(N2 * G * l) <= 28, "fft1_shard: m exceeds the 2-adicity of Fr");
+    ZKG_TRY(ctx->ws.reserve(N2 * sizeof(Fr)));
+    HFr w = host::h_pow(gen, l);
+    ZKG_TRY(ntt_bitrev_in(ctx, d_block, d_block, (Fr*)ctx->ws.p, N2, host::h_pow(w, G), 0, pre_scale, nullptr));
+    uint32_t i1 = 0;
+    for (int b = 0, lg = ilog2(G); b < lg; ++b) i1 |= ((rank >> b) & 1u) << (lg - 1 - b);
+    if (i1 && N2 > 1) {
+        PowTable tw;
+        ZKG_TRY(build_pow_table(ctx, host::h_pow(w, i1), N2, &tw));
+        k_distribute_powers<<<(unsigned)((N2 + 255) / 256), 256, 0, ctx->stream>>>(d_block, N2, tw);
+        ctx->launches += 1;
+        ZKG_CUDA(cudaGetLastError());
+    }
+    return ZKG_OK;
+}
+
+static int32_t fft1_shard_outer(zkg_ctx* ctx, const Fr* d_recv, size_t cnt, size_t N2, uint32_t l, uint32_t G,
+                                const HFr& gen, Fr* d_out) {
+    ZKG_REQUIRE(is_pow2(G) && G <= 64 && is_pow2(N2) && is_pow2(l), "fft1_shard: ranks %u / block %zu / l %u must be powers of two", G, N2, l);
+    const Fr* wG;
+    ZKG_TRY(cached_pow_seq(ctx, "shardG", host::h_pow(gen, (uint64_t)l * N2), G, &wG));
+    k_fft1_shard_outer<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(d_recv, cnt, (int)G, ilog2(G), wG, d_out);
+    ctx->launches += 1;
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
 }  // namespace zkg
 
 using namespace zkg;
@@ -735,6 +793,24 @@ int32_t zkg_fft1_bn254_dev(zkg_ctx* ctx, uint64_t* d_px, size_t mbyl, uint32_t l
     HFr hs;
     if (pre_scale) hs = host::h_load(pre_scale);
     return fft1_dev(ctx, (Fr*)d_px, mbyl, l, host::h_load(gen), pre_scale ? &hs : nullptr, (const Fr*)d_in_mask);
+}
+
+int32_t zkg_fft1_shard_local_bn254_dev(zkg_ctx* ctx, uint64_t* d_block, size_t block_len, uint32_t l, uint32_t n_ranks,
+                                       uint32_t rank, const uint64_t gen[4], const uint64_t* pre_scale) {
+    ZKG_REQUIRE(ctx && gen && (block_len == 0 || d_block), "fft1_shard_local: NULL argument");
+    if (block_len == 0) return ZKG_OK;
+    DeviceGuard dg(ctx->device);
+    HFr hs;
+    if (pre_scale) hs = host::h_load(pre_scale);
+    return fft1_shard_local(ctx, (Fr*)d_block, block_len, l, n_ranks, rank, host::h_load(gen), pre_scale ? &hs : nullptr);
+}
+
+int32_t zkg_fft1_shard_outer_bn254_dev(zkg_ctx* ctx, const uint64_t* d_recv, size_t cols, size_t block_len, uint32_t l,
+                                       uint32_t n_ranks, const uint64_t gen[4], uint64_t* d_out) {
+    ZKG_REQUIRE(ctx && gen && (cols == 0 || (d_recv && d_out)), "fft1_shard_outer: NULL argument");
+    if (cols == 0) return ZKG_OK;
+    DeviceGuard dg(ctx->device);
+    return fft1_shard_outer(ctx, (const Fr*)d_recv, cols, block_len, l, n_ranks, host::h_load(gen), (Fr*)d_out);
 }
 
 int32_t zkg_fft1_bn254(int32_t device, uint64_t* px, size_t mbyl, uint32_t l, const uint64_t gen[4],

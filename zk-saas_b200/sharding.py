@@ -91,3 +91,59 @@ def king_fft2_sharded_cuda(ctx, lib, torch, dist, shares_local, mbyl, l, gen, g,
         return out
 
     return king_sharded(mbyl, world, rank, stage1, reduce_scatter, stage2)
+
+
+# ------------------------------------------------------------------------------------------------
+# fft1 of ONE lane sharded over the ranks: four-step with a single all-to-all
+# ------------------------------------------------------------------------------------------------
+def fft1_sharded(mbyl: int, world: int, rank: int, local_fn, all_to_all_fn, outer_fn):
+    """fft1_in_place (dist-primitives/src/dfft/mod.rs:178-208) of a lane of mbyl = m/l elements whose
+    contiguous block [rank*N2, (rank+1)*N2), N2 = mbyl/world, lives on this rank.
+
+    local_fn()            -> send buffer of N2 elements (inner transform + twiddles), ordered by column:
+                             chunk d (N2/world elements) is what rank d needs;
+    all_to_all_fn(send)   -> receive buffer, chunk g from rank g (world x N2/world elements);
+    outer_fn(recv)        -> (world x N2/world) array: row k1, column j  =  X[(rank*N2/world + j) + N2*k1],
+                             with fft1(px)[k] = X[(k+1) mod mbyl]  (see fft1_sharded_index).
+    """
+    if world & (world - 1) or mbyl % (world * world):
+        raise ValueError("fft1_sharded: ranks must be a power of two and m/l divisible by ranks^2")
+    return outer_fn(all_to_all_fn(local_fn()))
+
+
+def fft1_sharded_index(mbyl: int, world: int, rank: int) -> np.ndarray:
+    """fft1 output positions held by `rank` after fft1_sharded, in the (k1, j) row-major order of its result."""
+    n2 = mbyl // world
+    cnt = n2 // world
+    k1 = np.arange(world, dtype=np.int64)[:, None]
+    j = np.arange(cnt, dtype=np.int64)[None, :]
+    return ((rank * cnt + j + n2 * k1 - 1) % mbyl).reshape(-1)
+
+
+def fft1_sharded_cuda(ctx, lib, torch, dist, block, mbyl, l, gen, rank, world, pre_scale=None):
+    """CUDA + NCCL instantiation.  block: (N2, 4) int64 device tensor (this rank's slice of the lane;
+    overwritten).  Returns a (world, N2/world, 4) device tensor laid out as fft1_sharded describes."""
+    import ctypes as C
+    from .capi import check
+    n2 = mbyl // world
+    cnt = n2 // world
+
+    def local():
+        check(lib.zkg_fft1_shard_local_bn254_dev(ctx, C.c_void_p(block.data_ptr()), n2, l, world, rank, gen.ctypes.data,
+                                                 pre_scale.ctypes.data if pre_scale is not None else None))
+        return block
+
+    def all_to_all(send):
+        if world == 1:
+            return send
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        return recv
+
+    def outer(recv):
+        out = torch.empty((world, cnt, 4), dtype=torch.int64, device=block.device)
+        check(lib.zkg_fft1_shard_outer_bn254_dev(ctx, C.c_void_p(recv.data_ptr()), cnt, n2, l, world, gen.ctypes.data,
+                                                 C.c_void_p(out.data_ptr())))
+        return out
+
+    return fft1_sharded(mbyl, world, rank, local, all_to_all, outer)
