@@ -181,6 +181,15 @@ int32_t zkg_dpp_king_bn254(int32_t device, const uint64_t *const *shares_by_part
                            uint32_t n_recv, size_t cols, uint32_t l, const uint64_t *rand,
                            uint64_t *const *out_by_party);
 
+/* Offline packing of whole vectors into the n parties' share vectors.
+ * layout 0: chunks of l consecutive values, last chunk zero-padded -- pack_from_witness
+ *           (groth16/examples/sha256.rs:131-156) and pack_vec + transpose (utils/pack.rs:8-20);
+ * layout 1: bit-reverse x (len a power of two), column i packs (x'[i], x'[i + len/l], ...) -- the
+ *           `pack` closure of QAP::pss (groth16/src/qap.rs:99-112).
+ * rand: ceil(len/l) * t host-RNG points; out_by_party[p] (p < 4l): ceil(len/l) shares of party p. */
+int32_t zkg_pss_pack_vec_bn254_fr(int32_t device, uint32_t l, int32_t layout, const uint64_t *x, size_t len,
+                                  const uint64_t *rand, uint64_t *const *out_by_party);
+
 /* ---- PackedSharingParams transforms over Fr, batched over `cols` columns -------------------
  * secret-sharing/src/pss.rs: pack :90-122 (rand != NULL), det_pack :69-87 (rand == NULL),
  * unpack :125-138, unpack2 :141-166.  Column-major contiguous: column c reads secrets[c*l..],

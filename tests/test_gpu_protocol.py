@@ -372,3 +372,74 @@ def test_crs_det_pack_group_vs_oracle(z, l, g2):
             e = exp[i * words:(i + 1) * words]
             want = api._xyz_to_affine_images([e], g2)[0]
             assert (got[i][j] == want).all(), (j, i)
+
+
+# ------------------------------------------------------------------------------------------------
+# offline packing (pack_from_witness, QAP::pss) and MsmMask::sample
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("l,length", [(2, 13), (2, 1), (4, 1000), (8, 64), (2, 0)])
+def test_pack_from_witness_vs_oracle(z, l, length):
+    """groth16/examples/sha256.rs:131-156: ragged last chunk is zero-padded."""
+    import random
+    rng = random.Random(l * 1000 + length)
+    pp = z.PackedSharingParams.new(l)
+    ref = pyref.PackedSharingParams(l)
+    w = [rng.randrange(R) for _ in range(length)]
+    cols = (length + l - 1) // l
+    rand = [[rng.randrange(R) for _ in range(ref.t)] for _ in range(cols)]
+    got = z.pack_from_witness(pp, ol.fr_np(w).reshape(-1, 4), ol.fr_np([x for r in rand for x in r]).reshape(-1, 4))
+    padded = w + [0] * (cols * l - length)
+    exp = pyref.transpose([ref.pack(padded[c * l:(c + 1) * l], rand[c]) for c in range(cols)]) if cols else [[] for _ in range(ref.n)]
+    assert len(got) == ref.n
+    for p in range(ref.n):
+        assert ol.np_fr(got[p]) == exp[p]
+
+
+@pytest.mark.parametrize("l,m", [(2, 32), (4, 256), (2, 1 << 12)])
+def test_qap_pss_pack_vs_oracle(z, l, m):
+    """groth16/src/qap.rs:99-133 with a = (0..m) as in ext_wit.rs:415-421."""
+    import random
+    rng = random.Random(m + l)
+    pp = z.PackedSharingParams.new(l)
+    ref = pyref.PackedSharingParams(l)
+    a = [(i * i + 7) % R for i in range(m)]
+    mbyl = m // l
+    rand = [[rng.randrange(R) for _ in range(ref.t)] for _ in range(mbyl)]
+    got = z.qap_pss_pack(ol.fr_np(a), pp, ol.fr_np([x for r in rand for x in r]))
+    xr = pyref.fft_in_place_rearrange(list(a))
+    exp = pyref.transpose([ref.pack([xr[i + j * mbyl] for j in range(l)], rand[i]) for i in range(mbyl)])
+    for p in range(ref.n):
+        assert ol.np_fr(got[p]) == exp[p]
+    # and through the three-vector wrapper
+    tri = z.qap_pss(ol.fr_np(a), ol.fr_np(a), ol.fr_np(a), pp, *([ol.fr_np([x for r in rand for x in r])] * 3))
+    assert all((tri[p][k] == got[p]).all() for p in range(ref.n) for k in range(3))
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_msm_mask_sample_vs_oracle(z, g2):
+    """dmsm/mod.rs:21-48: in-mask shares pack gen*x_i, out-mask shares pack -(sum) repeated l times;
+    unpacking the shares (over the group) returns the mask values, which cancel."""
+    import random
+    rng = random.Random(99 + g2)
+    l = 2
+    pp = z.PackedSharingParams.new(l)
+    ref = pyref.PackedSharingParams(l)
+    curve, gen = (pyref.G2, pyref.G2_GEN_PT) if g2 else (pyref.G1, pyref.G1_GEN)
+    to_xyz = ol.g2_point_to_xyz if g2 else ol.g1_point_to_xyz
+    to_pt = ol.g2_xyz_to_point if g2 else ol.g1_xyz_to_point
+    xs = [rng.randrange(R) for _ in range(l)]
+    rin = [curve.mul(gen, rng.randrange(R)) for _ in range(ref.t)]
+    rout = [curve.mul(gen, rng.randrange(R)) for _ in range(ref.t)]
+    masks = z.MsmMask.sample(pp, ol.fr_np(xs), [to_xyz(p) for p in rin], [to_xyz(p) for p in rout], g2=g2)
+    assert len(masks) == ref.n
+    ops = pyref.group_ops(curve)
+    values = [curve.mul(gen, x) for x in xs]
+    total = None
+    for v in values:
+        total = curve.add(total, v)
+    out_value = curve.neg(total)
+    exp_in = ref.pack(values, rin, ops)
+    exp_out = ref.pack([out_value] * l, rout, ops)
+    assert [to_pt(mk.in_mask) for mk in masks] == exp_in
+    assert [to_pt(mk.out_mask) for mk in masks] == exp_out
+    assert z.group_generator(g2).tolist() == to_xyz(gen).tolist()

@@ -183,6 +183,34 @@ def pack_vec(secrets, pp: PackedSharingParams, rand_points):
     return [shares[c * pp.n:(c + 1) * pp.n] for c in range(shares.shape[0] // pp.n)]
 
 
+def _pack_vec_by_party(x, pp: "PackedSharingParams", rand_points, layout):
+    x, rand_points = _fr_vec(x, "x"), _fr_vec(rand_points, "rand_points")
+    cols = (x.shape[0] + pp.l - 1) // pp.l
+    assert rand_points.shape[0] == cols * pp.t, "rand_points length mismatch"
+    outs = [np.zeros((cols, 4), dtype=np.uint64) for _ in range(pp.n)]
+    arr = (C.POINTER(C.c_uint64) * pp.n)(*[o.ctypes.data_as(C.POINTER(C.c_uint64)) for o in outs])
+    check(lib().zkg_pss_pack_vec_bn254_fr(pp.device, pp.l, layout, _ptr(x), x.shape[0], _ptr(rand_points), arr))
+    return outs
+
+
+def pack_from_witness(pp: "PackedSharingParams", full_assignment, rand_points):
+    """groth16/examples/sha256.rs:131-156: l-chunks of the assignment (the last one zero-padded) packed,
+    returned as the n parties' share vectors.  rand_points: ceil(len/l)*t host-RNG values."""
+    return _pack_vec_by_party(full_assignment, pp, rand_points, 0)
+
+
+def qap_pss_pack(x, pp: "PackedSharingParams", rand_points):
+    """The `pack` closure of QAP::pss (groth16/src/qap.rs:99-112): fft_in_place_rearrange(x), column i packs
+    x[i], x[i + m/l], ...; returned party-major (what the closing loop at :118-133 builds)."""
+    return _pack_vec_by_party(x, pp, rand_points, 1)
+
+
+def qap_pss(a, b, c, pp: "PackedSharingParams", rand_a, rand_b, rand_c):
+    """QAP::pss (groth16/src/qap.rs:92-134): per party the (a, b, c) share vectors of a PackedQAPShare."""
+    pa, pb, pc = qap_pss_pack(a, pp, rand_a), qap_pss_pack(b, pp, rand_b), qap_pss_pack(c, pp, rand_c)
+    return [(pa[i], pb[i], pc[i]) for i in range(pp.n)]
+
+
 # ---- G::msm -------------------------------------------------------------------------------------
 class MsmLengthMismatch(ValueError):
     """`G::msm` returns Err(min(bases.len(), scalars.len())) on a length mismatch."""
@@ -397,6 +425,65 @@ class MsmMask:
         z[:4] = _one_img_fq()
         z[w:w + 4] = _one_img_fq()
         return MsmMask(z.copy(), z.copy())
+
+    @staticmethod
+    def sample(pp: "PackedSharingParams", mask_scalars, rand_in_points, rand_out_points, g2=False):
+        """dmsm/mod.rs:21-48.  mask_scalars: the l field draws x_i (mask value i = gen * x_i);
+        rand_in_points / rand_out_points: the t random GROUP elements each `pp.pack` call draws
+        (normalised Jacobian images; the host RNG stays with the caller).  Returns the n parties' masks.
+        Every group operation is a tiny device MSM; pack over group elements applies the rows of the
+        pack matrix (pss.rs:90-122 with T = G)."""
+        mask_scalars = _fr_vec(mask_scalars, "mask_scalars")
+        assert mask_scalars.shape[0] == pp.l and len(rand_in_points) == pp.t and len(rand_out_points) == pp.t
+        dev = pp.device
+        gen = group_generator(g2)
+        values = [group_lincomb([gen], [x], g2, dev) for x in mask_scalars]                 # gen * x_i
+        minus_one = fr_sub(np.zeros((1, 4), dtype=np.uint64), _one_img().reshape(1, 4), dev)[0]
+        out_value = group_lincomb(values, [minus_one] * pp.l, g2, dev)                     # -(sum of the mask values)
+        M = _pack_matrix(pp)                                                               # (n, l + t) Fr images
+        ins = [group_lincomb(values + list(rand_in_points), list(M[i]), g2, dev) for i in range(pp.n)]
+        outs = [group_lincomb([out_value] * pp.l + list(rand_out_points), list(M[i]), g2, dev) for i in range(pp.n)]
+        return [MsmMask(i, o) for i, o in zip(ins, outs)]
+
+
+_G2_GEN = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+            11559732032986387107991004021392285783925812861821192530917403151452391805634),
+           (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+            4082367875863433681332203403145435568316851327593401208105741076214120093531))
+
+
+def _fq_image(v: int) -> np.ndarray:
+    m = (v % Q_MOD) * (1 << 256) % Q_MOD
+    return np.array([(m >> (64 * i)) & _MASK64 for i in range(4)], dtype=np.uint64)
+
+
+def group_generator(g2=False) -> np.ndarray:
+    """G::generator() as a normalised Jacobian image: G1 (1, 2); G2 the standard BN254 generator
+    (fixtures/verification_key.json:24-37, vk_gamma_2)."""
+    if not g2:
+        return np.concatenate([_fq_image(1), _fq_image(2), _fq_image(1)])
+    (x0, x1), (y0, y1) = _G2_GEN
+    return np.concatenate([_fq_image(x0), _fq_image(x1), _fq_image(y0), _fq_image(y1), _fq_image(1), _fq_image(0)])
+
+
+_PACK_M = {}
+
+
+def _pack_matrix(pp: "PackedSharingParams") -> np.ndarray:
+    """(n, l + t, 4) Montgomery images of the pack matrix, read off the device by packing unit vectors."""
+    if pp.l not in _PACK_M:
+        k = pp.l + pp.t
+        one = _one_img()
+        sec = np.zeros((k * pp.l, 4), dtype=np.uint64)
+        rnd = np.zeros((k * pp.t, 4), dtype=np.uint64)
+        for c in range(k):
+            if c < pp.l:
+                sec[c * pp.l + c] = one
+            else:
+                rnd[c * pp.t + (c - pp.l)] = one
+        shares = pp.pack(sec, rnd).reshape(k, pp.n, 4)          # column c = image of unit vector c
+        _PACK_M[pp.l] = np.ascontiguousarray(shares.transpose(1, 0, 2))
+    return _PACK_M[pp.l]
 
 
 def _one_img_fq():

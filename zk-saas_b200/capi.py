@@ -61,6 +61,7 @@ SIGNATURES = {
     "zkg_deg_red_king_bn254": (C.c_int32, [C.c_int32, pp_u64, u32p, C.c_uint32, C.c_size_t, C.c_uint32, C.c_void_p, pp_u64]),
     "zkg_deg_red_king_bn254_dev": (C.c_int32, [ctx_p, C.c_void_p, u32p, C.c_uint32, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]),
     "zkg_dpp_king_bn254": (C.c_int32, [C.c_int32, pp_u64, u32p, C.c_uint32, C.c_size_t, C.c_uint32, C.c_void_p, pp_u64]),
+    "zkg_pss_pack_vec_bn254_fr": (C.c_int32, [C.c_int32, C.c_uint32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, pp_u64]),
     "zkg_pss_pack_bn254_fr": (C.c_int32, [C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zkg_pss_unpack_bn254_fr": (C.c_int32, [C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zkg_pss_unpack2_bn254_fr": (C.c_int32, [C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -978,6 +978,59 @@ static int32_t pss_host(int device, uint32_t l, int which, const uint64_t* in, c
     return ZKG_OK;
 }
 
+// Vector packing into per-party share vectors (party-major output), the two layouts the reference uses:
+//   layout 0  chunks of l consecutive values, the last one zero-padded   (pack_from_witness, sha256.rs:131-156;
+//             pack_vec + transpose, utils/pack.rs:8-20)
+//   layout 1  bit-reverse x, then column i packs (x'[i], x'[i + m/l], ...)   (QAP::pss, groth16/src/qap.rs:99-112)
+static int32_t pack_vec_host(int device, uint32_t l, int layout, const uint64_t* x, size_t len, const uint64_t* rand,
+                             uint64_t* const* out_by_party) {
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    ZKG_REQUIRE(layout == 0 || layout == 1, "pack_vec: layout %d unknown", layout);
+    ZKG_REQUIRE(out_by_party && (len == 0 || (x && rand)), "pack_vec: NULL argument");
+    if (len == 0) return ZKG_OK;
+    ZKG_REQUIRE(layout == 0 || (is_pow2(len) && len >= l), "pack_vec: bit-reversed layout needs a power-of-two length >= l, got %zu", len);
+    const size_t n = pm->n, t = pm->t;
+    const size_t cols = (len + l - 1) / l, padded = cols * l;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    const size_t x_b = align_up(padded * 32, 256), rand_b = align_up(cols * t * 32, 256), out_b = align_up(cols * n * 32, 256);
+    ZKG_TRY(ctx->io.reserve(2 * x_b + rand_b + out_b));
+    Fr* d_x = (Fr*)ctx->io.p;
+    Fr* d_rev = (Fr*)((uint8_t*)ctx->io.p + x_b);
+    Fr* d_rand = (Fr*)((uint8_t*)ctx->io.p + 2 * x_b);
+    Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + 2 * x_b + rand_b);
+    ZKG_CUDA(cudaMemcpyAsync(d_x, x, len * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (padded > len) ZKG_CUDA(cudaMemsetAsync(d_x + len, 0, (padded - len) * 32, ctx->stream));
+    ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, cols * t * 32, cudaMemcpyHostToDevice, ctx->stream));
+    HostKeep keep;
+    const Fr* dM;
+    const int K = (int)(l + t) <= 4 ? 4 : (int)(l + t) <= 8 ? 8 : 16;
+    keep.v.push_back(pad_rows(pm->pack, (int)n, (int)(l + t), K));
+    ZKG_TRY(upload(ctx, keep.v.back(), &dM));
+    if (layout == 1) {
+        k_bitrev<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(d_x, d_rev, ilog2(len));
+        ctx->launches += 1;
+        ZKG_CUDA(cudaGetLastError());
+        ZKG_TRY(launch_pack(ctx, dM, K, (int)n, (int)l, (int)t, d_rev, 1, cols, d_rand, t, 1, d_out, 1, cols, cols));
+    } else {
+        ZKG_TRY(launch_pack(ctx, dM, K, (int)n, (int)l, (int)t, d_x, l, 1, d_rand, t, 1, d_out, 1, cols, cols));
+    }
+    for (size_t p = 0; p < n; ++p) {
+        ZKG_REQUIRE(out_by_party[p], "NULL output vector for party %zu", p);
+        ZKG_CUDA(cudaMemcpyAsync(out_by_party[p], d_out + p * cols, cols * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+int32_t zkg_pss_pack_vec_bn254_fr(int32_t device, uint32_t l, int32_t layout, const uint64_t* x, size_t len,
+                                  const uint64_t* rand, uint64_t* const* out_by_party) {
+    return pack_vec_host(device, l, layout, x, len, rand, out_by_party);
+}
+
 int32_t zkg_pss_pack_bn254_fr(int32_t device, uint32_t l, const uint64_t* secrets, const uint64_t* rand, uint64_t* shares, size_t cols) {
     return pss_host(device, l, 0, secrets, rand, shares, cols);
 }
