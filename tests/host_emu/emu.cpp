@@ -29,6 +29,15 @@ static void st(uint64_t* p, const F& a) { memcpy(p, a.v, 32); }
     extern "C" void emu_##NAME##_inv(const uint64_t* a, uint64_t* o, size_t n) {                   \
         for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_inv(ld<F>(a + 4 * i)));                    \
     }                                                                                              \
+    extern "C" void emu_##NAME##_dot(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n, int k) { \
+        for (size_t i = 0; i < n; ++i) {                                                           \
+            F x[4], y[4];                                                                          \
+            for (int j = 0; j < k; ++j) { x[j] = ld<F>(a + 4 * (i * k + j)); y[j] = ld<F>(b + 4 * (i * k + j)); } \
+            F r = k == 1 ? fp_dot<F::Params, 1>(x, y) : k == 2 ? fp_dot<F::Params, 2>(x, y)        \
+                : k == 3 ? fp_dot<F::Params, 3>(x, y) : fp_dot<F::Params, 4>(x, y);                \
+            st(o + 4 * i, r);                                                                      \
+        }                                                                                          \
+    }                                                                                              \
     extern "C" void emu_##NAME##_inv_fermat(const uint64_t* a, uint64_t* o, size_t n) {            \
         for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_inv_fermat(ld<F>(a + 4 * i)));             \
     }                                                                                              \

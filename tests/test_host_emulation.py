@@ -74,6 +74,35 @@ def test_montgomery_limb_schedule(emu, fld, p):
     assert unraw(O) == [x * rinv % p for x in a]
 
 
+@pytest.mark.parametrize("fld,p", [("fr", R), ("fq", Q)])
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_montgomery_dot_product(emu, fld, p, k):
+    """fp_dot<K>: one reduction row per K accumulated product rows; must equal the sum of K products,
+    including the extremes that drive the running value to its (K+1) p bound."""
+    rng = random.Random(31 * k + len(fld))
+    rinv = pow(1 << 256, -1, p)
+    n = 4000
+    a = [rng.randrange(p) for _ in range(n * k)]
+    b = [rng.randrange(p) for _ in range(n * k)]
+    ext = [p - 1, p - 2, (1 << 253) + 12345, (1 << 32) - 1, 0, 1, p >> 1, (p - 1) ^ ((1 << 192) - 1)]
+    for x in ext:
+        for y in ext:
+            a += [x] * k
+            b += [y] * k
+    # mixed extremes inside one dot product
+    for _ in range(200):
+        a += [rng.choice(ext) for _ in range(k)]
+        b += [rng.choice(ext) for _ in range(k)]
+    cnt = len(a) // k
+    A, B = raw(a), raw(b)
+    O = np.zeros((cnt, 4), dtype=np.uint64)
+    fn = getattr(emu, f"emu_{fld}_dot")
+    fn.argtypes = [u64p, u64p, u64p, C.c_size_t, C.c_int]
+    fn(_p(A), _p(B), _p(O), cnt, k)
+    exp = [sum(a[i * k + j] * b[i * k + j] for j in range(k)) * rinv % p for i in range(cnt)]
+    assert unraw(O) == exp
+
+
 def test_fq2_vs_oracle(emu):
     o = ol.oracle()
     rng = np.random.default_rng(5)

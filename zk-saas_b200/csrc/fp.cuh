@@ -110,6 +110,7 @@ struct FqParams {
 
 template <class P>
 struct Fp {
+    typedef P Params;
     static constexpr int N = 8;
     uint32_t v[N];
 
@@ -267,6 +268,65 @@ ZKG_D Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+
+// --------------------------------------------------------------------------------------------
+// Montgomery dot product  r = (a_0*b_0 + ... + a_(K-1)*b_(K-1)) * 2^-256 mod p,  K <= 4.
+// Same two-accumulator CIOS rows as fp_mul, but every row adds the K partial products before the
+// ONE reduction row, so a K-term inner product costs 8*(8K + 8) wide MADs instead of 8*16K: 0.75x
+// at K = 2, 0.625x at K = 4 -- the constant-matrix maps of the PSS transforms (unpack2, pack,
+// Lagrange) are made of these.  Bounds: with a_k < p and the running value t < (K+1) p, a row
+// leaves t' = (t + sum_k a_k b_k[i] + m p) / 2^32 < (K+1) p again, and (K+1) p < 2^256 for K <= 4
+// (5 p = 0.947 * 2^256 for both BN254 moduli), so no column beyond the ninth is ever needed: chains
+// into the out-of-phase accumulator cannot carry out, chains into the in-phase one hand their
+// carry to its top limb exactly as in fp_mul.  K final conditional subtractions give the
+// canonical residue -- bit-identical to summing K fp_mul results.
+// --------------------------------------------------------------------------------------------
+template <class P, int K, bool FIRST>
+ZKG_D void mont_row_dot(uint32_t* x, uint32_t* y, const Fp<P>* a, const Fp<P>* b, int i) {
+    uint32_t pm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pm[j] = P::mod(j);
+    if (FIRST) {
+        mul_row(y, a[0].v + 1, b[0].v[i]);
+        mul_row(x, a[0].v, b[0].v[i]);
+    } else {
+        x[0] = add_cc(x[0], y[1]);
+        madc_row_rshift(y, a[0].v + 1, b[0].v[i]);
+        cmad_row(x, a[0].v, b[0].v[i]);
+        y[7] = addc(y[7], 0);
+    }
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        cmad_row(y, a[k].v + 1, b[k].v[i]);      // cannot carry out (value bound above)
+        cmad_row(x, a[k].v, b[k].v[i]);
+        y[7] = addc(y[7], 0);
+    }
+    uint32_t m = mul_lo(x[0], P::INV);
+    cmad_row(y, pm + 1, m);
+    cmad_row(x, pm, m);
+    y[7] = addc(y[7], 0);
+}
+
+template <class P, int K>
+ZKG_D Fp<P> fp_dot(const Fp<P>* a, const Fp<P>* b) {
+    static_assert(K >= 1 && K <= 4, "fp_dot: (K+1) p must stay below 2^256");
+    uint32_t even[8], odd[8];
+    mont_row_dot<P, K, true>(even, odd, a, b, 0);
+    mont_row_dot<P, K, false>(odd, even, a, b, 1);
+#pragma unroll
+    for (int i = 2; i < 8; i += 2) {
+        mont_row_dot<P, K, false>(even, odd, a, b, i);
+        mont_row_dot<P, K, false>(odd, even, a, b, i + 1);
+    }
+    Fp<P> r;
+    r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) r.v[i] = addc_cc(even[i], odd[i + 1]);
+    r.v[7] = addc(even[7], 0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) final_sub<P>(r.v);
+    return r;
+}
 
 // --------------------------------------------------------------------------------------------
 // EXPERIMENT (not used by the kernels; kept with its measurement because it decides the design):

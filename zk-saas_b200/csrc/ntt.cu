@@ -101,7 +101,7 @@ struct NttPass {
     FrArg scale;                     // pre-multiplier applied on the first pass (d_ifft's size_inv)
 };
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr* __restrict__ tw_small, PowTable tw,
            const Fr* __restrict__ mask) {
     extern __shared__ uint32_t smem[];
@@ -197,7 +197,20 @@ k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restri
     } else {
 #pragma unroll
         for (int j = 0; j < LL; ++j) v[j] = Fr::zero();
-        for (uint32_t r = 0; r < n_recv; ++r) {
+        // rows of U times the share column, four terms per Montgomery reduction (fp_dot)
+        uint32_t r = 0;
+        for (; r + 4 <= n_recv; r += 4) {
+            Fr x[4], u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = ld_fr(shares + (size_t)(r + q) * cols + kk);
+#pragma unroll
+            for (int j = 0; j < LL; ++j) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) u[q] = ld_fr(U + (size_t)j * n_recv + r + q);
+                v[j] = fp_add(v[j], fp_dot<FrParams, 4>(u, x));
+            }
+        }
+        for (; r < n_recv; ++r) {
             Fr x = ld_fr(shares + (size_t)r * cols + kk);
 #pragma unroll
             for (int j = 0; j < LL; ++j) v[j] = fp_add(v[j], fp_mul(ld_fr(U + (size_t)j * n_recv + r), x));
@@ -270,12 +283,17 @@ k_map_in_regs(const Fr* __restrict__ M, int rows, int k1, const Fr* __restrict__
         else if (j < k1 + k2) x[j] = ld_fr(in2 + c * in2_cs + (size_t)(j - k1) * in2_rs);
         else x[j] = Fr::zero();
     }
-    const int kk = k1 + k2;             // row length of M is k1 + (declared k2 columns)
+    // M is zero-padded to K columns and x to K entries, so whole groups of four can always be used
     for (int i = 0; i < rows; ++i) {
         Fr acc = Fr::zero();
 #pragma unroll
-        for (int j = 0; j < K; ++j)
-            if (j < kk) acc = fp_add(acc, fp_mul(ld_fr(M + (size_t)i * K + j), x[j]));
+        for (int j = 0; j < K; j += 4) {
+            Fr mrow[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mrow[q] = ld_fr(M + (size_t)i * K + j + q);
+            Fr d = fp_dot<FrParams, 4>(mrow, x + j);
+            acc = j == 0 ? d : fp_add(acc, d);
+        }
         st_fr(out + c * out_cs + (size_t)i * out_rs, acc);
     }
 }
@@ -322,7 +340,19 @@ k_map_acc_regs(const Fr* __restrict__ M, int k, const Fr* __restrict__ in, size_
     Fr acc[ROWS];
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) acc[i] = Fr::zero();
-    for (int j = 0; j < k; ++j) {
+    int j = 0;
+    for (; j + 4 <= k; j += 4) {
+        Fr x[4], mrow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = ld_fr(in + c * in_cs + (size_t)(j + q) * in_rs);
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mrow[q] = ld_fr(M + (size_t)i * k + j + q);
+            acc[i] = fp_add(acc[i], fp_dot<FrParams, 4>(mrow, x));
+        }
+    }
+    for (; j < k; ++j) {
         Fr x = ld_fr(in + c * in_cs + (size_t)j * in_rs);
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) acc[i] = fp_add(acc[i], fp_mul(ld_fr(M + (size_t)i * k + j), x));
