@@ -211,13 +211,13 @@ static int32_t fr_wire(int32_t device, int dir, const void* in, void* out, size_
     uint8_t* d = (uint8_t*)ctx->io.p;
     int* d_err = (int*)(d + 2 * bytes);
     ZKG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
-    ZKG_CUDA(cudaMemcpyAsync(d, in, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d, in, n * 32, ctx->stream));
     k_fr_wire<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dir, (const Fr*)d, (Fr*)(d + bytes), n, d_err);
     ctx->launches += 1;
     ZKG_CUDA(cudaGetLastError());
     int h_err = 0;
-    ZKG_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    ZKG_CUDA(cudaMemcpyAsync(out, d + bytes, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(&h_err, d_err, sizeof(int), ctx->stream));
+    ZKG_TRY(copy_d2h(out, d + bytes, n * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     ZKG_REQUIRE(h_err == 0, "fr_from_wire: an element is not below the field modulus");
     return ZKG_OK;
@@ -248,13 +248,13 @@ int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t* 
     size_t bytes = align_up(n * 32, 256);
     ZKG_TRY(ctx->io.reserve(3 * bytes));
     uint8_t* d = (uint8_t*)ctx->io.p;
-    ZKG_CUDA(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKG_CUDA(cudaMemcpyAsync(d + bytes, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d, a, n * 32, ctx->stream));
+    ZKG_TRY(copy_h2d(d + bytes, b, n * 32, ctx->stream));
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (field == 0) k_field_op<Fr><<<blocks, 256, 0, ctx->stream>>>(op, (const Fr*)d, (const Fr*)(d + bytes), (Fr*)(d + 2 * bytes), n);
     else k_field_op<Fq><<<blocks, 256, 0, ctx->stream>>>(op, (const Fq*)d, (const Fq*)(d + bytes), (Fq*)(d + 2 * bytes), n);
     ZKG_CUDA(cudaGetLastError());
-    ZKG_CUDA(cudaMemcpyAsync(out, d + 2 * bytes, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(out, d + 2 * bytes, n * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }

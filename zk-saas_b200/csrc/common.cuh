@@ -84,6 +84,10 @@ struct PooledCtx {
 };
 
 int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events);
+// host <-> device copies that take pageable host memory at PCIe speed (staging.cu); stream semantics of
+// cudaMemcpyAsync on pageable memory
+int32_t copy_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);
+int32_t copy_d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st);
 // Look up (or reserve) a persistent device block for the parameter identified by `key`.
 // *fresh = true means the caller must fill it (on ctx->stream) before use.
 int32_t ctx_cache_get(zkg_ctx* ctx, const void* key, size_t key_bytes, size_t bytes, void** out, bool* fresh);

@@ -141,7 +141,7 @@ int32_t zkg_bases_register(int32_t device, int32_t group, const void* bases, siz
     uint8_t* d_ark = (uint8_t*)ctx->io.p;
     uint8_t* d_pk = d_ark + ark_bytes;
     if (n) {
-        ZKG_CUDA(cudaMemcpyAsync(d_ark, bases, n * base_stride, cudaMemcpyHostToDevice, ctx->stream));
+        ZKG_TRY(copy_h2d(d_ark, bases, n * base_stride, ctx->stream));
         ZKG_TRY(group == 1 ? pack_bases_g1(ctx, d_ark, base_stride, n, d_pk) : pack_bases_g2(ctx, d_ark, base_stride, n, d_pk));
     }
     ZKG_TRY(base_set_create(ctx, group, d_pk, n, handle));
@@ -199,7 +199,7 @@ int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t* scalars, size_
     void* d_out = (uint8_t*)ctx->io.p + sc_bytes;
     ZKG_TRY(bs.group == 1 ? msm_run_prepared_host_g1(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out)
                           : msm_run_prepared_host_g2(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out));
-    ZKG_CUDA(cudaMemcpyAsync(out_xyz, d_out, bs.group == 1 ? 96 : 192, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(out_xyz, d_out, bs.group == 1 ? 96 : 192, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }

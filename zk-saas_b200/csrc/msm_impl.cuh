@@ -745,12 +745,8 @@ static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int
         for (int j = 0; j < K; ++j) {
             size_t lo = (size_t)j * chunk, hi = lo + chunk < n ? lo + chunk : n;
             if (lo >= hi) break;
-            ZKG_CUDA(cudaMemcpyAsync(d_sc + lo * 32, (const uint8_t*)h_scalars + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ZKG_TRY(copy_h2d(d_sc + lo * 32, (const uint8_t*)h_scalars + lo * 32, (hi - lo) * 32, ctx->copy_stream));
             ZKG_CUDA(cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
-        }
-        for (int j = 0; j < K; ++j) {
-            size_t lo = (size_t)j * chunk, hi = lo + chunk < n ? lo + chunk : n;
-            if (lo >= hi) break;
             ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[j], 0));
             ZKG_TRY(msm_chunk<F>(ctx, &pl, d_table, (const Fr*)d_sc + lo, hi - lo, lo));
         }
@@ -818,8 +814,8 @@ static int32_t crs_det_pack_host(int device, const void* bases, size_t stride, s
     ZKG_TRY(ctx->io.reserve(ark_b + pk_b + sc_b + o_pk + o_ark));
     uint8_t* d = (uint8_t*)ctx->io.p;
     uint8_t *d_ark = d, *d_pk = d + ark_b, *d_sc = d_pk + pk_b, *d_opk = d_sc + sc_b, *d_oark = d_opk + o_pk;
-    ZKG_CUDA(cudaMemcpyAsync(d_ark, bases, n * stride, cudaMemcpyHostToDevice, ctx->stream));
-    ZKG_CUDA(cudaMemcpyAsync(d_sc, h_scal, (size_t)n_parties * l * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d_ark, bases, n * stride, ctx->stream));
+    ZKG_TRY(copy_h2d(d_sc, h_scal, (size_t)n_parties * l * 32, ctx->stream));
     ZKG_TRY(pack_bases<F>(ctx, d_ark, stride, n, d_pk));
     k_det_pack_group<F><<<(unsigned)((outs + 127) / 128), 128, 0, ctx->stream>>>((const Affine<F>*)d_pk, chunks, l, n_parties,
                                                                               (const uint32_t*)d_sc, (Affine<F>*)d_opk);
@@ -828,8 +824,7 @@ static int32_t crs_det_pack_host(int device, const void* bases, size_t stride, s
     ZKG_CUDA(cudaGetLastError());
     for (int i = 0; i < n_parties; ++i) {
         ZKG_REQUIRE(out_by_party[i], "crs_det_pack: NULL output for party %d", i);
-        ZKG_CUDA(cudaMemcpyAsync(out_by_party[i], d_oark + (size_t)i * chunks * out_stride, chunks * out_stride,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+        ZKG_TRY(copy_d2h(out_by_party[i], d_oark + (size_t)i * chunks * out_stride, chunks * out_stride, ctx->stream));
     }
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
@@ -897,23 +892,22 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
         // order the copy stream after whatever the compute stream last did with these buffers
         ZKG_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
         ZKG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+        // copy chunk j, then launch its compute, then copy chunk j+1 ...: with pinned sources the copies
+        // simply run ahead on the copy stream; with pageable sources the host thread stages chunk j+1
+        // while the device works on chunk j
         for (int j = 0; j < K; ++j) {
             size_t lo = bounds[j], hi = bounds[j + 1];
             if (lo >= hi) continue;
-            ZKG_CUDA(cudaMemcpyAsync(d_sc + lo * 32, (const uint8_t*)scalars + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-            ZKG_CUDA(cudaMemcpyAsync(d_ark + lo * stride, (const uint8_t*)bases + lo * stride, (hi - lo) * stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ZKG_TRY(copy_h2d(d_sc + lo * 32, (const uint8_t*)scalars + lo * 32, (hi - lo) * 32, ctx->copy_stream));
+            ZKG_TRY(copy_h2d(d_ark + lo * stride, (const uint8_t*)bases + lo * stride, (hi - lo) * stride, ctx->copy_stream));
             ZKG_CUDA(cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
-        }
-        for (int j = 0; j < K; ++j) {
-            size_t lo = bounds[j], hi = bounds[j + 1];
-            if (lo >= hi) continue;
             ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[j], 0));
             ZKG_TRY(pack_bases<F>(ctx, d_ark + lo * stride, stride, hi - lo, d_pk + lo * sizeof(Affine<F>)));
             ZKG_TRY(msm_chunk<F>(ctx, &pl, (const Affine<F>*)d_pk + lo, (const Fr*)d_sc + lo, hi - lo));
         }
     }
     ZKG_TRY(msm_finish<F>(ctx, &pl, d_out, 0));
-    ZKG_CUDA(cudaMemcpyAsync(out_xyz, d_out, 3 * sizeof(F), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(out_xyz, d_out, 3 * sizeof(F), ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }

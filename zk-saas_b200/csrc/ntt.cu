@@ -722,7 +722,7 @@ static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* partie
 static int32_t h2d_party_major(zkg_ctx* ctx, const uint64_t* const* by_party, uint32_t np, size_t len, Fr* d) {
     for (uint32_t r = 0; r < np; ++r) {
         ZKG_REQUIRE(by_party[r], "NULL share vector for index %u", r);
-        ZKG_CUDA(cudaMemcpyAsync(d + (size_t)r * len, by_party[r], len * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ZKG_TRY(copy_h2d(d + (size_t)r * len, by_party[r], len * 32, ctx->stream));
     }
     return ZKG_OK;
 }
@@ -746,13 +746,13 @@ static int32_t king_host(int device, const uint64_t* const* shares_by_party, con
     Fr* d_rand = (Fr*)((uint8_t*)ctx->io.p + in_b);
     Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + in_b + rand_b);
     ZKG_TRY(h2d_party_major(ctx, shares_by_party, n_recv, mbyl, d_in));
-    ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, mbyl * pm->t * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d_rand, rand, mbyl * pm->t * 32, ctx->stream));
     HostKeep keep;
     HFr hgen = mode_fft ? host::h_load(gen) : host::h_one(), hg = mode_fft ? host::h_load(g) : host::h_one();
     ZKG_TRY(king_dev(ctx, d_in, parties, n_recv, mbyl, l, &hgen, &hg, rearrange, d_rand, d_out, mode_fft, keep));
     for (uint32_t p = 0; p < pm->n; ++p) {
         ZKG_REQUIRE(out_by_party[p], "NULL output vector for party %u", p);
-        ZKG_CUDA(cudaMemcpyAsync(out_by_party[p], d_out + (size_t)p * mbyl, mbyl * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        ZKG_TRY(copy_d2h(out_by_party[p], d_out + (size_t)p * mbyl, mbyl * 32, ctx->stream));
     }
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
@@ -855,12 +855,12 @@ int32_t zkg_fft1_bn254(int32_t device, uint64_t* px, size_t mbyl, uint32_t l, co
     ZKG_TRY(ctx->io.reserve(2 * bytes));
     Fr* d_px = (Fr*)ctx->io.p;
     Fr* d_mask = (Fr*)((uint8_t*)ctx->io.p + bytes);
-    ZKG_CUDA(cudaMemcpyAsync(d_px, px, mbyl * 32, cudaMemcpyHostToDevice, ctx->stream));
-    if (in_mask) ZKG_CUDA(cudaMemcpyAsync(d_mask, in_mask, mbyl * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d_px, px, mbyl * 32, ctx->stream));
+    if (in_mask) ZKG_TRY(copy_h2d(d_mask, in_mask, mbyl * 32, ctx->stream));
     HFr hs;
     if (pre_scale) hs = host::h_load(pre_scale);
     ZKG_TRY(fft1_dev(ctx, d_px, mbyl, l, host::h_load(gen), pre_scale ? &hs : nullptr, in_mask ? d_mask : nullptr));
-    ZKG_CUDA(cudaMemcpyAsync(px, d_px, mbyl * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(px, d_px, mbyl * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }
@@ -929,7 +929,7 @@ int32_t zkg_dpp_king_bn254(int32_t device, const uint64_t* const* shares_by_part
     Fr* scratch = S + 2 * m;
     Fr* tot = scratch + m;
     ZKG_TRY(h2d_party_major(ctx, shares_by_party, n_recv, 2 * cols, d_in));
-    ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, cols * pm->t * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d_rand, rand, cols * pm->t * 32, ctx->stream));
     ZKG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
     HostKeep keep;
     HFr one = host::h_one();
@@ -944,10 +944,10 @@ int32_t zkg_dpp_king_bn254(int32_t device, const uint64_t* const* shares_by_part
     ZKG_CUDA(cudaGetLastError());
     ZKG_TRY(king_stage2(ctx, S, d_rand, cols, l, d_out, keep));                             // pack_vec, :71
     int h_err = 0;
-    ZKG_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(&h_err, d_err, sizeof(int), ctx->stream));
     for (uint32_t p = 0; p < pm->n; ++p) {
         ZKG_REQUIRE(out_by_party[p], "NULL output vector for party %u", p);
-        ZKG_CUDA(cudaMemcpyAsync(out_by_party[p], d_out + (size_t)p * cols, cols * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        ZKG_TRY(copy_d2h(out_by_party[p], d_out + (size_t)p * cols, cols * 32, ctx->stream));
     }
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     ZKG_REQUIRE(h_err == 0, "dpp_king: a denominator is zero (the reference's inverse().unwrap() would panic)");
@@ -989,8 +989,8 @@ static int32_t pss_host(int device, uint32_t l, int which, const uint64_t* in, c
     Fr* d_in = (Fr*)ctx->io.p;
     Fr* d_rand = (Fr*)((uint8_t*)ctx->io.p + in_b);
     Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + in_b + rand_b);
-    ZKG_CUDA(cudaMemcpyAsync(d_in, in, in_elems * 32, cudaMemcpyHostToDevice, ctx->stream));
-    if (which == 0 && rand) ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, cols * t * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d_in, in, in_elems * 32, ctx->stream));
+    if (which == 0 && rand) ZKG_TRY(copy_h2d(d_rand, rand, cols * t * 32, ctx->stream));
     HostKeep keep;
     const Fr* dM;
     if (which == 0) {
@@ -1003,7 +1003,7 @@ static int32_t pss_host(int device, uint32_t l, int which, const uint64_t* in, c
         ZKG_TRY(upload(ctx, which == 1 ? pm->unpack : pm->unpack2, &dM));
         ZKG_TRY(launch_unpack(ctx, dM, (int)l, (int)n, d_in, n, 1, d_out, l, 1, cols));
     }
-    ZKG_CUDA(cudaMemcpyAsync(out, d_out, out_elems * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(out, d_out, out_elems * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }
@@ -1032,9 +1032,9 @@ static int32_t pack_vec_host(int device, uint32_t l, int layout, const uint64_t*
     Fr* d_rev = (Fr*)((uint8_t*)ctx->io.p + x_b);
     Fr* d_rand = (Fr*)((uint8_t*)ctx->io.p + 2 * x_b);
     Fr* d_out = (Fr*)((uint8_t*)ctx->io.p + 2 * x_b + rand_b);
-    ZKG_CUDA(cudaMemcpyAsync(d_x, x, len * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d_x, x, len * 32, ctx->stream));
     if (padded > len) ZKG_CUDA(cudaMemsetAsync(d_x + len, 0, (padded - len) * 32, ctx->stream));
-    ZKG_CUDA(cudaMemcpyAsync(d_rand, rand, cols * t * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d_rand, rand, cols * t * 32, ctx->stream));
     HostKeep keep;
     const Fr* dM;
     const int K = (int)(l + t) <= 4 ? 4 : (int)(l + t) <= 8 ? 8 : 16;
@@ -1050,7 +1050,7 @@ static int32_t pack_vec_host(int device, uint32_t l, int layout, const uint64_t*
     }
     for (size_t p = 0; p < n; ++p) {
         ZKG_REQUIRE(out_by_party[p], "NULL output vector for party %zu", p);
-        ZKG_CUDA(cudaMemcpyAsync(out_by_party[p], d_out + p * cols, cols * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        ZKG_TRY(copy_d2h(out_by_party[p], d_out + p * cols, cols * 32, ctx->stream));
     }
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
@@ -1084,7 +1084,7 @@ int32_t zkg_fft2_bn254(int32_t device, uint64_t* s1, size_t m, uint32_t l, const
     ZKG_TRY(ctx->io.reserve(2 * m * 32));
     Fr* d_in = (Fr*)ctx->io.p;
     Fr* d_out = d_in + m;
-    ZKG_CUDA(cudaMemcpyAsync(d_in, s1, m * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d_in, s1, m * 32, ctx->stream));
     PowTable gen_tw, none{nullptr, nullptr};
     ZKG_TRY(build_pow_table(ctx, host::h_load(gen), m, &gen_tw));
     size_t mbyl = m / l;
@@ -1094,7 +1094,7 @@ int32_t zkg_fft2_bn254(int32_t device, uint64_t* s1, size_t m, uint32_t l, const
     else if (l == 4) k_king_stage1<4><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, d_out);
     else k_king_stage1<8><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, d_out);
     ZKG_CUDA(cudaGetLastError());
-    ZKG_CUDA(cudaMemcpyAsync(s1, d_out, m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(s1, d_out, m * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }
@@ -1108,12 +1108,12 @@ int32_t zkg_distribute_powers_bn254(int32_t device, uint64_t* v, size_t n, const
     DeviceGuard dg(ctx->device);
     ZKG_TRY(ctx->io.reserve(n * 32));
     Fr* d = (Fr*)ctx->io.p;
-    ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d, v, n * 32, ctx->stream));
     PowTable tw;
     ZKG_TRY(build_pow_table(ctx, host::h_load(g), n, &tw));
     k_distribute_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, n, tw);
     ZKG_CUDA(cudaGetLastError());
-    ZKG_CUDA(cudaMemcpyAsync(v, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(v, d, n * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }
@@ -1128,10 +1128,10 @@ int32_t zkg_bitrev_bn254(int32_t device, uint64_t* v, size_t n) {
     DeviceGuard dg(ctx->device);
     ZKG_TRY(ctx->io.reserve(2 * n * 32));
     Fr* d = (Fr*)ctx->io.p;
-    ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d, v, n * 32, ctx->stream));
     k_bitrev<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, d + n, ilog2(n));
     ZKG_CUDA(cudaGetLastError());
-    ZKG_CUDA(cudaMemcpyAsync(v, d + n, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(v, d + n, n * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }
@@ -1148,7 +1148,7 @@ int32_t zkg_fr_fft_bn254(int32_t device, uint64_t* v, size_t n, const uint64_t* 
     Fr* d = (Fr*)ctx->io.p;
     Fr* d_rev = d + n;
     Fr* d_tmp = d + 2 * n;
-    ZKG_CUDA(cudaMemcpyAsync(d, v, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKG_TRY(copy_h2d(d, v, n * 32, ctx->stream));
     HFr w = host::h_root_of_unity(n), one = host::h_one();
     HFr off = offset ? host::h_load(offset) : one;
     bool coset = !(off == one);
@@ -1170,7 +1170,7 @@ int32_t zkg_fr_fft_bn254(int32_t device, uint64_t* v, size_t n, const uint64_t* 
         k_scale_powers<<<blocks, 256, 0, ctx->stream>>>(d, n, to_arg(n_inv), coset ? 1 : 0, tw);
     }
     ZKG_CUDA(cudaGetLastError());
-    ZKG_CUDA(cudaMemcpyAsync(v, d, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKG_TRY(copy_d2h(v, d, n * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }
