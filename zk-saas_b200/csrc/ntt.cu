@@ -180,7 +180,7 @@ k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr*
 // mode 3: fft2 only, natural positions, input read directly from `direct` ([k*l + j])
 // ------------------------------------------------------------------------------------------
 template <int LL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restrict__ U, const Fr* __restrict__ direct,
               size_t mbyl, size_t col0, size_t cols, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw,
               Fr* __restrict__ S) {
@@ -200,15 +200,13 @@ k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restri
         // rows of U times the share column, four terms per Montgomery reduction (fp_dot)
         uint32_t r = 0;
         for (; r + 4 <= n_recv; r += 4) {
-            Fr x[4], u[4];
+            Fr x[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) x[q] = ld_fr(shares + (size_t)(r + q) * cols + kk);
+            // the matrix row is the `b` operand: one limb per CIOS row, read from the (L1-resident) table
+            // as it is needed instead of being held in 32 registers
 #pragma unroll
-            for (int j = 0; j < LL; ++j) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) u[q] = ld_fr(U + (size_t)j * n_recv + r + q);
-                v[j] = fp_add(v[j], fp_dot<FrParams, 4>(u, x));
-            }
+            for (int j = 0; j < LL; ++j) v[j] = fp_add(v[j], fp_dot<FrParams, 4>(x, U + (size_t)j * n_recv + r));
         }
         for (; r < n_recv; ++r) {
             Fr x = ld_fr(shares + (size_t)r * cols + kk);
@@ -288,10 +286,7 @@ k_map_in_regs(const Fr* __restrict__ M, int rows, int k1, const Fr* __restrict__
         Fr acc = Fr::zero();
 #pragma unroll
         for (int j = 0; j < K; j += 4) {
-            Fr mrow[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) mrow[q] = ld_fr(M + (size_t)i * K + j + q);
-            Fr d = fp_dot<FrParams, 4>(mrow, x + j);
+            Fr d = fp_dot<FrParams, 4>(x + j, M + (size_t)i * K + j);      // matrix limbs read as needed
             acc = j == 0 ? d : fp_add(acc, d);
         }
         st_fr(out + c * out_cs + (size_t)i * out_rs, acc);
@@ -342,15 +337,11 @@ k_map_acc_regs(const Fr* __restrict__ M, int k, const Fr* __restrict__ in, size_
     for (int i = 0; i < ROWS; ++i) acc[i] = Fr::zero();
     int j = 0;
     for (; j + 4 <= k; j += 4) {
-        Fr x[4], mrow[4];
+        Fr x[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) x[q] = ld_fr(in + c * in_cs + (size_t)(j + q) * in_rs);
 #pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) mrow[q] = ld_fr(M + (size_t)i * k + j + q);
-            acc[i] = fp_add(acc[i], fp_dot<FrParams, 4>(mrow, x));
-        }
+        for (int i = 0; i < ROWS; ++i) acc[i] = fp_add(acc[i], fp_dot<FrParams, 4>(x, M + (size_t)i * k + j));
     }
     for (; j < k; ++j) {
         Fr x = ld_fr(in + c * in_cs + (size_t)j * in_rs);
