@@ -194,6 +194,32 @@ def test_msm_g1_skewed_scalars(z, kind, chunks, monkeypatch):
     assert (z.msm_g1(bases, S) == ol.o_g1_msm(bases, S, threads=8)).all()
 
 
+@pytest.mark.parametrize("reps", [41, 100, 150, 192])
+def test_msm_g1_repeated_points_in_one_bucket(z, reps):
+    """Buckets of 40..192 points made of identical and opposite points: the pairwise (batched-affine,
+    ZKG_MSM_BA=1) accumulation meets P + P, P + (-P) and infinity operands in every tree round; the
+    chain path sees the same input.  Compared with the oracle."""
+    rng = random.Random(reps)
+    dl, bases = _g1_points(rng, 8)
+    pts = [pyref.G1.mul(pyref.G1_GEN, d) for d in dl]
+    neg0 = np.frombuffer(pyref.g1_affine_image(pyref.G1.neg(pts[0])), dtype=np.uint8)
+    inf = np.frombuffer(pyref.g1_affine_image(None), dtype=np.uint8)
+    s0, s1 = rng.randrange(R), rng.randrange(R)
+    rows, sc = [], []
+    for i in range(reps):                                   # one scalar -> the same bucket in every window
+        kind = i % 7
+        rows.append(bases[0] if kind in (0, 1, 2) else neg0 if kind == 3 else inf if kind == 4 else bases[1 + kind % 3])
+        sc.append(s0)
+    for i in range(reps):                                   # all-equal bases and scalars (dmsm/mod.rs:144-147)
+        rows.append(bases[5]); sc.append(s1)
+    for i in range(reps + 1):                               # exact cancellation inside one bucket
+        rows.append(bases[6] if i % 2 == 0 else np.frombuffer(pyref.g1_affine_image(pyref.G1.neg(pts[6])), dtype=np.uint8))
+        sc.append((s1 * 3 + 1) % R)
+    B = np.stack(rows)
+    S = ol.fr_np(sc)
+    assert (z.msm_g1(B, S) == ol.o_g1_msm(B, S, threads=8)).all()
+
+
 def test_msm_skewed_registered_and_g2(z):
     from zksaas_b200 import capi
     rng = random.Random(4242)

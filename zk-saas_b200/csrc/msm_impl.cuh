@@ -258,6 +258,204 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
     store_vec(buckets + slot, acc);
 }
 
+// ------------------------------------------------------------------------------------------
+// Batched-affine bucket accumulation.  An XYZZ mixed add costs 10 field products; an AFFINE add
+// costs 3 plus an inversion, and Montgomery's trick turns k inversions into one plus 3(k-1)
+// products -- 6 products per add once the one inversion is shared widely enough.  One thread still
+// owns one bucket (slots ordered by population, so a block is homogeneous), but it sums its points
+// as a pairwise tree instead of a chain:
+//   round 1   the sorted entries are paired (2i, 2i+1) straight from the base table;
+//             forward pass: denominators d_i and their running product (kept in local memory),
+//             ONE inversion per BLOCK of the product of all threads' totals (prefix/suffix scans in
+//             shared memory, binary-Euclid inverse by one thread while other blocks keep the SM busy),
+//             backward pass: 1/d_i recovered with 2 products, the affine sum written to local memory;
+//   round r   the same on the previous round's results (ping-pong between two local buffers);
+// until at most BA_FINISH points are left, which join the bucket by the ordinary XYZZ chain (so
+// the reduction kernels and the chunked / multi-GPU paths see the same bucket format).
+// P = Q (doubling), P = -Q and infinities are handled per pair: the pair contributes d = 2y or
+// d = 1 to the batch and takes the matching formula on the way back.
+// ------------------------------------------------------------------------------------------
+static constexpr int BA_THREADS = 256;
+static constexpr int BA_MAXP = 96;            // pairs in round 1: buckets of up to 192 points
+static constexpr uint32_t BA_FINISH = 32;     // points left to the XYZZ chain
+static constexpr uint32_t BA_MIN = 40;        // blocks whose largest bucket is smaller keep the plain chain
+
+template <class F>
+struct BaPair { int kind; F d; };             // kind 0: generic add, 1: doubling, 2: result is p, 3: result is q, 4: result is infinity
+
+template <class F>
+__device__ __forceinline__ BaPair<F> ba_classify(const Affine<F>& p, const Affine<F>& q) {
+    BaPair<F> r;
+    r.d = F::one();
+    if (p.is_inf()) { r.kind = 3; return r; }
+    if (q.is_inf()) { r.kind = 2; return r; }
+    F dx = f_sub(q.x, p.x);
+    if (!dx.is_zero()) { r.kind = 0; r.d = dx; return r; }
+    if (p.y == q.y && !p.y.is_zero()) { r.kind = 1; r.d = f_dbl(p.y); return r; }
+    r.kind = 4;
+    return r;
+}
+template <class F>
+__device__ __forceinline__ Affine<F> ba_finish_pair(const Affine<F>& p, const Affine<F>& q, int kind, const F& dinv) {
+    if (kind == 2) return p;
+    if (kind == 3) return q;
+    if (kind == 4) return Affine<F>::inf();
+    F lam;
+    if (kind == 0) lam = f_mul(f_sub(q.y, p.y), dinv);
+    else { F xx = f_sqr(p.x); lam = f_mul(f_add(f_dbl(xx), xx), dinv); }
+    Affine<F> r;
+    r.x = f_sub(f_sub(f_sqr(lam), p.x), q.x);
+    r.y = f_sub(f_mul(lam, f_sub(p.x, r.x)), p.y);
+    return r;
+}
+
+// 1 / t for every thread of the block from ONE field inversion: inclusive prefix and suffix product
+// scans in shared memory, inverse of the grand total by thread 0, 1/t = inv * prefix_excl * suffix_excl.
+template <class F>
+__device__ __forceinline__ F ba_block_inverse(const F& t, F* sh_pre, F* sh_suf, F* sh_inv) {
+    const int tid = threadIdx.x;
+    sh_pre[tid] = t;
+    sh_suf[tid] = t;
+    __syncthreads();
+    for (int off = 1; off < BA_THREADS; off <<= 1) {
+        F a, b;
+        const bool ha = tid >= off, hb = tid + off < BA_THREADS;
+        if (ha) a = sh_pre[tid - off];
+        if (hb) b = sh_suf[tid + off];
+        __syncthreads();
+        if (ha) sh_pre[tid] = f_mul(sh_pre[tid], a);
+        if (hb) sh_suf[tid] = f_mul(sh_suf[tid], b);
+        __syncthreads();
+    }
+    if (tid == 0) *sh_inv = f_inv(sh_pre[BA_THREADS - 1]);
+    __syncthreads();
+    F r = *sh_inv;
+    if (tid > 0) r = f_mul(r, sh_pre[tid - 1]);
+    if (tid + 1 < BA_THREADS) r = f_mul(r, sh_suf[tid + 1]);
+    __syncthreads();                       // the scratch is reused by the next round
+    return r;
+}
+
+template <class F>
+__global__ void __launch_bounds__(BA_THREADS, 3)
+k_accumulate_ba(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
+                const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
+                XYZZ<F>* __restrict__ buckets) {
+    __shared__ __align__(16) unsigned char raw_pre[BA_THREADS * sizeof(F)];
+    __shared__ __align__(16) unsigned char raw_suf[BA_THREADS * sizeof(F)];
+    __shared__ __align__(16) unsigned char raw_inv[sizeof(F)];
+    __shared__ uint32_t cnt0_sh;
+    F* sh_pre = reinterpret_cast<F*>(raw_pre);
+    F* sh_suf = reinterpret_cast<F*>(raw_suf);
+    F* sh_inv = reinterpret_cast<F*>(raw_inv);
+
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < (size_t)W * nb;
+    size_t slot = 0;
+    uint32_t end = 0, cnt = 0;
+    const uint32_t* idx = sorted;
+    if (valid) {
+        slot = order[t];
+        end = cursor_end[slot];
+        cnt = counts[slot];
+        idx = sorted + (size_t)(slot / nb) * sstride + (end - cnt);
+    }
+    if (threadIdx.x == 0) cnt0_sh = cnt;          // descending order: the block's largest bucket
+    __syncthreads();
+    const uint32_t cnt0 = cnt0_sh;
+    if (!valid) cnt = 0;
+
+    if (cnt0 > 2 * BA_MAXP || cnt0 < BA_MIN) {     // block-uniform: plain chain (heavy buckets are skipped as in k_accumulate)
+        if (!valid || (accumulate_into && cnt == 0)) return;
+        if (cnt >= SIZE_KEYS - 1) {
+            if (!accumulate_into) store_vec(buckets + slot, XYZZ<F>::inf());
+            return;
+        }
+        XYZZ<F> acc = accumulate_into ? load_vec_rw(buckets + slot) : XYZZ<F>::inf();
+        for (uint32_t k = 0; k < cnt; ++k) {
+            uint32_t e = idx[k];
+            xyzz_madd(acc, load_vec(bases + (e & 0x7fffffffu)), (e >> 31) != 0);
+        }
+        store_vec(buckets + slot, acc);
+        return;
+    }
+
+    Affine<F> bufA[BA_MAXP];
+    Affine<F> bufB[BA_MAXP / 2];
+    F pre[BA_MAXP];
+    auto load_signed = [&](uint32_t e) {
+        Affine<F> p = load_vec(bases + (e & 0x7fffffffu));
+        if ((e >> 31) && !p.is_inf()) p.y = f_neg(p.y);
+        return p;
+    };
+
+    // ---- round 1: pairs straight from the base table ----
+    uint32_t npts = cnt, n0 = cnt0;
+    {
+        const uint32_t pairs = npts >> 1;
+        F run = F::one();
+        // forward pass: the common case needs only the two x coordinates (one 32-byte sector per point);
+        // equal or zero x sends the pair through the full classification
+#pragma unroll 2
+        for (uint32_t i = 0; i < pairs; ++i) {
+            const uint32_t e0 = idx[2 * i], e1 = idx[2 * i + 1];
+            F px = load_vec(&bases[e0 & 0x7fffffffu].x), qx = load_vec(&bases[e1 & 0x7fffffffu].x);
+            F d = f_sub(qx, px);
+            if (d.is_zero() || px.is_zero() || qx.is_zero()) d = ba_classify(load_signed(e0), load_signed(e1)).d;
+            pre[i] = run;
+            run = f_mul(run, d);
+        }
+        F inv = ba_block_inverse(run, sh_pre, sh_suf, sh_inv);
+        for (uint32_t i = pairs; i-- > 0;) {
+            Affine<F> p = load_signed(idx[2 * i]), q = load_signed(idx[2 * i + 1]);
+            BaPair<F> c = ba_classify(p, q);
+            F dinv = f_mul(inv, pre[i]);
+            inv = f_mul(inv, c.d);
+            bufA[i] = ba_finish_pair(p, q, c.kind, dinv);
+        }
+        if (npts & 1) bufA[pairs] = load_signed(idx[npts - 1]);
+        npts = pairs + (npts & 1);
+        n0 = (n0 >> 1) + (n0 & 1);
+    }
+    // ---- further rounds on the previous results (A -> B -> A ...) ----
+    bool in_a = true;
+    while (n0 > BA_FINISH) {                       // block-uniform
+        const uint32_t pairs = npts >> 1;
+        F run = F::one();
+        for (uint32_t i = 0; i < pairs; ++i) {
+            const Affine<F>& p = in_a ? bufA[2 * i] : bufB[2 * i];
+            const Affine<F>& q = in_a ? bufA[2 * i + 1] : bufB[2 * i + 1];
+            BaPair<F> c = ba_classify(p, q);
+            pre[i] = run;
+            run = f_mul(run, c.d);
+        }
+        F inv = ba_block_inverse(run, sh_pre, sh_suf, sh_inv);
+        // ascending writes into the OTHER buffer; the inverse recovery runs descending, so recover
+        // first into pre[] (1/d_i replaces the prefix product) and finish the pairs afterwards
+        for (uint32_t i = pairs; i-- > 0;) {
+            const Affine<F>& p = in_a ? bufA[2 * i] : bufB[2 * i];
+            const Affine<F>& q = in_a ? bufA[2 * i + 1] : bufB[2 * i + 1];
+            BaPair<F> c = ba_classify(p, q);
+            F dinv = f_mul(inv, pre[i]);
+            inv = f_mul(inv, c.d);
+            Affine<F> r = ba_finish_pair(p, q, c.kind, dinv);
+            if (in_a) bufB[i] = r; else bufA[i] = r;
+        }
+        if (npts & 1) {
+            if (in_a) bufB[pairs] = bufA[npts - 1]; else bufA[pairs] = bufB[npts - 1];
+        }
+        npts = pairs + (npts & 1);
+        n0 = (n0 >> 1) + (n0 & 1);
+        in_a = !in_a;
+    }
+    // ---- the few remaining points join the bucket through the XYZZ chain ----
+    if (!valid || (accumulate_into && cnt == 0)) return;
+    XYZZ<F> acc = accumulate_into ? load_vec_rw(buckets + slot) : XYZZ<F>::inf();
+    for (uint32_t i = 0; i < npts; ++i) xyzz_madd(acc, in_a ? bufA[i] : bufB[i], false);
+    store_vec(buckets + slot, acc);
+}
+
 // Skewed scalar distributions (many equal scalars, boolean witnesses, structured inputs) put thousands
 // of points into one bucket; one thread per bucket would serialise them.  Buckets with at least
 // SIZE_KEYS-1 points are the first hist[SIZE_KEYS-1] entries of `order`: blocks (x = heavy bucket,
@@ -615,8 +813,13 @@ static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases,
     k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(pl->shist, sstart);
     k_size_scatter<<<(unsigned)((pl->slots + 255) / 256), 256, 0, st>>>(pl->counts, pl->slots, sstart, pl->order);
     if (first) phase_mark(ctx, 1);
-    k_accumulate<F><<<(unsigned)((pl->slots + 127) / 128), 128, 0, st>>>(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order,
-                                                                       sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
+    static const int use_ba = env_int("ZKG_MSM_BA", 0);
+    if (use_ba)
+        k_accumulate_ba<F><<<(unsigned)((pl->slots + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, st>>>(
+            d_bases, pl->sorted, pl->cursor, pl->counts, pl->order, sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
+    else
+        k_accumulate<F><<<(unsigned)((pl->slots + 127) / 128), 128, 0, st>>>(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order,
+                                                                           sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
     {
         size_t max_heavy = (n * (size_t)pl->W) / (SIZE_KEYS - 1);
         if (max_heavy > pl->slots) max_heavy = pl->slots;
