@@ -17,6 +17,9 @@ static void st(uint64_t* p, const F& a) { memcpy(p, a.v, 32); }
     extern "C" void emu_##NAME##_mul(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) { \
         for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_mul(ld<F>(a + 4 * i), ld<F>(b + 4 * i)));  \
     }                                                                                              \
+    extern "C" void emu_##NAME##_sqr(const uint64_t* a, uint64_t* o, size_t n) {                   \
+        for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_sqr(ld<F>(a + 4 * i)));                    \
+    }                                                                                              \
     extern "C" void emu_##NAME##_add(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) { \
         for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_add(ld<F>(a + 4 * i), ld<F>(b + 4 * i)));  \
     }                                                                                              \

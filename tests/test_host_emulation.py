@@ -58,6 +58,14 @@ def test_montgomery_limb_schedule(emu, fld, p):
     fn = getattr(emu, f"emu_{fld}_neg"); fn.argtypes = [u64p, u64p, C.c_size_t]
     fn(_p(A), _p(O), len(a))
     assert unraw(O) == [(-x) % p for x in a]
+    # dedicated squaring (triangular product + word-by-word reduction): random values, the edge set, and
+    # values with saturated limbs / top bits of every limb set (the doubling folded into the multiplicand)
+    sq = a + [p - 1 - (1 << (32 * k)) for k in range(8)] + [((1 << 254) - 1) % p, int("7fffffff" * 8, 16) % p,
+              int("80000000" * 8, 16) % p, int("ffffffff" * 7, 16), ((1 << 253) | (1 << 31) | 1)]
+    SA = raw(sq); SO = np.zeros_like(SA)
+    fn = getattr(emu, f"emu_{fld}_sqr"); fn.argtypes = [u64p, u64p, C.c_size_t]
+    fn(_p(SA), _p(SO), len(sq))
+    assert unraw(SO) == [x * x * rinv % p for x in sq]
     # binary-Euclid inversion (production) and the Fermat ladder, on random values and the edge set
     inv_in = a[:3000] + edge + [3, 4, p - 3, (p + 1) // 2, 1 << 255 & (p - 1), pow(1 << 256, 1, p), pow(1 << 256, 2, p)]
     IA = raw(inv_in)

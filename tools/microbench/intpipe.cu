@@ -23,8 +23,10 @@ __global__ void k_int(uint32_t* out, uint32_t a, uint32_t b, int iters) {
             for (int c = 0; c < CHAINS; ++c) {
                 if (MODE == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
                 if (MODE == 1) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
-                if (MODE == 2) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(x[c]));
-                if (MODE == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
+                // data-dependent forms (a loop-invariant product or addend is hoisted / strength-reduced by ptxas:
+                // the first version of this file measured 64-bit adds here and called them IMAD.WIDE)
+                if (MODE == 2) asm volatile("{ .reg .u64 t; mul.wide.u32 t, %0, %1; mov.b64 {%0, %1}, t; }" : "+r"(x[c]), "+r"(x[(c + 1) % CHAINS]));
+                if (MODE == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(x[(c + 1) % CHAINS]));
                 if (MODE == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
                 // 3-input adds that cannot be strength-reduced (each chain mixes its two neighbours)
                 if (MODE == 6) asm volatile("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, %0, t; }" : "+r"(x[c]) : "r"(x[(c + 1) % CHAINS]), "r"(x[(c + 3) % CHAINS]));
@@ -53,7 +55,7 @@ __global__ void k_modmul(F* io, int iters) {
     for (int c = 0; c < ILP; ++c) { x[c] = y; x[c].v[0] ^= c; }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int c = 0; c < ILP; ++c) x[c] = VARIANT == 0 ? fp_mul_r29(x[c], y) : fp_mul(x[c], y);
+        for (int c = 0; c < ILP; ++c) x[c] = VARIANT == 0 ? fp_mul_r29(x[c], y) : VARIANT == 2 ? fp_sqr(x[c]) : fp_mul(x[c], y);
     }
     F s = x[0];
 #pragma unroll
@@ -113,6 +115,7 @@ int main() {
         ms = time_ms([&] { k_modmul<Fq, 1, 0><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul29_ilp1_t%d_G\": %.2f", th, mm / ms / 1e6);
         ms = time_ms([&] { k_modmul<Fq, 2, 0><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul29_ilp2_t%d_G\": %.2f", th, 2 * mm / ms / 1e6);
         ms = time_ms([&] { k_modmul<Fq, 1, 1><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modmul_cios_ilp1_t%d_G\": %.2f", th, mm / ms / 1e6);
+        ms = time_ms([&] { k_modmul<Fq, 1, 2><<<bl, th>>>((Fq*)d, mi); }); printf(", \"modsqr_ilp1_t%d_G\": %.2f", th, mm / ms / 1e6);
     }
     {
         int th = 256, bl = sms * 8;

@@ -24,7 +24,7 @@ template <class P> ZKG_D Fp<P> f_sqr(const Fp<P>& a) { return fp_sqr(a); }
 // (tried for the cold formulas: an out-of-line shared multiplier body -- slower, 2.89 vs 2.67 ms tail;
 //  the flag-free fp_mul_r29 so that ptxas may interleave independent products -- slower, 2.47 vs 1.35 ms)
 template <class P> ZKG_D Fp<P> f_mul_hot(const Fp<P>& a, const Fp<P>& b) { return fp_mul(a, b); }
-template <class P> ZKG_D Fp<P> f_sqr_hot(const Fp<P>& a) { return fp_mul(a, a); }
+template <class P> ZKG_D Fp<P> f_sqr_hot(const Fp<P>& a) { return fp_sqr(a); }
 // a*b - c*d with ONE Montgomery reduction (fp_dot: 192 wide MADs instead of 256); canonical, so it is
 // bit-identical to f_sub(f_mul(a, b), f_mul(c, d)).  Every group formula ends its Y coordinate this way.
 template <class P> ZKG_D Fp<P> f_mulsub(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
