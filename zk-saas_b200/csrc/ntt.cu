@@ -74,6 +74,12 @@ __global__ void k_pow_table(FrArg base_, uint32_t count, Fr* __restrict__ out) {
     }
     st_fr(out + i, acc);
 }
+// t[i] *= mult  (turns a power table w^i into c * w^i)
+__global__ void k_scale_table(Fr* __restrict__ t, uint32_t count, FrArg mult_) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    st_fr(t + i, fp_mul(ld_fr_rw(t + i), from_arg(mult_)));
+}
 
 // Two-level power table of a root w: w^e = lo[e & (LO-1)] * hi[e >> LO_BITS]
 static constexpr int TW_LO_BITS = 12;
@@ -260,6 +266,86 @@ k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restri
         }
         st_fr(S + dst, x);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// King, kernel 1 specialised for l = 2 with all n = 8 shares present (the reference's one real
+// configuration; anything else takes the generic kernel above).  Same results; fewer products:
+// a thread owns T = k + 1 (the exponent of the fft2 twiddle AND the position of the column's first
+// output), blocks are aligned on 256 values of T, so the HIGH factor of every two-level power lookup
+// (exponent >> 12) is uniform over the block.  The block folds those factors into its own copy of the
+// 2 x 8 unpack matrix in shared memory (Us0 = U0 * Ghi, Us1 = U1 * Whi * Ghi: 16 threads, two
+// products each), after which a column needs only the LOW table entries:
+//     v0 = <Us0, shares>, v1 = <Us1, shares>            (4 x fp_dot<4>)
+//     y  = v1 * gen_lo[T & 4095]
+//     out(pos = T)        = (v0 + y) * g_lo [T & 4095]
+//     out(pos = T + m/2)  = (v0 - y) * g_lo2[T & 4095],   g_lo2[i] = g^(i + m/2)
+// i.e. 3 products after the dots instead of 6 (1 instead of 2 when g = 1).  The one column whose second
+// position wraps to 0 (T = m/2, factor g^0) recomputes the plain way.
+// ------------------------------------------------------------------------------------------
+// v0 = <M0, column>, v1 = <M1, column> for the 8 shares of column kk (four terms per Montgomery reduction)
+__device__ __forceinline__ void king_l2_dots(const Fr* __restrict__ shares, size_t cols, size_t kk, const Fr* M0, const Fr* M1,
+                                             Fr& v0, Fr& v1) {
+    v0 = Fr::zero(); v1 = Fr::zero();
+#pragma unroll
+    for (int r = 0; r < 8; r += 4) {
+        Fr x[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = ld_fr(shares + (size_t)(r + q) * cols + kk);
+        v0 = fp_add(v0, fp_dot<FrParams, 4>(x, M0 + r));
+        v1 = fp_add(v1, fp_dot<FrParams, 4>(x, M1 + r));
+    }
+}
+
+__global__ void __launch_bounds__(256, 3)
+k_king_stage1_l2(const Fr* __restrict__ shares, const Fr* __restrict__ U, size_t mbyl, size_t col0, size_t cols, int log_m,
+                 int mode, PowTable gen_tw, int has_g, PowTable g_tw, const Fr* __restrict__ g_lo2, Fr* __restrict__ S) {
+    __shared__ Fr Us[16];
+    const size_t Tlo = col0 + 1;
+    const size_t T = (Tlo & ~(size_t)255) + (size_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t hi = (uint32_t)(T >> TW_LO_BITS);                 // uniform over the block
+    if (threadIdx.x < 16) {
+        Fr u = ld_fr(U + threadIdx.x);
+        if (hi) {
+            if (threadIdx.x >= 8) u = fp_mul(u, ld_fr(gen_tw.hi + hi));
+            if (has_g) u = fp_mul(u, ld_fr(g_tw.hi + hi));
+        }
+        Us[threadIdx.x] = u;
+    }
+    __syncthreads();
+    if (T < Tlo || T > col0 + cols) return;
+    const size_t k = T - 1, kk = k - col0;
+    const size_t m = (size_t)1 << log_m;
+    const uint32_t lo = (uint32_t)(T & (TW_LO - 1));
+    Fr a, b;
+    if (T != mbyl) {
+        Fr v0, v1;
+        king_l2_dots(shares, cols, kk, Us, Us + 8, v0, v1);
+        Fr y = fp_mul(v1, ld_fr(gen_tw.lo + lo));
+        a = fp_add(v0, y);
+        b = fp_sub(v0, y);
+        if (has_g) {
+            a = fp_mul(a, ld_fr(g_tw.lo + lo));
+            b = fp_mul(b, ld_fr(g_lo2 + lo));
+        }
+    } else {                                                         // pos1 = m -> 0: no g factor there; one column per job
+        Fr v0, v1;
+        king_l2_dots(shares, cols, kk, U, U + 8, v0, v1);
+        Fr y = fp_mul(v1, pow_lookup(gen_tw, T));
+        a = fp_add(v0, y);
+        b = fp_sub(v0, y);
+        if (has_g) a = fp_mul(a, pow_lookup(g_tw, T));
+    }
+    const size_t pos0 = T, pos1 = (T + mbyl) & (m - 1);
+    size_t d0 = pos0, d1 = pos1;
+    if (mode == 1) {
+        size_t p0 = (size_t)(__brevll((unsigned long long)pos0) >> (64 - log_m));
+        size_t p1 = (size_t)(__brevll((unsigned long long)pos1) >> (64 - log_m));
+        d0 = (p0 & (mbyl - 1)) * 2 + (p0 / mbyl);
+        d1 = (p1 & (mbyl - 1)) * 2 + (p1 / mbyl);
+    }
+    st_fr(S + d0, a);
+    st_fr(S + d1, b);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -492,6 +578,26 @@ static int32_t cached_pow_seq(zkg_ctx* ctx, const char* tag, const HFr& w, size_
     return ZKG_OK;
 }
 
+// out[i] = c * w^i, i < count, cached (keyed by w, c and count)
+static int32_t cached_pow_seq_scaled(zkg_ctx* ctx, const char* tag, const HFr& w, const HFr& c, size_t count, const Fr** out) {
+    struct { PowKey k; uint64_t c[4]; } key;
+    memset(&key, 0, sizeof key);
+    strncpy(key.k.tag, tag, sizeof key.k.tag - 1);
+    memcpy(key.k.w, w.v, 32);
+    key.k.count = count;
+    memcpy(key.c, c.v, 32);
+    void* p; bool fresh;
+    ZKG_TRY(ctx_cache_get(ctx, &key, sizeof key, (count ? count : 1) * sizeof(Fr), &p, &fresh));
+    if (fresh && count) {
+        k_pow_table<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(to_arg(w), (uint32_t)count, (Fr*)p);
+        k_scale_table<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>((Fr*)p, (uint32_t)count, to_arg(c));
+        ctx->launches += 2;
+        ZKG_CUDA(cudaGetLastError());
+    }
+    *out = (const Fr*)p;
+    return ZKG_OK;
+}
+
 static int32_t build_pow_table(zkg_ctx* ctx, const HFr& w, size_t max_exp_excl, PowTable* out) {
     size_t hi_n = (max_exp_excl + TW_LO - 1) >> TW_LO_BITS;
     if (hi_n == 0) hi_n = 1;
@@ -673,6 +779,19 @@ static int32_t king_stage1(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* par
     }
     unsigned blocks = (unsigned)((cols + 255) / 256);
     int mode = mode_fft ? (rearrange ? 1 : 0) : 2;
+    if (l == 2 && n_recv == 8 && mode_fft && !getenv("ZKG_KING_GENERIC")) {
+        // specialised kernel: thread <-> T = k + 1, blocks aligned on 256 values of T
+        const Fr* g_lo2 = nullptr;
+        if (has_g) ZKG_TRY(cached_pow_seq_scaled(ctx, "pow_l2", *g, host::h_pow(*g, mbyl), TW_LO, &g_lo2));
+        const size_t Tlo = col0 + 1, Thi = col0 + cols, A = Tlo & ~(size_t)255;
+        unsigned blocks2 = (unsigned)((Thi - A) / 256 + 1);
+        phase_mark(ctx, 1);
+        k_king_stage1_l2<<<blocks2, 256, 0, ctx->stream>>>(d_shares, dU, mbyl, col0, cols, log_m, mode, gen_tw, has_g, g_tw, g_lo2, S);
+        ctx->launches += 1;
+        ZKG_CUDA(cudaGetLastError());
+        phase_mark(ctx, 2);
+        return ZKG_OK;
+    }
     phase_mark(ctx, 1);
 #define KS(LLv) k_king_stage1<LLv><<<blocks, 256, 0, ctx->stream>>>(d_shares, n_recv, dU, nullptr, mbyl, col0, cols, log_m, mode, gen_tw, has_g, g_tw, S)
     if (l == 2) KS(2); else if (l == 4) KS(4); else KS(8);
