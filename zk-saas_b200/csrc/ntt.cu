@@ -100,6 +100,16 @@ __device__ __forceinline__ uint32_t bitrev32(uint32_t x, int bits) { return bits
 // size-2^b DFTs (bit-reversed rows in, natural rows out) after multiplying element (row, klow) by
 // rho^(klow * bitrev_b(row)), rho = w_N^(N / 2^(s+b)).
 // ------------------------------------------------------------------------------------------
+// Inter-pass twiddles of one pass as a table in tile order: out[(row << s) + klow] = rho^(klow * bitrev_b(row)),
+// rho = w_N^(N / 2^(s+b)).  Built once per (root, pass shape) and cached with the other parameter tables.
+__global__ void k_ntt_twiddle_table(Fr* __restrict__ out, int s, int b, int rho_shift, PowTable tw) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((size_t)1 << (s + b))) return;
+    uint32_t row = (uint32_t)(idx >> s), klow = (uint32_t)(idx & (((size_t)1 << s) - 1));
+    uint64_t e = (uint64_t)klow * bitrev32(row, b);
+    st_fr(out + idx, e ? pow_lookup(tw, e << rho_shift) : Fr::one());
+}
+
 struct NttPass {
     int logN, s, b, cw_log;
     int first, last, shift;          // shift: store X[k] at (k-1) mod N (fft1 convention)
@@ -109,7 +119,7 @@ struct NttPass {
 
 __global__ void __launch_bounds__(512, 2)
 k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr* __restrict__ tw_small, PowTable tw,
-           const Fr* __restrict__ mask) {
+           const Fr* __restrict__ tw_full, const Fr* __restrict__ mask) {
     extern __shared__ uint32_t smem[];
     const uint32_t T = 1u << P.b, CW = 1u << P.cw_log, E = T * CW;   // elements per block
     uint32_t* S = smem;                       // 8 limb planes of E words
@@ -131,8 +141,14 @@ k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr*
         Fr x = ld_fr(in + base + ((size_t)row << P.s) + col);
         if (P.first && P.has_scale) x = fp_mul(x, scale);
         if (!P.first) {
-            uint64_t e = (uint64_t)(klow0 + col) * bitrev32(row, P.b);
-            if (e) x = fp_mul(x, pow_lookup(tw, e << rho_shift));
+            if (tw_full) {
+                // inter-pass twiddle straight from the per-pass table, laid out like the tile ([row][klow]):
+                // one coalesced 32-byte read instead of a second product on the binding (integer MAD) pipe
+                if (row) x = fp_mul(x, ld_fr(tw_full + ((size_t)row << P.s) + klow0 + col));
+            } else {
+                uint64_t e = (uint64_t)(klow0 + col) * bitrev32(row, P.b);
+                if (e) x = fp_mul(x, pow_lookup(tw, e << rho_shift));
+            }
         }
 #pragma unroll
         for (int l = 0; l < 8; ++l) S[l * E + idx] = x.v[l];
@@ -638,6 +654,24 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp,
         const Fr* tws;
         HFr wT = host::h_pow(wN, N >> b);
         ZKG_TRY(cached_pow_seq(ctx, "tw_small", wT, T / 2, &tws));
+        // inter-pass twiddle table (passes after the first); beyond 2^24 entries the pass composes them on the fly
+        const Fr* tw_full = nullptr;
+        if (q > 0 && s + b <= 24 && !getenv("ZKG_NTT_ONTHEFLY")) {
+            struct { PowKey k; int s, b, logN, pad; } key;
+            memset(&key, 0, sizeof key);
+            strncpy(key.k.tag, "ntt_tw", sizeof key.k.tag - 1);
+            memcpy(key.k.w, wN.v, 32);
+            key.s = s; key.b = b; key.logN = logN;
+            const size_t cnt = (size_t)1 << (s + b);
+            void* tp; bool fresh;
+            ZKG_TRY(ctx_cache_get(ctx, &key, sizeof key, cnt * sizeof(Fr), &tp, &fresh));
+            if (fresh) {
+                k_ntt_twiddle_table<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((Fr*)tp, s, b, logN - s - b, tw);
+                ctx->launches += 1;
+                ZKG_CUDA(cudaGetLastError());
+            }
+            tw_full = (const Fr*)tp;
+        }
         // destination: last pass -> d_out; otherwise the scratch (in place on scratch is safe: a
         // block reads and writes the same index set when no shift is applied)
         Fr* dst = P.last ? d_out : d_tmp;
@@ -647,7 +681,7 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp,
         unsigned blocks = (unsigned)(N / E);
         ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         if (q == 0) phase_mark(ctx, 1);
-        k_ntt_pass<<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, P.last ? d_mask : nullptr);
+        k_ntt_pass<<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, tw_full, P.last ? d_mask : nullptr);
         ctx->launches += 1;
         if (P.last) phase_mark(ctx, 2);
         ZKG_CUDA(cudaGetLastError());
