@@ -193,6 +193,143 @@ k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr*
 }
 
 // ------------------------------------------------------------------------------------------
+// The same pass with the radix-2 stages grouped three at a time in REGISTERS (radix-8 units): a
+// thread owns 8 elements, runs up to three stages on them without touching shared memory, and the
+// tile is exchanged through shared memory only between groups (two barriers per pass instead of
+// b).  The first group loads straight from global memory (scale / inter-pass twiddle applied on the
+// way in) and the last one stores straight to global memory (shift / mask applied on the way out).
+// Shared layout: two planes of 16-byte half elements, one padding slot per 8 (stride-8 row access
+// of the first group stays conflict free), then the small twiddles.  Units are numbered column-fastest,
+// so a quarter warp always touches 8 consecutive slots.
+//   sub_mode (pass 0, s = 0): the block owns CW consecutive sub-transforms of T contiguous elements;
+//   "column" c is then the sub-transform: global index = base + c*T + row.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ntt_slot(uint32_t idx) { return idx + (idx >> 3); }
+
+__global__ void __launch_bounds__(256, 2)
+k_ntt_pass8(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr* __restrict__ tw_small, PowTable tw,
+            const Fr* __restrict__ tw_full, const Fr* __restrict__ mask, int sub_mode) {
+    extern __shared__ uint4 sm4[];
+    const uint32_t T = 1u << P.b, CW = 1u << P.cw_log, E = T * CW;
+    const uint32_t PL = E + (E >> 3) + 1;
+    uint4* S0 = sm4;
+    uint4* S1 = sm4 + PL;
+    uint4* TW = sm4 + 2 * PL;                                 // entry i: TW[2i] (limbs 0..3), TW[2i+1] (limbs 4..7)
+    size_t base;
+    uint32_t klow0 = 0;
+    if (sub_mode) {
+        base = (size_t)blockIdx.x * E;
+    } else {
+        const uint32_t cols_per_upper = (1u << P.s) >> P.cw_log;
+        const uint32_t upper = blockIdx.x / cols_per_upper;
+        klow0 = (blockIdx.x % cols_per_upper) << P.cw_log;
+        base = ((size_t)upper << (P.s + P.b)) + klow0;
+    }
+    const int rho_shift = P.logN - P.s - P.b;
+    const size_t N = (size_t)1 << P.logN;
+    const uint32_t units = E >> 3 ? E >> 3 : 1;               // threads that own elements
+    const uint32_t uidx = threadIdx.x;
+
+    for (uint32_t i = threadIdx.x; i < T / 2; i += blockDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(tw_small + i);
+        TW[2 * i] = __ldg(src);
+        TW[2 * i + 1] = __ldg(src + 1);
+    }
+    const Fr scale = from_arg(P.scale);
+
+    // groups of stages: as even as possible, at most 3 each
+    const int ngroups = (P.b + 2) / 3 ? (P.b + 2) / 3 : 1;
+    int sg0 = 0;
+    for (int gi = 0; gi < ngroups; ++gi) {
+        const int G = (P.b - sg0 + (ngroups - gi) - 1) / (ngroups - gi);    // stages in this group (0 when b == 0)
+        const bool from_global = gi == 0, to_global = gi == ngroups - 1;
+        Fr v[8];
+        uint32_t rowv[8], colv[8];
+        const bool active = uidx < units && (E >= 8 || uidx == 0);
+        // element e of this thread: sub-butterfly q = e >> G, member j = e & (2^G - 1)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t q = (uint32_t)e >> G, j = (uint32_t)e & ((1u << G) - 1);
+            const uint32_t beta = q * units + uidx;
+            const uint32_t col = beta & (CW - 1), rest = beta >> P.cw_log;
+            const uint32_t low = rest & ((1u << sg0) - 1), high = rest >> sg0;
+            rowv[e] = (high << (sg0 + G)) | (j << sg0) | low;
+            colv[e] = col;
+        }
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (E < 8 && (uint32_t)e >= E) continue;
+                const uint32_t row = rowv[e], col = colv[e];
+                if (from_global) {
+                    const size_t g = sub_mode ? base + (size_t)col * T + row : base + ((size_t)row << P.s) + col;
+                    Fr x = ld_fr(in + g);
+                    if (P.first && P.has_scale) x = fp_mul(x, scale);
+                    if (!P.first && row) {
+                        if (tw_full) x = fp_mul(x, ld_fr(tw_full + ((size_t)row << P.s) + klow0 + col));
+                        else {
+                            uint64_t ex = (uint64_t)(klow0 + col) * bitrev32(row, P.b);
+                            if (ex) x = fp_mul(x, pow_lookup(tw, ex << rho_shift));
+                        }
+                    }
+                    v[e] = x;
+                } else {
+                    const uint32_t sl = ntt_slot(row * CW + col);
+                    uint4 a = S0[sl], b4 = S1[sl];
+                    v[e].v[0] = a.x; v[e].v[1] = a.y; v[e].v[2] = a.z; v[e].v[3] = a.w;
+                    v[e].v[4] = b4.x; v[e].v[5] = b4.y; v[e].v[6] = b4.z; v[e].v[7] = b4.w;
+                }
+            }
+        }
+        if (from_global) __syncthreads();                      // small twiddles are in place
+        if (active) {
+#pragma unroll
+            for (int sp = 0; sp < 3; ++sp) {
+                if (sp >= G) break;
+                const int sigma = sg0 + sp;                      // global stage
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if ((e >> sp) & 1) continue;
+                    const int f = e + (1 << sp);
+                    if (E < 8 && (uint32_t)f >= E) continue;
+                    const uint32_t kin = rowv[e] & ((1u << sigma) - 1);
+                    Fr y = v[f];
+                    if (kin) {
+                        const uint32_t ti = kin << (P.b - 1 - sigma);
+                        uint4 a = TW[2 * ti], b4 = TW[2 * ti + 1];
+                        Fr w;
+                        w.v[0] = a.x; w.v[1] = a.y; w.v[2] = a.z; w.v[3] = a.w;
+                        w.v[4] = b4.x; w.v[5] = b4.y; w.v[6] = b4.z; w.v[7] = b4.w;
+                        y = fp_mul(y, w);
+                    }
+                    const Fr x = v[e];
+                    v[e] = fp_add(x, y);
+                    v[f] = fp_sub(x, y);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (E < 8 && (uint32_t)e >= E) continue;
+                const uint32_t row = rowv[e], col = colv[e];
+                if (to_global) {
+                    size_t k = sub_mode ? base + (size_t)col * T + row : base + ((size_t)row << P.s) + col;
+                    if (P.last && P.shift) k = (k + N - 1) & (N - 1);
+                    Fr x = v[e];
+                    if (P.last && mask) x = fp_add(x, ld_fr(mask + k));
+                    st_fr(out + k, x);
+                } else {
+                    const uint32_t sl = ntt_slot(row * CW + col);
+                    S0[sl] = make_uint4(v[e].v[0], v[e].v[1], v[e].v[2], v[e].v[3]);
+                    S1[sl] = make_uint4(v[e].v[4], v[e].v[5], v[e].v[6], v[e].v[7]);
+                }
+            }
+        }
+        if (!to_global) __syncthreads();
+        sg0 += G;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // King, kernel 1: per share column k: secrets = U * shares (unpack2 or Lagrange matrix), the
 // column-local fft2 butterflies, g^pos powers, and the store in *pack order*:
 //   S[c*l + j] = j-th secret of output column c.
@@ -289,9 +426,9 @@ k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restri
 // configuration; anything else takes the generic kernel above).  Same results; fewer products:
 // a thread owns T = k + 1 (the exponent of the fft2 twiddle AND the position of the column's first
 // output), blocks are aligned on 256 values of T, so the HIGH factor of every two-level power lookup
-// (exponent >> 12) is uniform over the block.  The block folds those factors into its own copy of the
-// 2 x 8 unpack matrix in shared memory (Us0 = U0 * Ghi, Us1 = U1 * Whi * Ghi: 16 threads, two
-// products each), after which a column needs only the LOW table entries:
+// (exponent >> 12) is uniform over the block.  Those factors are folded into per-`hi` copies of the
+// 2 x 8 unpack matrix (Us0 = U0 * Ghi, Us1 = U1 * Whi * Ghi; a cached table of m/2^13 x 16 elements built
+// by k_king_scaled_matrices), after which a column needs only the LOW table entries:
 //     v0 = <Us0, shares>, v1 = <Us1, shares>            (4 x fp_dot<4>)
 //     y  = v1 * gen_lo[T & 4095]
 //     out(pos = T)        = (v0 + y) * g_lo [T & 4095]
@@ -313,44 +450,43 @@ __device__ __forceinline__ void king_l2_dots(const Fr* __restrict__ shares, size
     }
 }
 
+// per value of hi = T >> 12: the 2 x 8 unpack matrix with the high power-table factors folded in
+//   Us[hi][0..7] = U0 * Ghi[hi],  Us[hi][8..15] = U1 * Whi[hi] * Ghi[hi]      (factors of hi = 0 are 1)
+__global__ void k_king_scaled_matrices(const Fr* __restrict__ U, uint32_t hi_n, PowTable gen_tw, int has_g, PowTable g_tw,
+                                       Fr* __restrict__ Us) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= hi_n * 16) return;
+    const uint32_t hi = t >> 4, i = t & 15;
+    Fr u = ld_fr(U + i);
+    if (hi) {
+        if (i >= 8) u = fp_mul(u, ld_fr(gen_tw.hi + hi));
+        if (has_g) u = fp_mul(u, ld_fr(g_tw.hi + hi));
+    }
+    st_fr(Us + t, u);
+}
+
 __global__ void __launch_bounds__(256, 3)
-k_king_stage1_l2(const Fr* __restrict__ shares, const Fr* __restrict__ U, size_t mbyl, size_t col0, size_t cols, int log_m,
-                 int mode, PowTable gen_tw, int has_g, PowTable g_tw, const Fr* __restrict__ g_lo2, Fr* __restrict__ S) {
-    __shared__ Fr Us[16];
+k_king_stage1_l2(const Fr* __restrict__ shares, const Fr* __restrict__ U, const Fr* __restrict__ UsTab, size_t mbyl, size_t col0,
+                 size_t cols, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw, const Fr* __restrict__ g_lo2,
+                 Fr* __restrict__ S) {
     const size_t Tlo = col0 + 1;
     const size_t T = (Tlo & ~(size_t)255) + (size_t)blockIdx.x * 256 + threadIdx.x;
-    const uint32_t hi = (uint32_t)(T >> TW_LO_BITS);                 // uniform over the block
-    if (threadIdx.x < 16) {
-        Fr u = ld_fr(U + threadIdx.x);
-        if (hi) {
-            if (threadIdx.x >= 8) u = fp_mul(u, ld_fr(gen_tw.hi + hi));
-            if (has_g) u = fp_mul(u, ld_fr(g_tw.hi + hi));
-        }
-        Us[threadIdx.x] = u;
-    }
-    __syncthreads();
+    const Fr* Us = UsTab + (size_t)(T >> TW_LO_BITS) * 16;             // uniform over the block (L1-resident)
     if (T < Tlo || T > col0 + cols) return;
     const size_t k = T - 1, kk = k - col0;
     const size_t m = (size_t)1 << log_m;
     const uint32_t lo = (uint32_t)(T & (TW_LO - 1));
-    Fr a, b;
-    if (T != mbyl) {
-        Fr v0, v1;
-        king_l2_dots(shares, cols, kk, Us, Us + 8, v0, v1);
-        Fr y = fp_mul(v1, ld_fr(gen_tw.lo + lo));
-        a = fp_add(v0, y);
-        b = fp_sub(v0, y);
-        if (has_g) {
-            a = fp_mul(a, ld_fr(g_tw.lo + lo));
-            b = fp_mul(b, ld_fr(g_lo2 + lo));
-        }
-    } else {                                                         // pos1 = m -> 0: no g factor there; one column per job
-        Fr v0, v1;
-        king_l2_dots(shares, cols, kk, U, U + 8, v0, v1);
-        Fr y = fp_mul(v1, pow_lookup(gen_tw, T));
-        a = fp_add(v0, y);
-        b = fp_sub(v0, y);
-        if (has_g) a = fp_mul(a, pow_lookup(g_tw, T));
+    // the one column whose second position wraps to 0 (T = m/2: factor g^0 there) takes the plain matrix and
+    // composes its own factors
+    const bool wrap = T == mbyl;
+    const Fr* M = wrap ? U : Us;
+    Fr v0, v1;
+    king_l2_dots(shares, cols, kk, M, M + 8, v0, v1);
+    Fr y = fp_mul(v1, wrap ? pow_lookup(gen_tw, T) : ld_fr(gen_tw.lo + lo));
+    Fr a = fp_add(v0, y), b = fp_sub(v0, y);
+    if (has_g) {
+        a = fp_mul(a, wrap ? pow_lookup(g_tw, T) : ld_fr(g_tw.lo + lo));
+        if (!wrap) b = fp_mul(b, ld_fr(g_lo2 + lo));
     }
     const size_t pos0 = T, pos1 = (T + mbyl) & (m - 1);
     size_t d0 = pos0, d1 = pos1;
@@ -622,6 +758,11 @@ static int32_t build_pow_table(zkg_ctx* ctx, const HFr& w, size_t max_exp_excl, 
     return ZKG_OK;
 }
 
+static int env_int_ntt(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 // In-order-output NTT of d_in (bit-reversed input order) with root w_N, into d_out.
 // shift = 1 stores X[k] at (k-1) mod N.  d_tmp: N-element scratch (used when > 2 passes or in == out).
 static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp, size_t N, const HFr& wN,
@@ -637,9 +778,13 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp,
     const Fr* src = d_in;
     for (int q = 0; q < npass; ++q) {
         int b = (logN - s + (npass - q) - 1) / (npass - q);      // spread the remaining bits evenly
+        // radix-8 register-blocked kernel for large transforms; small ones keep the radix-2 kernel, whose four
+        // times as many threads hide latency better when there is less than one tile per SM
+        const bool r8 = logN >= env_int_ntt("ZKG_NTT_R8_MIN", 18);
+        const int elog = env_int_ntt("ZKG_NTT_ELOG", 11);
         int cw_log = 0;
-        if (q > 0) {
-            cw_log = 11 - b; if (cw_log > s) cw_log = s; if (cw_log < 0) cw_log = 0;
+        if (q > 0 || r8) {
+            cw_log = (r8 ? elog : 11) - b; if (cw_log > (q > 0 ? s : logN - b)) cw_log = q > 0 ? s : logN - b; if (cw_log < 0) cw_log = 0;
             // small transforms: prefer more, narrower tiles (>= 4 columns = 128-byte rows) so that the
             // pass spreads over the 148 SMs instead of a dozen fat blocks
             while (cw_log > 2 && (N >> (b + cw_log)) < 296) --cw_log;
@@ -676,12 +821,20 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp,
         // block reads and writes the same index set when no shift is applied)
         Fr* dst = P.last ? d_out : d_tmp;
         size_t E = T << cw_log;
-        size_t shmem = (8 * E + 8 * (T / 2 ? T / 2 : 1)) * sizeof(uint32_t);
-        unsigned threads = (unsigned)(E / 2 < 32 ? 32 : (E / 2 > 512 ? 512 : E / 2));
         unsigned blocks = (unsigned)(N / E);
-        ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         if (q == 0) phase_mark(ctx, 1);
-        k_ntt_pass<<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, tw_full, P.last ? d_mask : nullptr);
+        if (r8) {
+            size_t PL = E + (E >> 3) + 1;
+            size_t shmem = (2 * PL + T) * sizeof(uint4);
+            unsigned threads = (unsigned)(E / 8 < 32 ? 32 : E / 8);
+            ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass8, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            k_ntt_pass8<<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, tw_full, P.last ? d_mask : nullptr, q == 0 ? 1 : 0);
+        } else {
+            size_t shmem = (8 * E + 8 * (T / 2 ? T / 2 : 1)) * sizeof(uint32_t);
+            unsigned threads = (unsigned)(E / 2 < 32 ? 32 : (E / 2 > 512 ? 512 : E / 2));
+            ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            k_ntt_pass<<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, tw_full, P.last ? d_mask : nullptr);
+        }
         ctx->launches += 1;
         if (P.last) phase_mark(ctx, 2);
         ZKG_CUDA(cudaGetLastError());
@@ -817,10 +970,25 @@ static int32_t king_stage1(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* par
         // specialised kernel: thread <-> T = k + 1, blocks aligned on 256 values of T
         const Fr* g_lo2 = nullptr;
         if (has_g) ZKG_TRY(cached_pow_seq_scaled(ctx, "pow_l2", *g, host::h_pow(*g, mbyl), TW_LO, &g_lo2));
+        const uint32_t hi_n = (uint32_t)((mbyl >> TW_LO_BITS) + 1);      // T = 1 .. m/2
+        struct { char tag[8]; uint64_t gen[4], g[4]; uint64_t hi_n; } key;
+        memset(&key, 0, sizeof key);
+        strncpy(key.tag, "kingUs", sizeof key.tag - 1);
+        memcpy(key.gen, gen->v, 32);
+        memcpy(key.g, g->v, 32);
+        key.hi_n = hi_n;
+        void* up; bool fresh;
+        ZKG_TRY(ctx_cache_get(ctx, &key, sizeof key, (size_t)hi_n * 16 * sizeof(Fr), &up, &fresh));
+        if (fresh) {
+            k_king_scaled_matrices<<<(hi_n * 16 + 127) / 128, 128, 0, ctx->stream>>>(dU, hi_n, gen_tw, has_g, g_tw, (Fr*)up);
+            ctx->launches += 1;
+            ZKG_CUDA(cudaGetLastError());
+        }
         const size_t Tlo = col0 + 1, Thi = col0 + cols, A = Tlo & ~(size_t)255;
         unsigned blocks2 = (unsigned)((Thi - A) / 256 + 1);
         phase_mark(ctx, 1);
-        k_king_stage1_l2<<<blocks2, 256, 0, ctx->stream>>>(d_shares, dU, mbyl, col0, cols, log_m, mode, gen_tw, has_g, g_tw, g_lo2, S);
+        k_king_stage1_l2<<<blocks2, 256, 0, ctx->stream>>>(d_shares, dU, (const Fr*)up, mbyl, col0, cols, log_m, mode, gen_tw, has_g,
+                                                          g_tw, g_lo2, S);
         ctx->launches += 1;
         ZKG_CUDA(cudaGetLastError());
         phase_mark(ctx, 2);
