@@ -28,7 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 INT_PEAK_TIMAD = 18.51              # profiles/r01_intpipe_microbench.json: 32-bit IMAD issue rate, B200, 148 SMs @1965 MHz
-MODMUL_PEAK_G = 67.3                # same file: this repo's Montgomery multiplier in isolation (G products/s)
+WIDE_MAD_PEAK_T = 9.27              # profiles/r01_widemad_microbench.json: IMAD.WIDE.U32 (any form: RZ / addend / .X) issue rate, 10^12/s
+WIDE_MADS_PER_MADD = 6 * 128 + 2 * 100 + 192   # XYZZ mixed add as executed: 6 products, 2 dedicated squarings, one 2-term dot
 ACC_TRAFFIC_BYTES = 7.329e9         # profiles/r01_ncu_k_accumulate.json: dram read+write of one k_accumulate launch at 2^22 (prepared path)
 HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
 
@@ -516,7 +517,20 @@ def run_ours(args):
         for _ in range(2):
             fg1()
         tg1 = timed(fg1, 5, collective=False) / 5
-        secondary["msm_g1_2^20"] = {"ms": round(tg1, 3), "Mpts_per_s": round(n1 / (tg1 * 1e-3) / 1e6, 2)}
+        # bottom of the north_star range with registered (prepared) bases: the first 2^20 points of the bench set
+        h20 = C.c_uint64(0)
+        capi.check(lib.zkg_bases_register_dev(ctx, 1, C.c_void_p(bases.data_ptr()), n1, C.byref(h20)))
+        o20 = torch.zeros(12, dtype=torch.int64, device=dev)
+
+        def fr20():
+            capi.check(lib.zkg_msm_bn254_registered_dev(ctx, h20.value, C.c_void_p(a1.data_ptr()), n1, C.c_void_p(o20.data_ptr()), 0))
+        for _ in range(2):
+            fr20()
+        tr20 = timed(fr20, 5, collective=False) / 5
+        secondary["msm_g1_2^20"] = {"ms": round(tg1, 3), "Mpts_per_s": round(n1 / (tg1 * 1e-3) / 1e6, 2),
+                                    "registered_ms": round(tr20, 3), "registered_Mpts_per_s": round(n1 / (tr20 * 1e-3) / 1e6, 2),
+                                    "paths_agree": bool((o20 == out_xyz).all())}
+        capi.check(lib.zkg_bases_release(h20.value))
         del a2, s2, b2, a1
         # top of the north_star range: 2^24 points on one GPU (generic path and registered bases)
         n24 = 1 << 24
@@ -724,7 +738,7 @@ def run_ours(args):
         achieved = n * imad_per_point / (acc_ms * 1e-3) / 1e12
         my_c = int(os.environ.get("ZKG_MSM_PREP_C", "0")) or {19: 20, 20: 20, 21: 20, 22: 20, 23: 20, 24: 20}.get(args.log2n, 20)
         my_W = 254 // my_c + 1
-        modmul_rate = n * my_W * 10 / (acc_ms * 1e-3) / 1e9      # products the kernel actually executes (XYZZ mixed add = 10)
+        wide_rate = n * my_W * WIDE_MADS_PER_MADD / (acc_ms * 1e-3) / 1e12   # 32x32->64 multiply-adds the kernel actually executes
         if not args.no_cpu and not args.no_secondary:
             secondary["cpu_d_fft_m2^16"] = cpu_dfft_sample(16)
         cpu_n, cpu_th, cpu_t = cpu_msm_sample(18, 3) if not args.no_cpu else (0, 0, [1.0])
@@ -760,10 +774,15 @@ def run_ours(args):
                          "achieved": round(achieved, 3), "peak": int_peak, "unit": "TIMAD/s",
                          "frac": round(achieved / int_peak, 4), "peak_source": int_how,
                          "algorithmic_imad_per_point": imad_per_point,
-                         "note": "SURVEY 8(d) formula k*11*W*272/T with arkworks' W; frac can exceed 1 because the XYZZ mixed "
-                                 "add needs 10 products where arkworks' Jacobian madd needs 11",
-                         "executed_modmul_G_per_s": round(modmul_rate, 2), "modmul_peak_G_per_s": MODMUL_PEAK_G,
-                         "modmul_frac": round(modmul_rate / MODMUL_PEAK_G, 4), "kernel_ms": round(acc_ms, 4),
+                         "note": "SURVEY 8(d) formula k*11*W*272/T with arkworks' W; frac exceeds 1 because the kernel does less "
+                                 "work than the formula charges: 13 windows instead of 15 (prepared table), and an XYZZ mixed "
+                                 "add of 1160 wide multiply-adds (6 products, 2 squarings of 100, one 2-term inner product) "
+                                 "where arkworks' Jacobian madd is 11 products of 128",
+                         "executed_wide_mad_T_per_s": round(wide_rate, 3), "wide_mad_peak_T_per_s": WIDE_MAD_PEAK_T,
+                         "wide_mad_frac": round(wide_rate / WIDE_MAD_PEAK_T, 4),
+                         "wide_mad_note": "the binding unit: IMAD.WIDE.U32 issues at half the 32-bit IMAD rate in every form "
+                                          "(tools/microbench/widemad.cu), so a 254-bit Montgomery product is 128 of them at best",
+                         "kernel_ms": round(acc_ms, 4),
                          "kernel_share_of_step": round(acc_ms / ms_per_step, 4),
                          "phase_ms": {"digits_sort": round(sort_ms, 4), "accumulate": round(acc_ms, 4),
                                       "reduce_final": round(red_ms, 4),

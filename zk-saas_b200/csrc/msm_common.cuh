@@ -55,9 +55,22 @@ ZKG_HD int msm_pick_c_merged(size_t n) {
         int used = r < c - 1 ? r : c - 1;
         if (used > fallback_used) { fallback = c; fallback_used = used; }
         if ((n >> used) > 1024) continue;
-        // + the latency of the reduction levels: each of the ceil((c-1)/3) launches is a chain of ~24
-        //   dependent group additions (~0.2 ms, i.e. the time of ~13 M multiplications at full rate)
-        double cost = (double)n * W * 10.0 + (double)((size_t)1 << (c - 1)) * 28.0 + (double)((c - 1 + 2) / 3) * 13e6;
+        // the top window's buckets are walked by one thread each, ~4 us (27.6 k addition units) per point: keep that
+        // chain under a quarter of the accumulation (measured: c = 22 at 2^22 points loses 3.5 ms to it)
+        {
+            double chain = (double)(n >> used) * 27.6e3, quarter = 0.25 * (double)n * W;
+            if (chain > (quarter > 2.0e6 ? quarter : 2.0e6)) continue;
+        }
+        // Calibrated on B200 (tools/scratch/msm_reg.py sweeps), in units of one bucket addition (0.145 ns):
+        //   accumulate  n*W, divided by an occupancy factor when there are fewer buckets (= threads) than the
+        //               ~75 k the 148 SMs want, plus 15 % for digits + counting sort;
+        //   reduction   2.8 per bucket (two full additions) + the latency chain: ~1.7 M for the serial
+        //               head and tail, 70 k per log-depth merge level.
+        double threads = (double)((size_t)1 << (c - 1));
+        double occ = threads >= 75000.0 ? 1.0 : threads / 75000.0;
+        double occ_sqrt = 1.0;                       // sqrt(occ) by Newton (no <cmath> in device builds of this header)
+        if (occ < 1.0) { occ_sqrt = 0.5 * (1.0 + occ); for (int it = 0; it < 6; ++it) occ_sqrt = 0.5 * (occ_sqrt + occ / occ_sqrt); }
+        double cost = (double)n * W * (1.0 / occ_sqrt + 0.15) + threads * 2.8 + 1.7e6 + 7.0e4 * (c - 4);
         if (best == 0 || cost < best_cost) { best = c; best_cost = cost; }
     }
     return best ? best : fallback;
