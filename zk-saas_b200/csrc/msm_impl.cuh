@@ -787,7 +787,7 @@ static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<
 // accumulate `n` points (n <= chunk_cap) into the plan's buckets.  Merged plans pass the whole
 // window-shifted table as d_bases and the chunk's first point index as point0.
 template <class F>
-static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, size_t point0 = 0) {
+static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const Fr* d_scalars, size_t n, size_t point0 = 0) {
     if (n == 0) return ZKG_OK;
     cudaStream_t st = ctx->stream;
     const int TB = 256;
@@ -813,6 +813,18 @@ static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases,
     k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(pl->shist, sstart);
     k_size_scatter<<<(unsigned)((pl->slots + 255) / 256), 256, 0, st>>>(pl->counts, pl->slots, sstart, pl->order);
     if (first) phase_mark(ctx, 1);
+    ctx->launches += 8;
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+// second half of a chunk: bucket accumulation of the points sorted by msm_chunk_sort (needs the bases)
+template <class F>
+static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, size_t n) {
+    if (n == 0) return ZKG_OK;
+    cudaStream_t st = ctx->stream;
+    const bool first = pl->chunks_done == 0;
+    const size_t sstride = pl->merged ? 0 : n;
     static const int use_ba = env_int("ZKG_MSM_BA", 0);
     if (use_ba)
         k_accumulate_ba<F><<<(unsigned)((pl->slots + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, st>>>(
@@ -831,10 +843,16 @@ static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases,
         }
     }
     if (first) phase_mark(ctx, 2);
-    ctx->launches += 9;
+    ctx->launches += 1;
     pl->chunks_done += 1;
     ZKG_CUDA(cudaGetLastError());
     return ZKG_OK;
+}
+
+template <class F>
+static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, size_t point0 = 0) {
+    ZKG_TRY(msm_chunk_sort<F>(ctx, pl, d_scalars, n, point0));
+    return msm_chunk_accumulate<F>(ctx, pl, d_bases, n);
 }
 
 template <class F>
@@ -937,8 +955,12 @@ static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int
                                      F* d_out) {
     MsmPlan<F> pl;
     if (n) {
-        const int K = n >= ((size_t)1 << 18) ? 4 : 1;
-        const size_t chunk = (n + K - 1) / K;
+        // graded chunks (1/16, 3/16, 1/4, 1/4, 1/4): the first copy, which nothing hides, is short
+        size_t bounds[6] = {0, n, n, n, n, n};
+        int K = 1;
+        if (n >= ((size_t)1 << 18)) { K = 5; bounds[1] = n / 16; bounds[2] = n / 4; bounds[3] = n / 2; bounds[4] = n / 4 * 3; }
+        size_t chunk = 0;
+        for (int j = 0; j < K; ++j) if (bounds[j + 1] - bounds[j] > chunk) chunk = bounds[j + 1] - bounds[j];
         ZKG_TRY(ctx->io.reserve(align_up(n * 32, 256) + 512));
         uint8_t* d_sc = (uint8_t*)ctx->io.p;
         ZKG_TRY(msm_plan<F>(ctx, n, chunk, &pl, c));
@@ -946,8 +968,8 @@ static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int
         ZKG_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
         ZKG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
         for (int j = 0; j < K; ++j) {
-            size_t lo = (size_t)j * chunk, hi = lo + chunk < n ? lo + chunk : n;
-            if (lo >= hi) break;
+            size_t lo = bounds[j], hi = bounds[j + 1];
+            if (lo >= hi) continue;
             ZKG_TRY(copy_h2d(d_sc + lo * 32, (const uint8_t*)h_scalars + lo * 32, (hi - lo) * 32, ctx->copy_stream));
             ZKG_CUDA(cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
             ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[j], 0));
@@ -1067,7 +1089,7 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
     // ZKG_MSM_CHUNKS=k forces k equal chunks.
     size_t bounds[18];
     int K = env_int("ZKG_MSM_CHUNKS", 0);
-    if (K > 16) K = 16;
+    if (K > 8) K = 8;
     if (K > 0) {
         for (int j = 0; j <= K; ++j) bounds[j] = n * (size_t)j / (size_t)K;
     } else if (n >= ((size_t)1 << 20)) {
@@ -1091,7 +1113,7 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
     MsmPlan<F> pl;
     if (n) {
         ZKG_TRY(msm_plan<F>(ctx, n, chunk_cap, &pl));
-        ZKG_TRY(ctx_copy_stream(ctx, K));
+        ZKG_TRY(ctx_copy_stream(ctx, 2 * K));
         // order the copy stream after whatever the compute stream last did with these buffers
         ZKG_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
         ZKG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
@@ -1101,12 +1123,17 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
         for (int j = 0; j < K; ++j) {
             size_t lo = bounds[j], hi = bounds[j + 1];
             if (lo >= hi) continue;
+            // the scalars go first: digits and the counting sort need nothing else, so the chunk's bases cross
+            // PCIe while its own sort runs
             ZKG_TRY(copy_h2d(d_sc + lo * 32, (const uint8_t*)scalars + lo * 32, (hi - lo) * 32, ctx->copy_stream));
+            ZKG_CUDA(cudaEventRecord(ctx->copy_ev[2 * j], ctx->copy_stream));
+            ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2 * j], 0));
+            ZKG_TRY(msm_chunk_sort<F>(ctx, &pl, (const Fr*)d_sc + lo, hi - lo));      // launched before the (possibly host-staged) bases copy
             ZKG_TRY(copy_h2d(d_ark + lo * stride, (const uint8_t*)bases + lo * stride, (hi - lo) * stride, ctx->copy_stream));
-            ZKG_CUDA(cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
-            ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[j], 0));
+            ZKG_CUDA(cudaEventRecord(ctx->copy_ev[2 * j + 1], ctx->copy_stream));
+            ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2 * j + 1], 0));
             ZKG_TRY(pack_bases<F>(ctx, d_ark + lo * stride, stride, hi - lo, d_pk + lo * sizeof(Affine<F>)));
-            ZKG_TRY(msm_chunk<F>(ctx, &pl, (const Affine<F>*)d_pk + lo, (const Fr*)d_sc + lo, hi - lo));
+            ZKG_TRY(msm_chunk_accumulate<F>(ctx, &pl, (const Affine<F>*)d_pk + lo, hi - lo));
         }
     }
     ZKG_TRY(msm_finish<F>(ctx, &pl, d_out, 0));
