@@ -27,10 +27,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-INT_PEAK_TIMAD = 18.51              # profiles/r01_intpipe_microbench.json: 32-bit IMAD issue rate, B200, 148 SMs @1965 MHz
+INT_PEAK_TIMAD = 18.51              # profiles/r01_intpipe_microbench_v2.json: 32-bit IMAD issue rate, B200, 148 SMs @1965 MHz
 WIDE_MAD_PEAK_T = 9.27              # profiles/r01_widemad_microbench.json: IMAD.WIDE.U32 (any form: RZ / addend / .X) issue rate, 10^12/s
 WIDE_MADS_PER_MADD = 6 * 128 + 2 * 100 + 192   # XYZZ mixed add as executed: 6 products, 2 dedicated squarings, one 2-term dot
-ACC_TRAFFIC_BYTES = 7.329e9         # profiles/r01_ncu_k_accumulate.json: dram read+write of one k_accumulate launch at 2^22 (prepared path)
+ACC_TRAFFIC_BYTES = 7.336e9         # profiles/r01_ncu_k_accumulate_v2.json: dram read+write of one k_accumulate launch at 2^22 (prepared path)
 HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
 
 
@@ -791,7 +791,7 @@ def run_ours(args):
                          "hbm": {"achieved_gbs": round(96 * n / (acc_ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
                                  "frac": round(96 * n / (acc_ms * 1e-3) / 1e9 / hbm_peak, 4), "peak_source": hbm_how},
                          "traffic": ACC_TRAFFIC_BYTES if args.log2n == 22 else None,
-                         "traffic_note": "ncu dram bytes per launch; 17x the 96 B/point because Pippenger re-reads every base once per window (15 x 64 B) -- 0.73 TB/s, 11% of HBM peak, not the bound"},
+                         "traffic_note": "ncu dram bytes per launch; 18x the 96 B/point because Pippenger gathers every base once per window (13 gathers that each pull 128 B) -- 0.92 TB/s, 14% of HBM peak, not the bound"},
             "cpu_baseline": {"value": round(cpu_val, 4), "unit": "Mpts/s", "cores": cpu_th, "kind": "port",
                              "sample": "G1 MSM of 2^18 points, best of 3, oracle/zkoracle.c (arkworks msm_bigint_wnaf restated), OpenMP over windows"},
             "secondary": secondary,

@@ -277,6 +277,55 @@ def test_fft1_sharded_steps_on_one_gpu(z, l, mbyl, world):
         lib.zkg_ctx_destroy(ctx)
 
 
+@pytest.mark.parametrize("l,mbyl,world,rearrange,coset", [(2, 16, 2, 1, 1), (2, 1 << 10, 4, 0, 0), (2, 1 << 13, 8, 1, 1),
+                                                           (2, 1 << 10, 8, 1, 1), (2, 64, 4, 0, 1), (4, 1 << 11, 4, 1, 1), (2, 1 << 16, 2, 1, 1)])
+def test_king_sharded_stages_on_one_gpu(z, l, mbyl, world, rearrange, coset):
+    """The two CUDA stages of the column-sharded king pipeline, with the reduce-scatter emulated on one device
+    (sum of the ranks' full-size pack-order buffers, sliced): together they must reproduce the single-GPU king
+    closure bit for bit.  Exercises column ranges that do not start at 0 (and, for 2^10 columns over 8 ranks or 64
+    over 4, ranges that are not multiples of the 256-aligned exponent tiles of the l = 2 kernel)."""
+    import torch
+    from zksaas_b200 import capi
+    lib = z.lib()
+    ctx = capi.ctx_p()
+    capi.check(lib.zkg_ctx_create(0, C.c_void_p(1), C.byref(ctx)))
+    try:
+        n, t = 4 * l, l
+        m = mbyl * l
+        g_ = torch.Generator(device="cuda"); g_.manual_seed(mbyl * 31 + world)
+
+        def rnd(k):
+            x = torch.randint(-2**63, 2**63 - 1, (k, 4), dtype=torch.int64, device="cuda", generator=g_)
+            x[:, 3] &= (1 << 61) - 1
+            return x
+        shares = rnd(n * mbyl).reshape(n, mbyl, 4)
+        rand = rnd(mbyl * t)
+        gen = z.Radix2EvaluationDomain.new(m).group_gen()
+        g = z.Radix2EvaluationDomain.new(2 * m).element(1) if coset else z.Radix2EvaluationDomain.new(m).element(0)
+        full = torch.empty((n, mbyl, 4), dtype=torch.int64, device="cuda")
+        capi.check(lib.zkg_king_fft2_bn254_dev(ctx, C.c_void_p(shares.data_ptr()), None, n, mbyl, l, gen.ctypes.data, g.ctypes.data,
+                                               rearrange, C.c_void_p(rand.data_ptr()), C.c_void_p(full.data_ptr())))
+        cols = mbyl // world
+        S_sum = torch.zeros((m, 4), dtype=torch.int64, device="cuda")
+        for r in range(world):
+            loc = shares[:, r * cols:(r + 1) * cols].contiguous()
+            S = torch.zeros((m, 4), dtype=torch.int64, device="cuda")
+            capi.check(lib.zkg_king_stage1_bn254_dev(ctx, C.c_void_p(loc.data_ptr()), None, n, r * cols, cols, mbyl, l,
+                                                     gen.ctypes.data, g.ctypes.data, rearrange, C.c_void_p(S.data_ptr())))
+            capi.check(lib.zkg_ctx_sync(ctx))
+            S_sum += S                                   # every slot is written by exactly one rank: lane sums never carry
+        for r in range(world):
+            S_r = S_sum[r * cols * l:(r + 1) * cols * l].contiguous()
+            rd = rand[r * cols * t:(r + 1) * cols * t].contiguous()
+            out = torch.empty((n, cols, 4), dtype=torch.int64, device="cuda")
+            capi.check(lib.zkg_king_stage2_bn254_dev(ctx, C.c_void_p(S_r.data_ptr()), C.c_void_p(rd.data_ptr()), cols, l,
+                                                     C.c_void_p(out.data_ptr())))
+            capi.check(lib.zkg_ctx_sync(ctx))
+            assert bool((out == full[:, r * cols:(r + 1) * cols]).all()), r
+    finally:
+        lib.zkg_ctx_destroy(ctx)
+
+
 @pytest.mark.parametrize("l,mbyl", [(2, 1), (2, 2), (2, 4), (2, 8), (2, 512), (2, 1024), (2, 2048), (2, 1 << 15),
                                     (4, 16), (4, 1 << 11), (8, 1 << 12), (2, 1 << 17)])
 def test_fft1_vs_literal_oracle(z, o, l, mbyl):
