@@ -536,7 +536,7 @@ k_map_in_regs(const Fr* __restrict__ M, int rows, int k1, const Fr* __restrict__
 // DFT on <zeta_8> of the zero-padded coefficients -- instead of the dense 8 x 4 matrix: 10 field
 // products per column instead of 32.  Same canonical results (the map is the same linear map).
 // cst[0] = zeta_4^-1, cst[1..4] = g^-d / 4 (d = 0..3), cst[5] = zeta_4, cst[6..8] = zeta_8^1..3
-struct Pack2Consts { FrArg c[9]; };
+struct Pack2Consts { FrArg c[9]; FrArg oa[4], ob[4]; };   // oa/ob: the odd half as 2-term inner products (see k_pack_l2)
 __global__ void __launch_bounds__(256)
 k_pack_l2(Pack2Consts K, const Fr* __restrict__ secrets, size_t s_cs, size_t s_rs, const Fr* __restrict__ rand, size_t r_cs,
           size_t r_rs, int has_rand, Fr* __restrict__ out, size_t out_cs, size_t out_rs, size_t cols) {
@@ -546,18 +546,18 @@ k_pack_l2(Pack2Consts K, const Fr* __restrict__ secrets, size_t s_cs, size_t s_r
     Fr v2 = has_rand ? ld_fr(rand + c * r_cs) : Fr::zero(), v3 = has_rand ? ld_fr(rand + c * r_cs + r_rs) : Fr::zero();
     // inverse DFT_4 (root zeta_4^-1), then coefficient d scaled by g^-d / 4
     Fr a0 = fp_add(v0, v2), a1 = fp_sub(v0, v2), b0 = fp_add(v1, v3);
-    Fr b1 = fp_mul(fp_sub(v1, v3), from_arg(K.c[0]));
     Fr c0 = fp_mul(fp_add(a0, b0), from_arg(K.c[1]));
-    Fr c1 = fp_mul(fp_add(a1, b1), from_arg(K.c[2]));
     Fr c2 = fp_mul(fp_sub(a0, b0), from_arg(K.c[3]));
-    Fr c3 = fp_mul(fp_sub(a1, b1), from_arg(K.c[4]));
     // DFT_8 of (c0, c1, c2, c3, 0, 0, 0, 0): s_j = E_(j mod 4) + zeta_8^j O_(j mod 4)
-    Fr t2 = fp_mul(c2, from_arg(K.c[5])), t3 = fp_mul(c3, from_arg(K.c[5]));
+    Fr t2 = fp_mul(c2, from_arg(K.c[5]));
     Fr E[4] = {fp_add(c0, c2), fp_add(c0, t2), fp_sub(c0, c2), fp_sub(c0, t2)};
-    Fr O[4] = {fp_add(c1, c3), fp_add(c1, t3), fp_sub(c1, c3), fp_sub(c1, t3)};
+    // the odd half never materialises c1, c3: zeta_8^k O_k = oa[k] * a1 + ob[k] * (v1 - v3), one 2-term inner product
+    // each (4 x 192 wide MADs instead of the 7 x 128 of b1, c1, c3, t3 and the three zeta_8^k factors)
+    Fr x[2] = {a1, fp_sub(v1, v3)};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        Fr o = k == 0 ? O[0] : fp_mul(O[k], from_arg(K.c[5 + k]));
+        Fr y[2] = {from_arg(K.oa[k]), from_arg(K.ob[k])};
+        Fr o = fp_dot<FrParams, 2>(x, y);
         st_fr(out + c * out_cs + (size_t)k * out_rs, fp_add(E[k], o));
         st_fr(out + c * out_cs + (size_t)(k + 4) * out_rs, fp_sub(E[k], o));
     }
@@ -885,6 +885,16 @@ static Pack2Consts pack2_consts() {
     K.c[6] = to_arg(z8);
     K.c[7] = to_arg(z4);
     K.c[8] = to_arg(h_mul(z8, z4));
+    // odd half: c1 = (a1 + b1) K2, c3 = (a1 - b1) K4, b1 = d K0 (d = v1 - v3);  O_k = c1 +- c3 [* K5];  o_k = z_k O_k
+    HFr K0 = h_inv(z4), K2 = h_mul(quarter, ginv), K4 = h_mul(h_mul(K2, ginv), ginv), K5 = z4;
+    HFr zk[4] = {h_one(), z8, z4, h_mul(z8, z4)};
+    for (int k = 0; k < 4; ++k) {
+        HFr w = (k & 1) ? h_mul(K4, K5) : K4;                       // the c3 coefficient of O_k before its sign
+        HFr pa = k < 2 ? h_add(K2, w) : h_sub(K2, w);               // a1 coefficient
+        HFr pb = k < 2 ? h_sub(K2, w) : h_add(K2, w);               // b1 coefficient (c3 carries -b1)
+        K.oa[k] = to_arg(h_mul(zk[k], pa));
+        K.ob[k] = to_arg(h_mul(zk[k], h_mul(K0, pb)));
+    }
     return K;
 }
 
