@@ -341,6 +341,30 @@ def test_fft1_vs_literal_oracle(z, o, l, mbyl):
     assert (got == exp).all()
 
 
+@pytest.mark.parametrize("mbyl", [1, 2, 4, 8, 16, 32, 128, 512, 1 << 10, 1 << 11, 1 << 12, 1 << 14, 1 << 16, 1 << 18])
+@pytest.mark.parametrize("elog,tables", [(11, 1), (9, 1), (11, 0)])
+def test_fft1_radix8_kernel_all_shapes(z, o, monkeypatch, mbyl, elog, tables):
+    """The register-blocked radix-8 pass kernel (production for N >= 2^18) forced onto every transform size, so that
+    all its group shapes (1, 2 and 3 stages per group; fewer than 8 elements; one, two and three passes; narrow
+    tiles) and both twiddle sources (per-pass table / on-the-fly powers) are pinned against the literal loops of
+    fft1_in_place."""
+    monkeypatch.setenv("ZKG_NTT_R8_MIN", "0")
+    monkeypatch.setenv("ZKG_NTT_ELOG", str(elog))
+    if not tables:
+        monkeypatch.setenv("ZKG_NTT_ONTHEFLY", "1")
+    l = 2
+    rng = np.random.default_rng(mbyl * 13 + elog)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(mbyl * l)
+    px = ol.rand_fr(rng, mbyl)
+    exp = px.copy()
+    gen = dom.group_gen()
+    o.zko_fft1_in_place(_p(exp), mbyl, l, _p(gen))
+    got = px.copy()
+    z.fft1_in_place(got, pp, gen)
+    assert (got == exp).all()
+
+
 def test_fft1_fused_scale_and_mask(z, o):
     l, mbyl = 2, 1 << 12
     rng = np.random.default_rng(3)
