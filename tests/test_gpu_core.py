@@ -365,6 +365,49 @@ def test_fft1_radix8_kernel_all_shapes(z, o, monkeypatch, mbyl, elog, tables):
     assert (got == exp).all()
 
 
+def test_parameter_cache_flush_mid_call(z, monkeypatch):
+    """The per-context parameter cache (power tables, per-pass twiddle tables, scaled unpack matrices) is bounded in
+    bytes; with a 1 MiB budget it is flushed in the middle of calls.  Results must not change, and pointers handed out
+    before a flush must stay valid until the call returns (deferred frees)."""
+    import torch
+    from zksaas_b200 import capi
+    lib = z.lib()
+    l, mbyl = 2, 1 << 14
+    m = mbyl * l
+    g_ = torch.Generator(device="cuda"); g_.manual_seed(77)
+
+    def rnd(k):
+        x = torch.randint(-2**63, 2**63 - 1, (k, 4), dtype=torch.int64, device="cuda", generator=g_)
+        x[:, 3] &= (1 << 61) - 1
+        return x
+    shares, rand, px = rnd(8 * mbyl), rnd(2 * mbyl), rnd(mbyl)
+    gen = z.Radix2EvaluationDomain.new(m).group_gen()
+    cosets = [z.Radix2EvaluationDomain.new(2 * m).element(k) for k in (1, 3, 5)]
+
+    def run_all():
+        ctx = capi.ctx_p()
+        capi.check(lib.zkg_ctx_create(0, C.c_void_p(1), C.byref(ctx)))
+        outs = []
+        try:
+            for rep in range(2):
+                for g in cosets:
+                    out = torch.empty((8 * mbyl, 4), dtype=torch.int64, device="cuda")
+                    capi.check(lib.zkg_king_fft2_bn254_dev(ctx, C.c_void_p(shares.data_ptr()), None, 8, mbyl, l, gen.ctypes.data,
+                                                           g.ctypes.data, 1, C.c_void_p(rand.data_ptr()), C.c_void_p(out.data_ptr())))
+                    f = px.clone()
+                    capi.check(lib.zkg_fft1_bn254_dev(ctx, C.c_void_p(f.data_ptr()), mbyl, l, g.ctypes.data, None, None))
+                    capi.check(lib.zkg_ctx_sync(ctx))
+                    outs.append((out, f))
+        finally:
+            lib.zkg_ctx_destroy(ctx)
+        return outs
+    base = run_all()
+    monkeypatch.setenv("ZKG_CACHE_MAX_MB", "1")
+    small = run_all()
+    for (a0, b0), (a1, b1) in zip(base, small):
+        assert bool((a0 == a1).all()) and bool((b0 == b1).all())
+
+
 def test_fft1_fused_scale_and_mask(z, o):
     l, mbyl = 2, 1 << 12
     rng = np.random.default_rng(3)

@@ -44,6 +44,7 @@ static void ctx_free(zkg_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->ws.release(); c->io.release();
     for (auto& e : c->cache) cudaFree(e.p);
+    for (void* d : c->cache_dead) cudaFree(d);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < c->copy_ev_count; ++i) cudaEventDestroy(c->copy_ev[i]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -81,14 +82,23 @@ int32_t ctx_cache_get(zkg_ctx* ctx, const void* key, size_t key_bytes, size_t by
     fnv2(key, key_bytes, &h1, &h2);
     for (auto& e : ctx->cache)
         if (e.h1 == h1 && e.h2 == h2 && e.bytes == bytes) { *out = e.p; *fresh = false; return ZKG_OK; }
-    if (ctx->cache.size() >= 256) {          // bounded: drop everything once nothing in flight can still read it
+    // bounded in entries and in bytes (the per-pass NTT twiddle tables of a 2^23-point transform are 256 MiB each; a
+    // prover cycling through many domains must not pin them all): drop everything once nothing in flight can still
+    // read it.  ZKG_CACHE_MAX_MB overrides the 16 GiB default.
+    const char* mv = getenv("ZKG_CACHE_MAX_MB");               // read on misses only
+    const size_t max_bytes = (mv && *mv ? (size_t)atoll(mv) : (size_t)16384) << 20;
+    if (ctx->cache.size() >= 256 || (ctx->cache_bytes + bytes > max_bytes && !ctx->cache.empty())) {
         ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (auto& e : ctx->cache) cudaFree(e.p);
+        for (void* d : ctx->cache_dead) cudaFree(d);
+        ctx->cache_dead.clear();
+        for (auto& e : ctx->cache) ctx->cache_dead.push_back(e.p);     // freed one flush later
         ctx->cache.clear();
+        ctx->cache_bytes = 0;
     }
     void* p = nullptr;
     ZKG_CUDA(cudaMalloc(&p, bytes ? bytes : 256));
     ctx->cache.push_back({h1, h2, bytes, p});
+    ctx->cache_bytes += bytes;
     *out = p; *fresh = true;
     return ZKG_OK;
 }

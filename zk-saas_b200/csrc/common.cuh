@@ -63,6 +63,9 @@ struct zkg_ctx {
     // persistent device-side parameter cache (twiddle/power tables, PSS matrices), keyed by content
     struct CacheEnt { uint64_t h1, h2; size_t bytes; void* p; };
     std::vector<CacheEnt> cache;
+    size_t cache_bytes = 0;            // sum of the entries' sizes (bounded: see ctx_cache_get)
+    std::vector<void*> cache_dead;     // entries dropped by the last flush; freed by the next one (pointers handed out
+                                       // earlier in the call that triggered the flush stay valid until it returns)
     // second stream + events for overlapping H2D copies with compute in host-pointer entry points
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev[16] = {};
