@@ -650,6 +650,108 @@ __global__ void k_final(const XYZZ<F>* __restrict__ R, const XYZZ<F>* __restrict
 }
 
 // identity result for n == 0
+// ------------------------------------------------------------------------------------------
+// The Horner over windows is a chain of c*(W-1) DEPENDENT doublings: one thread runs it at the speed of one
+// SM sub-partition's multiplier (~3.5 us per doubling).  A formula's independent products cannot overlap inside a
+// warp -- every warp instruction of a sub-partition goes through the same multiply pipe, four cycles each -- but
+// they can across the FOUR sub-partitions of an SM: this kernel runs one block of four warps, lane 0 of each
+// evaluating one product of a formula level, shared memory + __syncthreads between levels.
+//   Jacobian doubling (dbl-2009-l, a = 0): 3 levels   {A = X^2, B = Y^2, YZ} {F = (3A)^2, C = B^2, t = (X+B)^2} {Y3}
+//   XYZZ addition (add-2008-s):            4 levels   {U1, U2, S1, S2} {PP, RR, ZZ1 ZZ2, ZZZ1 ZZZ2} {PPP, Q, ZZ3} {Y3, ZZZ3}
+// Same values as k_final (a group element has one normal form); the exceptional cases of the addition (equal or
+// opposite points, infinity) are block-uniform and fall back to the plain routine on one thread.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_final_coop(const XYZZ<F>* __restrict__ R, const XYZZ<F>* __restrict__ Cs, int c, int W, int mode, F* __restrict__ out) {
+    __shared__ XYZZ<F> Ssh[64];                  // S_w = R_w + Cs_w
+    __shared__ XYZZ<F> acc;
+    __shared__ F t[10];                          // level results
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool lead = (tid & 31) == 0;
+    if (tid < W) { XYZZ<F> s_ = load_vec_rw(R + tid); xyzz_add(s_, load_vec_rw(Cs + tid)); Ssh[tid] = s_; }
+    if (tid == 0) acc = XYZZ<F>::inf();
+    __syncthreads();
+    for (int w = W - 1; w >= 0; --w) {
+        // ---- acc = 2^c * acc ----
+        if (!acc.is_inf() && c > 0) {            // block-uniform (acc is shared)
+            // XYZZ -> Jacobian (zz^2 x, zz^3 y, zzz): X -> t[0], Y -> t[1], Z -> t[2]
+            if (lead && warp == 0) t[3] = f_sqr(acc.zz);
+            if (lead && warp == 1) t[2] = acc.zzz;
+            __syncthreads();
+            if (lead && warp == 0) t[0] = f_mul(acc.x, t[3]);
+            if (lead && warp == 1) t[4] = f_mul(t[3], acc.zz);
+            __syncthreads();
+            if (lead && warp == 1) t[1] = f_mul(acc.y, t[4]);
+            __syncthreads();
+            for (int i = 0; i < c; ++i) {
+                // level 1
+                if (lead && warp == 0) t[3] = f_sqr(t[0]);                       // A
+                if (lead && warp == 1) t[4] = f_sqr(t[1]);                       // B
+                if (lead && warp == 2) t[5] = f_mul(t[1], t[2]);                 // Y Z
+                __syncthreads();
+                // level 2
+                if (lead && warp == 0) { F e = f_add(f_dbl(t[3]), t[3]); t[6] = e; t[7] = f_sqr(e); }   // E, F
+                if (lead && warp == 1) t[8] = f_sqr(t[4]);                       // C
+                if (lead && warp == 2) t[9] = f_sqr(f_add(t[0], t[4]));          // (X + B)^2
+                __syncthreads();
+                // level 3
+                if (lead && warp == 0) {
+                    F D = f_dbl(f_sub(f_sub(t[9], t[3]), t[8]));
+                    F X3 = f_sub(f_sub(t[7], D), D);
+                    F C8 = f_dbl(f_dbl(f_dbl(t[8])));
+                    t[1] = f_sub(f_mul(t[6], f_sub(D, X3)), C8);
+                    t[0] = X3;
+                }
+                if (lead && warp == 2) t[2] = f_dbl(t[5]);                       // Z3 = 2 Y Z
+                __syncthreads();
+            }
+            if (lead && warp == 0) { F zz = f_sqr(t[2]); acc.zz = zz; acc.zzz = f_mul(zz, t[2]); acc.x = t[0]; acc.y = t[1]; }
+            __syncthreads();
+        }
+        // ---- acc += S_w ----
+        const XYZZ<F>& b = Ssh[w];
+        if (b.is_inf()) continue;                                                // block-uniform
+        if (acc.is_inf()) { if (tid == 0) acc = b; __syncthreads(); continue; }
+        if (lead && warp == 0) t[0] = f_mul(acc.x, b.zz);                        // U1
+        if (lead && warp == 1) t[1] = f_mul(b.x, acc.zz);                        // U2
+        if (lead && warp == 2) t[2] = f_mul(acc.y, b.zzz);                       // S1
+        if (lead && warp == 3) t[3] = f_mul(b.y, acc.zzz);                       // S2
+        __syncthreads();
+        if (t[0] == t[1]) {                                                      // same x: doubling or cancellation (rare)
+            __syncthreads();
+            if (tid == 0) { XYZZ<F> a_ = acc; xyzz_add(a_, b); acc = a_; }
+            __syncthreads();
+            continue;
+        }
+        F pp_, rr_;
+        if (lead && warp == 0) { pp_ = f_sub(t[1], t[0]); t[4] = f_sqr(pp_); }   // PP
+        if (lead && warp == 1) { rr_ = f_sub(t[3], t[2]); t[5] = f_sqr(rr_); }   // RR
+        if (lead && warp == 2) t[6] = f_mul(acc.zz, b.zz);
+        if (lead && warp == 3) t[7] = f_mul(acc.zzz, b.zzz);
+        __syncthreads();
+        if (lead && warp == 0) t[1] = f_mul(pp_, t[4]);                          // PPP (U2 is dead)
+        if (lead && warp == 2) t[0] = f_mul(t[0], t[4]);                         // Q = U1 PP (only this thread reads U1 here)
+        if (lead && warp == 3) acc.zz = f_mul(t[6], t[4]);                       // ZZ3
+        __syncthreads();
+        if (lead && warp == 1) {                                                 // X3, Y3 (needs R = rr_, RR = t[5], PPP, Q, S1)
+            F x3 = f_sub(f_sub(f_sub(t[5], t[1]), t[0]), t[0]);
+            acc.y = f_mulsub(rr_, f_sub(t[0], x3), t[2], t[1]);
+            acc.x = x3;
+        }
+        if (lead && warp == 3) acc.zzz = f_mul(t[7], t[1]);                      // ZZZ3
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    if (mode == 1) {
+        out[0] = acc.x; out[1] = acc.y; out[2] = acc.zz; out[3] = acc.zzz;
+        return;
+    }
+    if (acc.is_inf()) { out[0] = F::one(); out[1] = F::one(); out[2] = F::zero(); return; }
+    Affine<F> a = xyzz_to_affine(acc);
+    out[0] = a.x; out[1] = a.y; out[2] = F::one();
+}
+
 template <class F>
 __global__ void k_identity(int mode, F* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -892,7 +994,11 @@ static int32_t msm_finish(zkg_ctx* ctx, MsmPlan<F>* pl, F* d_out, int mode) {
     ctx->launches += 1;
     const XYZZ<F>* Rin = S_arr;
     const XYZZ<F>* Cin = Z_arr;
-    k_final<F><<<1, 32, 0, st>>>(Rin, Cin, pl->merged ? 0 : pl->c, pl->Wb, mode, d_out);
+    static const int coop_tail = env_int("ZKG_MSM_COOP_TAIL", 1);
+    if (!pl->merged && pl->Wb > 1 && pl->Wb <= 64 && coop_tail)
+        k_final_coop<F><<<1, 128, 0, st>>>(Rin, Cin, pl->c, pl->Wb, mode, d_out);       // Horner over windows on four warps
+    else
+        k_final<F><<<1, 32, 0, st>>>(Rin, Cin, pl->merged ? 0 : pl->c, pl->Wb, mode, d_out);
     ctx->launches += 1;
     phase_mark(ctx, 3);
     ZKG_CUDA(cudaGetLastError());
