@@ -232,7 +232,7 @@ static __global__ void k_size_scatter(const uint32_t* __restrict__ counts, size_
 // bucket accumulation: one thread per (window, bucket)
 // ------------------------------------------------------------------------------------------
 template <class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, sizeof(F) > 32 ? 3 : 1)     // G2: stay at three blocks per SM (<= 168 registers)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
              const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
@@ -661,86 +661,75 @@ __global__ void k_final(const XYZZ<F>* __restrict__ R, const XYZZ<F>* __restrict
 // Same values as k_final (a group element has one normal form); the exceptional cases of the addition (equal or
 // opposite points, infinity) are block-uniform and fall back to the plain routine on one thread.
 // ------------------------------------------------------------------------------------------
+// The two formulas on four warps.  `acc`, `b` and the scratch `t` (>= 8 values) live in shared memory; every thread
+// of the 128-thread block calls them (the barriers are inside), only lane 0 of each warp computes.
+template <class F>
+__device__ __forceinline__ void coop_dbl(XYZZ<F>& acc, F* t, int warp, bool lead) {      // dbl-2008-s-1 (a = 0), 3 levels
+    if (acc.is_inf()) return;                                                            // block-uniform
+    if (lead && warp == 0) { F u = f_dbl(acc.y); t[0] = u; t[1] = f_sqr(u); }           // U, V
+    if (lead && warp == 1) { F xx = f_sqr(acc.x); t[2] = f_add(f_dbl(xx), xx); }         // M
+    __syncthreads();
+    if (lead && warp == 0) t[3] = f_mul(t[0], t[1]);                                     // W
+    if (lead && warp == 1) t[4] = f_mul(acc.x, t[1]);                                    // S
+    if (lead && warp == 2) t[5] = f_sqr(t[2]);                                           // M^2
+    if (lead && warp == 3) acc.zz = f_mul(t[1], acc.zz);                                 // ZZ3 (no other reader in this level)
+    __syncthreads();
+    if (lead && warp == 0) {
+        F x3 = f_sub(f_sub(t[5], t[4]), t[4]);
+        acc.y = f_mulsub(t[2], f_sub(t[4], x3), t[3], acc.y);
+        acc.x = x3;
+    }
+    if (lead && warp == 1) acc.zzz = f_mul(t[3], acc.zzz);                               // ZZZ3
+    __syncthreads();
+}
+template <class F>
+__device__ __forceinline__ void coop_add(XYZZ<F>& acc, const XYZZ<F>& b, F* t, int warp, bool lead, int tid) {   // add-2008-s, 4 levels
+    if (b.is_inf()) return;                                                              // block-uniform
+    if (acc.is_inf()) { __syncthreads(); if (tid == 0) acc = b; __syncthreads(); return; }
+    if (lead && warp == 0) t[0] = f_mul(acc.x, b.zz);                                    // U1
+    if (lead && warp == 1) t[1] = f_mul(b.x, acc.zz);                                    // U2
+    if (lead && warp == 2) t[2] = f_mul(acc.y, b.zzz);                                   // S1
+    if (lead && warp == 3) t[3] = f_mul(b.y, acc.zzz);                                   // S2
+    __syncthreads();
+    if (t[0] == t[1]) {                                                                  // same x: doubling or cancellation (rare)
+        __syncthreads();
+        if (tid == 0) { XYZZ<F> a_ = acc; xyzz_add(a_, b); acc = a_; }
+        __syncthreads();
+        return;
+    }
+    F pp_, rr_;
+    if (lead && warp == 0) { pp_ = f_sub(t[1], t[0]); t[4] = f_sqr(pp_); }               // PP
+    if (lead && warp == 1) { rr_ = f_sub(t[3], t[2]); t[5] = f_sqr(rr_); }               // RR
+    if (lead && warp == 2) t[6] = f_mul(acc.zz, b.zz);
+    if (lead && warp == 3) t[7] = f_mul(acc.zzz, b.zzz);
+    __syncthreads();
+    if (lead && warp == 0) t[1] = f_mul(pp_, t[4]);                                      // PPP (U2 is dead)
+    if (lead && warp == 2) t[0] = f_mul(t[0], t[4]);                                     // Q = U1 PP (only this thread reads U1 here)
+    if (lead && warp == 3) acc.zz = f_mul(t[6], t[4]);                                   // ZZ3
+    __syncthreads();
+    if (lead && warp == 1) {                                                             // X3, Y3
+        F x3 = f_sub(f_sub(f_sub(t[5], t[1]), t[0]), t[0]);
+        acc.y = f_mulsub(rr_, f_sub(t[0], x3), t[2], t[1]);
+        acc.x = x3;
+    }
+    if (lead && warp == 3) acc.zzz = f_mul(t[7], t[1]);                                  // ZZZ3
+    __syncthreads();
+}
+
 template <class F>
 __global__ void __launch_bounds__(128)
 k_final_coop(const XYZZ<F>* __restrict__ R, const XYZZ<F>* __restrict__ Cs, int c, int W, int mode, F* __restrict__ out) {
     __shared__ XYZZ<F> Ssh[64];                  // S_w = R_w + Cs_w
     __shared__ XYZZ<F> acc;
-    __shared__ F t[10];                          // level results
+    __shared__ F t[8];
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool lead = (tid & 31) == 0;
     if (tid < W) { XYZZ<F> s_ = load_vec_rw(R + tid); xyzz_add(s_, load_vec_rw(Cs + tid)); Ssh[tid] = s_; }
     if (tid == 0) acc = XYZZ<F>::inf();
     __syncthreads();
     for (int w = W - 1; w >= 0; --w) {
-        // ---- acc = 2^c * acc ----
-        if (!acc.is_inf() && c > 0) {            // block-uniform (acc is shared)
-            // XYZZ -> Jacobian (zz^2 x, zz^3 y, zzz): X -> t[0], Y -> t[1], Z -> t[2]
-            if (lead && warp == 0) t[3] = f_sqr(acc.zz);
-            if (lead && warp == 1) t[2] = acc.zzz;
-            __syncthreads();
-            if (lead && warp == 0) t[0] = f_mul(acc.x, t[3]);
-            if (lead && warp == 1) t[4] = f_mul(t[3], acc.zz);
-            __syncthreads();
-            if (lead && warp == 1) t[1] = f_mul(acc.y, t[4]);
-            __syncthreads();
-            for (int i = 0; i < c; ++i) {
-                // level 1
-                if (lead && warp == 0) t[3] = f_sqr(t[0]);                       // A
-                if (lead && warp == 1) t[4] = f_sqr(t[1]);                       // B
-                if (lead && warp == 2) t[5] = f_mul(t[1], t[2]);                 // Y Z
-                __syncthreads();
-                // level 2
-                if (lead && warp == 0) { F e = f_add(f_dbl(t[3]), t[3]); t[6] = e; t[7] = f_sqr(e); }   // E, F
-                if (lead && warp == 1) t[8] = f_sqr(t[4]);                       // C
-                if (lead && warp == 2) t[9] = f_sqr(f_add(t[0], t[4]));          // (X + B)^2
-                __syncthreads();
-                // level 3
-                if (lead && warp == 0) {
-                    F D = f_dbl(f_sub(f_sub(t[9], t[3]), t[8]));
-                    F X3 = f_sub(f_sub(t[7], D), D);
-                    F C8 = f_dbl(f_dbl(f_dbl(t[8])));
-                    t[1] = f_sub(f_mul(t[6], f_sub(D, X3)), C8);
-                    t[0] = X3;
-                }
-                if (lead && warp == 2) t[2] = f_dbl(t[5]);                       // Z3 = 2 Y Z
-                __syncthreads();
-            }
-            if (lead && warp == 0) { F zz = f_sqr(t[2]); acc.zz = zz; acc.zzz = f_mul(zz, t[2]); acc.x = t[0]; acc.y = t[1]; }
-            __syncthreads();
-        }
-        // ---- acc += S_w ----
-        const XYZZ<F>& b = Ssh[w];
-        if (b.is_inf()) continue;                                                // block-uniform
-        if (acc.is_inf()) { if (tid == 0) acc = b; __syncthreads(); continue; }
-        if (lead && warp == 0) t[0] = f_mul(acc.x, b.zz);                        // U1
-        if (lead && warp == 1) t[1] = f_mul(b.x, acc.zz);                        // U2
-        if (lead && warp == 2) t[2] = f_mul(acc.y, b.zzz);                       // S1
-        if (lead && warp == 3) t[3] = f_mul(b.y, acc.zzz);                       // S2
-        __syncthreads();
-        if (t[0] == t[1]) {                                                      // same x: doubling or cancellation (rare)
-            __syncthreads();
-            if (tid == 0) { XYZZ<F> a_ = acc; xyzz_add(a_, b); acc = a_; }
-            __syncthreads();
-            continue;
-        }
-        F pp_, rr_;
-        if (lead && warp == 0) { pp_ = f_sub(t[1], t[0]); t[4] = f_sqr(pp_); }   // PP
-        if (lead && warp == 1) { rr_ = f_sub(t[3], t[2]); t[5] = f_sqr(rr_); }   // RR
-        if (lead && warp == 2) t[6] = f_mul(acc.zz, b.zz);
-        if (lead && warp == 3) t[7] = f_mul(acc.zzz, b.zzz);
-        __syncthreads();
-        if (lead && warp == 0) t[1] = f_mul(pp_, t[4]);                          // PPP (U2 is dead)
-        if (lead && warp == 2) t[0] = f_mul(t[0], t[4]);                         // Q = U1 PP (only this thread reads U1 here)
-        if (lead && warp == 3) acc.zz = f_mul(t[6], t[4]);                       // ZZ3
-        __syncthreads();
-        if (lead && warp == 1) {                                                 // X3, Y3 (needs R = rr_, RR = t[5], PPP, Q, S1)
-            F x3 = f_sub(f_sub(f_sub(t[5], t[1]), t[0]), t[0]);
-            acc.y = f_mulsub(rr_, f_sub(t[0], x3), t[2], t[1]);
-            acc.x = x3;
-        }
-        if (lead && warp == 3) acc.zzz = f_mul(t[7], t[1]);                      // ZZZ3
-        __syncthreads();
+        for (int i = 0; i < c; ++i) coop_dbl(acc, t, warp, lead);
+        coop_add(acc, Ssh[w], t, warp, lead, tid);
     }
     if (tid != 0) return;
     if (mode == 1) {
