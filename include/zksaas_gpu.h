@@ -217,7 +217,8 @@ int32_t zkg_fr_from_wire_bn254(int32_t device, const void *wire, uint64_t *out_m
 int32_t zkg_fr_to_wire_bn254(int32_t device, const uint64_t *in_mont, void *wire, size_t n);
 
 /* ---- element-wise helpers used by kernel unit tests (out[i] = a[i] op b[i]; op: 0 mul, 1 add,
- * 2 sub; field: 0 Fr, 1 Fq) ---- */
+ * 2 sub; unit-test views of the routines the kernels are built from: 3 dedicated squaring a^2, 4 the two-term
+ * inner product a*b - (a+1)*b (= -b, one Montgomery reduction), 5 inverse of a (0 -> 0); field: 0 Fr, 1 Fq) ---- */
 int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t *a, const uint64_t *b, uint64_t *out,
                      size_t n);
 /* device form; also the share-wise h = a*b - c of groth16/src/ext_wit.rs:82-86,173-177 and the mask adds */

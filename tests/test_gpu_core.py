@@ -51,6 +51,15 @@ def test_field_ops_bit_exact(z, field, p):
     assert unraw(api._field_op(0, A, B, field)) == [x * y * rinv % p for x, y in zip(a, b)]
     assert unraw(api._field_op(1, A, B, field)) == [(x + y) % p for x, y in zip(a, b)]
     assert unraw(api._field_op(2, A, B, field)) == [(x - y) % p for x, y in zip(a, b)]
+    # the dedicated squaring (values with saturated limbs and every limb's top bit set exercise the folded doubling),
+    # the two-term inner product (one reduction for a*b - (a+1)*b = -b) and the binary-Euclid inverse
+    sq = a + [p - 1 - (1 << (32 * k)) for k in range(8)] + [((1 << 254) - 1) % p, int("7fffffff" * 8, 16) % p,
+              int("80000000" * 8, 16) % p, int("ffffffff" * 7, 16), (1 << 253) | (1 << 31) | 1]
+    S = raw_np(sq)
+    assert unraw(api._field_op(3, S, S, field)) == [x * x * rinv % p for x in sq]
+    assert unraw(api._field_op(4, A, B, field)) == [(-y) % p for y in b]
+    R1 = pow(1 << 256, 1, p)
+    assert unraw(api._field_op(5, S, S, field)) == [pow(x * rinv % p, -1, p) * R1 % p if x else 0 for x in sq]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -140,6 +140,12 @@ __global__ void k_field_op(int op, const F* __restrict__ a, const F* __restrict_
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     F x = a[i], y = b[i];
+    // 0 mul, 1 add, 2 sub; unit-test views of the other field routines the kernels are built from:
+    // 3 dedicated squaring a^2, 4 two-term inner product a*b - b*a' with a' = a + 1 (fp_dot via f_mulsub's pattern:
+    // a*b - (a+1)*b = -b), 5 inverse of a (0 -> 0)
+    if (op == 3) { o[i] = fp_sqr(x); return; }
+    if (op == 4) { F xs[2] = {x, fp_neg(fp_add(x, F::one()))}, ys[2] = {y, y}; o[i] = fp_dot<typename F::Params, 2>(xs, ys); return; }
+    if (op == 5) { o[i] = fp_inv(x); return; }
     o[i] = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
 }
 
@@ -237,7 +243,7 @@ int32_t zkg_fr_from_wire_bn254(int32_t device, const void* wire, uint64_t* out_m
 int32_t zkg_fr_to_wire_bn254(int32_t device, const uint64_t* in_mont, void* wire, size_t n) { return fr_wire(device, 1, in_mont, wire, n); }
 
 int32_t zkg_field_op_dev(zkg_ctx* ctx, int32_t field, int32_t op, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n) {
-    ZKG_REQUIRE(ctx && (field == 0 || field == 1) && op >= 0 && op <= 2 && (n == 0 || (d_a && d_b && d_out)), "field_op_dev: bad argument");
+    ZKG_REQUIRE(ctx && (field == 0 || field == 1) && op >= 0 && op <= 5 && (n == 0 || (d_a && d_b && d_out)), "field_op_dev: bad argument");
     if (n == 0) return ZKG_OK;
     DeviceGuard dg(ctx->device);
     unsigned blocks = (unsigned)((n + 255) / 256);
@@ -249,7 +255,7 @@ int32_t zkg_field_op_dev(zkg_ctx* ctx, int32_t field, int32_t op, const uint64_t
 }
 
 int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
-    ZKG_REQUIRE((field == 0 || field == 1) && op >= 0 && op <= 2 && (n == 0 || (a && b && out)), "field_op: bad argument");
+    ZKG_REQUIRE((field == 0 || field == 1) && op >= 0 && op <= 5 && (n == 0 || (a && b && out)), "field_op: bad argument");
     if (n == 0) return ZKG_OK;
     PooledCtx pc;
     ZKG_TRY(pc.acquire(device));

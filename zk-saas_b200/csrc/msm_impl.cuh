@@ -896,6 +896,8 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const Fr* d_scalars,
         k_scan_tiles<<<pl->Wb, 1024, 0, st>>>(tile_sum, tiles);
         k_scan_final<<<dim3(tiles, pl->Wb), 256, 0, st>>>(pl->counts, pl->nb, tiles, tile_sum, pl->cursor);
     }
+    // (measured and dropped: scattering one window at a time, to keep the destination region L2-sized, changes nothing --
+    //  1.28 vs 1.20 ms at 2^22 -- so the counting sort is not bound by the footprint of its scattered 4-byte stores)
     k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), pl->W), TB, 0, st>>>(pl->digits, n, bstride, sstride, ioff, point0, pl->cursor, pl->sorted);
     unsigned hb = (unsigned)((pl->slots + 1023) / 1024);
     if (hb > 592) hb = 592;
