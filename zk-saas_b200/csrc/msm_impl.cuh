@@ -897,7 +897,10 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const Fr* d_scalars,
         k_scan_final<<<dim3(tiles, pl->Wb), 256, 0, st>>>(pl->counts, pl->nb, tiles, tile_sum, pl->cursor);
     }
     // (measured and dropped: scattering one window at a time, to keep the destination region L2-sized, changes nothing --
-    //  1.28 vs 1.20 ms at 2^22 -- so the counting sort is not bound by the footprint of its scattered 4-byte stores)
+    //  1.28 vs 1.20 ms at 2^22 -- so the counting sort is not bound by the footprint of its scattered 4-byte stores;
+    //  a two-level variant -- block-aggregated scatter into <= 1024 partitions of consecutive buckets, then one block per
+    //  partition with shared-memory cursors -- was parity-green and twice as slow, 2.2 vs 1.15 ms: its first pass still
+    //  issues one isolated store per entry, now 8 bytes, and its second pays a shared-memory atomic per entry)
     k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), pl->W), TB, 0, st>>>(pl->digits, n, bstride, sstride, ioff, point0, pl->cursor, pl->sorted);
     unsigned hb = (unsigned)((pl->slots + 1023) / 1024);
     if (hb > 592) hb = 592;
