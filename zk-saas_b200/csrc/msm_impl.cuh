@@ -232,7 +232,7 @@ static __global__ void k_size_scatter(const uint32_t* __restrict__ counts, size_
 // bucket accumulation: one thread per (window, bucket)
 // ------------------------------------------------------------------------------------------
 template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) > 32 ? 3 : 1)     // G2: stay at three blocks per SM (<= 168 registers)
+__global__ void __launch_bounds__(128, sizeof(F) > 32 ? 3 : 5)     // G2: three blocks per SM (<= 168 registers); G1: five (<= 102)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
              const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
