@@ -245,9 +245,9 @@ ZKG_D void mont_row(uint32_t* x, uint32_t* y, const uint32_t* a, uint32_t bi) {
     y[7] = addc(y[7], 0);
 }
 
-// r = a * b * 2^-256 mod p, fully reduced -- carry-chain (CIOS) schedule: 128 IMAD.WIDE.U32.X.
-// This is the production multiplier: 67 G products/s on B200 (tools/microbench/intpipe.cu), i.e.
-// the rate of the half-speed carry-propagating wide MAD it is made of.
+// r = a * b * 2^-256 mod p, fully reduced -- carry-chain (CIOS) schedule: 128 IMAD.WIDE.U32[.X].
+// This is the production multiplier: 67 G products/s on B200 (tools/microbench/intpipe.cu), 93 % of the
+// 9.27e12/s at which the 32x32->64 multiplier issues in any form (tools/microbench/widemad.cu).
 template <class P>
 ZKG_D Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     uint32_t even[8], odd[8];
@@ -330,13 +330,12 @@ ZKG_D Fp<P> fp_dot(const Fp<P>* a, const Fp<P>* b) {
 
 // --------------------------------------------------------------------------------------------
 // EXPERIMENT (not used by the kernels; kept with its measurement because it decides the design):
-// carry-free multiplier.  IMAD.WIDE.U32 without carry issues at 18.4e12/s on B200 and its carry-
-// propagating form at 9.0e12/s, so in principle an unsaturated radix-2^29 product (162 carry-free
-// MADs) should beat the CIOS schedule (128 half-rate MADs).  It does not: ptxas de-fuses every
-// `mad.wide` accumulate into IMAD.WIDE(+RZ) + IADD3/IADD3.X trees, the re-slicing adds ~150 ALU
-// instructions, and the MAD and ALU pipes do not overlap well enough (tools/microbench/coissue.cu:
-// IMAD.WIDE + LOP3 co-issue collapses to 5.9e12 pairs/s).  Measured: 40 G products/s vs 67 G/s for
-// CIOS (profiles/r01_intpipe_microbench.json).  The product is formed on
+// carry-free multiplier.  The idea was that wide MADs without carry might issue faster than the carry-propagating
+// form, so that an unsaturated radix-2^29 product (162 carry-free MADs) would beat the CIOS schedule (128).  It does
+// not, and cannot: IMAD.WIDE.U32 issues at 9.3e12/s in EVERY form on B200 (tools/microbench/widemad.cu; the 18.4e12/s
+// first quoted here was a loop ptxas had hoisted), ptxas splits every `mad.wide` accumulate into IMAD.WIDE(+RZ) +
+// IADD3/IADD3.X, and the re-slicing adds ~150 ALU instructions.  Measured: 40 G products/s vs 67 G/s for CIOS
+// (profiles/r01_intpipe_microbench_v2.json).  The product is formed on
 // an UNSATURATED radix-2^29 view of the operands: 9 limbs of 29 bits, 58-bit partial products, and
 // every column of the product (<= 18 terms + carry < 2^63) accumulates in one 64-bit register pair
 // with plain wide MADs -- no carry flags anywhere.  Montgomery reduction is interleaved column by
