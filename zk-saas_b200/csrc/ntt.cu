@@ -54,6 +54,11 @@ __device__ __forceinline__ void st_fr(Fr* p, const Fr& r) {
     d[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
+static int env_int_ntt(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 struct FrArg { uint32_t v[8]; };       // Fr passed by value as a kernel argument
 static FrArg to_arg(const HFr& h) { FrArg a; memcpy(a.v, h.v, 32); return a; }
 __device__ __forceinline__ Fr from_arg(const FrArg& a) {
@@ -500,6 +505,53 @@ k_king_stage1_l2(const Fr* __restrict__ shares, const Fr* __restrict__ U, const 
     st_fr(S + d1, b);
 }
 
+// The same for latency-bound sizes (<= 2^13 columns: 17.6 -> 13.8 us; no gain from 2^15 up): TWO threads per column,
+// lane j of a pair computing secret j (two 4-term inner
+// products), one exchange through warp shuffles (lane 1 hands over y = v1 * twiddle, lane 0 hands over v0), and each
+// lane finishing and storing one of the two outputs.  ~900 wide MADs on the critical path instead of 1664.
+__global__ void __launch_bounds__(256)
+k_king_stage1_l2_split(const Fr* __restrict__ shares, const Fr* __restrict__ U, const Fr* __restrict__ UsTab, size_t mbyl, size_t col0,
+                       size_t cols, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw, const Fr* __restrict__ g_lo2,
+                       Fr* __restrict__ S) {
+    const size_t Tlo = col0 + 1;
+    const uint32_t j = threadIdx.x & 1;
+    const size_t T = (Tlo & ~(size_t)127) + (size_t)blockIdx.x * 128 + (threadIdx.x >> 1);
+    const bool valid = T >= Tlo && T <= col0 + cols;                 // the same for both lanes of a pair
+    const bool wrap = T == mbyl;
+    const size_t m = (size_t)1 << log_m;
+    const uint32_t lo = (uint32_t)(T & (TW_LO - 1));
+    Fr v = Fr::zero(), y = Fr::zero();
+    if (valid) {
+        const size_t kk = T - 1 - col0;
+        const Fr* M = (wrap ? U : UsTab + (size_t)(T >> TW_LO_BITS) * 16) + 8 * j;
+#pragma unroll
+        for (int r = 0; r < 8; r += 4) {
+            Fr x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = ld_fr(shares + (size_t)(r + q) * cols + kk);
+            v = fp_add(v, fp_dot<FrParams, 4>(x, M + r));
+        }
+        if (j) y = fp_mul(v, wrap ? pow_lookup(gen_tw, T) : ld_fr(gen_tw.lo + lo));
+    }
+    // lane 0 receives y, lane 1 receives v0 (every lane of the warp takes part in the shuffles)
+    Fr other;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) other.v[i] = __shfl_xor_sync(0xffffffffu, j ? y.v[i] : v.v[i], 1);
+    if (!valid) return;
+    Fr o = j ? fp_sub(other, y) : fp_add(v, other);
+    if (has_g) {
+        if (!j) o = fp_mul(o, wrap ? pow_lookup(g_tw, T) : ld_fr(g_tw.lo + lo));
+        else if (!wrap) o = fp_mul(o, ld_fr(g_lo2 + lo));
+    }
+    const size_t pos = j ? (T + mbyl) & (m - 1) : T;
+    size_t d = pos;
+    if (mode == 1) {
+        size_t pb = (size_t)(__brevll((unsigned long long)pos) >> (64 - log_m));
+        d = (pb & (mbyl - 1)) * 2 + (pb / mbyl);
+    }
+    st_fr(S + d, o);
+}
+
 // ------------------------------------------------------------------------------------------
 // Dense map with the INPUT vector in registers (few inputs, many outputs): pack / det_pack.
 //   out(c, i) = sum_{j<K1} M[i][j] * in1(c, j) + sum_{j<K2} M[i][K1+j] * in2(c, j)
@@ -560,6 +612,36 @@ k_pack_l2(Pack2Consts K, const Fr* __restrict__ secrets, size_t s_cs, size_t s_r
         Fr o = fp_dot<FrParams, 2>(x, y);
         st_fr(out + c * out_cs + (size_t)k * out_rs, fp_add(E[k], o));
         st_fr(out + c * out_cs + (size_t)(k + 4) * out_rs, fp_sub(E[k], o));
+    }
+}
+
+// Small batches (<= 2^13 columns; measured: 13.3 -> 11.3 us at 2^13, but 13.2 -> 15.4 us at 2^15, where the duplicated
+// even half costs more than the shorter chain saves) are latency-bound: the same pack with TWO threads per column,
+// lane h of a pair producing outputs h, h+2, h+4, h+6 (E_h, E_(h+2) and the two inner products that go with them; the
+// three products of the even half are computed by both lanes).  768 wide MADs on the critical path instead of 1152.
+__global__ void __launch_bounds__(256)
+k_pack_l2_split(Pack2Consts K, const Fr* __restrict__ secrets, size_t s_cs, size_t s_rs, const Fr* __restrict__ rand, size_t r_cs,
+                size_t r_rs, int has_rand, Fr* __restrict__ out, size_t out_cs, size_t out_rs, size_t cols) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t c = t >> 1;
+    const int h = (int)(t & 1);
+    if (c >= cols) return;
+    Fr v0 = ld_fr(secrets + c * s_cs), v1 = ld_fr(secrets + c * s_cs + s_rs);
+    Fr v2 = has_rand ? ld_fr(rand + c * r_cs) : Fr::zero(), v3 = has_rand ? ld_fr(rand + c * r_cs + r_rs) : Fr::zero();
+    Fr a0 = fp_add(v0, v2), a1 = fp_sub(v0, v2), b0 = fp_add(v1, v3);
+    Fr c0 = fp_mul(fp_add(a0, b0), from_arg(K.c[1]));
+    Fr c2 = fp_mul(fp_sub(a0, b0), from_arg(K.c[3]));
+    if (h) c2 = fp_mul(c2, from_arg(K.c[5]));            // E_1, E_3 use zeta_8^2 c2
+    Fr E0 = fp_add(c0, c2), E2 = fp_sub(c0, c2);          // E_h, E_(h+2)
+    Fr x[2] = {a1, fp_sub(v1, v3)};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int k = h + 2 * q;
+        Fr y[2] = {from_arg(K.oa[k]), from_arg(K.ob[k])};
+        Fr o = fp_dot<FrParams, 2>(x, y);
+        const Fr& E = q ? E2 : E0;
+        st_fr(out + c * out_cs + (size_t)k * out_rs, fp_add(E, o));
+        st_fr(out + c * out_cs + (size_t)(k + 4) * out_rs, fp_sub(E, o));
     }
 }
 
@@ -758,11 +840,6 @@ static int32_t build_pow_table(zkg_ctx* ctx, const HFr& w, size_t max_exp_excl, 
     return ZKG_OK;
 }
 
-static int env_int_ntt(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
 // In-order-output NTT of d_in (bit-reversed input order) with root w_N, into d_out.
 // shift = 1 stores X[k] at (k-1) mod N.  d_tmp: N-element scratch (used when > 2 passes or in == out).
 static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp, size_t N, const HFr& wN,
@@ -907,7 +984,10 @@ static int32_t launch_pack(zkg_ctx* ctx, const Fr* dM, int K, int rows, int l, i
     unsigned blocks = (unsigned)((cols + 255) / 256);
     if (l == 2 && rows == 8 && !getenv("ZKG_PACK_DENSE")) {
         static const Pack2Consts P2 = pack2_consts();
-        k_pack_l2<<<blocks, 256, 0, ctx->stream>>>(P2, secrets, s_cs, s_rs, rand, r_cs, r_rs, t_used ? 1 : 0, out, o_cs, o_rs, cols);
+        if (cols <= (size_t)env_int_ntt("ZKG_KING_SPLIT_MAX", 1 << 13))      // latency-bound sizes: two threads per column
+            k_pack_l2_split<<<(unsigned)((2 * cols + 255) / 256), 256, 0, ctx->stream>>>(P2, secrets, s_cs, s_rs, rand, r_cs, r_rs, t_used ? 1 : 0, out, o_cs, o_rs, cols);
+        else
+            k_pack_l2<<<blocks, 256, 0, ctx->stream>>>(P2, secrets, s_cs, s_rs, rand, r_cs, r_rs, t_used ? 1 : 0, out, o_cs, o_rs, cols);
         ctx->launches += 1;
         ZKG_CUDA(cudaGetLastError());
         return ZKG_OK;
@@ -999,6 +1079,11 @@ static int32_t king_stage1(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* par
         const size_t Tlo = col0 + 1, Thi = col0 + cols, A = Tlo & ~(size_t)255;
         unsigned blocks2 = (unsigned)((Thi - A) / 256 + 1);
         phase_mark(ctx, 1);
+        if (cols <= (size_t)env_int_ntt("ZKG_KING_SPLIT_MAX", 1 << 13)) {     // latency-bound sizes: two threads per column
+            const size_t A2 = Tlo & ~(size_t)127;
+            k_king_stage1_l2_split<<<(unsigned)((Thi - A2) / 128 + 1), 256, 0, ctx->stream>>>(d_shares, dU, (const Fr*)up, mbyl, col0, cols,
+                                                                                          log_m, mode, gen_tw, has_g, g_tw, g_lo2, S);
+        } else
         k_king_stage1_l2<<<blocks2, 256, 0, ctx->stream>>>(d_shares, dU, (const Fr*)up, mbyl, col0, cols, log_m, mode, gen_tw, has_g,
                                                           g_tw, g_lo2, S);
         ctx->launches += 1;
