@@ -351,14 +351,15 @@ def test_fft1_vs_literal_oracle(z, o, l, mbyl):
 
 
 @pytest.mark.parametrize("mbyl", [1, 2, 4, 8, 16, 32, 128, 512, 1 << 10, 1 << 11, 1 << 12, 1 << 14, 1 << 16, 1 << 18])
-@pytest.mark.parametrize("elog,tables", [(11, 1), (9, 1), (11, 0)])
-def test_fft1_radix8_kernel_all_shapes(z, o, monkeypatch, mbyl, elog, tables):
+@pytest.mark.parametrize("elog,tables,ept_log", [(11, 1, 3), (9, 1, 3), (11, 0, 3), (10, 1, 2), (8, 0, 2)])
+def test_fft1_radix8_kernel_all_shapes(z, o, monkeypatch, mbyl, elog, tables, ept_log):
     """The register-blocked radix-8 pass kernel (production for N >= 2^18) forced onto every transform size, so that
     all its group shapes (1, 2 and 3 stages per group; fewer than 8 elements; one, two and three passes; narrow
     tiles) and both twiddle sources (per-pass table / on-the-fly powers) are pinned against the literal loops of
     fft1_in_place."""
     monkeypatch.setenv("ZKG_NTT_R8_MIN", "0")
     monkeypatch.setenv("ZKG_NTT_ELOG", str(elog))
+    monkeypatch.setenv("ZKG_NTT_EPT_LOG", str(ept_log))          # 8 or 4 elements per thread (radix-8 / radix-4 groups)
     if not tables:
         monkeypatch.setenv("ZKG_NTT_ONTHEFLY", "1")
     l = 2

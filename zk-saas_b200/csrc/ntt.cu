@@ -211,7 +211,8 @@ k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr*
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ntt_slot(uint32_t idx) { return idx + (idx >> 3); }
 
-__global__ void __launch_bounds__(256, 2)
+template <int LE>          // elements per thread = 2^LE: 8 (radix-8 groups, 16 warps/SM) or 4 (radix-4 groups, 24 warps/SM)
+__global__ void __launch_bounds__(256, LE == 3 ? 2 : 3)
 k_ntt_pass8(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr* __restrict__ tw_small, PowTable tw,
             const Fr* __restrict__ tw_full, const Fr* __restrict__ mask, int sub_mode) {
     extern __shared__ uint4 sm4[];
@@ -232,7 +233,8 @@ k_ntt_pass8(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr
     }
     const int rho_shift = P.logN - P.s - P.b;
     const size_t N = (size_t)1 << P.logN;
-    const uint32_t units = E >> 3 ? E >> 3 : 1;               // threads that own elements
+    constexpr int EPT = 1 << LE;
+    const uint32_t units = E >> LE ? E >> LE : 1;             // threads that own elements
     const uint32_t uidx = threadIdx.x;
 
     for (uint32_t i = threadIdx.x; i < T / 2; i += blockDim.x) {
@@ -243,17 +245,17 @@ k_ntt_pass8(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr
     const Fr scale = from_arg(P.scale);
 
     // groups of stages: as even as possible, at most 3 each
-    const int ngroups = (P.b + 2) / 3 ? (P.b + 2) / 3 : 1;
+    const int ngroups = (P.b + LE - 1) / LE ? (P.b + LE - 1) / LE : 1;
     int sg0 = 0;
     for (int gi = 0; gi < ngroups; ++gi) {
         const int G = (P.b - sg0 + (ngroups - gi) - 1) / (ngroups - gi);    // stages in this group (0 when b == 0)
         const bool from_global = gi == 0, to_global = gi == ngroups - 1;
-        Fr v[8];
-        uint32_t rowv[8], colv[8];
-        const bool active = uidx < units && (E >= 8 || uidx == 0);
+        Fr v[EPT];
+        uint32_t rowv[EPT], colv[EPT];
+        const bool active = uidx < units && (E >= (uint32_t)EPT || uidx == 0);
         // element e of this thread: sub-butterfly q = e >> G, member j = e & (2^G - 1)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < EPT; ++e) {
             const uint32_t q = (uint32_t)e >> G, j = (uint32_t)e & ((1u << G) - 1);
             const uint32_t beta = q * units + uidx;
             const uint32_t col = beta & (CW - 1), rest = beta >> P.cw_log;
@@ -263,8 +265,8 @@ k_ntt_pass8(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr
         }
         if (active) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (E < 8 && (uint32_t)e >= E) continue;
+            for (int e = 0; e < EPT; ++e) {
+                if (E < (uint32_t)EPT && (uint32_t)e >= E) continue;
                 const uint32_t row = rowv[e], col = colv[e];
                 if (from_global) {
                     const size_t g = sub_mode ? base + (size_t)col * T + row : base + ((size_t)row << P.s) + col;
@@ -289,14 +291,14 @@ k_ntt_pass8(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr
         if (from_global) __syncthreads();                      // small twiddles are in place
         if (active) {
 #pragma unroll
-            for (int sp = 0; sp < 3; ++sp) {
+            for (int sp = 0; sp < LE; ++sp) {
                 if (sp >= G) break;
                 const int sigma = sg0 + sp;                      // global stage
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
+                for (int e = 0; e < EPT; ++e) {
                     if ((e >> sp) & 1) continue;
                     const int f = e + (1 << sp);
-                    if (E < 8 && (uint32_t)f >= E) continue;
+                    if (E < (uint32_t)EPT && (uint32_t)f >= E) continue;
                     const uint32_t kin = rowv[e] & ((1u << sigma) - 1);
                     Fr y = v[f];
                     if (kin) {
@@ -313,8 +315,8 @@ k_ntt_pass8(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (E < 8 && (uint32_t)e >= E) continue;
+            for (int e = 0; e < EPT; ++e) {
+                if (E < (uint32_t)EPT && (uint32_t)e >= E) continue;
                 const uint32_t row = rowv[e], col = colv[e];
                 if (to_global) {
                     size_t k = sub_mode ? base + (size_t)col * T + row : base + ((size_t)row << P.s) + col;
@@ -858,7 +860,14 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp,
         // radix-8 register-blocked kernel for large transforms; small ones keep the radix-2 kernel, whose four
         // times as many threads hide latency better when there is less than one tile per SM
         const bool r8 = logN >= env_int_ntt("ZKG_NTT_R8_MIN", 18);
-        const int elog = env_int_ntt("ZKG_NTT_ELOG", 11);
+        // elements per thread of the register-blocked kernel: 8 (radix-8 groups, 122 registers, 16 warps/SM), or 4
+        // (radix-4 groups, 76 registers, 24 warps/SM) for the largest transforms, where the extra resident warps win
+        // 3-5 % (N = 2^21: 0.472 -> 0.450 ms, 2^23: 1.894 -> 1.841 ms) and lose nothing below
+        const int ept_env = env_int_ntt("ZKG_NTT_EPT_LOG", 0);
+        const int ept_log = ept_env == 2 || ept_env == 3 ? ept_env : (logN >= 21 ? 2 : 3);
+        int elog = env_int_ntt("ZKG_NTT_ELOG", ept_log == 3 ? 11 : 10);
+        if (elog > 8 + ept_log) elog = 8 + ept_log;                          // at most 256 threads per block
+        if (elog < 5) elog = 5;
         int cw_log = 0;
         if (q > 0 || r8) {
             cw_log = (r8 ? elog : 11) - b; if (cw_log > (q > 0 ? s : logN - b)) cw_log = q > 0 ? s : logN - b; if (cw_log < 0) cw_log = 0;
@@ -905,9 +914,15 @@ static int32_t ntt_bitrev_in(zkg_ctx* ctx, const Fr* d_in, Fr* d_out, Fr* d_tmp,
         if (r8) {
             size_t PL = E + (E >> 3) + 1;
             size_t shmem = (2 * PL + T) * sizeof(uint4);
-            unsigned threads = (unsigned)(E / 8 < 32 ? 32 : E / 8);
-            ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass8, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            k_ntt_pass8<<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, tw_full, P.last ? d_mask : nullptr, q == 0 ? 1 : 0);
+            if (ept_log == 3) {
+                unsigned threads = (unsigned)(E / 8 < 32 ? 32 : E / 8);
+                ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass8<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                k_ntt_pass8<3><<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, tw_full, P.last ? d_mask : nullptr, q == 0 ? 1 : 0);
+            } else {
+                unsigned threads = (unsigned)(E / 4 < 32 ? 32 : E / 4);
+                ZKG_CUDA(cudaFuncSetAttribute(k_ntt_pass8<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                k_ntt_pass8<2><<<blocks, threads, shmem, ctx->stream>>>(src, dst, P, tws, tw, tw_full, P.last ? d_mask : nullptr, q == 0 ? 1 : 0);
+            }
         } else {
             size_t shmem = (8 * E + 8 * (T / 2 ? T / 2 : 1)) * sizeof(uint32_t);
             unsigned threads = (unsigned)(E / 2 < 32 ? 32 : (E / 2 > 512 ? 512 : E / 2));
