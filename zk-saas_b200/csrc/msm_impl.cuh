@@ -900,7 +900,10 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const Fr* d_scalars,
     //  1.28 vs 1.20 ms at 2^22 -- so the counting sort is not bound by the footprint of its scattered 4-byte stores;
     //  a two-level variant -- block-aggregated scatter into <= 1024 partitions of consecutive buckets, then one block per
     //  partition with shared-memory cursors -- was parity-green and twice as slow, 2.2 vs 1.15 ms: its first pass still
-    //  issues one isolated store per entry, now 8 bytes, and its second pays a shared-memory atomic per entry)
+    //  issues one isolated store per entry, now 8 bytes, and its second pays a shared-memory atomic per entry;
+    //  letting the histogram atomic of k_digits return the entry's rank, so that this scatter needs no atomic, is slower
+    //  too -- 2.2 ms on the prepared path: an atomic WITH a return value costs more than the fire-and-forget reduction
+    //  the histogram compiles to now, +0.18 ms for k_digits alone)
     k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), pl->W), TB, 0, st>>>(pl->digits, n, bstride, sstride, ioff, point0, pl->cursor, pl->sorted);
     unsigned hb = (unsigned)((pl->slots + 1023) / 1024);
     if (hb > 592) hb = 592;
