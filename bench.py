@@ -198,6 +198,23 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = None
+    if world > 1:
+        # one process per GPU: keep the rank (and the pinned host buffers it first-touches) on the CPUs next to its GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(local)
+            bus = "%08x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+            ncpu = os.cpu_count() or 1
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                affinity = len(cpus)
+        except Exception:
+            affinity = None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -754,7 +771,8 @@ def run_ours(args):
                                 f"{register_s:.2f} s one-time); the e2e leg re-ships unregistered bases every step",
                        "window_bits": my_c, "windows": my_W,
                        "l2_policy": "inputs larger than L2 (bases 256 MiB + scalars 128 MiB per step at 2^22)",
-                       "multi_gpu": "point-range sharding; one NCCL all-gather of 128 B partial sums + device add"},
+                       "multi_gpu": "point-range sharding; one NCCL all-gather of 128 B partial sums + device add",
+                       "rank_cpu_affinity": affinity},
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 2), "unit": "Mpts/s", "h2d_bytes_per_step": n * (72 + 32),
                     "d2h_bytes_per_step": 96, "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3),
