@@ -199,7 +199,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     affinity = None
-    if world > 1:
+    if world > 1 and not os.environ.get("ZKG_BENCH_NO_AFFINITY"):
         # one process per GPU: keep the rank (and the pinned host buffers it first-touches) on the CPUs next to its GPU
         try:
             import pynvml
