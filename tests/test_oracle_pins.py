@@ -289,3 +289,57 @@ def test_dpp_king_c_vs_bigint_model(o):
         ins[0][cols] = 0                           # a den share column that unpacks to a zero secret is unlikely; zero ALL den
         zero_den = [np.concatenate([ins[p][:cols], np.zeros((cols, 4), dtype=np.uint64)]) for p in range(pp.n)]
         assert o.zko_dpp_king(ol.ptr_array(zero_den), par, pp.n, cols, l, _p(ol.fr_np(sum(rand, []))), ol.ptr_array(outs)) == -2
+
+
+# ---------------------------------------------------------------------------------------------------
+# The one numerical relation the reference tree holds over this path's arithmetic:
+#   fixtures/verification_key.json:52-81  vk_alphabeta_12 = e(vk_alpha_1, vk_beta_2)
+# evaluated with pyref's own Fq2 / G1 / G2 code (oracle/pairing.py), then extended by bilinearity to
+# pyref's scalar multiplication and to the C oracle's Pippenger.
+# ---------------------------------------------------------------------------------------------------
+def _vk():
+    import pairing
+    g = gu.load("vk_pairing.json")
+    alpha = tuple(int(x) for x in g["vk_alpha_1"])
+    beta = tuple(pyref.Fq2(int(c[0]), int(c[1])) for c in g["vk_beta_2"])
+    ic = [tuple(int(x) for x in p) for p in g["IC"]]
+    ab = [[[int(x) for x in f] for f in h] for h in g["vk_alphabeta_12"]]
+    return pairing, alpha, beta, ic, ab
+
+
+def _gt_from_json(pairing, js):
+    f6 = lambda h: pairing.Fq6(*[pyref.Fq2(a, b) for a, b in h])
+    return pairing.Fq12(f6(js[0]), f6(js[1]))
+
+
+def test_pairing_reproduces_reference_vk_alphabeta():
+    """e(vk_alpha_1, vk_beta_2) == vk_alphabeta_12, bit for bit (the Fuentes-Castaneda multiple of the reduced
+    ate pairing, which is what arkworks / snarkjs return)."""
+    pairing, alpha, beta, _, ab = _vk()
+    e = pairing.pairing(alpha, beta, fuentes=True)
+    assert e.to_json_ints() == ab
+    # the un-multiplied reduced pairing is a different GT element: the comparison above is not vacuous
+    assert pairing.pairing(alpha, beta).to_json_ints() != ab
+
+
+def test_pairing_bilinearity_pins_scalar_multiplication(o):
+    """e([a]alpha, [b]beta) == vk_alphabeta_12^(ab): pyref's G1.mul / G2.mul against the fixture; then the C
+    oracle's Pippenger: e(MSM_C(bases, s), beta) == prod e(bases_i, beta)^(s_i) over the reference-held G1 points."""
+    pairing, alpha, beta, ic, ab = _vk()
+    gt = _gt_from_json(pairing, ab)
+    rnd = random.Random(0xA1FA)
+    a, b = rnd.randrange(2, 1 << 40), rnd.randrange(2, 1 << 40)
+    lhs = pairing.pairing(pyref.G1.mul(alpha, a), pyref.G2.mul(beta, b), fuentes=True)
+    assert lhs == gt.pow(a * b)
+    bases = [alpha] + ic
+    scal = [rnd.randrange(R) for _ in bases]
+    got = ol.g1_xyz_to_point(ol.o_g1_msm(ol.g1_aff_np(bases), ol.fr_np(scal)))
+    assert got == pyref.msm_naive(pyref.G1, bases, scal)
+    rhs = pairing.Fq12.one()
+    for P, s in zip(bases, scal):
+        rhs = rhs * pairing.pairing(P, beta, fuentes=True).pow(s)
+    assert pairing.pairing(got, beta, fuentes=True) == rhs
+    # and the G2 side of the C oracle: e(alpha, MSM_C([beta, gamma], t)) == e(alpha,beta)^t0 * e(alpha,gamma)^t1
+    t = [rnd.randrange(R) for _ in range(2)]
+    q = ol.g2_xyz_to_point(ol.o_g2_msm(ol.g2_aff_np([beta, pyref.G2_GEN_PT]), ol.fr_np(t)))
+    assert pairing.pairing(alpha, q, fuentes=True) == gt.pow(t[0]) * pairing.pairing(alpha, pyref.G2_GEN_PT, fuentes=True).pow(t[1])
