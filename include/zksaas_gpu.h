@@ -38,6 +38,7 @@ extern "C" {
 #define ZKG_ERR_CUDA (-3)
 #define ZKG_ERR_OOM (-4)
 #define ZKG_ERR_UNSUPPORTED (-5)
+#define ZKG_ERR_NCCL (-6)       /* a multi-GPU entry point could not set up or run its exchange (no peer access and no NCCL) */
 
 #define ZKG_G1_AFFINE_BYTES 72u
 #define ZKG_G2_AFFINE_BYTES 136u
@@ -215,6 +216,54 @@ int32_t zkg_fr_fft_bn254(int32_t device, uint64_t *v, size_t n, const uint64_t *
  * from_wire fails with ZKG_ERR_BAD_ARG if an element is >= r, as arkworks' deserializer does. */
 int32_t zkg_fr_from_wire_bn254(int32_t device, const void *wire, uint64_t *out_mont, size_t n);
 int32_t zkg_fr_to_wire_bn254(int32_t device, const uint64_t *in_mont, void *wire, size_t n);
+
+
+/* ---- king side of d_msm: dist-primitives/src/dmsm/mod.rs:85-87 ---------------------------------
+ * `pp.unpack_missing_shares(&rs.shares, &rs.parties)` over GROUP elements (secret-sharing/src/pss.rs:141-166 when all
+ * n = 4l shares arrived, the Lagrange path :170-221 otherwise -- d_msm tolerates dropouts like d_fft) followed by
+ * `result.iter().sum()`.  Also the A / B / C recombination of groth16/examples/sha256.rs:375-377.
+ * shares_xyz: n_recv Projective images (Jacobian X, Y, Z of 3 x 32 B / 3 x 64 B; any Z, identity Z = 0) in the order of
+ * `parties` (NULL = parties 0..n-1).  out_unpacked_xyz (nullable): the l unpacked points; out_sum_xyz (nullable): their
+ * sum (the value the king replicates to every party, :87).  Outputs are normalised. */
+int32_t zkg_pss_unpack2_bn254_g1(int32_t device, uint32_t l, const uint64_t *shares_xyz, const uint32_t *parties,
+                                 uint32_t n_recv, uint64_t *out_unpacked_xyz, uint64_t *out_sum_xyz);
+int32_t zkg_pss_unpack2_bn254_g2(int32_t device, uint32_t l, const uint64_t *shares_xyz, const uint32_t *parties,
+                                 uint32_t n_recv, uint64_t *out_unpacked_xyz, uint64_t *out_sum_xyz);
+
+/* ---- wire format of group elements: ark-serialize 0.4 COMPRESSED points, the payload d_msm
+ * ships through mpc-net/src/ser_net.rs:25 (serialize_compressed) and reads back at :40 / :119 (deserialize_compressed =
+ * Compress::Yes + Validate::Yes); call sites dist-primitives/src/dmsm/mod.rs:79-81, :90-92.
+ *   G1: 32 B = x canonical little-endian;  G2: 64 B = x.c0 then x.c1;  flags in the two top bits of the LAST byte:
+ *   0x80 = y > -y ("negative"; Fq2 compares c1 first), 0x40 = point at infinity (x = 0).
+ * to_wire takes Projective images (any Z); from_wire returns normalised images and fails with ZKG_ERR_BAD_ARG on an
+ * invalid encoding, as arkworks does: both flags set, x >= q, x not on the curve, (G2) point outside the r-torsion. */
+int32_t zkg_g1_to_wire_bn254(int32_t device, const uint64_t *points_xyz, void *wire, size_t n);
+int32_t zkg_g1_from_wire_bn254(int32_t device, const void *wire, uint64_t *points_xyz, size_t n);
+int32_t zkg_g2_to_wire_bn254(int32_t device, const uint64_t *points_xyz, void *wire, size_t n);
+int32_t zkg_g2_from_wire_bn254(int32_t device, const void *wire, uint64_t *points_xyz, size_t n);
+
+/* ---- share-wise h = a*b - c of the QAP, fused with the out-mask additions of the three d_fft calls before it
+ * (SURVEY.md 8f row 1): groth16/src/ext_wit.rs:173-177 (circom_h), :82-86 (libsnark_h, with factor = 1/Z(g));
+ * the mask adds are dist-primitives/src/dfft/mod.rs:313-317.
+ *   out[i] = ((a[i] + mask_a[i]) * (b[i] + mask_b[i]) - (c[i] + mask_c[i])) * factor
+ * mask_* and factor (one Fr image, host memory in both forms) are nullable; out may alias an input. */
+int32_t zkg_qap_h_bn254(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *c, const uint64_t *mask_a,
+                        const uint64_t *mask_b, const uint64_t *mask_c, const uint64_t *factor, uint64_t *out, size_t n);
+int32_t zkg_qap_h_bn254_dev(zkg_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, const uint64_t *d_c,
+                            const uint64_t *d_mask_a, const uint64_t *d_mask_b, const uint64_t *d_mask_c,
+                            const uint64_t *factor, uint64_t *d_out, size_t n);
+
+/* ---- offline masks on the device, random draws supplied by the caller's RNG:
+ * FftMask::sample, dist-primitives/src/dfft/mod.rs:30-85: mask_values (m), rand_in / rand_out (m/l * t packing draws) ->
+ * the n parties' in_mask / out_mask vectors (m/l each).  One upload, one download; pack, fft2, powers, negation,
+ * bit-reversal and the strided re-pack never leave the GPU.
+ * DegRedMask::sample over Fr with gen = 1, dist-primitives/src/utils/deg_red.rs:40-66: mask_values (num*l). */
+int32_t zkg_fft_mask_sample_bn254(int32_t device, int32_t rearrange, const uint64_t g[4], const uint64_t gen[4], size_t m,
+                                  uint32_t l, const uint64_t *mask_values, const uint64_t *rand_in, const uint64_t *rand_out,
+                                  uint64_t *const *in_by_party, uint64_t *const *out_by_party);
+int32_t zkg_deg_red_mask_sample_bn254(int32_t device, size_t num, uint32_t l, const uint64_t *mask_values,
+                                      const uint64_t *rand_in, const uint64_t *rand_out, uint64_t *const *in_by_party,
+                                      uint64_t *const *out_by_party);
 
 /* ---- element-wise helpers used by kernel unit tests (out[i] = a[i] op b[i]; op: 0 mul, 1 add,
  * 2 sub; unit-test views of the routines the kernels are built from: 3 dedicated squaring a^2, 4 the two-term

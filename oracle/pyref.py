@@ -511,7 +511,10 @@ class Curve:
         return v.is_zero() if isinstance(v, Fq2) else v % Q_MOD == 0
 
     def mul(self, P, k: int):
-        k %= R_MOD
+        return self.mul_raw(P, k % R_MOD)
+
+    def mul_raw(self, P, k: int):
+        """double-and-add without reducing k (points outside the r-torsion subgroup, e.g. the wire-format checks)."""
         acc = None
         while k:
             if k & 1:
@@ -615,3 +618,115 @@ def g2_affine_image(P) -> bytes:
     limbs = to_mont_limbs(x.c0, Q_MOD) + to_mont_limbs(x.c1, Q_MOD) + \
         to_mont_limbs(y.c0, Q_MOD) + to_mont_limbs(y.c1, Q_MOD)
     return struct.pack("<17Q", *limbs, 0)
+
+
+# ----------------------------------------------------------------------------------------
+# ark-serialize 0.4 compressed form of short-Weierstrass points -- the wire form of the group element
+# d_msm ships (mpc-net/src/ser_net.rs:25 serialize_compressed, :40,:119 deserialize_compressed; call sites
+# dist-primitives/src/dmsm/mod.rs:79-81,90-92).  ark-serialize / ark-ec are un-vendored: the
+# layout below restates their public 0.4.2 behaviour and is NOT pinned by any vector in the reference tree.
+#   x canonical little-endian (G1: 32 B; G2: c0 then c1, 64 B); SWFlags in the two top bits of the LAST byte:
+#   bit 7 = YIsNegative (y > -y), bit 6 = PointAtInfinity (x = 0), both clear = YIsPositive (y <= -y).
+#   Fq2 ordering is lexicographic with c1 most significant (ark-ff QuadExtField::cmp).
+#   deserialize_compressed validates: both flags set / x >= q / x^3 + b a non-residue / (G2) point outside the
+#   r-torsion subgroup are errors.
+# ----------------------------------------------------------------------------------------
+class WireError(ValueError):
+    pass
+
+
+def _fq_sqrt(a: int):
+    """q = 3 mod 4: a^((q+1)/4), or None for a non-residue."""
+    a %= Q_MOD
+    y = pow(a, (Q_MOD + 1) // 4, Q_MOD)
+    return y if y * y % Q_MOD == a else None
+
+
+def _fq2_sqrt(a: Fq2):
+    """Square root in Fq[u]/(u^2+1) by the norm method; None for a non-residue.  Either root may be returned."""
+    if a.is_zero():
+        return Fq2(0)
+    if a.c1 == 0:
+        s = _fq_sqrt(a.c0)
+        if s is not None:
+            return Fq2(s, 0)
+        return Fq2(0, _fq_sqrt(-a.c0))                 # -1 is a non-residue, so -a0 is a residue
+    alpha = _fq_sqrt(a.c0 * a.c0 + a.c1 * a.c1)
+    if alpha is None:
+        return None
+    half = finv(2, Q_MOD)
+    delta = (a.c0 + alpha) * half % Q_MOD
+    c0 = _fq_sqrt(delta)
+    if c0 is None:
+        c0 = _fq_sqrt((delta - alpha) % Q_MOD)
+    c1 = a.c1 * finv(2 * c0 % Q_MOD, Q_MOD) % Q_MOD
+    r = Fq2(c0, c1)
+    assert r * r == a
+    return r
+
+
+def _fq2_gt(a: Fq2, b: Fq2) -> bool:
+    return (a.c1, a.c0) > (b.c1, b.c0)
+
+
+def g1_serialize_compressed(P) -> bytes:
+    if P is None:
+        return bytes(31) + bytes([0x40])
+    x, y = P
+    out = bytearray(x.to_bytes(32, "little"))
+    if y > (-y) % Q_MOD:
+        out[31] |= 0x80
+    return bytes(out)
+
+
+def g1_deserialize_compressed(b: bytes):
+    if len(b) != 32:
+        raise WireError("length")
+    flags = b[31] >> 6
+    if flags == 3:
+        raise WireError("both flags set")
+    x = int.from_bytes(bytes(b[:31]) + bytes([b[31] & 0x3F]), "little")
+    if x >= Q_MOD:
+        raise WireError("x not below the modulus")
+    if flags == 1:
+        return None
+    y = _fq_sqrt(x * x * x + G1_B)
+    if y is None:
+        raise WireError("x is not on the curve")
+    small, large = sorted((y, (-y) % Q_MOD))
+    return (x, large if flags == 2 else small)
+
+
+def g2_serialize_compressed(P) -> bytes:
+    if P is None:
+        return bytes(63) + bytes([0x40])
+    x, y = P
+    out = bytearray(x.c0.to_bytes(32, "little") + x.c1.to_bytes(32, "little"))
+    if _fq2_gt(y, -y):
+        out[63] |= 0x80
+    return bytes(out)
+
+
+def g2_deserialize_compressed(b: bytes):
+    if len(b) != 64:
+        raise WireError("length")
+    flags = b[63] >> 6
+    if flags == 3:
+        raise WireError("both flags set")
+    c0 = int.from_bytes(b[:32], "little")
+    c1 = int.from_bytes(bytes(b[32:63]) + bytes([b[63] & 0x3F]), "little")
+    if c0 >= Q_MOD or c1 >= Q_MOD:
+        raise WireError("x not below the modulus")
+    if flags == 1:
+        return None
+    x = Fq2(c0, c1)
+    y = _fq2_sqrt(x * x * x + G2_B)
+    if y is None:
+        raise WireError("x is not on the curve")
+    ny = -y
+    small, large = (ny, y) if _fq2_gt(y, ny) else (y, ny)
+    P = (x, large if flags == 2 else small)
+    # Validate::Yes: r-torsion check (G1 has cofactor 1 and needs none)
+    if G2.add(G2.mul_raw(P, R_MOD - 1), P) is not None:
+        raise WireError("point is not in the prime-order subgroup")
+    return P

@@ -831,6 +831,43 @@ API void zko_fr_sum(const uint64_t *a, size_t n, uint64_t *o) {
     fr_set(o, acc);
 }
 
+
+/* One output of Radix2EvaluationDomain::fft by its definition: out = sum_j x_j * point^j (Horner), point = offset * w^k.
+ * O(n) per output: lets a test check sampled outputs of a transform far larger than the in-order oracle FFT can hold
+ * in seconds (d_fft at m = 2^24).  OpenMP over `blocks` contiguous segments, each folded by Horner and weighted. */
+API void zko_fr_eval_poly(const uint64_t *x, size_t n, const uint64_t *point, uint64_t *o, int threads) {
+    if (threads < 1) threads = 1;
+    size_t blocks = (size_t)threads * 4;
+    if (blocks > n) blocks = n ? n : 1;
+    uint64_t *part = (uint64_t *)malloc(blocks * 32);
+    size_t seg = (n + blocks - 1) / blocks;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (long b = 0; b < (long)blocks; ++b) {
+        size_t lo = (size_t)b * seg, hi = lo + seg < n ? lo + seg : n;
+        uint64_t acc[4];
+        fr_zero(acc);
+        for (size_t j = hi; j-- > lo;) { fr_mul(acc, acc, point); fr_add(acc, acc, x + 4 * j); }
+        fr_set(part + 4 * b, acc);
+    }
+    /* total = sum_b part_b * point^(b*seg) */
+    uint64_t pseg[4], w[4], acc[4], t[4];
+    fr_set(pseg, point);
+    { /* point^seg by square-and-multiply */
+        uint64_t base[4], r[4];
+        fr_set(base, point); fr_one(r);
+        for (size_t e = seg; e; e >>= 1) { if (e & 1) fr_mul(r, r, base); fr_sqr(base, base); }
+        fr_set(pseg, r);
+    }
+    fr_one(w); fr_zero(acc);
+    for (size_t b = 0; b < blocks; ++b) {
+        fr_mul(t, part + 4 * b, w);
+        fr_add(acc, acc, t);
+        fr_mul(w, w, pseg);
+    }
+    fr_set(o, acc);
+    free(part);
+}
+
 /* King closure of d_pp: dist-primitives/src/dpp/mod.rs:41-76.  shares_by_party[r] = the 2*cols-element
  * vector (num shares then den shares) received from parties[r]; rand = cols x t packing randomness;
  * out_by_party[p] = cols elements.  Returns -2 if a denominator is zero (the reference unwraps). */

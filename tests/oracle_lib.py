@@ -43,6 +43,7 @@ def oracle():
                 getattr(lib, f"zko_{fld}_{op}").argtypes = [u64p, u64p, C.c_size_t]
         lib.zko_g1_sequence.argtypes = [u64p, u64p, C.c_size_t, C.c_void_p, C.c_size_t]
         lib.zko_fr_sum.argtypes = [u64p, C.c_size_t, u64p]
+        lib.zko_fr_eval_poly.argtypes = [u64p, C.c_size_t, u64p, u64p, C.c_int]
         lib.zko_fq2_mul.argtypes = [u64p, u64p, u64p, C.c_size_t]
         lib.zko_fq2_sqr.argtypes = [u64p, u64p, C.c_size_t]
         lib.zko_fq2_inv.argtypes = [u64p, u64p, C.c_size_t]

@@ -171,7 +171,7 @@ def test_d_fft_round_reconstructs_plain_fft(env, log2m):
     assert (got == expect).all()
 
 
-@pytest.mark.parametrize("group,log2n", [(1, 10), (1, 15), (1, 19), (1, 22), (1, 24), (2, 13)])
+@pytest.mark.parametrize("group,log2n", [(1, 10), (1, 15), (1, 19), (1, 22), (1, 24), (2, 13), (2, 19)])
 def test_msm_registered_dev_closed_form(env, group, log2n):
     """Prepared bases (window-shifted table, merged buckets, no Horner) give the same group element."""
     z, capi, torch, ctx = env
@@ -207,3 +207,44 @@ def test_msm_registered_dev_closed_form(env, group, log2n):
     assert bool((comb == out).all())
     assert lib.zkg_msm_bn254_registered_dev(ctx, h.value, C.c_void_p(a.data_ptr()), n - 1, C.c_void_p(out.data_ptr()), 0) == capi.ZKG_ERR_LEN_MISMATCH
     capi.check(lib.zkg_bases_release(h.value))
+
+
+def test_d_fft_2p24_sampled_against_the_dft_definition(env):
+    """The top of the north_star range (bench.py reports d_fft at m = 2^24): one d_fft round through the host-pointer
+    C ABI -- QAP-style packing (zkg_pss_pack_vec layout 1), client fft1 per party, king pipeline -- then sampled output
+    positions are unpacked and compared with X[k] = sum_j x_j w^(jk) evaluated by the CPU oracle (Horner, O(m) each).
+    Nothing here leans on the device's own plain FFT."""
+    z, capi, torch, ctx = env
+    o = ol.oracle()
+    lib = z.lib()
+    l, log2m = 2, 24
+    m = 1 << log2m
+    mbyl = m // l
+    rng = np.random.default_rng(24)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    x = rng.integers(0, 2**64, size=(m, 4), dtype=np.uint64)
+    x[:, 3] &= np.uint64((1 << 61) - 1)                               # any value below 2^253 is a valid Montgomery image
+    shares = z.qap_pss_pack(x, pp, ol.rand_fr(rng, 64)[np.arange(mbyl * pp.t) % 64])     # 64 draws, tiled
+    for p in range(pp.n):                                             # clients: dfft/mod.rs:121
+        z.fft1_in_place(shares[p], pp, dom.group_gen())
+    rnd = ol.rand_fr(rng, 64)[np.arange(mbyl * pp.t) % 64]
+    out = z.king_fft2(shares, list(range(pp.n)), pp, dom.group_gen(), dom.element(0),
+                      False, rnd)                                     # king: dfft/mod.rs:264-304, consecutive packing
+    del shares
+    ks = [0, 1, 2, m // 2 - 1, m // 2, m - 1] + [int(v) for v in rng.integers(0, m, size=6)]
+    cols = sorted({k // l for k in ks})
+    col_shares = np.ascontiguousarray(np.stack([np.stack([out[p][c] for p in range(pp.n)]) for c in cols])).reshape(-1, 4)
+    secrets = pp.unpack(col_shares).reshape(len(cols), l, 4)
+    from zksaas_b200.api import fr_image
+    w = pyref_root(m)
+    for k in ks:
+        got = secrets[cols.index(k // l), k % l]
+        pt = fr_image(pow(w, k, ol.pyref.R_MOD))
+        exp = np.zeros(4, dtype=np.uint64)
+        o.zko_fr_eval_poly(_p(x), m, _p(pt), _p(exp), 16)
+        assert (got == exp).all(), k
+
+
+def pyref_root(m):
+    return ol.pyref.Radix2Domain(m).group_gen

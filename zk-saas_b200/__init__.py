@@ -11,4 +11,5 @@ from .api import (  # noqa: F401
     PackedSharingParams, MsmLengthMismatch, Radix2EvaluationDomain, FftMask, MsmMask, DegRedMask,
     msm_g1, msm_g2, fft1_in_place, fft2_in_place, fft_in_place_rearrange, distribute_powers,
     king_fft2, deg_red_king, dpp_king, pack_vec, pack_from_witness, qap_pss_pack, qap_pss, group_generator, transpose, d_fft, d_ifft, d_msm, deg_red, d_pp, LocalTestNet,
+    pss_unpack2_group, group_to_wire, group_from_wire, qap_h,
 )

@@ -51,6 +51,12 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def _require(cond, msg):
+    """Argument checks that must survive `python -O` (the C side reads the buffers it is told about)."""
+    if not cond:
+        raise ValueError(msg)
+
+
 def _fr_vec(a, name="vector"):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     if a.ndim != 2 or a.shape[1] != 4:
@@ -124,9 +130,9 @@ class PackedSharingParams:
         """pss.rs:90-122; secrets (cols*l, 4), rand_points (cols*t, 4) -> shares (cols*n, 4).
         The t random points per column are an input (the host RNG stays with the caller)."""
         secrets, rand_points = _fr_vec(secrets, "secrets"), _fr_vec(rand_points, "rand_points")
-        assert secrets.shape[0] % self.l == 0, "Secrets length mismatch"
+        _require(secrets.shape[0] % self.l == 0, "Secrets length mismatch")
         cols = secrets.shape[0] // self.l
-        assert rand_points.shape[0] == cols * self.t, "rand_points length mismatch"
+        _require(rand_points.shape[0] == cols * self.t, "rand_points length mismatch")
         out = np.empty((cols * self.n, 4), dtype=np.uint64)
         check(lib().zkg_pss_pack_bn254_fr(self.device, self.l, _ptr(secrets), _ptr(rand_points), _ptr(out), cols))
         return out
@@ -134,7 +140,7 @@ class PackedSharingParams:
     def det_pack(self, secrets):
         """pss.rs:69-87."""
         secrets = _fr_vec(secrets, "secrets")
-        assert secrets.shape[0] % self.l == 0, "Secrets length mismatch"
+        _require(secrets.shape[0] % self.l == 0, "Secrets length mismatch")
         cols = secrets.shape[0] // self.l
         out = np.empty((cols * self.n, 4), dtype=np.uint64)
         check(lib().zkg_pss_pack_bn254_fr(self.device, self.l, _ptr(secrets), None, _ptr(out), cols))
@@ -143,6 +149,7 @@ class PackedSharingParams:
     def unpack(self, shares):
         """pss.rs:125-138."""
         shares = _fr_vec(shares, "shares")
+        _require(shares.shape[0] % self.n == 0, "shares length is not a multiple of n")
         cols = shares.shape[0] // self.n
         out = np.empty((cols * self.l, 4), dtype=np.uint64)
         check(lib().zkg_pss_unpack_bn254_fr(self.device, self.l, _ptr(shares), _ptr(out), cols))
@@ -151,6 +158,7 @@ class PackedSharingParams:
     def unpack2(self, shares):
         """pss.rs:141-166."""
         shares = _fr_vec(shares, "shares")
+        _require(shares.shape[0] % self.n == 0, "shares length is not a multiple of n")
         cols = shares.shape[0] // self.n
         out = np.empty((cols * self.l, 4), dtype=np.uint64)
         check(lib().zkg_pss_unpack2_bn254_fr(self.device, self.l, _ptr(shares), _ptr(out), cols))
@@ -172,7 +180,7 @@ PackedSharingParams.unpack2_matrix = _unpack2_matrix
 
 def transpose(matrix):
     """utils/pack.rs:22-35 for a list of equal-length (k,4) vectors -> list of (len,4) vectors."""
-    assert len(matrix) > 0
+    _require(len(matrix) > 0, "transpose of an empty matrix")
     a = np.stack([_fr_vec(r) for r in matrix])            # rows x cols x 4
     return [np.ascontiguousarray(a[:, c, :]) for c in range(a.shape[1])]
 
@@ -186,7 +194,7 @@ def pack_vec(secrets, pp: PackedSharingParams, rand_points):
 def _pack_vec_by_party(x, pp: "PackedSharingParams", rand_points, layout):
     x, rand_points = _fr_vec(x, "x"), _fr_vec(rand_points, "rand_points")
     cols = (x.shape[0] + pp.l - 1) // pp.l
-    assert rand_points.shape[0] == cols * pp.t, "rand_points length mismatch"
+    _require(rand_points.shape[0] == cols * pp.t, "rand_points length mismatch")
     outs = [np.zeros((cols, 4), dtype=np.uint64) for _ in range(pp.n)]
     arr = (C.POINTER(C.c_uint64) * pp.n)(*[o.ctypes.data_as(C.POINTER(C.c_uint64)) for o in outs])
     check(lib().zkg_pss_pack_vec_bn254_fr(pp.device, pp.l, layout, _ptr(x), x.shape[0], _ptr(rand_points), arr))
@@ -247,7 +255,8 @@ def crs_det_pack(bases, pp: "PackedSharingParams", g2=False):
     CRS query over group elements; returns the n parties' affine share vectors ((chunks, 72|136) uint8 each)."""
     stride = 136 if g2 else 72
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
-    assert bases.ndim == 2 and bases.shape[1] == stride and bases.shape[0] % pp.l == 0
+    _require(bases.ndim == 2 and bases.shape[1] == stride and bases.shape[0] % pp.l == 0,
+             f"bases: expected (chunks*l, {stride}) uint8 affine images")
     chunks = bases.shape[0] // pp.l
     outs = [np.zeros((chunks, stride), dtype=np.uint8) for _ in range(pp.n)]
     arr = (C.c_void_p * pp.n)(*[o.ctypes.data for o in outs])
@@ -288,34 +297,87 @@ def group_add(a, b, g2=False, device=0):
     return group_lincomb([a, b], [_one_img(), _one_img()], g2, device)
 
 
+def pss_unpack2_group(pp: "PackedSharingParams", shares, parties=None, g2=False, want_unpacked=True):
+    """pp.unpack_missing_shares(&shares, &parties) over group elements + the sum of the results
+    (dmsm/mod.rs:85-86; sha256.rs:375-377).  shares: Projective images (any Z), one per entry of `parties`.
+    Returns (list of the l unpacked points or None, their sum), normalised Jacobian images."""
+    w = 24 if g2 else 12
+    pts = np.ascontiguousarray(np.stack([np.asarray(x, dtype=np.uint64).reshape(w) for x in shares]))
+    parties = list(range(len(shares))) if parties is None else list(parties)
+    _require(len(parties) == pts.shape[0], "one share per received party expected")
+    par = (C.c_uint32 * len(parties))(*parties)
+    rows = np.zeros((pp.l, w), dtype=np.uint64) if want_unpacked else None
+    total = np.zeros(w, dtype=np.uint64)
+    fn = lib().zkg_pss_unpack2_bn254_g2 if g2 else lib().zkg_pss_unpack2_bn254_g1
+    check(fn(pp.device, pp.l, _ptr(pts), par, len(parties), _ptr(rows), _ptr(total)))
+    return (list(rows) if want_unpacked else None), total
+
+
+def group_to_wire(points, g2=False, device=0):
+    """ark-serialize compressed form of Projective images (ser_net.rs:25): (k, 32 | 64) uint8."""
+    w, nb = (24, 64) if g2 else (12, 32)
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.uint64).reshape(-1, w))
+    out = np.zeros((pts.shape[0], nb), dtype=np.uint8)
+    fn = lib().zkg_g2_to_wire_bn254 if g2 else lib().zkg_g1_to_wire_bn254
+    check(fn(device, _ptr(pts), _ptr(out), pts.shape[0]))
+    return out
+
+
+def group_from_wire(wire, g2=False, device=0):
+    """deserialize_compressed (ser_net.rs:40,119; Validate::Yes) -> normalised Jacobian images; raises ZkgError
+    (ZKG_ERR_BAD_ARG) on an invalid encoding."""
+    w, nb = (24, 64) if g2 else (12, 32)
+    wire = np.ascontiguousarray(wire, dtype=np.uint8)
+    _require(wire.ndim == 2 and wire.shape[1] == nb, f"wire: (k, {nb}) uint8 expected")
+    out = np.zeros((wire.shape[0], w), dtype=np.uint64)
+    fn = lib().zkg_g2_from_wire_bn254 if g2 else lib().zkg_g1_from_wire_bn254
+    check(fn(device, _ptr(wire), _ptr(out), wire.shape[0]))
+    return out
+
+
+def qap_h(a, b, c, mask_a=None, mask_b=None, mask_c=None, factor=None, device=0):
+    """h = (a + mask_a)(b + mask_b) - (c + mask_c) [* factor] on share vectors: ext_wit.rs:173-177 / :82-86 fused with
+    the out-mask additions of dfft/mod.rs:313-317."""
+    a, b, c = _fr_vec(a, "a"), _fr_vec(b, "b"), _fr_vec(c, "c")
+    _require(a.shape == b.shape == c.shape, "a, b, c of different lengths")
+    ms = [None if m is None else _fr_vec(m, "mask") for m in (mask_a, mask_b, mask_c)]
+    _require(all(m is None or m.shape == a.shape for m in ms), "mask length differs from the share vectors")
+    out = np.empty_like(a)
+    check(lib().zkg_qap_h_bn254(device, _ptr(a), _ptr(b), _ptr(c), _ptr(ms[0]), _ptr(ms[1]), _ptr(ms[2]), _ptr(factor), _ptr(out),
+                                a.shape[0]))
+    return out
+
+
 # ---- dist-primitives/src/dfft ---------------------------------------------------------------------
 def fft1_in_place(px, pp: PackedSharingParams, gen, pre_scale=None, in_mask=None, device=None):
     """dfft/mod.rs:178-208, in place on the (m/l, 4) share vector.  pre_scale / in_mask are the fused
     forms of dfft/mod.rs:159 and :254-258."""
-    assert px.dtype == np.uint64 and px.flags.c_contiguous and px.shape[1] == 4
+    _require(px.dtype == np.uint64 and px.flags.c_contiguous and px.ndim == 2 and px.shape[1] == 4, "px: (m/l, 4) uint64 expected")
     dev = pp.device if device is None else device
-    check(lib().zkg_fft1_bn254(dev, _ptr(px), px.shape[0], pp.l, _ptr(gen), _ptr(pre_scale),
-                               _ptr(_fr_vec(in_mask)) if in_mask is not None else None))
+    if in_mask is not None:
+        in_mask = _fr_vec(in_mask, "in_mask")
+        _require(in_mask.shape == px.shape, "in_mask length differs from the share vector")
+    check(lib().zkg_fft1_bn254(dev, _ptr(px), px.shape[0], pp.l, _ptr(gen), _ptr(pre_scale), _ptr(in_mask)))
     return px
 
 
 def fft2_in_place(s1, pp: PackedSharingParams, gen):
     """dfft/mod.rs:210-237."""
-    assert s1.dtype == np.uint64 and s1.flags.c_contiguous and s1.shape[1] == 4
+    _require(s1.dtype == np.uint64 and s1.flags.c_contiguous and s1.ndim == 2 and s1.shape[1] == 4, "(k, 4) uint64 expected")
     check(lib().zkg_fft2_bn254(pp.device, _ptr(s1), s1.shape[0], pp.l, _ptr(gen)))
     return s1
 
 
 def fft_in_place_rearrange(data, device=0):
     """dfft/mod.rs:322-335."""
-    assert data.dtype == np.uint64 and data.flags.c_contiguous and data.shape[1] == 4
+    _require(data.dtype == np.uint64 and data.flags.c_contiguous and data.ndim == 2 and data.shape[1] == 4, "(k, 4) uint64 expected")
     check(lib().zkg_bitrev_bn254(device, _ptr(data), data.shape[0]))
     return data
 
 
 def distribute_powers(v, g, device=0):
     """Radix2EvaluationDomain::distribute_powers (dfft/mod.rs:49,279)."""
-    assert v.dtype == np.uint64 and v.flags.c_contiguous and v.shape[1] == 4
+    _require(v.dtype == np.uint64 and v.flags.c_contiguous and v.ndim == 2 and v.shape[1] == 4, "(k, 4) uint64 expected")
     check(lib().zkg_distribute_powers_bn254(device, _ptr(v), v.shape[0], _ptr(g)))
     return v
 
@@ -325,12 +387,22 @@ def _ptr_array(arrs):
     return T(*[a.ctypes.data_as(u64p) for a in arrs])
 
 
+def _share_vectors(shares, parties, pp):
+    """The vectors the king received: one per entry of `parties`, all of the same length."""
+    shares = [_fr_vec(s, "shares") for s in shares]
+    _require(len(shares) >= 1 and len(shares) == len(parties), "one share vector per received party expected")
+    _require(len(shares) <= pp.n, "more share vectors than parties")
+    length = shares[0].shape[0]
+    _require(all(s.shape[0] == length for s in shares), "share vectors of different lengths")
+    return shares, length
+
+
 def king_fft2(shares, parties, pp: PackedSharingParams, gen, g, rearrange, rand_points):
     """King closure of fft2_with_rearrange, dfft/mod.rs:264-304.  shares[r] is the vector received
     from parties[r]; returns the n per-party output vectors."""
-    shares = [_fr_vec(s) for s in shares]
-    mbyl = shares[0].shape[0]
+    shares, mbyl = _share_vectors(shares, parties, pp)
     rand_points = _fr_vec(rand_points, "rand_points")
+    _require(rand_points.shape[0] == mbyl * pp.t, "rand_points: m/l * t draws expected")
     outs = [np.empty((mbyl, 4), dtype=np.uint64) for _ in range(pp.n)]
     par = (C.c_uint32 * len(parties))(*parties)
     check(lib().zkg_king_fft2_bn254(pp.device, _ptr_array(shares), par, len(shares), mbyl, pp.l, _ptr(gen), _ptr(g),
@@ -340,9 +412,9 @@ def king_fft2(shares, parties, pp: PackedSharingParams, gen, g, rearrange, rand_
 
 def deg_red_king(shares, parties, pp: PackedSharingParams, rand_points):
     """King closure of deg_red, utils/deg_red.rs:103-111."""
-    shares = [_fr_vec(s) for s in shares]
-    cols = shares[0].shape[0]
+    shares, cols = _share_vectors(shares, parties, pp)
     rand_points = _fr_vec(rand_points, "rand_points")
+    _require(rand_points.shape[0] == cols * pp.t, "rand_points: cols * t draws expected")
     outs = [np.empty((cols, 4), dtype=np.uint64) for _ in range(pp.n)]
     par = (C.c_uint32 * len(parties))(*parties)
     check(lib().zkg_deg_red_king_bn254(pp.device, _ptr_array(shares), par, len(shares), cols, pp.l,
@@ -352,9 +424,11 @@ def deg_red_king(shares, parties, pp: PackedSharingParams, rand_points):
 
 def dpp_king(shares, parties, pp: PackedSharingParams, rand_points):
     """King closure of d_pp, dpp/mod.rs:41-76.  shares[r]: (2*cols, 4) = num shares then den shares."""
-    shares = [_fr_vec(s) for s in shares]
-    cols = shares[0].shape[0] // 2
+    shares, two_cols = _share_vectors(shares, parties, pp)
+    _require(two_cols % 2 == 0, "d_pp: each party sends num shares followed by den shares")
+    cols = two_cols // 2
     rand_points = _fr_vec(rand_points, "rand_points")
+    _require(rand_points.shape[0] == cols * pp.t, "rand_points: cols * t draws expected")
     outs = [np.empty((cols, 4), dtype=np.uint64) for _ in range(pp.n)]
     par = (C.c_uint32 * len(parties))(*parties)
     check(lib().zkg_dpp_king_bn254(pp.device, _ptr_array(shares), par, len(shares), cols, pp.l,
@@ -364,6 +438,7 @@ def dpp_king(shares, parties, pp: PackedSharingParams, rand_points):
 
 def _field_op(op, a, b, field=0, device=0):
     a, b = _fr_vec(a), _fr_vec(b)
+    _require(a.shape == b.shape, "element-wise operands of different lengths")
     out = np.empty_like(a)
     check(lib().zkg_field_op(device, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
     return out
@@ -396,19 +471,14 @@ class FftMask:
     def sample(rearrange, g, gen, m, pp: PackedSharingParams, mask_values, rand_in, rand_out):
         """dfft/mod.rs:30-85 with the random draws passed in: mask_values (m,4), rand_in / rand_out
         (m/l*t, 4) packing randomness.  Returns the n parties' FftMask shares."""
-        mask_values = _fr_vec(mask_values).copy()
-        in_shares = transpose(pack_vec(mask_values, pp, rand_in))
-        fft2_in_place(mask_values, pp, gen)
-        if fr_value(g) != 1:
-            distribute_powers(mask_values, g, pp.device)
-        mask_values = fr_sub(np.zeros_like(mask_values), mask_values, pp.device)      # negate
-        if rearrange:
-            fft_in_place_rearrange(mask_values, pp.device)
-            mbyl = m // pp.l
-            strided = np.ascontiguousarray(mask_values.reshape(pp.l, mbyl, 4).transpose(1, 0, 2)).reshape(-1, 4)
-            out_shares = transpose(pack_vec(strided, pp, rand_out))
-        else:
-            out_shares = transpose(pack_vec(mask_values, pp, rand_out))
+        mask_values, rand_in, rand_out = _fr_vec(mask_values, "mask_values"), _fr_vec(rand_in, "rand_in"), _fr_vec(rand_out, "rand_out")
+        _require(mask_values.shape[0] == m and m % pp.l == 0, "mask_values: m draws expected")
+        mbyl = m // pp.l
+        _require(rand_in.shape[0] == mbyl * pp.t and rand_out.shape[0] == mbyl * pp.t, "rand_in / rand_out: m/l * t draws expected")
+        in_shares = [np.empty((mbyl, 4), dtype=np.uint64) for _ in range(pp.n)]
+        out_shares = [np.empty((mbyl, 4), dtype=np.uint64) for _ in range(pp.n)]
+        check(lib().zkg_fft_mask_sample_bn254(pp.device, 1 if rearrange else 0, _ptr(g), _ptr(gen), m, pp.l, _ptr(mask_values),
+                                              _ptr(rand_in), _ptr(rand_out), _ptr_array(in_shares), _ptr_array(out_shares)))
         return [FftMask(i, o) for i, o in zip(in_shares, out_shares)]
 
 
@@ -434,7 +504,8 @@ class MsmMask:
         Every group operation is a tiny device MSM; pack over group elements applies the rows of the
         pack matrix (pss.rs:90-122 with T = G)."""
         mask_scalars = _fr_vec(mask_scalars, "mask_scalars")
-        assert mask_scalars.shape[0] == pp.l and len(rand_in_points) == pp.t and len(rand_out_points) == pp.t
+        _require(mask_scalars.shape[0] == pp.l and len(rand_in_points) == pp.t and len(rand_out_points) == pp.t,
+                 "MsmMask.sample: l mask scalars and t + t random points expected")
         dev = pp.device
         gen = group_generator(g2)
         values = [group_lincomb([gen], [x], g2, dev) for x in mask_scalars]                 # gen * x_i
@@ -495,7 +566,7 @@ class DegRedMask:
     """utils/deg_red.rs:14-77."""
 
     def __init__(self, in_mask, out_mask):
-        assert in_mask.shape == out_mask.shape
+        _require(in_mask.shape == out_mask.shape, "in_mask / out_mask of different lengths")
         self.in_mask, self.out_mask = in_mask, out_mask
 
     @staticmethod
@@ -506,11 +577,13 @@ class DegRedMask:
     def sample(pp: PackedSharingParams, num, mask_values, rand_in, rand_out):
         """utils/deg_red.rs:40-66 over Fr with gen = 1: mask_values (num*l, 4) are the random draws,
         rand_in / rand_out (num*t, 4) the packing randomness.  Returns the n parties' shares."""
-        mask_values = _fr_vec(mask_values)
-        assert mask_values.shape[0] == num * pp.l
-        neg = fr_sub(np.zeros_like(mask_values), mask_values, pp.device)
-        ins = transpose(pack_vec(mask_values, pp, rand_in))
-        outs = transpose(pack_vec(neg, pp, rand_out))
+        mask_values, rand_in, rand_out = _fr_vec(mask_values, "mask_values"), _fr_vec(rand_in, "rand_in"), _fr_vec(rand_out, "rand_out")
+        _require(mask_values.shape[0] == num * pp.l, "mask_values: num * l draws expected")
+        _require(rand_in.shape[0] == num * pp.t and rand_out.shape[0] == num * pp.t, "rand_in / rand_out: num * t draws expected")
+        ins = [np.empty((num, 4), dtype=np.uint64) for _ in range(pp.n)]
+        outs = [np.empty((num, 4), dtype=np.uint64) for _ in range(pp.n)]
+        check(lib().zkg_deg_red_mask_sample_bn254(pp.device, num, pp.l, _ptr(mask_values), _ptr(rand_in), _ptr(rand_out),
+                                                  _ptr_array(ins), _ptr_array(outs)))
         return [DegRedMask(i, o) for i, o in zip(ins, outs)]
 
 
@@ -545,7 +618,7 @@ def d_ifft(peval_shares, fft_masks, rearrange, dom, g, pp, net, rand_points, dev
 
 def _d_fft_impl(shares, masks, rearrange, dom, g, pp, net, rand_points, inverse, device_of_party):
     mbyl = shares[0].shape[0]
-    assert mbyl * pp.l == dom.size(), f"Mismatch of size in FFT, {mbyl * pp.l}, {dom.size()}."
+    _require(mbyl * pp.l == dom.size(), f"Mismatch of size in FFT, {mbyl * pp.l}, {dom.size()}.")
     gen = dom.group_gen_inv() if inverse else dom.group_gen()
     pre = dom.size_inv() if inverse else None
     sent = []
@@ -576,18 +649,15 @@ def d_pp(num_shares, den_shares, masks, pp, net, rand_king, rand_degred):
 
 
 def d_msm(bases_by_party, scalars_by_party, masks, pp, net, g2=False, device_of_party=None):
-    """dmsm/mod.rs:59-102 for all parties at once.  The king's `unpack_missing_shares` over group
-    elements (pss.rs:141-166) is the l x n unpack2 matrix applied as tiny device MSMs."""
+    """dmsm/mod.rs:59-102 for all parties at once.  The king's `unpack_missing_shares` over group elements
+    (pss.rs:141-166; the Lagrange path :170-221 when `net` drops parties) and the sum run in
+    zkg_pss_unpack2_bn254_g1/g2."""
     msm = msm_g2 if g2 else msm_g1
-    unpack2_matrix = pp.unpack2_matrix()
     c_shares = []
     for p in range(net.n_parties()):
         dev = device_of_party(p) if device_of_party else pp.device
         c = msm(bases_by_party[p], scalars_by_party[p], dev)                           # :73
         c_shares.append(group_add(c, masks[p].in_mask, g2, dev))                       # :74
     recv, parties = net.received(c_shares)
-    assert len(recv) == pp.n, "dropout path of d_msm needs the Lagrange matrix; not wired in this mirror"
-    unpacked = [group_lincomb(recv, [unpack2_matrix[i][j] for j in range(pp.n)], g2, pp.device)
-                for i in range(pp.l)]                                                  # :85
-    output = group_lincomb(unpacked, [_one_img()] * pp.l, g2, pp.device)               # :86
+    _, output = pss_unpack2_group(pp, recv, parties, g2, want_unpacked=False)          # :85-86
     return [group_add(output, masks[p].out_mask, g2, pp.device) for p in range(net.n_parties())]  # :98

@@ -16,6 +16,7 @@ ZKG_ERR_BAD_ARG = -2
 ZKG_ERR_CUDA = -3
 ZKG_ERR_OOM = -4
 ZKG_ERR_UNSUPPORTED = -5
+ZKG_ERR_NCCL = -6
 
 # name -> (restype, argtypes); every symbol include/zksaas_gpu.h declares
 SIGNATURES = {
@@ -71,6 +72,17 @@ SIGNATURES = {
     "zkg_fr_fft_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32]),
     "zkg_fr_from_wire_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zkg_fr_to_wire_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zkg_pss_unpack2_bn254_g1": (C.c_int32, [C.c_int32, C.c_uint32, C.c_void_p, u32p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "zkg_pss_unpack2_bn254_g2": (C.c_int32, [C.c_int32, C.c_uint32, C.c_void_p, u32p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "zkg_g1_to_wire_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zkg_g1_from_wire_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zkg_g2_to_wire_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zkg_g2_from_wire_bn254": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zkg_qap_h_bn254": (C.c_int32, [C.c_int32] + [C.c_void_p] * 8 + [C.c_size_t]),
+    "zkg_qap_h_bn254_dev": (C.c_int32, [ctx_p] + [C.c_void_p] * 8 + [C.c_size_t]),
+    "zkg_fft_mask_sample_bn254": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, pp_u64, pp_u64]),
+    "zkg_deg_red_mask_sample_bn254": (C.c_int32, [C.c_int32, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, pp_u64, pp_u64]),
     "zkg_field_op_dev": (C.c_int32, [ctx_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zkg_field_op": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }

@@ -149,6 +149,32 @@ __global__ void k_field_op(int op, const F* __restrict__ a, const F* __restrict_
     o[i] = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
 }
 
+
+// Share-wise h = a*b - c of the QAP (groth16/src/ext_wit.rs:173-177; :82-86 with the 1/Z(g) factor), fused with the
+// out-mask additions that end the three preceding d_fft calls (dist-primitives/src/dfft/mod.rs:313-317): one pass over
+// the share vectors instead of three mask adds, a product and a subtraction.  (a+ma)(b+mb) - (c+mc) is formed as a
+// two-term inner product with ONE Montgomery reduction; canonical, so identical to the separate operations.
+struct FrArgH { uint32_t v[8]; };
+__global__ void __launch_bounds__(256) k_qap_h(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c,
+                                               const Fr* __restrict__ ma, const Fr* __restrict__ mb, const Fr* __restrict__ mc,
+                                               int has_factor, FrArgH factor_, Fr* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = a[i], y = b[i], z = c[i];
+    if (ma) x = fp_add(x, ma[i]);
+    if (mb) y = fp_add(y, mb[i]);
+    if (mc) z = fp_add(z, mc[i]);
+    Fr xs[2] = {x, fp_neg(z)}, ys[2] = {y, Fr::one()};
+    Fr h = fp_dot<FrParams, 2>(xs, ys);
+    if (has_factor) {
+        Fr f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f.v[k] = factor_.v[k];
+        h = fp_mul(h, f);
+    }
+    out[i] = h;
+}
+
 }  // namespace zkg
 
 using namespace zkg;
@@ -271,6 +297,47 @@ int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t* 
     else k_field_op<Fq><<<blocks, 256, 0, ctx->stream>>>(op, (const Fq*)d, (const Fq*)(d + bytes), (Fq*)(d + 2 * bytes), n);
     ZKG_CUDA(cudaGetLastError());
     ZKG_TRY(copy_d2h(out, d + 2 * bytes, n * 32, ctx->stream));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+
+int32_t zkg_qap_h_bn254_dev(zkg_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_c, const uint64_t* d_mask_a,
+                            const uint64_t* d_mask_b, const uint64_t* d_mask_c, const uint64_t* factor, uint64_t* d_out, size_t n) {
+    ZKG_REQUIRE(ctx && (n == 0 || (d_a && d_b && d_c && d_out)), "qap_h_dev: NULL argument");
+    if (n == 0) return ZKG_OK;
+    DeviceGuard dg(ctx->device);
+    FrArgH f;
+    memset(&f, 0, sizeof f);
+    if (factor) memcpy(f.v, factor, 32);
+    k_qap_h<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c, (const Fr*)d_mask_a,
+                                                                 (const Fr*)d_mask_b, (const Fr*)d_mask_c, factor ? 1 : 0, f, (Fr*)d_out, n);
+    ctx->launches += 1;
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+int32_t zkg_qap_h_bn254(int32_t device, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* mask_a,
+                        const uint64_t* mask_b, const uint64_t* mask_c, const uint64_t* factor, uint64_t* out, size_t n) {
+    ZKG_REQUIRE(n == 0 || (a && b && c && out), "qap_h: NULL argument");
+    if (n == 0) return ZKG_OK;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    const size_t bytes = align_up(n * 32, 256);
+    ZKG_TRY(ctx->io.reserve(7 * bytes));
+    uint8_t* d = (uint8_t*)ctx->io.p;
+    const uint64_t* src[6] = {a, b, c, mask_a, mask_b, mask_c};
+    const uint64_t* dv[6];
+    for (int k = 0; k < 6; ++k) {
+        dv[k] = nullptr;
+        if (!src[k]) continue;
+        ZKG_TRY(copy_h2d(d + k * bytes, src[k], n * 32, ctx->stream));
+        dv[k] = (const uint64_t*)(d + k * bytes);
+    }
+    ZKG_TRY(zkg_qap_h_bn254_dev(ctx, dv[0], dv[1], dv[2], dv[3], dv[4], dv[5], factor, (uint64_t*)(d + 6 * bytes), n));
+    ZKG_TRY(copy_d2h(out, d + 6 * bytes, n * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }

@@ -2,6 +2,8 @@
 // Declarations and reference citations: include/zksaas_gpu.h.
 #include "common.cuh"
 #include "host_fr.hpp"
+#include <condition_variable>
+#include <utility>
 
 namespace zkg {
 #define ZKG_MSM_DECLARE(G)                                                                                          \
@@ -18,13 +20,72 @@ namespace zkg {
                              const uint32_t* h_scal, void* const* out_by_party, size_t out_stride);
 ZKG_MSM_DECLARE(g1)
 ZKG_MSM_DECLARE(g2)
+#define ZKG_GROUP_DECLARE(G)                                                                                              \
+    int32_t group_unpack_##G(int device, const uint64_t* shares_xyz, uint32_t n_recv, const uint32_t* h_scal, uint32_t rows, \
+                             uint64_t* out_rows, uint64_t* out_sum);                                                     \
+    int32_t point_wire_##G(int device, int dir, const void* in, void* out, size_t n);
+ZKG_GROUP_DECLARE(g1)
+ZKG_GROUP_DECLARE(g2)
 
-// device-resident CRS share: table[w*n + i] = 2^(c*w) * P_i (packed affine), W = 254/c + 1 window shifts
-struct BaseSet { int device; int group; size_t n; int c; void* d_table; };
+// device-resident CRS share: table[w*n + i] = 2^(c*w) * P_i (packed affine), W = 254/c + 1 window shifts.
+// Lifetime: a handle is (generation << 32) | (slot + 1); slots are reused, stale handles are rejected by the
+// generation.  A call that uses the table holds a reference from lookup until its work is ordered behind an
+// event (`_dev` entry points: recorded on the context's stream right after the enqueue) or finished (blocking
+// entry points); zkg_bases_release waits for the references to drain and for every recorded event before it
+// frees the table, so a release that races an MSM on another thread can never free memory a kernel still reads.
+struct BaseSet {
+    int device = 0, group = 0;
+    size_t n = 0;
+    int c = 0;
+    void* d_table = nullptr;
+    uint32_t generation = 0;
+    int refs = 0;                    // calls between lookup and "ordered behind an event / finished"
+    bool released = false;
+    std::vector<std::pair<zkg_ctx*, cudaEvent_t>> last_use;     // one event per context that enqueued work on the table
+};
 int msm_pick_c_merged_host(size_t n);
 static std::mutex g_bases_mu;
-static std::vector<BaseSet*> g_bases;   // handle = index + 1
+static std::condition_variable g_bases_cv;
+static std::vector<BaseSet*> g_bases;        // slot -> live set or nullptr
+static std::vector<uint32_t> g_bases_gen;    // slot -> generation of the last set stored there
 static inline size_t packed_bytes(int group) { return group == 1 ? 64 : 128; }
+
+static BaseSet* base_set_lookup_locked(uint64_t handle) {
+    const uint64_t slot = (handle & 0xffffffffu), gen = handle >> 32;
+    if (slot < 1 || slot > g_bases.size()) return nullptr;
+    BaseSet* bs = g_bases[slot - 1];
+    if (!bs || bs->released || bs->generation != (uint32_t)gen) return nullptr;
+    return bs;
+}
+// RAII reference on a registered base set
+struct BaseRef {
+    BaseSet* bs = nullptr;
+    int32_t acquire(uint64_t handle) {
+        std::lock_guard<std::mutex> lk(g_bases_mu);
+        bs = base_set_lookup_locked(handle);
+        ZKG_REQUIRE(bs, "bad bases handle %llu (never registered, or already released)", (unsigned long long)handle);
+        bs->refs += 1;
+        return ZKG_OK;
+    }
+    // order a later release behind everything `ctx` has enqueued so far (asynchronous entry points)
+    int32_t mark_use(zkg_ctx* ctx) {
+        std::lock_guard<std::mutex> lk(g_bases_mu);
+        cudaEvent_t ev = nullptr;
+        for (auto& e : bs->last_use) if (e.first == ctx) ev = e.second;
+        if (!ev) {
+            ZKG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            bs->last_use.emplace_back(ctx, ev);
+        }
+        ZKG_CUDA(cudaEventRecord(ev, ctx->stream));
+        return ZKG_OK;
+    }
+    ~BaseRef() {
+        if (!bs) return;
+        std::lock_guard<std::mutex> lk(g_bases_mu);
+        bs->refs -= 1;
+        if (bs->refs == 0) g_bases_cv.notify_all();
+    }
+};
 }  // namespace zkg
 
 using namespace zkg;
@@ -80,12 +141,21 @@ int32_t zkg_fixed_base_dev(zkg_ctx* ctx, int32_t group, const uint64_t* d_scalar
 }
 
 static int32_t base_set_create(zkg_ctx* ctx, int32_t group, const void* d_packed, size_t n, uint64_t* handle) {
-    BaseSet* bs = new BaseSet{ctx->device, group, n, 0, nullptr};
+    BaseSet* bs = new BaseSet();
+    bs->device = ctx->device; bs->group = group; bs->n = n;
     if (n) {
         bs->c = msm_pick_c_merged_host(n);
         int env_c = getenv("ZKG_MSM_PREP_C") ? atoi(getenv("ZKG_MSM_PREP_C")) : 0;
         if (env_c >= 4 && env_c <= 23) bs->c = env_c;
+        // a sorted entry is (window * n + point) with the sign in bit 31 (msm_plan): shrink the table (larger windows)
+        // until it is addressable, and refuse what cannot be made so, BEFORE allocating gigabytes
+        while (bs->c < 23 && n * (size_t)(254 / bs->c + 1) >= ((size_t)1 << 31)) bs->c += 1;
         const int W = 254 / bs->c + 1;
+        if (n * (size_t)W >= ((size_t)1 << 31)) {
+            delete bs;
+            set_error("bases_register: %zu points x %d window shifts exceeds the 2^31-1 table entries an MSM can address", n, W);
+            return ZKG_ERR_BAD_ARG;
+        }
         size_t bytes = n * (size_t)W * packed_bytes(group);
         cudaError_t e = cudaMalloc(&bs->d_table, bytes);
         if (e != cudaSuccess) {
@@ -97,15 +167,12 @@ static int32_t base_set_create(zkg_ctx* ctx, int32_t group, const void* d_packed
         if (rc != ZKG_OK) { cudaFree(bs->d_table); delete bs; return rc; }
     }
     std::lock_guard<std::mutex> lk(g_bases_mu);
-    g_bases.push_back(bs);
-    *handle = g_bases.size();
-    return ZKG_OK;
-}
-
-static int32_t base_set_get(uint64_t handle, BaseSet* out) {
-    std::lock_guard<std::mutex> lk(g_bases_mu);
-    ZKG_REQUIRE(handle >= 1 && handle <= g_bases.size() && g_bases[handle - 1], "bad bases handle %llu", (unsigned long long)handle);
-    *out = *g_bases[handle - 1];
+    size_t slot = g_bases.size();
+    for (size_t i = 0; i < g_bases.size(); ++i) if (!g_bases[i]) { slot = i; break; }       // reuse a released slot
+    if (slot == g_bases.size()) { g_bases.push_back(nullptr); g_bases_gen.push_back(0); }
+    bs->generation = ++g_bases_gen[slot];
+    g_bases[slot] = bs;
+    *handle = ((uint64_t)bs->generation << 32) | (uint64_t)(slot + 1);
     return ZKG_OK;
 }
 
@@ -156,12 +223,20 @@ int32_t zkg_bases_register_dev(zkg_ctx* ctx, int32_t group, const void* d_bases_
 }
 
 int32_t zkg_bases_release(uint64_t handle) {
-    std::lock_guard<std::mutex> lk(g_bases_mu);
-    ZKG_REQUIRE(handle >= 1 && handle <= g_bases.size() && g_bases[handle - 1], "bases_release: bad handle");
-    BaseSet* bs = g_bases[handle - 1];
-    g_bases[handle - 1] = nullptr;
+    BaseSet* bs = nullptr;
+    {
+        std::unique_lock<std::mutex> lk(g_bases_mu);
+        bs = base_set_lookup_locked(handle);
+        ZKG_REQUIRE(bs, "bases_release: bad handle %llu (never registered, or already released)", (unsigned long long)handle);
+        bs->released = true;                                  // no new references from here on
+        g_bases_cv.wait(lk, [&] { return bs->refs == 0; });   // calls that already hold the table finish (or record their event) first
+        g_bases[(handle & 0xffffffffu) - 1] = nullptr;        // the slot may be reused under a new generation
+    }
     DeviceGuard dg(bs->device);
-    cudaDeviceSynchronize();
+    for (auto& e : bs->last_use) {                            // asynchronous users: wait for the work they enqueued
+        cudaEventSynchronize(e.second);
+        cudaEventDestroy(e.second);
+    }
     if (bs->d_table) cudaFree(bs->d_table);
     delete bs;
     return ZKG_OK;
@@ -170,21 +245,26 @@ int32_t zkg_bases_release(uint64_t handle) {
 int32_t zkg_msm_bn254_registered_dev(zkg_ctx* ctx, uint64_t handle, const uint64_t* d_scalars, size_t n_scalars,
                                      uint64_t* d_out, int32_t partial) {
     ZKG_REQUIRE(ctx && d_out, "msm_registered_dev: NULL argument");
-    BaseSet bs;
-    ZKG_TRY(base_set_get(handle, &bs));
+    BaseRef ref;
+    ZKG_TRY(ref.acquire(handle));
+    const BaseSet& bs = *ref.bs;
     ZKG_REQUIRE(bs.device == ctx->device, "msm_registered_dev: bases live on device %d, context on %d", bs.device, ctx->device);
     if (bs.n != n_scalars) {
         set_error("msm: bases.len() = %zu, scalars.len() = %zu", bs.n, n_scalars);
         return ZKG_ERR_LEN_MISMATCH;
     }
     DeviceGuard dg(ctx->device);
-    return bs.group == 1 ? msm_run_prepared_g1(ctx, bs.d_table, bs.c, d_scalars, n_scalars, d_out, partial ? 1 : 0)
-                         : msm_run_prepared_g2(ctx, bs.d_table, bs.c, d_scalars, n_scalars, d_out, partial ? 1 : 0);
+    int32_t rc = bs.group == 1 ? msm_run_prepared_g1(ctx, bs.d_table, bs.c, d_scalars, n_scalars, d_out, partial ? 1 : 0)
+                               : msm_run_prepared_g2(ctx, bs.d_table, bs.c, d_scalars, n_scalars, d_out, partial ? 1 : 0);
+    // whatever was enqueued (even by a call that failed half way) must finish before the table may be freed
+    int32_t rc2 = ref.mark_use(ctx);
+    return rc != ZKG_OK ? rc : rc2;
 }
 
 int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t* scalars, size_t n_scalars, uint64_t* out_xyz) {
-    BaseSet bs;
-    ZKG_TRY(base_set_get(handle, &bs));
+    BaseRef ref;
+    ZKG_TRY(ref.acquire(handle));
+    const BaseSet& bs = *ref.bs;
     if (bs.n != n_scalars) {
         set_error("msm: bases.len() = %zu, scalars.len() = %zu", bs.n, n_scalars);
         return ZKG_ERR_LEN_MISMATCH;
@@ -197,11 +277,64 @@ int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t* scalars, size_
     size_t sc_bytes = align_up(n_scalars * 32, 256);
     ZKG_TRY(ctx->io.reserve(sc_bytes + 512));
     void* d_out = (uint8_t*)ctx->io.p + sc_bytes;
-    ZKG_TRY(bs.group == 1 ? msm_run_prepared_host_g1(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out)
-                          : msm_run_prepared_host_g2(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out));
-    ZKG_TRY(copy_d2h(out_xyz, d_out, bs.group == 1 ? 96 : 192, ctx->stream));
-    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
-    return ZKG_OK;
+    int32_t rc = bs.group == 1 ? msm_run_prepared_host_g1(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out)
+                               : msm_run_prepared_host_g2(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out);
+    if (rc == ZKG_OK) rc = copy_d2h(out_xyz, d_out, bs.group == 1 ? 96 : 192, ctx->stream);
+    // blocking call: the reference is held until the stream has drained, also on the error paths
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    if (rc == ZKG_OK && se != cudaSuccess) { set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(se)); rc = ZKG_ERR_CUDA; }
+    return rc;
 }
+
+
+// King side of d_msm (dmsm/mod.rs:85-87): unpack_missing_shares over n_recv group elements, then the sum.
+static int32_t pss_unpack2_group(int32_t device, int group, uint32_t l, const uint64_t* shares_xyz, const uint32_t* parties,
+                                 uint32_t n_recv, uint64_t* out_unpacked, uint64_t* out_sum) {
+    ZKG_REQUIRE(shares_xyz && (out_unpacked || out_sum), "pss_unpack2 over group elements: NULL argument");
+    ZKG_REQUIRE(l == 2 || l == 4 || l == 8, "packing factor l = %u unsupported (2, 4, 8)", l);
+    host::PssMatrices pm;
+    host::pss_matrices(l, &pm);
+    std::vector<host::HFr> lag;
+    const std::vector<host::HFr>* M = &pm.unpack2;                   // l x n_recv, row-major
+    if (n_recv != pm.n) {
+        ZKG_REQUIRE(parties, "parties list required when shares are missing");
+        if (!host::pss_lagrange_matrix(l, parties, n_recv, &lag)) {
+            set_error("not enough shares to reconstruct: got %u of n = %u (need > %u distinct parties)", n_recv, pm.n,
+                      2 * (pm.t + pm.l - 1));
+            return ZKG_ERR_BAD_ARG;
+        }
+        M = &lag;
+    }
+    host::HFr raw_one = host::h_zero();
+    raw_one.v[0] = 1;
+    // the sum alone needs one row: the column sums of the matrix (sum_i sum_j M_ij S_j = sum_j (sum_i M_ij) S_j)
+    const uint32_t rows = out_unpacked ? l : 1;
+    std::vector<uint32_t> scal((size_t)rows * n_recv * 8);
+    for (uint32_t j = 0; j < n_recv; ++j) {
+        host::HFr col = host::h_zero();
+        for (uint32_t i = 0; i < l; ++i) {
+            const host::HFr& e = (*M)[(size_t)i * n_recv + j];
+            col = host::h_add(col, e);
+            if (out_unpacked) { host::HFr c = host::h_mul(e, raw_one); memcpy(&scal[((size_t)i * n_recv + j) * 8], c.v, 32); }
+        }
+        if (!out_unpacked) { host::HFr c = host::h_mul(col, raw_one); memcpy(&scal[(size_t)j * 8], c.v, 32); }
+    }
+    return group == 1 ? group_unpack_g1(device, shares_xyz, n_recv, scal.data(), rows, out_unpacked, out_sum)
+                      : group_unpack_g2(device, shares_xyz, n_recv, scal.data(), rows, out_unpacked, out_sum);
+}
+
+int32_t zkg_pss_unpack2_bn254_g1(int32_t device, uint32_t l, const uint64_t* shares_xyz, const uint32_t* parties, uint32_t n_recv,
+                                 uint64_t* out_unpacked_xyz, uint64_t* out_sum_xyz) {
+    return pss_unpack2_group(device, 1, l, shares_xyz, parties, n_recv, out_unpacked_xyz, out_sum_xyz);
+}
+int32_t zkg_pss_unpack2_bn254_g2(int32_t device, uint32_t l, const uint64_t* shares_xyz, const uint32_t* parties, uint32_t n_recv,
+                                 uint64_t* out_unpacked_xyz, uint64_t* out_sum_xyz) {
+    return pss_unpack2_group(device, 2, l, shares_xyz, parties, n_recv, out_unpacked_xyz, out_sum_xyz);
+}
+
+int32_t zkg_g1_from_wire_bn254(int32_t device, const void* wire, uint64_t* points_xyz, size_t n) { return point_wire_g1(device, 0, wire, points_xyz, n); }
+int32_t zkg_g1_to_wire_bn254(int32_t device, const uint64_t* points_xyz, void* wire, size_t n) { return point_wire_g1(device, 1, points_xyz, wire, n); }
+int32_t zkg_g2_from_wire_bn254(int32_t device, const void* wire, uint64_t* points_xyz, size_t n) { return point_wire_g2(device, 0, wire, points_xyz, n); }
+int32_t zkg_g2_to_wire_bn254(int32_t device, const uint64_t* points_xyz, void* wire, size_t n) { return point_wire_g2(device, 1, points_xyz, wire, n); }
 
 }  // extern "C"

@@ -927,7 +927,7 @@ static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F
     cudaStream_t st = ctx->stream;
     const bool first = pl->chunks_done == 0;
     const size_t sstride = pl->merged ? 0 : n;
-    static const int use_ba = env_int("ZKG_MSM_BA", 0);
+    const int use_ba = env_int("ZKG_MSM_BA", 0);            // read per call, like ZKG_MSM_C (tests flip it inside one process)
     if (use_ba)
         k_accumulate_ba<F><<<(unsigned)((pl->slots + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, st>>>(
             d_bases, pl->sorted, pl->cursor, pl->counts, pl->order, sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
@@ -994,7 +994,7 @@ static int32_t msm_finish(zkg_ctx* ctx, MsmPlan<F>* pl, F* d_out, int mode) {
     ctx->launches += 1;
     const XYZZ<F>* Rin = S_arr;
     const XYZZ<F>* Cin = Z_arr;
-    static const int coop_tail = env_int("ZKG_MSM_COOP_TAIL", 1);
+    const int coop_tail = env_int("ZKG_MSM_COOP_TAIL", 1);
     if (!pl->merged && pl->Wb > 1 && pl->Wb <= 64 && coop_tail)
         k_final_coop<F><<<1, 128, 0, st>>>(Rin, Cin, pl->c, pl->Wb, mode, d_out);       // Horner over windows on four warps
     else

@@ -789,6 +789,12 @@ k_dpp_scan_apply(Fr* __restrict__ q, size_t m, const Fr* __restrict__ tot) {
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
+
+__global__ void k_negate(Fr* __restrict__ v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fr(v + i, fp_neg(ld_fr(v + i)));
+}
+
 static int ilog2(size_t x) { int r = 0; while (((size_t)1 << r) < x) ++r; return r; }
 static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 
@@ -1493,6 +1499,78 @@ int32_t zkg_pss_unpack_bn254_fr(int32_t device, uint32_t l, const uint64_t* shar
 }
 int32_t zkg_pss_unpack2_bn254_fr(int32_t device, uint32_t l, const uint64_t* shares, uint64_t* secrets, size_t cols) {
     return pss_host(device, l, 2, shares, nullptr, secrets, cols);
+}
+
+
+// FftMask::sample (dist-primitives/src/dfft/mod.rs:30-85) with the random draws as inputs, every step on the device:
+// one upload of the m mask values and the 2 x (m/l * t) packing draws, one download of the 2 x n share vectors (the
+// Python mirror of round 1 crossed PCIe between each of its five steps).
+//   in shares  = transpose(pack_vec(mask))                                            :41-42
+//   S          = -(fft2_in_place(mask, gen) .* g^i)                                   :44-51
+//   out shares = rearrange ? pack of the bit-reversed, stride-m/l columns : pack_vec  :55-74
+// fft2 + powers + the rearrange permutation are one launch of the king's stage-1 kernel reading the mask directly.
+// mode_fft == 0 is DegRedMask::sample over Fr with gen = 1 (utils/deg_red.rs:40-66): S = -mask, no transform.
+static int32_t mask_sample_host(int device, int mode_fft, int rearrange, const uint64_t* g, const uint64_t* gen, size_t m, uint32_t l,
+                                const uint64_t* mask_values, const uint64_t* rand_in, const uint64_t* rand_out,
+                                uint64_t* const* in_by_party, uint64_t* const* out_by_party) {
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    ZKG_REQUIRE(in_by_party && out_by_party && (m == 0 || (mask_values && rand_in && rand_out)), "mask_sample: NULL argument");
+    ZKG_REQUIRE(!mode_fft || (g && gen), "fft_mask_sample: g / gen are NULL");
+    if (m == 0) return ZKG_OK;
+    ZKG_REQUIRE(m % l == 0, "mask_sample: %zu values is not a multiple of l = %u", m, l);
+    ZKG_REQUIRE(!mode_fft || (is_pow2(m) && m >= l && ilog2(m) <= 28), "fft_mask_sample: m = %zu must be a power of two in [l, 2^28]", m);
+    const size_t n = pm->n, t = pm->t, cols = m / l;
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    const size_t m_b = align_up(m * 32, 256), r_b = align_up(cols * t * 32, 256), o_b = align_up(cols * n * 32, 256);
+    ZKG_TRY(ctx->io.reserve(2 * m_b + 2 * r_b + 2 * o_b));
+    uint8_t* d = (uint8_t*)ctx->io.p;
+    Fr *d_mask = (Fr*)d, *d_S = (Fr*)(d + m_b), *d_ri = (Fr*)(d + 2 * m_b), *d_ro = (Fr*)(d + 2 * m_b + r_b);
+    Fr *d_in = (Fr*)(d + 2 * m_b + 2 * r_b), *d_out = (Fr*)(d + 2 * m_b + 2 * r_b + o_b);
+    ZKG_TRY(copy_h2d(d_mask, mask_values, m * 32, ctx->stream));
+    ZKG_TRY(copy_h2d(d_ri, rand_in, cols * t * 32, ctx->stream));
+    ZKG_TRY(copy_h2d(d_ro, rand_out, cols * t * 32, ctx->stream));
+    HostKeep keep;
+    ZKG_TRY(king_stage2(ctx, d_mask, d_ri, cols, l, d_in, keep));                       // in shares: consecutive chunks
+    if (mode_fft) {
+        PowTable gen_tw{nullptr, nullptr}, g_tw{nullptr, nullptr};
+        HFr hgen = host::h_load(gen), hg = host::h_load(g);
+        ZKG_TRY(build_pow_table(ctx, hgen, m, &gen_tw));
+        const int has_g = !(hg == host::h_one());
+        if (has_g) ZKG_TRY(build_pow_table(ctx, hg, m, &g_tw));
+        const unsigned blocks = (unsigned)((cols + 255) / 256);
+        const int log_m = ilog2(m), mode = rearrange ? 1 : 0;
+#define KS(LLv) k_king_stage1<LLv><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_mask, cols, 0, cols, log_m, mode, gen_tw, has_g, g_tw, d_S)
+        if (l == 2) KS(2); else if (l == 4) KS(4); else KS(8);
+#undef KS
+        ctx->launches += 1;
+    } else {
+        ZKG_CUDA(cudaMemcpyAsync(d_S, d_mask, m * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    k_negate<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(d_S, m);
+    ctx->launches += 1;
+    ZKG_CUDA(cudaGetLastError());
+    ZKG_TRY(king_stage2(ctx, d_S, d_ro, cols, l, d_out, keep));
+    for (size_t p = 0; p < n; ++p) {
+        ZKG_REQUIRE(in_by_party[p] && out_by_party[p], "NULL output vector for party %zu", p);
+        ZKG_TRY(copy_d2h(in_by_party[p], d_in + p * cols, cols * 32, ctx->stream));
+        ZKG_TRY(copy_d2h(out_by_party[p], d_out + p * cols, cols * 32, ctx->stream));
+    }
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKG_OK;
+}
+
+int32_t zkg_fft_mask_sample_bn254(int32_t device, int32_t rearrange, const uint64_t g[4], const uint64_t gen[4], size_t m, uint32_t l,
+                                  const uint64_t* mask_values, const uint64_t* rand_in, const uint64_t* rand_out,
+                                  uint64_t* const* in_by_party, uint64_t* const* out_by_party) {
+    return mask_sample_host(device, 1, rearrange, g, gen, m, l, mask_values, rand_in, rand_out, in_by_party, out_by_party);
+}
+int32_t zkg_deg_red_mask_sample_bn254(int32_t device, size_t num, uint32_t l, const uint64_t* mask_values, const uint64_t* rand_in,
+                                      const uint64_t* rand_out, uint64_t* const* in_by_party, uint64_t* const* out_by_party) {
+    return mask_sample_host(device, 0, 0, nullptr, nullptr, num * l, l, mask_values, rand_in, rand_out, in_by_party, out_by_party);
 }
 
 // ---- stand-alone pieces ----------------------------------------------------------------------
