@@ -218,6 +218,58 @@ int32_t zkg_fr_from_wire_bn254(int32_t device, const void *wire, uint64_t *out_m
 int32_t zkg_fr_to_wire_bn254(int32_t device, const uint64_t *in_mont, void *wire, size_t n);
 
 
+/* ---- several GPUs of one box behind ONE call (SURVEY.md 8b last row, 8e) ------------------------------------------
+ * The Rust callers (`d_msm` at dist-primitives/src/dmsm/mod.rs:73, the king closure at dfft/mod.rs:264-304, the client
+ * step at :121/:162) make one call per operation from one process; these entry points take a device LIST instead of a
+ * device ordinal and shard that one operation.  Same argument meaning, same results bit for bit as the single-GPU
+ * entry points above (tests/test_gpu_multi.py).  n_devices must be a power of two for the king / fft1 forms.
+ *   MSM        point-range split; every GPU runs the whole pipeline on its slice (its slice of the host buffers crosses
+ *              its own PCIe link, driven by its own host thread); the 128 / 256-byte XYZZ partials go to devices[0] over
+ *              NVLink peer copies and are added there.  No bucket exchange: MSM is linear.
+ *   king       share-column split; stage 1 (unpack, fft2, g^i) stores every value straight into the memory of the GPU
+ *              that owns its output column -- NVLink peer stores ARE the rotate / bit-reverse / stride permutation of
+ *              dfft/mod.rs:284-300, so there is no separate collective -- then every GPU packs its own columns.
+ *   fft1       four-step over one lane: inner transforms on contiguous blocks, twiddle multiplication fused with the
+ *              peer-store all-to-all, G-point outer transforms; the result is laid back into px in fft1 order.
+ * Peer access between the listed GPUs is required (NVLink / NVSwitch on a B200 box); without it: ZKG_ERR_NCCL. */
+int32_t zkg_msm_bn254_g1_sharded(const int32_t *devices, int32_t n_devices, const void *bases, size_t base_stride,
+                                 size_t n_bases, const uint64_t *scalars, size_t n_scalars, uint64_t out_xyz[12]);
+int32_t zkg_msm_bn254_g2_sharded(const int32_t *devices, int32_t n_devices, const void *bases, size_t base_stride,
+                                 size_t n_bases, const uint64_t *scalars, size_t n_scalars, uint64_t out_xyz[24]);
+/* Registers consecutive point ranges of one CRS share on the listed GPUs; the handle works with zkg_msm_bn254_registered
+ * (host scalars; each GPU receives only its range) and zkg_bases_release.  Not usable with the `_dev` form. */
+int32_t zkg_bases_register_sharded(const int32_t *devices, int32_t n_devices, int32_t group, const void *bases,
+                                   size_t base_stride, size_t n, uint64_t *handle);
+int32_t zkg_king_fft2_bn254_sharded(const int32_t *devices, int32_t n_devices, const uint64_t *const *shares_by_party,
+                                    const uint32_t *parties, uint32_t n_recv, size_t mbyl, uint32_t l,
+                                    const uint64_t gen[4], const uint64_t g[4], int32_t rearrange, const uint64_t *rand,
+                                    uint64_t *const *out_by_party);
+int32_t zkg_deg_red_king_bn254_sharded(const int32_t *devices, int32_t n_devices, const uint64_t *const *shares_by_party,
+                                       const uint32_t *parties, uint32_t n_recv, size_t cols, uint32_t l,
+                                       const uint64_t *rand, uint64_t *const *out_by_party);
+int32_t zkg_fft1_bn254_sharded(const int32_t *devices, int32_t n_devices, uint64_t *px, size_t mbyl, uint32_t l,
+                               const uint64_t gen[4], const uint64_t *pre_scale, const uint64_t *in_mask);
+
+/* The same exchanges for ONE PROCESS PER GPU (torchrun-style launchers): buffers that the kernels of the other ranks
+ * store into are allocated with zkg_shared_alloc, their 64-byte CUDA IPC handles are exchanged by the host (any
+ * transport), and each rank maps its peers' buffers with zkg_shared_open.  The caller orders "all ranks have run the
+ * scatter step" before the consuming step (one barrier; e.g. a 4-byte NCCL all-reduce on the same stream).
+ *   zkg_king_stage1_scatter_bn254_dev: like zkg_king_stage1_bn254_dev, but d_S_by_rank[r] is rank r's OWN segment of the
+ *   pack-order buffer (m / n_ranks elements: its output columns), this rank's entry being its local allocation.
+ *   zkg_fft1_shard_local_scatter_bn254_dev: zkg_fft1_shard_local_bn254_dev fused with the all-to-all: chunk d of the
+ *   twiddled inner transform is stored into d_recv_by_rank[d] at chunk position `rank` (block_len elements per buffer). */
+int32_t zkg_shared_alloc(zkg_ctx *ctx, size_t bytes, void **d_ptr, uint8_t ipc_handle[64]);
+int32_t zkg_shared_open(zkg_ctx *ctx, const uint8_t ipc_handle[64], void **d_ptr);
+int32_t zkg_shared_close(zkg_ctx *ctx, void *d_ptr);
+int32_t zkg_shared_free(zkg_ctx *ctx, void *d_ptr);
+int32_t zkg_king_stage1_scatter_bn254_dev(zkg_ctx *ctx, const uint64_t *d_shares_local, const uint32_t *parties,
+                                          uint32_t n_recv, size_t col0, size_t cols, size_t mbyl, uint32_t l,
+                                          const uint64_t gen[4], const uint64_t g[4], int32_t rearrange,
+                                          void *const *d_S_by_rank, uint32_t n_ranks);
+int32_t zkg_fft1_shard_local_scatter_bn254_dev(zkg_ctx *ctx, uint64_t *d_block, size_t block_len, uint32_t l,
+                                               uint32_t n_ranks, uint32_t rank, const uint64_t gen[4],
+                                               const uint64_t *pre_scale, void *const *d_recv_by_rank);
+
 /* ---- king side of d_msm: dist-primitives/src/dmsm/mod.rs:85-87 ---------------------------------
  * `pp.unpack_missing_shares(&rs.shares, &rs.parties)` over GROUP elements (secret-sharing/src/pss.rs:141-166 when all
  * n = 4l shares arrived, the Lagrange path :170-221 otherwise -- d_msm tolerates dropouts like d_fft) followed by

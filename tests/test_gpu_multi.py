@@ -1,7 +1,11 @@
-"""GPU, >= 2 devices: the NCCL paths (one process per GPU) against the single-GPU results.
-  - one king pipeline sharded by share columns: stage 1 -> ONE sum reduce-scatter -> stage 2
+"""GPU, >= 2 devices: the multi-GPU paths against the single-GPU results.
+  one process per GPU (torchrun-style):
+  - one king pipeline sharded by share columns: stage 1 storing straight into the owners' memory over NVLink (CUDA IPC peer
+    buffers) + a 4-byte barrier + stage 2; and the round-1 path (zero-filled buffer + ONE sum reduce-scatter)
+  - one fft1 lane sharded by contiguous blocks: inner transforms, twiddles fused with the peer-store all-to-all, outer DFT;
+    and the round-1 path (ONE NCCL all-to-all)
   - one large MSM sharded by point range: partial sums -> all-gather -> combine
-  - one fft1 lane sharded by contiguous blocks: inner transforms -> ONE all-to-all -> outer DFT
+  one process, a device list (the C-ABI entry points a Rust host calls): zkg_*_sharded
 Skipped on single-GPU boxes; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
 import ctypes as C
 import os
@@ -59,6 +63,15 @@ def _worker(rank, world, port, q):
         got = sharding.king_fft2_sharded_cuda(ctx, lib, torch, dist, loc, mbyl, l, gen, g, rearr, rloc, rank, world)
         torch.cuda.synchronize()
         ok[f"king_l{l}_r{rearr}"] = bool((got == full[:, lo:hi, :]).all())
+        peers = sharding.PeerBuffers(ctx, lib, dist, m // world * 32, rank, world)
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
+        for rep in range(3):                                       # repeated: the two buffer copies alternate
+            got = sharding.king_fft2_sharded_cuda(ctx, lib, torch, dist, loc, mbyl, l, gen, g, rearr, rloc, rank, world,
+                                                  peers=peers, token=token)
+            torch.cuda.synchronize()
+            ok[f"king_peer_l{l}_r{rearr}_{rep}"] = bool((got == full[:, lo:hi, :]).all())
+        dist.barrier()
+        peers.close()
 
     # ---- sharded fft1 (four-step, ONE all-to-all) vs the single-GPU fft1 ----
     for l, mbyl in ((2, 1 << 14), (2, 1 << 21), (8, 1 << 6)):
@@ -72,6 +85,15 @@ def _worker(rank, world, port, q):
         idx = torch.from_numpy(sharding.fft1_sharded_index(mbyl, world, rank)).to(dev)
         torch.cuda.synchronize()
         ok[f"fft1_l{l}_n{mbyl}"] = bool((got.reshape(-1, 4) == full[idx]).all())
+        peers = sharding.PeerBuffers(ctx, lib, dist, n2 * 32, rank, world)
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
+        for rep in range(3):
+            blk = px[rank * n2:(rank + 1) * n2].clone()
+            got = sharding.fft1_sharded_cuda(ctx, lib, torch, dist, blk, mbyl, l, gen, rank, world, peers=peers, token=token)
+            torch.cuda.synchronize()
+            ok[f"fft1_peer_l{l}_n{mbyl}_{rep}"] = bool((got.reshape(-1, 4) == full[idx]).all())
+        dist.barrier()
+        peers.close()
 
     # ---- sharded MSM vs the single-GPU MSM ----
     npts = 1 << 14
@@ -106,10 +128,10 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_sharded_king_and_msm_nccl():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_king_and_msm_nccl(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + os.getpid() % 1000
@@ -121,3 +143,78 @@ def test_sharded_king_and_msm_nccl():
         p.join(timeout=60)
     for rank, ok in res:
         assert all(ok.values()), (rank, ok)
+
+
+@pytest.mark.parametrize("n_dev", [2, 4, 8])
+def test_single_process_device_list_entry_points(n_dev):
+    """zkg_*_sharded (one process, a device list: what the unchanged Rust caller of INTEGRATION.md uses) against the
+    single-GPU entry points, bit for bit: MSM G1 / G2, registered bases, king closure (both packings, with a dropout),
+    deg_red king, fft1 (with pre-scale and in-mask)."""
+    if torch.cuda.device_count() < n_dev:
+        pytest.skip(f"needs >= {n_dev} GPUs")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from oracle_lib import _p
+    import zksaas_b200 as z
+    from zksaas_b200 import capi
+    lib = z.lib()
+    o = ol.oracle()
+    rng = np.random.default_rng(40 + n_dev)
+    devs = (C.c_int32 * n_dev)(*range(n_dev))
+    u64p = C.POINTER(C.c_uint64)
+    # ---- MSM ----
+    n = (1 << 16) + 123                                              # not divisible by the device count
+    bases = np.zeros((n, 72), dtype=np.uint8)
+    o.zko_g1_fixed_base(_p(ol.rand_fr(rng, n)), n, bases.ctypes.data, 72)
+    sc = ol.rand_fr(rng, n)
+    ref = z.msm_g1(bases, sc)
+    out = np.zeros(12, dtype=np.uint64)
+    capi.check(lib.zkg_msm_bn254_g1_sharded(devs, n_dev, bases.ctypes.data, 72, n, _p(sc), n, _p(out)))
+    assert (out == ref).all()
+    h = C.c_uint64(0)
+    capi.check(lib.zkg_bases_register_sharded(devs, n_dev, 1, bases.ctypes.data, 72, n, C.byref(h)))
+    for _ in range(2):
+        out[:] = 0
+        capi.check(lib.zkg_msm_bn254_registered(h.value, _p(sc), n, _p(out)))
+        assert (out == ref).all()
+    capi.check(lib.zkg_bases_release(h.value))
+    n2 = 1 << 13
+    b2 = np.zeros((n2, 136), dtype=np.uint8)
+    o.zko_g2_fixed_base(_p(ol.rand_fr(rng, n2)), n2, b2.ctypes.data, 136)
+    s2 = ol.rand_fr(rng, n2)
+    out2 = np.zeros(24, dtype=np.uint64)
+    capi.check(lib.zkg_msm_bn254_g2_sharded(devs, n_dev, b2.ctypes.data, 136, n2, _p(s2), n2, _p(out2)))
+    assert (out2 == z.msm_g2(b2, s2)).all()
+    # ---- king closure / deg_red ----
+    l, mbyl = 2, 1 << 14
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(mbyl * l)
+    gen, g = dom.group_gen(), z.Radix2EvaluationDomain.new(2 * mbyl * l).element(1)
+    shares = [ol.rand_fr(rng, mbyl) for _ in range(pp.n)]
+    rnd = ol.rand_fr(rng, mbyl * pp.t)
+    for parties, rearr in ((list(range(8)), 1), (list(range(8)), 0), ([0, 1, 2, 4, 5, 6, 7], 1)):
+        sh = [shares[p] for p in parties]
+        ref_out = z.king_fft2(sh, parties, pp, gen, g, bool(rearr), rnd)
+        outs = [np.zeros((mbyl, 4), dtype=np.uint64) for _ in range(pp.n)]
+        in_arr = (u64p * len(sh))(*[x.ctypes.data_as(u64p) for x in sh])
+        out_arr = (u64p * pp.n)(*[x.ctypes.data_as(u64p) for x in outs])
+        par = (C.c_uint32 * len(parties))(*parties)
+        capi.check(lib.zkg_king_fft2_bn254_sharded(devs, n_dev, in_arr, par, len(parties), mbyl, l, _p(gen), _p(g), rearr, _p(rnd), out_arr))
+        assert all((a == b).all() for a, b in zip(outs, ref_out)), (parties, rearr)
+    ref_out = z.deg_red_king(shares, list(range(8)), pp, rnd)
+    outs = [np.zeros((mbyl, 4), dtype=np.uint64) for _ in range(pp.n)]
+    in_arr = (u64p * 8)(*[x.ctypes.data_as(u64p) for x in shares])
+    out_arr = (u64p * 8)(*[x.ctypes.data_as(u64p) for x in outs])
+    capi.check(lib.zkg_deg_red_king_bn254_sharded(devs, n_dev, in_arr, None, 8, mbyl, l, _p(rnd), out_arr))
+    assert all((a == b).all() for a, b in zip(outs, ref_out))
+    # ---- fft1 ----
+    for lg in (16, 20):
+        mb = 1 << lg
+        d2 = z.Radix2EvaluationDomain.new(mb * l)
+        px, mask = ol.rand_fr(rng, 64)[np.arange(mb) % 64].copy(), ol.rand_fr(rng, 64)[(np.arange(mb) * 7) % 64].copy()
+        px[:, 0] += np.arange(mb, dtype=np.uint64)                   # distinct values (low limb cannot overflow past 2^253)
+        e = z.fft1_in_place(px.copy(), pp, d2.group_gen_inv(), pre_scale=d2.size_inv(), in_mask=mask)
+        got = px.copy()
+        capi.check(lib.zkg_fft1_bn254_sharded(devs, n_dev, _p(got), mb, l, _p(d2.group_gen_inv()), _p(d2.size_inv()), _p(mask)))
+        assert (got == e).all(), lg

@@ -349,3 +349,122 @@ def test_python_mirror_validates_lengths(z):
         z.king_fft2(shares, list(range(8)), pp, gen, gen, False, ol.rand_fr(rng, 15))
     with pytest.raises(ValueError):
         z.fft1_in_place(ol.rand_fr(rng, 8), pp, gen, in_mask=ol.rand_fr(rng, 7))
+
+
+# ---------------------------------------------------------------------------------------------------
+# the peer-store exchange kernels, with all "ranks" on one device (the same launches the multi-GPU paths make;
+# tests/test_gpu_multi.py runs them across real GPUs)
+# ---------------------------------------------------------------------------------------------------
+def _dev_ctx(z):
+    from zksaas_b200 import capi
+    ctx = capi.ctx_p()
+    capi.check(z.lib().zkg_ctx_create(0, C.c_void_p(1), C.byref(ctx)))
+    return ctx
+
+
+def _rand_dev(torch, k, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    t = torch.randint(-2**63, 2**63 - 1, (k, 4), dtype=torch.int64, device="cuda", generator=g)
+    t[:, 3] &= (1 << 61) - 1
+    return t
+
+
+@pytest.mark.parametrize("l,mbyl,world,rearrange,coset", [(2, 16, 2, 1, 1), (2, 1 << 10, 8, 1, 1), (2, 1 << 13, 4, 0, 0), (4, 1 << 11, 4, 1, 1),
+                                                           (2, 1 << 16, 8, 1, 1), (8, 1 << 8, 2, 1, 0)])
+def test_king_scatter_stages_on_one_gpu(z, l, mbyl, world, rearrange, coset):
+    """zkg_king_stage1_scatter_bn254_dev writes each value into the segment of the rank that owns its output column; with
+    the `world` segments on one device the G launches + G stage-2 launches must equal the single-GPU king closure."""
+    import torch
+    from zksaas_b200 import capi
+    lib = z.lib()
+    ctx = _dev_ctx(z)
+    try:
+        n, t, m = 4 * l, l, mbyl * l
+        dom = z.Radix2EvaluationDomain.new(m)
+        gen = dom.group_gen()
+        g = z.Radix2EvaluationDomain.new(2 * m).element(1) if coset else dom.element(0)
+        shares = _rand_dev(torch, n * mbyl, 3).reshape(n, mbyl, 4)
+        rnd = _rand_dev(torch, mbyl * t, 4)
+        full = torch.empty((n, mbyl, 4), dtype=torch.int64, device="cuda")
+        capi.check(lib.zkg_king_fft2_bn254_dev(ctx, C.c_void_p(shares.data_ptr()), None, n, mbyl, l, gen.ctypes.data, g.ctypes.data,
+                                               rearrange, C.c_void_p(rnd.data_ptr()), C.c_void_p(full.data_ptr())))
+        cols = mbyl // world
+        segs = [torch.full((cols * l, 4), -1, dtype=torch.int64, device="cuda") for _ in range(world)]      # poisoned: every slot must be written
+        arr = (C.c_void_p * world)(*[s_.data_ptr() for s_ in segs])
+        for r in range(world):
+            loc = shares[:, r * cols:(r + 1) * cols, :].contiguous()
+            capi.check(lib.zkg_king_stage1_scatter_bn254_dev(ctx, C.c_void_p(loc.data_ptr()), None, n, r * cols, cols, mbyl, l,
+                                                             gen.ctypes.data, g.ctypes.data, rearrange, arr, world))
+        for r in range(world):
+            out = torch.empty((n, cols, 4), dtype=torch.int64, device="cuda")
+            rloc = rnd[r * cols * t:(r + 1) * cols * t].contiguous()
+            capi.check(lib.zkg_king_stage2_bn254_dev(ctx, C.c_void_p(segs[r].data_ptr()), C.c_void_p(rloc.data_ptr()), cols, l,
+                                                     C.c_void_p(out.data_ptr())))
+            capi.check(lib.zkg_ctx_sync(ctx))
+            assert bool((out == full[:, r * cols:(r + 1) * cols, :]).all()), r
+    finally:
+        lib.zkg_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("l,mbyl,world", [(2, 1 << 6, 2), (2, 1 << 14, 4), (2, 1 << 18, 8), (8, 1 << 10, 8), (4, 1 << 20, 2)])
+def test_fft1_scatter_steps_on_one_gpu(z, l, mbyl, world):
+    """zkg_fft1_shard_local_scatter_bn254_dev (inner transform + twiddles + all-to-all by direct stores) followed by the
+    outer step reproduces the single-GPU fft1 (pinned against the literal loops in test_gpu_core)."""
+    import torch
+    from zksaas_b200 import capi, sharding
+    lib = z.lib()
+    ctx = _dev_ctx(z)
+    try:
+        px = _rand_dev(torch, mbyl, mbyl + world)
+        gen = z.Radix2EvaluationDomain.new(mbyl * l).group_gen()
+        full = px.clone()
+        capi.check(lib.zkg_fft1_bn254_dev(ctx, C.c_void_p(full.data_ptr()), mbyl, l, gen.ctypes.data, None, None))
+        n2, cnt = mbyl // world, mbyl // world // world
+        recvs = [torch.full((n2, 4), -1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        arr = (C.c_void_p * world)(*[r_.data_ptr() for r_ in recvs])
+        for r in range(world):
+            blk = px[r * n2:(r + 1) * n2].clone()
+            capi.check(lib.zkg_fft1_shard_local_scatter_bn254_dev(ctx, C.c_void_p(blk.data_ptr()), n2, l, world, r, gen.ctypes.data, None, arr))
+        for r in range(world):
+            out = torch.empty((world * cnt, 4), dtype=torch.int64, device="cuda")
+            capi.check(lib.zkg_fft1_shard_outer_bn254_dev(ctx, C.c_void_p(recvs[r].data_ptr()), cnt, n2, l, world, gen.ctypes.data,
+                                                          C.c_void_p(out.data_ptr())))
+            capi.check(lib.zkg_ctx_sync(ctx))
+            idx = torch.from_numpy(sharding.fft1_sharded_index(mbyl, world, r)).cuda()
+            assert bool((out == full[idx]).all()), r
+    finally:
+        lib.zkg_ctx_destroy(ctx)
+
+
+def test_sharded_entry_points_with_one_device_match(z):
+    """The device-list entry points degrade to the single-GPU ones for a one-element list (what a 1-GPU host gets)."""
+    from zksaas_b200 import capi
+    lib = z.lib()
+    o = ol.oracle()
+    rng = np.random.default_rng(2)
+    devs = (C.c_int32 * 1)(0)
+    n = 1 << 12
+    bases = np.zeros((n, 72), dtype=np.uint8)
+    o.zko_g1_fixed_base(_p(ol.rand_fr(rng, n)), n, bases.ctypes.data, 72)
+    sc = ol.rand_fr(rng, n)
+    out = np.zeros(12, dtype=np.uint64)
+    capi.check(lib.zkg_msm_bn254_g1_sharded(devs, 1, bases.ctypes.data, 72, n, _p(sc), n, _p(out)))
+    assert (out == z.msm_g1(bases, sc)).all()
+    assert lib.zkg_msm_bn254_g1_sharded(devs, 1, bases.ctypes.data, 72, n, _p(sc), n - 1, _p(out)) == capi.ZKG_ERR_LEN_MISMATCH
+    h = C.c_uint64(0)
+    capi.check(lib.zkg_bases_register_sharded(devs, 1, 1, bases.ctypes.data, 72, n, C.byref(h)))
+    out2 = np.zeros(12, dtype=np.uint64)
+    capi.check(lib.zkg_msm_bn254_registered(h.value, _p(sc), n, _p(out2)))
+    capi.check(lib.zkg_bases_release(h.value))
+    assert (out2 == out).all()
+    l, mbyl = 2, 1 << 10
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(mbyl * l)
+    px = ol.rand_fr(rng, mbyl)
+    e = z.fft1_in_place(px.copy(), pp, dom.group_gen())
+    g_ = px.copy()
+    capi.check(lib.zkg_fft1_bn254_sharded(devs, 1, _p(g_), mbyl, l, _p(dom.group_gen()), None, None))
+    assert (g_ == e).all()
+    bad = (C.c_int32 * 2)(0, 0)
+    assert lib.zkg_fft1_bn254_sharded(bad, 2, _p(g_), mbyl, l, _p(dom.group_gen()), None, None) == capi.ZKG_ERR_BAD_ARG

@@ -83,6 +83,22 @@ SIGNATURES = {
     "zkg_fft_mask_sample_bn254": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p,
                                                C.c_void_p, C.c_void_p, pp_u64, pp_u64]),
     "zkg_deg_red_mask_sample_bn254": (C.c_int32, [C.c_int32, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, pp_u64, pp_u64]),
+    "zkg_msm_bn254_g1_sharded": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "zkg_msm_bn254_g2_sharded": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "zkg_bases_register_sharded": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_size_t, u64p]),
+    "zkg_king_fft2_bn254_sharded": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32, pp_u64, u32p, C.c_uint32, C.c_size_t, C.c_uint32,
+                                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, pp_u64]),
+    "zkg_deg_red_king_bn254_sharded": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32, pp_u64, u32p, C.c_uint32, C.c_size_t, C.c_uint32,
+                                                    C.c_void_p, pp_u64]),
+    "zkg_fft1_bn254_sharded": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zkg_shared_alloc": (C.c_int32, [ctx_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "zkg_shared_open": (C.c_int32, [ctx_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "zkg_shared_close": (C.c_int32, [ctx_p, C.c_void_p]),
+    "zkg_shared_free": (C.c_int32, [ctx_p, C.c_void_p]),
+    "zkg_king_stage1_scatter_bn254_dev": (C.c_int32, [ctx_p, C.c_void_p, u32p, C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32,
+                                                       C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_uint32]),
+    "zkg_fft1_shard_local_scatter_bn254_dev": (C.c_int32, [ctx_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                            C.c_void_p, C.POINTER(C.c_void_p)]),
     "zkg_field_op_dev": (C.c_int32, [ctx_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zkg_field_op": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }

@@ -302,6 +302,43 @@ int32_t zkg_field_op(int32_t device, int32_t field, int32_t op, const uint64_t* 
 }
 
 
+// ---- peer-visible buffers for one-process-per-GPU sharding (CUDA IPC) ------------------------------------------------
+int32_t zkg_shared_alloc(zkg_ctx* ctx, size_t bytes, void** d_ptr, uint8_t ipc_handle[64]) {
+    ZKG_REQUIRE(ctx && d_ptr && ipc_handle && bytes, "shared_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DeviceGuard dg(ctx->device);
+    void* p = nullptr;
+    ZKG_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); return ZKG_ERR_NCCL; }
+    memcpy(ipc_handle, &h, 64);
+    *d_ptr = p;
+    return ZKG_OK;
+}
+int32_t zkg_shared_open(zkg_ctx* ctx, const uint8_t ipc_handle[64], void** d_ptr) {
+    ZKG_REQUIRE(ctx && d_ptr && ipc_handle, "shared_open: bad argument");
+    DeviceGuard dg(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle failed: %s (no peer access between the two GPUs?)", cudaGetErrorString(e)); return ZKG_ERR_NCCL; }
+    return ZKG_OK;
+}
+int32_t zkg_shared_close(zkg_ctx* ctx, void* d_ptr) {
+    ZKG_REQUIRE(ctx && d_ptr, "shared_close: bad argument");
+    DeviceGuard dg(ctx->device);
+    ZKG_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return ZKG_OK;
+}
+int32_t zkg_shared_free(zkg_ctx* ctx, void* d_ptr) {
+    ZKG_REQUIRE(ctx && d_ptr, "shared_free: bad argument");
+    DeviceGuard dg(ctx->device);
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZKG_CUDA(cudaFree(d_ptr));
+    return ZKG_OK;
+}
+
 int32_t zkg_qap_h_bn254_dev(zkg_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_c, const uint64_t* d_mask_a,
                             const uint64_t* d_mask_b, const uint64_t* d_mask_c, const uint64_t* factor, uint64_t* d_out, size_t n) {
     ZKG_REQUIRE(ctx && (n == 0 || (d_a && d_b && d_c && d_out)), "qap_h_dev: NULL argument");

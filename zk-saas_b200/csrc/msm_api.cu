@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "host_fr.hpp"
 #include <condition_variable>
+#include <string>
+#include <thread>
 #include <utility>
 
 namespace zkg {
@@ -11,11 +13,13 @@ namespace zkg {
     int32_t pack_bases_##G(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t n, void* d_packed);               \
     int32_t msm_host_##G(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,     \
                          size_t n_scalars, uint64_t* out_xyz);                                                      \
+    int32_t msm_host_sharded_##G(const int32_t* devices, int32_t n_dev, const void* bases, size_t stride, size_t n_bases, \
+                                 const uint64_t* scalars, size_t n_scalars, uint64_t* out_xyz);                     \
     int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out);                          \
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);                      \
     int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table);                         \
     int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode); \
-    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out); \
+    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out, int mode); \
     int32_t crs_det_pack_##G(int device, const void* bases, size_t stride, size_t n, int l, int n_parties,          \
                              const uint32_t* h_scal, void* const* out_by_party, size_t out_stride);
 ZKG_MSM_DECLARE(g1)
@@ -42,6 +46,9 @@ struct BaseSet {
     int refs = 0;                    // calls between lookup and "ordered behind an event / finished"
     bool released = false;
     std::vector<std::pair<zkg_ctx*, cudaEvent_t>> last_use;     // one event per context that enqueued work on the table
+    // a set registered over several GPUs (zkg_bases_register_sharded): per-device handles of consecutive point ranges
+    std::vector<uint64_t> shard_handles;
+    std::vector<size_t> shard_lo;                               // shard k owns points [shard_lo[k], shard_lo[k+1])
 };
 int msm_pick_c_merged_host(size_t n);
 static std::mutex g_bases_mu;
@@ -86,6 +93,73 @@ struct BaseRef {
         if (bs->refs == 0) g_bases_cv.notify_all();
     }
 };
+
+// MSM against a set registered over several GPUs: every shard runs the prepared pipeline on its own scalar range (one
+// host thread per device for the chunked scalar upload), leaves an XYZZ partial, and the first shard's device adds them.
+static int32_t msm_registered_sharded(const BaseSet& bs, const uint64_t* scalars, uint64_t* out_xyz) {
+    const int K = (int)bs.shard_handles.size();
+    const size_t part_b = bs.group == 1 ? 128 : 256;
+    std::vector<BaseRef> refs(K);
+    std::vector<PooledCtx> pcs(K);
+    for (int k = 0; k < K; ++k) {
+        ZKG_TRY(refs[k].acquire(bs.shard_handles[k]));
+        ZKG_TRY(pcs[k].acquire(refs[k].bs->device));
+    }
+    std::vector<int32_t> rc(K, ZKG_OK);
+    std::vector<std::string> msg(K);
+    std::vector<void*> d_part(K, nullptr);
+    std::vector<cudaEvent_t> done(K, nullptr);
+    auto work = [&](int k) {
+        zkg_ctx* ctx = pcs[k].ctx;
+        const BaseSet& sh = *refs[k].bs;
+        DeviceGuard dg(ctx->device);
+        const size_t cnt = sh.n, sc_bytes = align_up(cnt * 32, 256);
+        rc[k] = ctx->io.reserve(sc_bytes + 512 + 16 * 256 + 256);
+        if (rc[k] == ZKG_OK) {
+            d_part[k] = (uint8_t*)ctx->io.p + sc_bytes;
+            rc[k] = bs.group == 1 ? msm_run_prepared_host_g1(ctx, sh.d_table, sh.c, scalars + bs.shard_lo[k] * 4, cnt, d_part[k], 1)
+                                  : msm_run_prepared_host_g2(ctx, sh.d_table, sh.c, scalars + bs.shard_lo[k] * 4, cnt, d_part[k], 1);
+        }
+        if (rc[k] == ZKG_OK && (cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming) != cudaSuccess ||
+                                cudaEventRecord(done[k], ctx->stream) != cudaSuccess)) {
+            set_error("msm_registered (sharded): event on device %d failed", ctx->device);
+            rc[k] = ZKG_ERR_CUDA;
+        }
+        if (rc[k] != ZKG_OK) msg[k] = zkg_last_error();
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < K; ++k) th.emplace_back(work, k);
+    work(0);
+    for (auto& t : th) t.join();
+    int32_t first = ZKG_OK;
+    for (int k = 0; k < K && first == ZKG_OK; ++k)
+        if (rc[k] != ZKG_OK) { first = rc[k]; set_error("%s", msg[k].c_str()); }
+    zkg_ctx* c0 = pcs[0].ctx;
+    {
+        DeviceGuard dg(c0->device);
+        if (first == ZKG_OK) {
+            uint8_t* gather = (uint8_t*)d_part[0] + 512;                 // 16 partial slots + the result, inside device 0's staging area
+            uint8_t* d_out = gather + 16 * 256;
+            for (int k = 0; k < K && first == ZKG_OK; ++k) {
+                cudaError_t e = cudaStreamWaitEvent(c0->stream, done[k], 0);
+                if (e == cudaSuccess)
+                    e = k == 0 ? cudaMemcpyAsync(gather, d_part[0], part_b, cudaMemcpyDeviceToDevice, c0->stream)
+                               : cudaMemcpyPeerAsync(gather + k * part_b, c0->device, d_part[k], pcs[k].ctx->device, part_b, c0->stream);
+                if (e != cudaSuccess) { set_error("msm_registered (sharded): gathering shard %d failed: %s", k, cudaGetErrorString(e)); first = ZKG_ERR_CUDA; }
+            }
+            if (first == ZKG_OK) first = bs.group == 1 ? combine_g1(c0, (const uint64_t*)gather, K, (uint64_t*)d_out)
+                                                       : combine_g2(c0, (const uint64_t*)gather, K, (uint64_t*)d_out);
+            if (first == ZKG_OK) first = copy_d2h(out_xyz, d_out, bs.group == 1 ? 96 : 192, c0->stream);
+        }
+    }
+    for (int k = 0; k < K; ++k) {
+        DeviceGuard dgk(pcs[k].ctx->device);
+        cudaStreamSynchronize(pcs[k].ctx->stream);
+        if (done[k]) cudaEventDestroy(done[k]);
+    }
+    return first;
+}
+
 }  // namespace zkg
 
 using namespace zkg;
@@ -99,6 +173,15 @@ int32_t zkg_msm_bn254_g1(int32_t device, const void* bases, size_t base_stride, 
 int32_t zkg_msm_bn254_g2(int32_t device, const void* bases, size_t base_stride, size_t n_bases, const uint64_t* scalars,
                          size_t n_scalars, uint64_t out_xyz[24]) {
     return msm_host_g2(device, bases, base_stride, n_bases, scalars, n_scalars, out_xyz);
+}
+
+int32_t zkg_msm_bn254_g1_sharded(const int32_t* devices, int32_t n_devices, const void* bases, size_t base_stride, size_t n_bases,
+                                 const uint64_t* scalars, size_t n_scalars, uint64_t out_xyz[12]) {
+    return msm_host_sharded_g1(devices, n_devices, bases, base_stride, n_bases, scalars, n_scalars, out_xyz);
+}
+int32_t zkg_msm_bn254_g2_sharded(const int32_t* devices, int32_t n_devices, const void* bases, size_t base_stride, size_t n_bases,
+                                 const uint64_t* scalars, size_t n_scalars, uint64_t out_xyz[24]) {
+    return msm_host_sharded_g2(devices, n_devices, bases, base_stride, n_bases, scalars, n_scalars, out_xyz);
 }
 
 int32_t zkg_pack_bases_dev(zkg_ctx* ctx, int32_t group, const void* d_bases_ark, size_t base_stride, size_t n,
@@ -216,6 +299,40 @@ int32_t zkg_bases_register(int32_t device, int32_t group, const void* bases, siz
     return ZKG_OK;
 }
 
+int32_t zkg_bases_register_sharded(const int32_t* devices, int32_t n_devices, int32_t group, const void* bases, size_t base_stride,
+                                   size_t n, uint64_t* handle) {
+    ZKG_REQUIRE(devices && n_devices >= 1 && n_devices <= 16 && handle && (group == 1 || group == 2) && (n == 0 || bases),
+                "bases_register_sharded: bad argument");
+    for (int a = 0; a < n_devices; ++a)
+        for (int b = 0; b < a; ++b) ZKG_REQUIRE(devices[a] != devices[b], "bases_register_sharded: device %d listed twice", devices[a]);
+    if (n_devices == 1 || n < (size_t)n_devices) return zkg_bases_register(devices[0], group, bases, base_stride, n, handle);
+    BaseSet* top = new BaseSet();
+    top->device = devices[0]; top->group = group; top->n = n;
+    int32_t rc = ZKG_OK;
+    for (int d = 0; d < n_devices && rc == ZKG_OK; ++d) {
+        const size_t lo = n * (size_t)d / (size_t)n_devices, hi = n * (size_t)(d + 1) / (size_t)n_devices;
+        uint64_t h = 0;
+        rc = zkg_bases_register(devices[d], group, (const uint8_t*)bases + lo * base_stride, base_stride, hi - lo, &h);
+        if (rc == ZKG_OK) { top->shard_handles.push_back(h); top->shard_lo.push_back(lo); }
+    }
+    if (rc != ZKG_OK) {
+        std::string keep = zkg_last_error();
+        for (uint64_t h : top->shard_handles) zkg_bases_release(h);
+        delete top;
+        set_error("%s", keep.c_str());
+        return rc;
+    }
+    top->shard_lo.push_back(n);
+    std::lock_guard<std::mutex> lk(g_bases_mu);
+    size_t slot = g_bases.size();
+    for (size_t i = 0; i < g_bases.size(); ++i) if (!g_bases[i]) { slot = i; break; }
+    if (slot == g_bases.size()) { g_bases.push_back(nullptr); g_bases_gen.push_back(0); }
+    top->generation = ++g_bases_gen[slot];
+    g_bases[slot] = top;
+    *handle = ((uint64_t)top->generation << 32) | (uint64_t)(slot + 1);
+    return ZKG_OK;
+}
+
 int32_t zkg_bases_register_dev(zkg_ctx* ctx, int32_t group, const void* d_bases_packed, size_t n, uint64_t* handle) {
     ZKG_REQUIRE(ctx && handle && (group == 1 || group == 2) && (n == 0 || d_bases_packed), "bases_register_dev: bad argument");
     DeviceGuard dg(ctx->device);
@@ -238,8 +355,10 @@ int32_t zkg_bases_release(uint64_t handle) {
         cudaEventDestroy(e.second);
     }
     if (bs->d_table) cudaFree(bs->d_table);
+    int32_t rc = ZKG_OK;
+    for (uint64_t h : bs->shard_handles) { int32_t r = zkg_bases_release(h); if (r != ZKG_OK) rc = r; }
     delete bs;
-    return ZKG_OK;
+    return rc;
 }
 
 int32_t zkg_msm_bn254_registered_dev(zkg_ctx* ctx, uint64_t handle, const uint64_t* d_scalars, size_t n_scalars,
@@ -248,6 +367,7 @@ int32_t zkg_msm_bn254_registered_dev(zkg_ctx* ctx, uint64_t handle, const uint64
     BaseRef ref;
     ZKG_TRY(ref.acquire(handle));
     const BaseSet& bs = *ref.bs;
+    ZKG_REQUIRE(bs.shard_handles.empty(), "msm_registered_dev: the handle is sharded over several GPUs; use zkg_msm_bn254_registered");
     ZKG_REQUIRE(bs.device == ctx->device, "msm_registered_dev: bases live on device %d, context on %d", bs.device, ctx->device);
     if (bs.n != n_scalars) {
         set_error("msm: bases.len() = %zu, scalars.len() = %zu", bs.n, n_scalars);
@@ -270,6 +390,7 @@ int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t* scalars, size_
         return ZKG_ERR_LEN_MISMATCH;
     }
     ZKG_REQUIRE(out_xyz && (n_scalars == 0 || scalars), "msm_registered: NULL argument");
+    if (!bs.shard_handles.empty()) return msm_registered_sharded(bs, scalars, out_xyz);
     PooledCtx pc;
     ZKG_TRY(pc.acquire(bs.device));
     zkg_ctx* ctx = pc.ctx;
@@ -277,8 +398,8 @@ int32_t zkg_msm_bn254_registered(uint64_t handle, const uint64_t* scalars, size_
     size_t sc_bytes = align_up(n_scalars * 32, 256);
     ZKG_TRY(ctx->io.reserve(sc_bytes + 512));
     void* d_out = (uint8_t*)ctx->io.p + sc_bytes;
-    int32_t rc = bs.group == 1 ? msm_run_prepared_host_g1(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out)
-                               : msm_run_prepared_host_g2(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out);
+    int32_t rc = bs.group == 1 ? msm_run_prepared_host_g1(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out, 0)
+                               : msm_run_prepared_host_g2(ctx, bs.d_table, bs.c, scalars, n_scalars, d_out, 0);
     if (rc == ZKG_OK) rc = copy_d2h(out_xyz, d_out, bs.group == 1 ? 96 : 192, ctx->stream);
     // blocking call: the reference is held until the stream has drained, also on the error paths
     cudaError_t se = cudaStreamSynchronize(ctx->stream);

@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "ec.cuh"
 #include "msm_common.cuh"
+#include <string>
+#include <thread>
 
 namespace zkg {
 
@@ -1058,7 +1060,7 @@ static int32_t msm_run_prepared(zkg_ctx* ctx, const Affine<F>* d_table, int c, c
 // previous quarter is being sorted and accumulated (merged plans take any point range of the table).
 template <class F>
 static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int c, const uint64_t* h_scalars, size_t n,
-                                     F* d_out) {
+                                     F* d_out, int mode = 0) {
     MsmPlan<F> pl;
     if (n) {
         // graded chunks (1/16, 3/16, 1/4, 1/4, 1/4): the first copy, which nothing hides, is short
@@ -1082,7 +1084,7 @@ static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int
             ZKG_TRY(msm_chunk<F>(ctx, &pl, d_table, (const Fr*)d_sc + lo, hi - lo, lo));
         }
     }
-    return msm_finish<F>(ctx, &pl, d_out, 0);
+    return msm_finish<F>(ctx, &pl, d_out, mode);
 }
 
 template <class F>
@@ -1174,21 +1176,14 @@ static int32_t pack_bases(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t
 // blocking host-pointer MSM (both curves).  Large inputs are fed in point-range chunks: the H2D
 // copy of chunk j+1 (copy stream) overlaps digits/sort/accumulate of chunk j (compute stream), so
 // the PCIe transfer of the 72+32 B/point inputs hides behind the bucket accumulation.
+// Enqueues the whole host-pointer MSM of `n` points on `ctx` (copies, sort, accumulation, reduction) and leaves the result in
+// the context's staging area: mode 0 = normalised Jacobian image (3 F), mode 1 = XYZZ partial (4 F) for multi-GPU combination.
+// Does not synchronise; *d_result stays valid until the next call on the context.
 template <class F>
-static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,
-                        size_t n_scalars, uint64_t* out_xyz) {
-    if (n_bases != n_scalars) {
-        set_error("msm: bases.len() = %zu, scalars.len() = %zu", n_bases, n_scalars);
-        return ZKG_ERR_LEN_MISMATCH;
-    }
-    ZKG_REQUIRE(out_xyz != nullptr, "msm: out is NULL");
-    ZKG_REQUIRE(n_bases == 0 || (bases && scalars), "msm: NULL input");
-    ZKG_REQUIRE(n_bases == 0 || stride >= sizeof(Affine<F>) + 1, "base stride %zu too small", stride);
-    PooledCtx pc;
-    ZKG_TRY(pc.acquire(device));
-    zkg_ctx* ctx = pc.ctx;
-    DeviceGuard dg(ctx->device);
-    const size_t n = n_bases;
+static int32_t msm_host_enqueue(zkg_ctx* ctx, const void* bases, size_t stride, size_t n, const uint64_t* scalars, int mode,
+                                F** d_result) {
+    ZKG_REQUIRE(n == 0 || (bases && scalars), "msm: NULL input");
+    ZKG_REQUIRE(n == 0 || stride >= sizeof(Affine<F>) + 1, "base stride %zu too small", stride);
     // Chunk boundaries (1/16, 3/16, 1/4, 1/4, 1/4): the first copy, which nothing can hide, is short;
     // every later copy (2 ms per quarter at 2^22 over PCIe 5) is covered by the ~3.4 ms the previous
     // quarter spends in digits/sort/accumulate.
@@ -1242,11 +1237,107 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
             ZKG_TRY(msm_chunk_accumulate<F>(ctx, &pl, (const Affine<F>*)d_pk + lo, hi - lo));
         }
     }
-    ZKG_TRY(msm_finish<F>(ctx, &pl, d_out, 0));
+    ZKG_TRY(msm_finish<F>(ctx, &pl, d_out, mode));
+    *d_result = d_out;
+    return ZKG_OK;
+}
+
+template <class F>
+static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,
+                        size_t n_scalars, uint64_t* out_xyz) {
+    if (n_bases != n_scalars) {
+        set_error("msm: bases.len() = %zu, scalars.len() = %zu", n_bases, n_scalars);
+        return ZKG_ERR_LEN_MISMATCH;
+    }
+    ZKG_REQUIRE(out_xyz != nullptr, "msm: out is NULL");
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(device));
+    zkg_ctx* ctx = pc.ctx;
+    DeviceGuard dg(ctx->device);
+    F* d_out = nullptr;
+    ZKG_TRY(msm_host_enqueue<F>(ctx, bases, stride, n_bases, scalars, 0, &d_out));
     ZKG_TRY(copy_d2h(out_xyz, d_out, 3 * sizeof(F), ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZKG_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// ONE MSM over several GPUs of the box from a single call (BASELINE configs[3]): the point range is
+// split evenly, device d runs the full host-pointer pipeline on its slice (one host thread per device drives the
+// chunked PCIe copies of that slice; the slices cross different PCIe links concurrently), the XYZZ partials travel
+// to the first device over NVLink (cudaMemcpyPeerAsync, 128 / 256 B each) behind cross-device events, and one tiny
+// kernel adds and normalises them.  MSM is linear, so the result is the single-GPU group element bit for bit.
+// ------------------------------------------------------------------------------------------
+template <class F>
+static int32_t msm_host_sharded(const int32_t* devices, int32_t n_dev, const void* bases, size_t stride, size_t n_bases,
+                                const uint64_t* scalars, size_t n_scalars, uint64_t* out_xyz) {
+    if (n_bases != n_scalars) {
+        set_error("msm: bases.len() = %zu, scalars.len() = %zu", n_bases, n_scalars);
+        return ZKG_ERR_LEN_MISMATCH;
+    }
+    ZKG_REQUIRE(devices && n_dev >= 1 && n_dev <= 16 && out_xyz, "msm_sharded: bad device list");
+    for (int a = 0; a < n_dev; ++a)
+        for (int b = 0; b < a; ++b) ZKG_REQUIRE(devices[a] != devices[b], "msm_sharded: device %d listed twice", devices[a]);
+    if (n_dev == 1 || n_bases < (size_t)n_dev * 1024) return msm_host<F>(devices[0], bases, stride, n_bases, scalars, n_scalars, out_xyz);
+    std::vector<PooledCtx> pcs(n_dev);
+    for (int d = 0; d < n_dev; ++d) ZKG_TRY(pcs[d].acquire(devices[d]));
+    std::vector<int32_t> rc(n_dev, ZKG_OK);
+    std::vector<std::string> msg(n_dev);
+    std::vector<F*> d_part(n_dev, nullptr);
+    std::vector<cudaEvent_t> done(n_dev, nullptr);
+    auto work = [&](int d) {
+        zkg_ctx* ctx = pcs[d].ctx;
+        DeviceGuard dg(ctx->device);
+        const size_t lo = n_bases * (size_t)d / (size_t)n_dev, hi = n_bases * (size_t)(d + 1) / (size_t)n_dev;
+        rc[d] = msm_host_enqueue<F>(ctx, (const uint8_t*)bases + lo * stride, stride, hi - lo, scalars + lo * 4, 1, &d_part[d]);
+        if (rc[d] == ZKG_OK) {
+            if (cudaEventCreateWithFlags(&done[d], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(done[d], ctx->stream) != cudaSuccess) {
+                set_error("msm_sharded: event on device %d failed", ctx->device);
+                rc[d] = ZKG_ERR_CUDA;
+            }
+        }
+        if (rc[d] != ZKG_OK) msg[d] = zkg_last_error();          // the message is thread-local: carry it to the caller
+    };
+    std::vector<std::thread> th;
+    for (int d = 1; d < n_dev; ++d) th.emplace_back(work, d);
+    work(0);
+    for (auto& t : th) t.join();
+    int32_t first = ZKG_OK;
+    for (int d = 0; d < n_dev && first == ZKG_OK; ++d)
+        if (rc[d] != ZKG_OK) { first = rc[d]; set_error("%s", msg[d].c_str()); }
+    zkg_ctx* c0 = pcs[0].ctx;
+    DeviceGuard dg(c0->device);
+    if (first == ZKG_OK) {
+        // gather area: a small persistent block of the first device's parameter cache
+        void* gather = nullptr; bool fresh = false;
+        const char key[] = "msm_sharded_gather";
+        first = ctx_cache_get(c0, key, sizeof key, 16 * sizeof(XYZZ<F>) + 3 * sizeof(F), &gather, &fresh);
+        if (first == ZKG_OK) {
+            XYZZ<F>* g = (XYZZ<F>*)gather;
+            F* d_out = (F*)((uint8_t*)gather + 16 * sizeof(XYZZ<F>));
+            for (int d = 0; d < n_dev && first == ZKG_OK; ++d) {
+                cudaError_t e = cudaStreamWaitEvent(c0->stream, done[d], 0);
+                if (e == cudaSuccess)
+                    e = d == 0 ? cudaMemcpyAsync(g, d_part[0], sizeof(XYZZ<F>), cudaMemcpyDeviceToDevice, c0->stream)
+                               : cudaMemcpyPeerAsync(g + d, c0->device, d_part[d], pcs[d].ctx->device, sizeof(XYZZ<F>), c0->stream);
+                if (e != cudaSuccess) { set_error("msm_sharded: gathering the partial of device %d failed: %s", pcs[d].ctx->device, cudaGetErrorString(e)); first = ZKG_ERR_CUDA; }
+            }
+            if (first == ZKG_OK) {
+                k_combine<F><<<1, 32, 0, c0->stream>>>(g, (size_t)n_dev, d_out);
+                c0->launches += 1;
+                first = copy_d2h(out_xyz, d_out, 3 * sizeof(F), c0->stream);
+            }
+        }
+    }
+    // every context is drained before it returns to the pool (also on the error paths)
+    for (int d = 0; d < n_dev; ++d) {
+        DeviceGuard dgd(pcs[d].ctx->device);
+        cudaStreamSynchronize(pcs[d].ctx->stream);
+        if (done[d]) cudaEventDestroy(done[d]);
+    }
+    return first;
+}
+
 
 // per-curve entry points, instantiated in msm_g1.cu (F = Fq) and msm_g2.cu (F = Fq2)
 #define ZKG_MSM_DECLARE(G)                                                                                          \
@@ -1254,11 +1345,13 @@ static int32_t msm_host(int device, const void* bases, size_t stride, size_t n_b
     int32_t pack_bases_##G(zkg_ctx* ctx, const void* d_ark, size_t stride, size_t n, void* d_packed);               \
     int32_t msm_host_##G(int device, const void* bases, size_t stride, size_t n_bases, const uint64_t* scalars,     \
                          size_t n_scalars, uint64_t* out_xyz);                                                      \
+    int32_t msm_host_sharded_##G(const int32_t* devices, int32_t n_dev, const void* bases, size_t stride, size_t n_bases, \
+                                 const uint64_t* scalars, size_t n_scalars, uint64_t* out_xyz);                     \
     int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out);                          \
     int32_t fixed_base_##G(zkg_ctx* ctx, const uint64_t* d_scalars, size_t n, void* d_packed);                      \
     int32_t prepare_##G(zkg_ctx* ctx, const void* d_bases, size_t n, int c, void* d_table);                         \
     int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode); \
-    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out); \
+    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out, int mode); \
     int32_t crs_det_pack_##G(int device, const void* bases, size_t stride, size_t n, int l, int n_parties,          \
                              const uint32_t* h_scal, void* const* out_by_party, size_t out_stride);
 ZKG_MSM_DECLARE(g1)
@@ -1275,6 +1368,10 @@ ZKG_MSM_DECLARE(g2)
                          size_t n_scalars, uint64_t* out_xyz) {                                                     \
         return msm_host<F>(device, bases, stride, n_bases, scalars, n_scalars, out_xyz);                            \
     }                                                                                                               \
+    int32_t msm_host_sharded_##G(const int32_t* devices, int32_t n_dev, const void* bases, size_t stride, size_t n_bases, \
+                                 const uint64_t* scalars, size_t n_scalars, uint64_t* out_xyz) {                    \
+        return msm_host_sharded<F>(devices, n_dev, bases, stride, n_bases, scalars, n_scalars, out_xyz);            \
+    }                                                                                                               \
     int32_t combine_##G(zkg_ctx* ctx, const uint64_t* d_parts, size_t n, uint64_t* d_out) {                         \
         k_combine<F><<<1, 32, 0, ctx->stream>>>((const XYZZ<F>*)d_parts, n, (F*)d_out);                             \
         ctx->launches += 1;                                                                                         \
@@ -1287,8 +1384,8 @@ ZKG_MSM_DECLARE(g2)
     int32_t msm_run_prepared_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* d_scalars, size_t n, void* d_out, int mode) { \
         return msm_run_prepared<F>(ctx, (const Affine<F>*)d_table, c, (const Fr*)d_scalars, n, (F*)d_out, mode);    \
     }                                                                                                               \
-    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out) { \
-        return msm_run_prepared_host<F>(ctx, (const Affine<F>*)d_table, c, h_scalars, n, (F*)d_out);                \
+    int32_t msm_run_prepared_host_##G(zkg_ctx* ctx, const void* d_table, int c, const uint64_t* h_scalars, size_t n, void* d_out, int mode) { \
+        return msm_run_prepared_host<F>(ctx, (const Affine<F>*)d_table, c, h_scalars, n, (F*)d_out, mode);          \
     }                                                                                                               \
     int32_t crs_det_pack_##G(int device, const void* bases, size_t stride, size_t n, int l, int n_parties,          \
                              const uint32_t* h_scal, void* const* out_by_party, size_t out_stride) {                \

@@ -24,6 +24,9 @@
 #include "fp.cuh"
 #include "host_fr.hpp"
 #include <deque>
+#include <string>
+#include <thread>
+#include <vector>
 
 namespace zkg {
 
@@ -337,6 +340,26 @@ k_ntt_pass8(const Fr* __restrict__ in, Fr* __restrict__ out, NttPass P, const Fr
 }
 
 // ------------------------------------------------------------------------------------------
+// Destination of the king's stage-1 scatter.  Unsharded: one buffer of m elements.  Sharded over G GPUs: the
+// pack-order buffer is cut into G segments of 2^log_seg elements, segment r living in the memory of GPU r (its own
+// output columns); p[r] is that segment as seen from THIS GPU -- a peer mapping over NVLink (cudaDeviceEnablePeerAccess
+// in one process, a CUDA IPC mapping across processes).  Every slot is written by exactly one thread of one GPU, so the
+// rotate / bit-reverse / stride permutation of dfft/mod.rs:284-300 IS the exchange: stage 1 stores straight into the
+// owner's memory and no collective (and no zero-filled full-size buffer) is needed.
+struct SDest {
+    Fr* p[16];
+    int log_seg;                  // 63 when unsharded (every index maps to p[0])
+};
+__device__ __forceinline__ Fr* sdest(const SDest& s, size_t dst) {
+    return s.p[dst >> s.log_seg] + (dst & (((size_t)1 << s.log_seg) - 1));
+}
+static SDest sdest_single(Fr* S) {
+    SDest d;
+    for (int i = 0; i < 16; ++i) d.p[i] = S;
+    d.log_seg = 63;
+    return d;
+}
+
 // King, kernel 1: per share column k: secrets = U * shares (unpack2 or Lagrange matrix), the
 // column-local fft2 butterflies, g^pos powers, and the store in *pack order*:
 //   S[c*l + j] = j-th secret of output column c.
@@ -349,7 +372,7 @@ template <int LL>
 __global__ void __launch_bounds__(256, 3)
 k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restrict__ U, const Fr* __restrict__ direct,
               size_t mbyl, size_t col0, size_t cols, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw,
-              Fr* __restrict__ S) {
+              SDest S) {
     // this launch owns the share columns [col0, col0 + cols) of the mbyl columns (cols == mbyl unsharded);
     // inputs are indexed locally (kk), twiddles and destinations by the global column k
     size_t kk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,7 +405,7 @@ k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restri
     }
     if (mode == 2) {
 #pragma unroll
-        for (int j = 0; j < LL; ++j) st_fr(S + k * LL + j, v[j]);
+        for (int j = 0; j < LL; ++j) st_fr(sdest(S, k * LL + j), v[j]);
         return;
     }
     const size_t m = (size_t)1 << log_m;
@@ -424,7 +447,7 @@ k_king_stage1(const Fr* __restrict__ shares, uint32_t n_recv, const Fr* __restri
         } else {
             dst = pos;        // mode 0: S[c*l + j] with c = pos / l, j = pos % l is S[pos]; mode 3 likewise
         }
-        st_fr(S + dst, x);
+        st_fr(sdest(S, dst), x);
     }
 }
 
@@ -475,7 +498,7 @@ __global__ void k_king_scaled_matrices(const Fr* __restrict__ U, uint32_t hi_n, 
 __global__ void __launch_bounds__(256, 3)
 k_king_stage1_l2(const Fr* __restrict__ shares, const Fr* __restrict__ U, const Fr* __restrict__ UsTab, size_t mbyl, size_t col0,
                  size_t cols, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw, const Fr* __restrict__ g_lo2,
-                 Fr* __restrict__ S) {
+                 SDest S) {
     const size_t Tlo = col0 + 1;
     const size_t T = (Tlo & ~(size_t)255) + (size_t)blockIdx.x * 256 + threadIdx.x;
     const Fr* Us = UsTab + (size_t)(T >> TW_LO_BITS) * 16;             // uniform over the block (L1-resident)
@@ -503,8 +526,8 @@ k_king_stage1_l2(const Fr* __restrict__ shares, const Fr* __restrict__ U, const 
         d0 = (p0 & (mbyl - 1)) * 2 + (p0 / mbyl);
         d1 = (p1 & (mbyl - 1)) * 2 + (p1 / mbyl);
     }
-    st_fr(S + d0, a);
-    st_fr(S + d1, b);
+    st_fr(sdest(S, d0), a);
+    st_fr(sdest(S, d1), b);
 }
 
 // The same for latency-bound sizes (<= 2^13 columns: 17.6 -> 13.8 us; no gain from 2^15 up): TWO threads per column,
@@ -514,7 +537,7 @@ k_king_stage1_l2(const Fr* __restrict__ shares, const Fr* __restrict__ U, const 
 __global__ void __launch_bounds__(256)
 k_king_stage1_l2_split(const Fr* __restrict__ shares, const Fr* __restrict__ U, const Fr* __restrict__ UsTab, size_t mbyl, size_t col0,
                        size_t cols, int log_m, int mode, PowTable gen_tw, int has_g, PowTable g_tw, const Fr* __restrict__ g_lo2,
-                       Fr* __restrict__ S) {
+                       SDest S) {
     const size_t Tlo = col0 + 1;
     const uint32_t j = threadIdx.x & 1;
     const size_t T = (Tlo & ~(size_t)127) + (size_t)blockIdx.x * 128 + (threadIdx.x >> 1);
@@ -551,7 +574,7 @@ k_king_stage1_l2_split(const Fr* __restrict__ shares, const Fr* __restrict__ U, 
         size_t pb = (size_t)(__brevll((unsigned long long)pos) >> (64 - log_m));
         d = (pb & (mbyl - 1)) * 2 + (pb / mbyl);
     }
-    st_fr(S + d, o);
+    st_fr(sdest(S, d), o);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -707,6 +730,26 @@ k_fft1_shard_outer(const Fr* __restrict__ recv, size_t cnt, int G, int logG, con
         }
         st_fr(out + (size_t)k1 * cnt + j, acc);
     }
+}
+
+
+// fft1 sharded, local step's last pass fused with the exchange: element k2 of this rank's twiddled inner transform
+// belongs to rank k2 / cnt (cnt = N2 / G columns per rank) and is stored straight into that rank's receive buffer
+// (chunk `rank` of it) -- over NVLink peer memory for the other ranks.  The twiddle product w^(i1 k2) that the local
+// step needs anyway is applied on the way, so the all-to-all costs no extra pass over the data.
+__global__ void __launch_bounds__(256)
+k_twiddle_scatter(const Fr* __restrict__ in, size_t N2, int has_tw, PowTable tw, SDest recv_by_rank, int log_cnt, uint32_t rank) {
+    size_t k2 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k2 >= N2) return;
+    Fr x = ld_fr_rw(in + k2);
+    if (has_tw && k2) x = fp_mul(x, pow_lookup(tw, k2));
+    const size_t cnt = (size_t)1 << log_cnt;
+    st_fr(recv_by_rank.p[k2 >> log_cnt] + ((size_t)rank << log_cnt) + (k2 & (cnt - 1)), x);
+}
+
+__global__ void k_vec_add(Fr* __restrict__ v, const Fr* __restrict__ a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fr(v + i, fp_add(ld_fr_rw(v + i), ld_fr(a + i)));
 }
 
 // out[bitrev(i)] = in[i]
@@ -1056,7 +1099,7 @@ static int32_t recv_matrix(uint32_t l, const uint32_t* parties, uint32_t n_recv,
 // stage 1 on the share columns [col0, col0+cols): unpack (+ fft2 + powers) and scatter into S (pack order)
 static int32_t king_stage1(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* parties, uint32_t n_recv, size_t mbyl,
                            size_t col0, size_t cols, uint32_t l, const HFr* gen, const HFr* g, int rearrange,
-                           int mode_fft, Fr* S, HostKeep& keep) {
+                           int mode_fft, const SDest& S, HostKeep& keep) {
     const host::PssMatrices* pm = pss_get(l);
     ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
     ZKG_REQUIRE(is_pow2(mbyl) || !mode_fft, "king: m/l = %zu is not a power of two", mbyl);
@@ -1138,6 +1181,12 @@ static int32_t king_stage2(zkg_ctx* ctx, const Fr* S, const Fr* d_rand, size_t c
 
 // ---- king pipeline on device buffers ------------------------------------------------------
 // mode_fft: 1 = fft2 + powers + (re)packing (d_fft/d_ifft king), 0 = deg_red king
+static int32_t king_stage1(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* parties, uint32_t n_recv, size_t mbyl,
+                           size_t col0, size_t cols, uint32_t l, const HFr* gen, const HFr* g, int rearrange,
+                           int mode_fft, Fr* S, HostKeep& keep) {
+    return king_stage1(ctx, d_shares, parties, n_recv, mbyl, col0, cols, l, gen, g, rearrange, mode_fft, sdest_single(S), keep);
+}
+
 static int32_t king_dev(zkg_ctx* ctx, const Fr* d_shares, const uint32_t* parties, uint32_t n_recv, size_t mbyl,
                         uint32_t l, const HFr* gen, const HFr* g, int rearrange, const Fr* d_rand, Fr* d_out,
                         int mode_fft, HostKeep& keep) {
@@ -1239,11 +1288,273 @@ static int32_t fft1_shard_outer(zkg_ctx* ctx, const Fr* d_recv, size_t cnt, size
     return ZKG_OK;
 }
 
+
+// local step + exchange in one: inner transform in place, then k_twiddle_scatter into the ranks' receive buffers
+static int32_t fft1_shard_local_scatter(zkg_ctx* ctx, Fr* d_block, size_t N2, uint32_t l, uint32_t G, uint32_t rank,
+                                        const HFr& gen, const HFr* pre_scale, Fr* const* recv_by_rank) {
+    ZKG_REQUIRE(is_pow2(G) && G <= 16 && is_pow2(N2) && N2 >= G && is_pow2(l) && rank < G,
+                "fft1_shard: block %zu, l %u, ranks %u must be powers of two (ranks <= 16, block >= ranks)", N2, l, G);
+    ZKG_REQUIRE(ilog2(N2 * G * l) <= 28, "fft1_shard: m exceeds the 2-adicity of Fr");
+    ZKG_TRY(ctx->ws.reserve(N2 * sizeof(Fr)));
+    HFr w = host::h_pow(gen, l);
+    ZKG_TRY(ntt_bitrev_in(ctx, d_block, d_block, (Fr*)ctx->ws.p, N2, host::h_pow(w, G), 0, pre_scale, nullptr));
+    uint32_t i1 = 0;
+    for (int b = 0, lg = ilog2(G); b < lg; ++b) i1 |= ((rank >> b) & 1u) << (lg - 1 - b);
+    PowTable tw{nullptr, nullptr};
+    if (i1) ZKG_TRY(build_pow_table(ctx, host::h_pow(w, i1), N2, &tw));
+    SDest dst;
+    for (uint32_t r = 0; r < 16; ++r) dst.p[r] = recv_by_rank[r < G ? r : 0];
+    dst.log_seg = 0;
+    k_twiddle_scatter<<<(unsigned)((N2 + 255) / 256), 256, 0, ctx->stream>>>(d_block, N2, i1 ? 1 : 0, tw, dst, ilog2(N2 / G), rank);
+    ctx->launches += 1;
+    ZKG_CUDA(cudaGetLastError());
+    return ZKG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Single-process multi-GPU entry points (SURVEY.md 8b last line, 8e): one call from the unchanged Rust caller drives
+// several GPUs of the box.  The exchange step of each pipeline is done by the kernels themselves, storing into peer
+// memory over NVLink (cudaDeviceEnablePeerAccess); without peer access the call fails with ZKG_ERR_NCCL.
+// ------------------------------------------------------------------------------------------------------------------
+static int32_t enable_peers(const int32_t* devices, int n_dev) {
+    for (int a = 0; a < n_dev; ++a) {
+        DeviceGuard dg(devices[a]);
+        for (int b = 0; b < n_dev; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            ZKG_CUDA(cudaDeviceCanAccessPeer(&can, devices[a], devices[b]));
+            if (!can) {
+                set_error("GPU %d cannot map the memory of GPU %d (no NVLink / PCIe peer access); the sharded entry points need it",
+                          devices[a], devices[b]);
+                return ZKG_ERR_NCCL;
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", devices[a], devices[b], cudaGetErrorString(e)); return ZKG_ERR_NCCL; }
+        }
+    }
+    return ZKG_OK;
+}
+
+static int32_t check_device_list(const int32_t* devices, int32_t n_dev, const char* who) {
+    ZKG_REQUIRE(devices && n_dev >= 1 && n_dev <= 16 && is_pow2((size_t)n_dev), "%s: the device list must hold 1, 2, 4, 8 or 16 GPUs", who);
+    for (int a = 0; a < n_dev; ++a)
+        for (int b = 0; b < a; ++b) ZKG_REQUIRE(devices[a] != devices[b], "%s: device %d listed twice", who, devices[a]);
+    return ZKG_OK;
+}
+
+// runs fn(d) for every device on its own host thread (device 0 on the caller's); first failure wins, message carried over
+template <class Fn>
+static int32_t for_each_device(int n_dev, Fn fn) {
+    std::vector<int32_t> rc(n_dev, ZKG_OK);
+    std::vector<std::string> msg(n_dev);
+    auto run = [&](int d) { rc[d] = fn(d); if (rc[d] != ZKG_OK) msg[d] = zkg_last_error(); };
+    std::vector<std::thread> th;
+    for (int d = 1; d < n_dev; ++d) th.emplace_back(run, d);
+    run(0);
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_dev; ++d)
+        if (rc[d] != ZKG_OK) { set_error("%s", msg[d].c_str()); return rc[d]; }
+    return ZKG_OK;
+}
+
+// King closure of fft2_with_rearrange (mode_fft = 1) or deg_red (0) sharded by share columns over the listed GPUs.
+static int32_t king_host_sharded(const int32_t* devices, int32_t n_dev, const uint64_t* const* shares_by_party, const uint32_t* parties,
+                                 uint32_t n_recv, size_t mbyl, uint32_t l, const uint64_t* gen, const uint64_t* g, int rearrange,
+                                 const uint64_t* rand, uint64_t* const* out_by_party, int mode_fft) {
+    ZKG_TRY(check_device_list(devices, n_dev, "king_sharded"));
+    const host::PssMatrices* pm = pss_get(l);
+    ZKG_REQUIRE(pm, "packing factor l = %u unsupported (2, 4, 8)", l);
+    if (n_dev == 1 || mbyl < (size_t)n_dev * 256 || !is_pow2(mbyl))
+        return king_host(devices[0], shares_by_party, parties, n_recv, mbyl, l, gen, g, rearrange, rand, out_by_party, mode_fft);
+    ZKG_REQUIRE(shares_by_party && out_by_party && rand, "king: NULL argument");
+    ZKG_REQUIRE(n_recv >= 1 && n_recv <= pm->n, "king: n_recv = %u out of range", n_recv);
+    ZKG_TRY(enable_peers(devices, n_dev));
+    const size_t cols = mbyl / n_dev, seg = cols * l;                 // columns and S elements per GPU
+    std::vector<PooledCtx> pcs(n_dev);
+    for (int d = 0; d < n_dev; ++d) ZKG_TRY(pcs[d].acquire(devices[d]));
+    std::vector<Fr*> S(n_dev), d_in(n_dev), d_rand(n_dev), d_out(n_dev);
+    std::vector<cudaEvent_t> ev(n_dev, nullptr);
+    const size_t in_b = align_up((size_t)n_recv * cols * 32, 256), rand_b = align_up(cols * pm->t * 32, 256), out_b = (size_t)pm->n * cols * 32;
+    for (int d = 0; d < n_dev; ++d) {                                // carve every GPU's buffers first: stage 1 needs all S pointers
+        zkg_ctx* ctx = pcs[d].ctx;
+        DeviceGuard dg(ctx->device);
+        ZKG_TRY(ctx->ws.reserve(seg * sizeof(Fr)));
+        ZKG_TRY(ctx->io.reserve(in_b + rand_b + out_b));
+        S[d] = (Fr*)ctx->ws.p;
+        d_in[d] = (Fr*)ctx->io.p;
+        d_rand[d] = (Fr*)((uint8_t*)ctx->io.p + in_b);
+        d_out[d] = (Fr*)((uint8_t*)ctx->io.p + in_b + rand_b);
+        ZKG_CUDA(cudaEventCreateWithFlags(&ev[d], cudaEventDisableTiming));
+    }
+    SDest dst;
+    for (int r = 0; r < 16; ++r) dst.p[r] = S[r < n_dev ? r : 0];
+    dst.log_seg = ilog2(seg);
+    HFr hgen = mode_fft ? host::h_load(gen) : host::h_one(), hg = mode_fft ? host::h_load(g) : host::h_one();
+    std::vector<HostKeep> keep(n_dev);
+    int32_t rc = for_each_device(n_dev, [&](int d) -> int32_t {     // upload the column slice, unpack + fft2 + powers, scatter to the owners
+        zkg_ctx* ctx = pcs[d].ctx;
+        DeviceGuard dg(ctx->device);
+        const size_t lo = (size_t)d * cols;
+        for (uint32_t r = 0; r < n_recv; ++r) {
+            ZKG_REQUIRE(shares_by_party[r], "NULL share vector for index %u", r);
+            ZKG_TRY(copy_h2d(d_in[d] + (size_t)r * cols, shares_by_party[r] + lo * 4, cols * 32, ctx->stream));
+        }
+        ZKG_TRY(copy_h2d(d_rand[d], rand + lo * pm->t * 4, cols * pm->t * 32, ctx->stream));
+        ZKG_TRY(king_stage1(ctx, d_in[d], parties, n_recv, mbyl, lo, cols, l, &hgen, &hg, rearrange, mode_fft, dst, keep[d]));
+        ZKG_CUDA(cudaEventRecord(ev[d], ctx->stream));
+        return ZKG_OK;
+    });
+    if (rc == ZKG_OK)
+        rc = for_each_device(n_dev, [&](int d) -> int32_t {         // once EVERY GPU has scattered: pack the own columns, download
+            zkg_ctx* ctx = pcs[d].ctx;
+            DeviceGuard dg(ctx->device);
+            for (int q = 0; q < n_dev; ++q) ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ev[q], 0));
+            ZKG_TRY(king_stage2(ctx, S[d], d_rand[d], cols, l, d_out[d], keep[d]));
+            const size_t lo = (size_t)d * cols;
+            for (uint32_t p = 0; p < pm->n; ++p) {
+                ZKG_REQUIRE(out_by_party[p], "NULL output vector for party %u", p);
+                ZKG_TRY(copy_d2h(out_by_party[p] + lo * 4, d_out[d] + (size_t)p * cols, cols * 32, ctx->stream));
+            }
+            return ZKG_OK;
+        });
+    for (int d = 0; d < n_dev; ++d) {
+        DeviceGuard dg(pcs[d].ctx->device);
+        cudaStreamSynchronize(pcs[d].ctx->stream);
+        if (ev[d]) cudaEventDestroy(ev[d]);
+    }
+    return rc;
+}
+
+// fft1_in_place of ONE lane over the listed GPUs: block d of the lane goes to GPU d, inner transforms + twiddles, exchange by
+// peer stores, G-point outer transforms, and the result is laid back into px in fft1 order (px[k] = X[(k+1) mod N]).
+static int32_t fft1_host_sharded(const int32_t* devices, int32_t n_dev, uint64_t* px, size_t mbyl, uint32_t l, const uint64_t* gen,
+                                 const uint64_t* pre_scale, const uint64_t* in_mask) {
+    ZKG_TRY(check_device_list(devices, n_dev, "fft1_sharded"));
+    ZKG_REQUIRE(gen && (mbyl == 0 || px), "fft1_sharded: NULL argument");
+    if (mbyl == 0) return ZKG_OK;
+    const size_t G = (size_t)n_dev;
+    if (n_dev == 1 || !is_pow2(mbyl) || mbyl < G * G * 256) return zkg_fft1_bn254(devices[0], px, mbyl, l, gen, pre_scale, in_mask);
+    ZKG_TRY(enable_peers(devices, n_dev));
+    const size_t N2 = mbyl / G, cnt = N2 / G;
+    std::vector<PooledCtx> pcs(n_dev);
+    for (int d = 0; d < n_dev; ++d) ZKG_TRY(pcs[d].acquire(devices[d]));
+    std::vector<Fr*> blk(n_dev), recv(n_dev), out(n_dev), msk(n_dev);
+    std::vector<cudaEvent_t> ev(n_dev, nullptr);
+    const size_t b = align_up(N2 * 32, 256);
+    for (int d = 0; d < n_dev; ++d) {
+        zkg_ctx* ctx = pcs[d].ctx;
+        DeviceGuard dg(ctx->device);
+        ZKG_TRY(ctx->io.reserve(4 * b));
+        blk[d] = (Fr*)ctx->io.p;
+        recv[d] = (Fr*)((uint8_t*)ctx->io.p + b);
+        out[d] = (Fr*)((uint8_t*)ctx->io.p + 2 * b);
+        msk[d] = (Fr*)((uint8_t*)ctx->io.p + 3 * b);
+        ZKG_CUDA(cudaEventCreateWithFlags(&ev[d], cudaEventDisableTiming));
+    }
+    HFr hgen = host::h_load(gen), hs;
+    if (pre_scale) hs = host::h_load(pre_scale);
+    // rank d's result row k1 (cnt elements) holds X[d*cnt + j + N2*k1], i.e. px positions starting at (d*cnt + N2*k1 - 1) mod N
+    auto for_rows = [&](int d, auto&& fn) -> int32_t {
+        for (size_t k1 = 0; k1 < G; ++k1) {
+            const size_t x0 = (size_t)d * cnt + N2 * k1;
+            Fr* row = nullptr; (void)row;
+            if (x0 == 0) {                                           // X[0] wraps to px[N-1]; the rest of the row starts at px[0]
+                ZKG_TRY(fn(k1 * cnt, mbyl - 1, (size_t)1));
+                ZKG_TRY(fn(k1 * cnt + 1, (size_t)0, cnt - 1));
+            } else {
+                ZKG_TRY(fn(k1 * cnt, x0 - 1, cnt));
+            }
+        }
+        return ZKG_OK;
+    };
+    int32_t rc = for_each_device(n_dev, [&](int d) -> int32_t {
+        zkg_ctx* ctx = pcs[d].ctx;
+        DeviceGuard dg(ctx->device);
+        ZKG_TRY(copy_h2d(blk[d], px + (size_t)d * N2 * 4, N2 * 32, ctx->stream));
+        if (in_mask)
+            ZKG_TRY(for_rows(d, [&](size_t o, size_t pos, size_t len) { return copy_h2d(msk[d] + o, in_mask + pos * 4, len * 32, ctx->stream); }));
+        ZKG_TRY(fft1_shard_local_scatter(ctx, blk[d], N2, l, (uint32_t)G, (uint32_t)d, hgen, pre_scale ? &hs : nullptr, recv.data()));
+        ZKG_CUDA(cudaEventRecord(ev[d], ctx->stream));
+        return ZKG_OK;
+    });
+    if (rc == ZKG_OK)
+        rc = for_each_device(n_dev, [&](int d) -> int32_t {
+            zkg_ctx* ctx = pcs[d].ctx;
+            DeviceGuard dg(ctx->device);
+            for (int q = 0; q < n_dev; ++q) ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ev[q], 0));
+            ZKG_TRY(fft1_shard_outer(ctx, recv[d], cnt, N2, l, (uint32_t)G, hgen, out[d]));
+            if (in_mask) {
+                k_vec_add<<<(unsigned)((N2 + 255) / 256), 256, 0, ctx->stream>>>(out[d], msk[d], N2);
+                ctx->launches += 1;
+                ZKG_CUDA(cudaGetLastError());
+            }
+            return for_rows(d, [&](size_t o, size_t pos, size_t len) { return copy_d2h(px + pos * 4, out[d] + o, len * 32, ctx->stream); });
+        });
+    for (int d = 0; d < n_dev; ++d) {
+        DeviceGuard dg(pcs[d].ctx->device);
+        cudaStreamSynchronize(pcs[d].ctx->stream);
+        if (ev[d]) cudaEventDestroy(ev[d]);
+    }
+    return rc;
+}
+
 }  // namespace zkg
 
 using namespace zkg;
 
 extern "C" {
+
+
+int32_t zkg_king_fft2_bn254_sharded(const int32_t* devices, int32_t n_devices, const uint64_t* const* shares_by_party,
+                                    const uint32_t* parties, uint32_t n_recv, size_t mbyl, uint32_t l, const uint64_t gen[4],
+                                    const uint64_t g[4], int32_t rearrange, const uint64_t* rand, uint64_t* const* out_by_party) {
+    ZKG_REQUIRE(gen && g, "king: gen / g are NULL");
+    return king_host_sharded(devices, n_devices, shares_by_party, parties, n_recv, mbyl, l, gen, g, rearrange, rand, out_by_party, 1);
+}
+int32_t zkg_deg_red_king_bn254_sharded(const int32_t* devices, int32_t n_devices, const uint64_t* const* shares_by_party,
+                                       const uint32_t* parties, uint32_t n_recv, size_t cols, uint32_t l, const uint64_t* rand,
+                                       uint64_t* const* out_by_party) {
+    return king_host_sharded(devices, n_devices, shares_by_party, parties, n_recv, cols, l, nullptr, nullptr, 0, rand, out_by_party, 0);
+}
+int32_t zkg_fft1_bn254_sharded(const int32_t* devices, int32_t n_devices, uint64_t* px, size_t mbyl, uint32_t l, const uint64_t gen[4],
+                               const uint64_t* pre_scale, const uint64_t* in_mask) {
+    return fft1_host_sharded(devices, n_devices, px, mbyl, l, gen, pre_scale, in_mask);
+}
+
+int32_t zkg_fft1_shard_local_scatter_bn254_dev(zkg_ctx* ctx, uint64_t* d_block, size_t block_len, uint32_t l, uint32_t n_ranks,
+                                               uint32_t rank, const uint64_t gen[4], const uint64_t* pre_scale,
+                                               void* const* d_recv_by_rank) {
+    ZKG_REQUIRE(ctx && gen && d_recv_by_rank && (block_len == 0 || d_block), "fft1_shard_local_scatter: NULL argument");
+    if (block_len == 0) return ZKG_OK;
+    ZKG_REQUIRE(n_ranks >= 1 && n_ranks <= 16, "fft1_shard_local_scatter: %u ranks unsupported (<= 16)", n_ranks);
+    for (uint32_t r = 0; r < n_ranks; ++r) ZKG_REQUIRE(d_recv_by_rank[r], "fft1_shard_local_scatter: NULL receive buffer for rank %u", r);
+    DeviceGuard dg(ctx->device);
+    HFr hs;
+    if (pre_scale) hs = host::h_load(pre_scale);
+    return fft1_shard_local_scatter(ctx, (Fr*)d_block, block_len, l, n_ranks, rank, host::h_load(gen), pre_scale ? &hs : nullptr,
+                                    (Fr* const*)d_recv_by_rank);
+}
+
+int32_t zkg_king_stage1_scatter_bn254_dev(zkg_ctx* ctx, const uint64_t* d_shares_local, const uint32_t* parties, uint32_t n_recv,
+                                          size_t col0, size_t cols, size_t mbyl, uint32_t l, const uint64_t gen[4],
+                                          const uint64_t g[4], int32_t rearrange, void* const* d_S_by_rank, uint32_t n_ranks) {
+    ZKG_REQUIRE(ctx && gen && g && d_S_by_rank && (cols == 0 || d_shares_local), "king_stage1_scatter: NULL argument");
+    ZKG_REQUIRE(n_ranks >= 1 && n_ranks <= 16 && is_pow2(n_ranks) && is_pow2(mbyl) && mbyl % n_ranks == 0,
+                "king_stage1_scatter: m/l = %zu and %u ranks must be powers of two", mbyl, n_ranks);
+    DeviceGuard dg(ctx->device);
+    SDest dst;
+    for (uint32_t r = 0; r < 16; ++r) {
+        dst.p[r] = (Fr*)d_S_by_rank[r < n_ranks ? r : 0];
+        ZKG_REQUIRE(dst.p[r], "king_stage1_scatter: NULL segment for rank %u", r);
+    }
+    dst.log_seg = n_ranks == 1 ? 63 : ilog2(mbyl / n_ranks * l);
+    HFr hgen = host::h_load(gen), hg = host::h_load(g);
+    HostKeep keep;
+    ZKG_TRY(king_stage1(ctx, (const Fr*)d_shares_local, parties, n_recv, mbyl, col0, cols, l, &hgen, &hg, rearrange, 1, dst, keep));
+    if (!keep.v.empty()) ZKG_CUDA(cudaStreamSynchronize(ctx->stream));     // a Lagrange matrix uploaded from host memory owned by this call
+    return ZKG_OK;
+}
 
 int32_t zkg_fft1_bn254_dev(zkg_ctx* ctx, uint64_t* d_px, size_t mbyl, uint32_t l, const uint64_t gen[4],
                            const uint64_t* pre_scale, const uint64_t* d_in_mask) {
@@ -1543,7 +1854,7 @@ static int32_t mask_sample_host(int device, int mode_fft, int rearrange, const u
         if (has_g) ZKG_TRY(build_pow_table(ctx, hg, m, &g_tw));
         const unsigned blocks = (unsigned)((cols + 255) / 256);
         const int log_m = ilog2(m), mode = rearrange ? 1 : 0;
-#define KS(LLv) k_king_stage1<LLv><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_mask, cols, 0, cols, log_m, mode, gen_tw, has_g, g_tw, d_S)
+#define KS(LLv) k_king_stage1<LLv><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_mask, cols, 0, cols, log_m, mode, gen_tw, has_g, g_tw, sdest_single(d_S))
         if (l == 2) KS(2); else if (l == 4) KS(4); else KS(8);
 #undef KS
         ctx->launches += 1;
@@ -1592,9 +1903,9 @@ int32_t zkg_fft2_bn254(int32_t device, uint64_t* s1, size_t m, uint32_t l, const
     size_t mbyl = m / l;
     unsigned blocks = (unsigned)((mbyl + 255) / 256);
     int log_m = ilog2(m);
-    if (l == 2) k_king_stage1<2><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, d_out);
-    else if (l == 4) k_king_stage1<4><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, d_out);
-    else k_king_stage1<8><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, d_out);
+    if (l == 2) k_king_stage1<2><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, sdest_single(d_out));
+    else if (l == 4) k_king_stage1<4><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, sdest_single(d_out));
+    else k_king_stage1<8><<<blocks, 256, 0, ctx->stream>>>(nullptr, 0, nullptr, d_in, mbyl, 0, mbyl, log_m, 3, gen_tw, 0, none, sdest_single(d_out));
     ZKG_CUDA(cudaGetLastError());
     ZKG_TRY(copy_d2h(s1, d_out, m * 32, ctx->stream));
     ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
