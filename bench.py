@@ -45,6 +45,21 @@ def measured_peaks():
     return hbm, how, imad, ihow
 
 
+def workload_config(log2n, world):
+    """The part of `config` that names the workload: identical for the GPU arm and the reference arm."""
+    n = 1 << log2n
+    return {"workload": f"d_msm local G1 MSM (dist-primitives/src/dmsm/mod.rs:73), BN254, 2^{log2n} points per GPU",
+            "points_per_gpu": n, "total_points": n * world, "curve": "BN254 G1", "l": 2}
+
+
+def host_threads():
+    """Host cores this process may use.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def ark_window(k):
     """arkworks' own rule, used only to state the ALGORITHMIC work per point."""
     lg = (k - 1).bit_length()
@@ -110,8 +125,10 @@ def cpu_msm_sample(log2n, reps, threads=None):
     import oracle_lib as ol
     from oracle_lib import _p
     lib = ol.oracle()
-    th = threads or min(lib.zko_max_threads(), os.cpu_count() or 1)
     n = 1 << log2n
+    # arkworks parallelises over the W windows (rayon, feature "parallel"); the port does the same with an explicit
+    # num_threads clause, so torchrun's OMP_NUM_THREADS=1 does not apply
+    th = threads or max(1, min(host_threads(), ark_window(n)[1]))
     rng = np.random.default_rng(0x7A6B)
     bases = np.zeros((n, 72), dtype=np.uint8)
     lib.zko_g1_sequence(_p(ol.rand_fr(rng, 1)), _p(ol.rand_fr(rng, 1)), n, bases.ctypes.data, 72)
@@ -153,30 +170,82 @@ def cpu_dfft_sample(log2m):
             "d_fft_elems_per_s": round(m / (t_fft1 + t_king), 1), "cores": 1, "kind": "port"}
 
 
+def cpu_prove_sample(log2m):
+    """The same emulated prove dataflow on the host with the oracle port: ONE party's local work (6 fft1 + 5 MSMs; the
+    parties are separate machines in the reference, so they run in parallel) plus the king's 6 d_fft closures and the
+    deg_red closure, every piece on one thread (dist-primitives has no `parallel` feature)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+    import numpy as np
+    import oracle_lib as ol
+    from oracle_lib import _p, pyref
+    o = ol.oracle()
+    l, m = 2, 1 << log2m
+    mbyl, n = m // l, 8
+    rng = np.random.default_rng(15)
+    gen = ol.fr_np([pyref.Radix2Domain(m).group_gen])
+    g = ol.fr_np([pyref.Radix2Domain(2 * m).element(1)])
+    px = ol.rand_fr(rng, 256)[np.arange(mbyl) % 256].copy()
+    t0 = time.perf_counter()
+    for _ in range(6):
+        o.zko_fft1_in_place(_p(px), mbyl, l, _p(gen))
+    t_fft1 = time.perf_counter() - t0
+    t_msm = 0.0
+    for grp, cnt in ((1, mbyl), (1, mbyl), (1, mbyl), (1, 2 * mbyl), (2, mbyl)):
+        sc = ol.rand_fr(rng, 256)[np.arange(cnt) % 256].copy()
+        sc[:, 0] ^= np.arange(cnt, dtype=np.uint64)
+        if grp == 1:
+            bases = np.zeros((cnt, 72), dtype=np.uint8)
+            o.zko_g1_sequence(_p(ol.rand_fr(rng, 1)), _p(ol.rand_fr(rng, 1)), cnt, bases.ctypes.data, 72)
+            t0 = time.perf_counter(); ol.o_g1_msm(bases, sc, threads=1); t_msm += time.perf_counter() - t0
+        else:
+            bases = np.zeros((cnt, 136), dtype=np.uint8)
+            dl = ol.rand_fr(rng, 64)[np.arange(cnt) % 64].copy()
+            o.zko_g2_fixed_base(_p(dl), cnt, bases.ctypes.data, 136)
+            t0 = time.perf_counter(); ol.o_g2_msm(bases, sc, threads=1); t_msm += time.perf_counter() - t0
+    shares = [ol.rand_fr(rng, 256)[(np.arange(mbyl) + p_) % 256].copy() for p_ in range(n)]
+    outs = [np.zeros((mbyl, 4), dtype=np.uint64) for _ in range(n)]
+    rand = ol.rand_fr(rng, 256)[np.arange(mbyl * l) % 256].copy()
+    par = (C.c_uint32 * n)(*range(n))
+    t0 = time.perf_counter()
+    o.zko_king_fft2(ol.ptr_array(shares), par, n, mbyl, l, _p(gen), _p(g), 1, _p(rand), ol.ptr_array(outs))
+    t_king = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    o.zko_deg_red_king(ol.ptr_array(shares), par, n, mbyl, l, _p(rand), ol.ptr_array(outs))
+    t_dr = time.perf_counter() - t0
+    total = t_fft1 + t_msm + 6 * t_king + t_dr
+    return {"prove_sec": round(total, 4), "one_party_fft1_sec": round(t_fft1, 4), "one_party_msm_sec": round(t_msm, 4),
+            "king_d_fft_closure_sec_each": round(t_king, 4), "king_deg_red_sec": round(t_dr, 4), "cores": 1, "kind": "port",
+            "what": "one party's 6 fft1 + 5 MSMs, plus 6 king d_fft closures + 1 deg_red closure, oracle port, single thread per piece; "
+                    "network excluded"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port), all host threads, bounded sample."""
+    """--impl reference: the reference's CPU path (oracle port of ark-ec msm_bigint_wnaf) on the host cores, on the SAME
+    workload as the GPU arm: one G1 MSM of 2^log2n points per step.  Rank 0 alone runs it under torchrun."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    log2n = min(args.log2n, 20)
+    log2n = args.log2n
     n, th, times = cpu_msm_sample(log2n, args.warmup + args.steps)
     timed = times[args.warmup:]
     ms = 1e3 * sum(timed) / len(timed)
     val = n / (ms * 1e-3) / 1e6
     c, W = ark_window(n)
-    sample = f"G1 MSM of 2^{log2n} points per step (arkworks window rule c={c}, W={W}), {th} OpenMP threads over windows"
+    sample = (f"the full workload: G1 MSM of 2^{log2n} points per step (arkworks window rule c={c}, W={W}), {th} OpenMP threads over "
+              f"the {W} windows (as rayon does under ark-ec's `parallel` feature), {os.cpu_count()} host CPUs visible")
     line = {
         "impl": "reference", "metric": "BN254 G1 MSM Mpts/s", "value": round(val, 4), "unit": "Mpts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs)",
         "data": "synthetic",
-        "config": {"workload": f"d_msm local G1 MSM, BN254, 2^{args.log2n} points per GPU (bounded CPU sample 2^{log2n})",
-                   "curve": "BN254 G1", "l": 2},
+        "config": workload_config(log2n, max(1, args.gpus)),
         "cpu_baseline": {"value": round(val, 4), "unit": "Mpts/s", "cores": th, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference = C restatement of ark-ec 0.4.2 msm_bigint_wnaf (oracle/zkoracle.c); the Rust reference "
-                "cannot be built here (no cargo/rustc, arkworks crates un-vendored)",
+                "cannot be built here (no cargo/rustc, arkworks crates un-vendored).  A CPU host does one MSM at a time, so "
+                "the value does not grow with --gpus; total_points in config is the GPU arm's aggregate",
     }
     print(json.dumps(line), flush=True)
 
@@ -239,12 +308,32 @@ def run_ours(args):
         t[:, 3] &= (1 << 61) - 1
         return t
 
+    R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+    def mont_sum_of_products(a_t, s_t):
+        """(sum_i a_i * s_i) mod r as a Python int holding its Montgomery image: the element-wise products come from the
+        library (zkg_field_op_dev), the modular sum of the images is plain integer plumbing (32-bit columns in int64)."""
+        k = a_t.shape[0]
+        prod = torch.empty_like(a_t)
+        capi.check(lib.zkg_field_op_dev(ctx, 0, 0, C.c_void_p(a_t.data_ptr()), C.c_void_p(s_t.data_ptr()), C.c_void_p(prod.data_ptr()), k))
+        torch.cuda.current_stream().synchronize()
+        w = prod.view(torch.int32).reshape(k, 8).to(torch.int64) & 0xffffffff
+        cols = w.sum(dim=0).cpu().tolist()
+        return sum(int(c_) << (32 * i) for i, c_ in enumerate(cols)) % R_MOD
+
+    def point_of_mont_scalar(t_mont):
+        """t * G1 as the (x, y) words of a packed affine point, computed by the device fixed-base kernel."""
+        img = torch.tensor([[(t_mont >> (64 * i)) & ((1 << 64) - 1) for i in range(4)]], dtype=torch.uint64).view(torch.int64).to(dev)
+        pt = torch.zeros((1, 64), dtype=torch.uint8, device=dev)
+        capi.check(lib.zkg_fixed_base_dev(ctx, 1, C.c_void_p(img.data_ptr()), 1, C.c_void_p(pt.data_ptr())))
+        torch.cuda.current_stream().synchronize()
+        return pt.cpu().numpy().view(np.uint64).reshape(8).copy()
+
     scalars = rand_fr_dev(n)
     dlogs = rand_fr_dev(n)
     bases = torch.empty((n, 64), dtype=torch.uint8, device=dev)
     capi.check(lib.zkg_fixed_base_dev(ctx, 1, C.c_void_p(dlogs.data_ptr()), n, C.c_void_p(bases.data_ptr())))
     torch.cuda.synchronize()
-    del dlogs
     # The CRS shares are static across proofs: register them once (window-shifted table in HBM).  The
     # device-resident `value` leg runs against the handle; the e2e leg below does NOT (it ships the
     # arkworks base images over PCIe every step, as the unmodified d_msm signature would).
@@ -302,13 +391,32 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    capi.check(lib.zkg_ctx_set_profiling(ctx, 1))      # phase events ride in the stream of the timed, pipelined calls
     total_ms = timed(step_device, args.steps)
     launches1 = C.c_uint64(0)
     lib.zkg_ctx_launch_count(ctx, C.byref(launches1))
+    phase_timed = []
+    for ph in range(3):                                # phases of the LAST timed call (the GPU was never idle before it)
+        f = C.c_float(0)
+        capi.check(lib.zkg_ctx_phase_ms(ctx, ph, C.byref(f)))
+        phase_timed.append(f.value)
+    capi.check(lib.zkg_ctx_set_profiling(ctx, 0))
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = n * world / (ms_per_step * 1e-3) / 1e6
     dev_result = out_xyz.cpu().numpy().copy()
+    # ---- the result against the closed form: bases are s_i * G, so MSM(bases, a) = (sum_i a_i s_i) * G ---------------------
+    t_local = mont_sum_of_products(scalars, dlogs)
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, t_local)
+        t_total = sum(parts) % R_MOD
+    else:
+        t_total = t_local
+    expect_xy = point_of_mont_scalar(t_total)
+    closed_form_ok = bool((dev_result.view(np.uint64)[:8] == expect_xy).all())
+    if not closed_form_ok:
+        raise SystemExit("bench.py: the MSM result differs from the closed form (sum a_i s_i) * G")
 
     # ---- same workload with two MSMs in flight (two contexts / streams): the latency-bound tail of one
     #      (bucket reduction) overlaps the bucket accumulation of the next -- how a prover that issues its
@@ -341,20 +449,9 @@ def run_ours(args):
         two_stream_same = bool((out2.cpu().numpy() == dev_result).all())
         lib.zkg_ctx_destroy(ctx2)
 
-    # ---- dominant kernel (bucket accumulation) timed live with CUDA events on the launch stream -------
-    capi.check(lib.zkg_ctx_set_profiling(ctx, 1))
-    phase = [[], [], []]
-    for _ in range(max(3, min(args.steps, 10))):
-        capi.check(lib.zkg_msm_bn254_registered_dev(ctx, handle.value, C.c_void_p(scalars.data_ptr()), n,
-                                                    C.c_void_p(partial.data_ptr()), 1))
-        for ph in range(3):
-            f = C.c_float(0)
-            capi.check(lib.zkg_ctx_phase_ms(ctx, ph, C.byref(f)))
-            phase[ph].append(f.value)
-    capi.check(lib.zkg_ctx_set_profiling(ctx, 0))
-    acc_ms = sum(phase[1]) / len(phase[1])
-    sort_ms = sum(phase[0]) / len(phase[0])
-    red_ms = sum(phase[2]) / len(phase[2])
+    # ---- dominant kernel (bucket accumulation): CUDA events recorded by the library on the launch stream INSIDE the timed
+    #      region above (zkg_ctx_set_profiling), read for its last call
+    sort_ms, acc_ms, red_ms = phase_timed
     # the same MSM without the prepared table (generic path: per-window buckets + Horner), for reference
     unprepared_ms = None
     if world == 1:
@@ -405,16 +502,34 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_val = n * world * e2e_steps / e2e_s / 1e6
     same = bool((e2e_result["xyz"] == dev_result).all())
-    # e2e against the registered handle: only the scalars cross PCIe each step
-    e2e_reg_ms = None
-    if world == 1:
-        for _ in range(2):
-            capi.check(lib.zkg_msm_bn254_registered(handle.value, C.c_void_p(h_scal.data_ptr()), n, C.c_void_p(h_out.data_ptr())))
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            capi.check(lib.zkg_msm_bn254_registered(handle.value, C.c_void_p(h_scal.data_ptr()), n, C.c_void_p(h_out.data_ptr())))
-        e2e_reg_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-        same = same and bool((h_out.numpy() == dev_result).all())
+    # e2e against the registered handle (the realistic PackedProvingKeyShare case, groth16/src/proving_key.rs:15-45: the
+    # CRS shares are static, only the scalars cross PCIe each step), at every N
+    def step_e2e_reg():
+        capi.check(lib.zkg_msm_bn254_registered(handle.value, C.c_void_p(h_scal.data_ptr()), n, C.c_void_p(h_out.data_ptr())))
+        if world > 1:
+            xyzz = torch.zeros(16, dtype=torch.int64)
+            if bool((h_out[8:12] != 0).any()):
+                xyzz[0:8] = h_out[0:8]; xyzz[8:12] = one_fq; xyzz[12:16] = one_fq
+            xyzz_dev.copy_(xyzz)
+            dist.all_gather_into_tensor(gathered, xyzz_dev)
+            capi.check(lib.zkg_msm_combine_dev(ctx, 1, C.c_void_p(gathered.data_ptr()), world, C.c_void_p(out_xyz.data_ptr())))
+            e2e_result["xyz_reg"] = out_xyz.cpu().numpy().copy()
+        else:
+            e2e_result["xyz_reg"] = h_out.numpy().copy()
+    for _ in range(2):
+        step_e2e_reg()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e_reg()
+    barrier()
+    e2e_reg_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_reg_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_reg_s = float(t.item())
+    e2e_reg_ms = e2e_reg_s / e2e_steps * 1e3
+    same = same and bool((e2e_result["xyz_reg"] == dev_result).all())
     # the same two calls with PAGEABLE host buffers (a Rust Vec<F> as the reference would pass it): the
     # library stages them through its own pinned slots with parallel memcpy (csrc/staging.cu)
     e2e_pageable = None
@@ -437,6 +552,21 @@ def run_ours(args):
             same = same and bool((pg_out.view(dev_result.dtype) == dev_result).all())
         e2e_pageable = res
         del pg_bases, pg_scal
+
+    hbm_peak, hbm_how, int_peak, int_how = measured_peaks()
+
+    def dfft_roofline(m, mbyl, t1_ms, tk_ms):
+        """SURVEY.md 8(d): fft1 = 64 B and 1/2 log2(m/l) modmul per share element; king = 256 B and 25.5 modmul per domain element;
+        a modmul is charged 272 IMAD-class instructions.  Both are bound by the integer multiplier, not HBM: both fractions are stated."""
+        lg = mbyl.bit_length() - 1
+        f_int = mbyl * 0.5 * lg * 272 / (t1_ms * 1e-3) / 1e12
+        k_int = m * 25.5 * 272 / (tk_ms * 1e-3) / 1e12
+        return {"bound": "int (IMAD pipe); hbm fraction beside it",
+                "fft1": {"int_achieved_TIMAD_s": round(f_int, 3), "int_frac": round(f_int / int_peak, 4),
+                         "hbm_achieved_gbs": round(64 * mbyl / (t1_ms * 1e-3) / 1e9, 1), "hbm_frac": round(64 * mbyl / (t1_ms * 1e-3) / 1e9 / hbm_peak, 4)},
+                "king": {"int_achieved_TIMAD_s": round(k_int, 3), "int_frac": round(k_int / int_peak, 4),
+                         "hbm_achieved_gbs": round(256 * m / (tk_ms * 1e-3) / 1e9, 1), "hbm_frac": round(256 * m / (tk_ms * 1e-3) / 1e9 / hbm_peak, 4)},
+                "peaks": {"int_TIMAD_s": int_peak, "hbm_gbs": hbm_peak, "hbm_source": hbm_how}}
 
     # ---- secondary: d_fft pieces (configs[1]: m = 2^16; and the 2^20-constraint size), rank 0 only -------
     secondary = {}
@@ -471,6 +601,7 @@ def run_ours(args):
                     "d_fft_elems_per_s": round(m / ((t1 + tk) * 1e-3), 1),
                     "king_hbm_gbs": round((256 + 32) * m / (tk * 1e-3) / 1e9, 1),
                     "fft1_hbm_gbs": round(64 * mbyl / (t1 * 1e-3) / 1e9, 1),
+                    "roofline": dfft_roofline(m, mbyl, t1, tk),
                 }
                 del px, shares, rnd, outp
                 continue
@@ -509,6 +640,7 @@ def run_ours(args):
                 "king_e2e_pinned_elems_per_s": round(m / tkp, 1), "king_e2e_paths_agree": pinned_ok,
                 "king_hbm_gbs": round((256 + 32) * m / (tk * 1e-3) / 1e9, 1),
                 "fft1_hbm_gbs": round(64 * mbyl / (t1 * 1e-3) / 1e9, 1),
+                "roofline": dfft_roofline(m, mbyl, t1, tk),
             }
             del px, shares, rnd, outp
 
@@ -525,7 +657,34 @@ def run_ours(args):
         for _ in range(2):
             fg2()
         tg2 = timed(fg2, 5, collective=False) / 5
-        secondary["msm_g2_2^19"] = {"ms": round(tg2, 3), "Mpts_per_s": round(n2 / (tg2 * 1e-3) / 1e6, 2)}
+        hg2 = C.c_uint64(0)
+        capi.check(lib.zkg_bases_register_dev(ctx, 2, C.c_void_p(b2.data_ptr()), n2, C.byref(hg2)))
+        o2r = torch.zeros(24, dtype=torch.int64, device=dev)
+
+        def fg2r():
+            capi.check(lib.zkg_msm_bn254_registered_dev(ctx, hg2.value, C.c_void_p(a2.data_ptr()), n2, C.c_void_p(o2r.data_ptr()), 0))
+        for _ in range(2):
+            fg2r()
+        capi.check(lib.zkg_ctx_set_profiling(ctx, 1))
+        tg2r = timed(fg2r, 5, collective=False) / 5
+        ph2 = []
+        for ph in range(3):
+            f = C.c_float(0)
+            capi.check(lib.zkg_ctx_phase_ms(ctx, ph, C.byref(f)))
+            ph2.append(f.value)
+        capi.check(lib.zkg_ctx_set_profiling(ctx, 0))
+        capi.check(lib.zkg_bases_release(hg2.value))
+        c2_, W2_ = ark_window(n2)
+        g2_alg = n2 * 29 * W2_ * 272 / (tg2r * 1e-3) / 1e12            # 29 W modmul per point
+        secondary["msm_g2_2^19"] = {"ms": round(tg2, 3), "Mpts_per_s": round(n2 / (tg2 * 1e-3) / 1e6, 2),
+                                    "registered_ms": round(tg2r, 3), "registered_Mpts_per_s": round(n2 / (tg2r * 1e-3) / 1e6, 2),
+                                    "paths_agree": bool((o2 == o2r).all()),
+                                    "roofline": {"bound": "int (IMAD pipe)", "kernel": "k_accumulate<Fq2>",
+                                                 "algorithmic_TIMAD_s": round(g2_alg, 3), "algorithmic_frac": round(g2_alg / int_peak, 4),
+                                                 "phase_ms": {"digits_sort": round(ph2[0], 4), "accumulate": round(ph2[1], 4),
+                                                              "reduce_final": round(ph2[2], 4)},
+                                                 "hbm_frac": round(160 * n2 / (tg2r * 1e-3) / 1e9 / hbm_peak, 4),
+                                                 "note": "SURVEY 8(d) formula k*29*W*272/T with arkworks' W (registered path)"}}
         n1 = 1 << 20
         a1 = rand_fr_dev(n1)
 
@@ -573,43 +732,261 @@ def run_ours(args):
         capi.check(lib.zkg_bases_release(h24.value))
         del a24, b24
 
-    # ---- secondary: ONE king pipeline (m = 2^20) sharded over all ranks: stage 1 -> reduce-scatter -> stage 2 ----
+    # ---- multi-GPU legs (N > 1).  Every sharded result is compared with the single-GPU call on the same inputs; a mismatch
+    #      fails the run (`sharded_paths_agree`).
+    sharded_agree = {}
     if world > 1 and not args.no_secondary:
         from zksaas_b200 import sharding
-        l_, mbyl_ = 2, 1 << 19
-        dom_ = z.Radix2EvaluationDomain.new(mbyl_ * l_)
-        gen_, g_ = dom_.group_gen(), z.Radix2EvaluationDomain.new(2 * mbyl_ * l_).element(1)
-        lo_, hi_ = sharding.shard_range(mbyl_, world, rank)
-        loc_ = rand_fr_dev(8 * (hi_ - lo_)).reshape(8, hi_ - lo_, 4)
-        rl_ = rand_fr_dev((hi_ - lo_) * 2)
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
 
-        def fks():
-            sharding.king_fft2_sharded_cuda(ctx, lib, torch, dist, loc_, mbyl_, l_, gen_, g_, True, rl_, rank, world)
+        def same_seed_fr(k, seed):
+            g2_ = torch.Generator(device=dev)
+            g2_.manual_seed(seed)
+            t_ = torch.randint(-2**63, 2**63 - 1, (k, 4), dtype=torch.int64, device=dev, generator=g2_)
+            t_[:, 3] &= (1 << 61) - 1
+            return t_
+
+        def all_true(flag):
+            t_ = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+            return bool(t_.item())
+
+        # -- ONE king pipeline (m = 2^20 and 2^24) sharded by share columns: stage 1 stores into the owners' memory over NVLink
+        #    (CUDA IPC peer buffers), a 4-byte barrier, stage 2.  The round-1 path (zero-filled buffer + NCCL reduce-scatter) beside it.
+        for lg_ in (20, 24):
+            l_, mbyl_ = 2, 1 << (lg_ - 1)
+            m_ = mbyl_ * l_
+            dom_ = z.Radix2EvaluationDomain.new(m_)
+            gen_, g_ = dom_.group_gen(), z.Radix2EvaluationDomain.new(2 * m_).element(1)
+            lo_, hi_ = sharding.shard_range(mbyl_, world, rank)
+            sh_full = same_seed_fr(8 * mbyl_, 700 + lg_).reshape(8, mbyl_, 4)          # same on every rank
+            rn_full = same_seed_fr(2 * mbyl_, 800 + lg_)
+            loc_ = sh_full[:, lo_:hi_, :].contiguous()
+            rl_ = rn_full[2 * lo_:2 * hi_].contiguous()
+            ref_ = torch.empty((8, mbyl_, 4), dtype=torch.int64, device=dev)
+
+            def fk1():
+                capi.check(lib.zkg_king_fft2_bn254_dev(ctx, C.c_void_p(sh_full.data_ptr()), None, 8, mbyl_, l_, gen_.ctypes.data,
+                                                       g_.ctypes.data, 1, C.c_void_p(rn_full.data_ptr()), C.c_void_p(ref_.data_ptr())))
+            for _ in range(3):
+                fk1()
+            t_single = timed(fk1, 10, collective=False) / 10
+            peers_ = sharding.PeerBuffers(ctx, lib, dist, m_ // world * 32, rank, world)
+
+            def fks():
+                return sharding.king_fft2_sharded_cuda(ctx, lib, torch, dist, loc_, mbyl_, l_, gen_, g_, True, rl_, rank, world,
+                                                       peers=peers_, token=token)
+            for _ in range(3):
+                got_ = fks()
+            torch.cuda.synchronize()
+            agree_ = all_true(bool((got_ == ref_[:, lo_:hi_, :]).all()))
+            tks = timed(fks, 10) / 10
+            entry = {"ms": round(tks, 4), "single_gpu_ms": round(t_single, 4), "ranks": world,
+                     "elems_per_s": round(m_ / (tks * 1e-3), 1), "speedup_vs_single_gpu": round(t_single / tks, 2),
+                     "exchange": "stage-1 kernel stores over NVLink peer memory (CUDA IPC); 4-byte NCCL barrier; no data collective",
+                     "agrees_with_single_gpu": agree_}
+            if lg_ == 20:
+                def fks_rs():
+                    return sharding.king_fft2_sharded_cuda(ctx, lib, torch, dist, loc_, mbyl_, l_, gen_, g_, True, rl_, rank, world)
+                for _ in range(3):
+                    got2_ = fks_rs()
+                torch.cuda.synchronize()
+                entry["reduce_scatter_path_ms"] = round(timed(fks_rs, 10) / 10, 4)
+                entry["reduce_scatter_path_agrees"] = all_true(bool((got2_ == ref_[:, lo_:hi_, :]).all()))
+            dist.barrier()
+            peers_.close()
+            sharded_agree[f"king_m2^{lg_}"] = agree_ and entry.get("reduce_scatter_path_agrees", True)
+            if rank == 0:
+                secondary[f"king_sharded_m2^{lg_}"] = entry
+            del sh_full, rn_full, loc_, rl_, ref_
+
+        # -- ONE fft1 lane (m = 2^24, l = 2) sharded by contiguous blocks: inner NTT, twiddles fused with the peer-store all-to-all,
+        #    G-point outer transforms.  The NCCL all_to_all_single path beside it.
+        if (world & (world - 1)) == 0:
+            l_, mbyl_ = 2, 1 << 23
+            gen_ = z.Radix2EvaluationDomain.new(mbyl_ * l_).group_gen()
+            px_full = same_seed_fr(mbyl_, 900)
+            n2_ = mbyl_ // world
+            ref_ = px_full.clone()
+
+            def f1s():
+                capi.check(lib.zkg_fft1_bn254_dev(ctx, C.c_void_p(ref_.data_ptr()), mbyl_, l_, gen_.ctypes.data, None, None))
+            f1s()                                                         # ref_ = fft1(px_full)
+            torch.cuda.synchronize()
+            scratch_ = px_full.clone()
+
+            def f1t():
+                capi.check(lib.zkg_fft1_bn254_dev(ctx, C.c_void_p(scratch_.data_ptr()), mbyl_, l_, gen_.ctypes.data, None, None))
+            for _ in range(3):
+                f1t()
+            t_single = timed(f1t, 10, collective=False) / 10
+            idx_ = torch.from_numpy(sharding.fft1_sharded_index(mbyl_, world, rank)).to(dev)
+            peers_ = sharding.PeerBuffers(ctx, lib, dist, n2_ * 32, rank, world)
+            blk0_ = px_full[rank * n2_:(rank + 1) * n2_].contiguous()
+            blk_ = blk0_.clone()
+
+            def ffs():
+                return sharding.fft1_sharded_cuda(ctx, lib, torch, dist, blk_, mbyl_, l_, gen_, rank, world, peers=peers_, token=token)
+            got_ = ffs()
+            torch.cuda.synchronize()
+            agree_ = all_true(bool((got_.reshape(-1, 4) == ref_[idx_]).all()))
+            for _ in range(3):
+                ffs()
+            tfs = timed(ffs, 10) / 10
+            blk_.copy_(blk0_)
+
+            def ffs_nccl():
+                return sharding.fft1_sharded_cuda(ctx, lib, torch, dist, blk_, mbyl_, l_, gen_, rank, world)
+            got2_ = ffs_nccl()
+            torch.cuda.synchronize()
+            agree2_ = all_true(bool((got2_.reshape(-1, 4) == ref_[idx_]).all()))
+            for _ in range(3):
+                ffs_nccl()
+            tfn = timed(ffs_nccl, 10) / 10
+            dist.barrier()
+            peers_.close()
+            sharded_agree["fft1_m2^24"] = agree_ and agree2_
+            if rank == 0:
+                secondary["fft1_sharded_m2^24"] = {"ms": round(tfs, 4), "single_gpu_ms": round(t_single, 4), "ranks": world,
+                                                   "share_elems_per_s": round(mbyl_ / (tfs * 1e-3), 1),
+                                                   "speedup_vs_single_gpu": round(t_single / tfs, 2),
+                                                   "exchange": "twiddle kernel stores each chunk into the destination rank's buffer over NVLink "
+                                                               "(CUDA IPC); 4-byte NCCL barrier; no data collective",
+                                                   "agrees_with_single_gpu": agree_,
+                                                   "nccl_all_to_all_path_ms": round(tfn, 4), "nccl_all_to_all_path_agrees": agree2_}
+            del px_full, ref_, scratch_, blk_, blk0_
+
+        # -- STRONG scaling of ONE MSM (BASELINE configs[3]: "2^22-2^24 points per party sharded across 1/2/4/8"): 2^24 points in total,
+        #    rank g owns the point range [g, g+1) * 2^24 / N (registered once), partial sums -> NCCL all-gather -> add.
+        n_tot = 1 << 24
+        n_loc = n_tot // world
+        a_s, s_s = rand_fr_dev(n_loc), rand_fr_dev(n_loc)
+        b_s = torch.empty((n_loc, 64), dtype=torch.uint8, device=dev)
+        capi.check(lib.zkg_fixed_base_dev(ctx, 1, C.c_void_p(s_s.data_ptr()), n_loc, C.c_void_p(b_s.data_ptr())))
+        h_s = C.c_uint64(0)
+        capi.check(lib.zkg_bases_register_dev(ctx, 1, C.c_void_p(b_s.data_ptr()), n_loc, C.byref(h_s)))
+        o_s = torch.zeros(12, dtype=torch.int64, device=dev)
+
+        def f_strong():
+            capi.check(lib.zkg_msm_bn254_registered_dev(ctx, h_s.value, C.c_void_p(a_s.data_ptr()), n_loc, C.c_void_p(partial.data_ptr()), 1))
+            dist.all_gather_into_tensor(gathered, partial)
+            capi.check(lib.zkg_msm_combine_dev(ctx, 1, C.c_void_p(gathered.data_ptr()), world, C.c_void_p(o_s.data_ptr())))
         for _ in range(3):
-            fks()
-        tks = timed(fks, 10) / 10
+            f_strong()
+        t_strong = timed(f_strong, 10) / 10
+        parts = [None] * world
+        dist.all_gather_object(parts, mont_sum_of_products(a_s, s_s))
+        exp_s = point_of_mont_scalar(sum(parts) % R_MOD)
+        agree_ = all_true(bool((o_s.cpu().numpy().view(np.uint64)[:8] == exp_s).all()))
+        sharded_agree["msm_strong_2^24"] = agree_
+        capi.check(lib.zkg_bases_release(h_s.value))
         if rank == 0:
-            secondary["king_sharded_m2^20"] = {"ms": round(tks, 4), "ranks": world,
-                                               "elems_per_s": round(mbyl_ * l_ / (tks * 1e-3), 1),
-                                               "collective": "one NCCL reduce_scatter (sum) of the pack-order buffer"}
+            secondary["msm_g1_strong_scaling_2^24"] = {"ms": round(t_strong, 4), "ranks": world, "points_per_gpu": n_loc,
+                                                       "Mpts_per_s": round(n_tot / (t_strong * 1e-3) / 1e6, 2),
+                                                       "matches_closed_form": agree_,
+                                                       "what": "ONE 2^24-point MSM, point range split over the ranks (registered bases), 128-byte "
+                                                               "partials all-gathered over NCCL and added; compare msm_g1_2^24.registered_ms at N = 1"}
+        del a_s, s_s, b_s
 
-    # ---- secondary: ONE fft1 lane (m = 2^24, l = 2) sharded over all ranks: inner NTT -> all-to-all -> outer DFT ----
-    if world > 1 and not args.no_secondary and (world & (world - 1)) == 0:
-        from zksaas_b200 import sharding
-        l_, mbyl_ = 2, 1 << 23
-        gen_ = z.Radix2EvaluationDomain.new(mbyl_ * l_).group_gen()
-        blk_ = rand_fr_dev(mbyl_ // world)
-
-        def ffs():
-            sharding.fft1_sharded_cuda(ctx, lib, torch, dist, blk_, mbyl_, l_, gen_, rank, world)
-        for _ in range(3):
-            ffs()
-        tfs = timed(ffs, 10) / 10
+        # -- the same operations from ONE process through the device-list C-ABI entry points (what the unchanged Rust caller binds):
+        #    rank 0 drives all N GPUs with host buffers; the other ranks wait at the barrier
+        dist.barrier()
         if rank == 0:
-            secondary["fft1_sharded_m2^24"] = {"ms": round(tfs, 4), "ranks": world,
-                                               "share_elems_per_s": round(mbyl_ / (tfs * 1e-3), 1),
-                                               "collective": "one NCCL all_to_all_single of the twiddled inner transforms (m/l x 32 B in total)"}
-        del blk_
+            devs_ = (C.c_int32 * world)(*range(world))
+            one_proc = {}
+            hb_all = torch.zeros((n * world, 72), dtype=torch.uint8).pin_memory()
+            hs_all = torch.empty((n * world, 4), dtype=torch.int64).pin_memory()
+            for r_ in range(world):                                   # N copies of rank 0's inputs: N * 2^22 points in one call
+                hb_all[r_ * n:(r_ + 1) * n] = h_bases
+                hs_all[r_ * n:(r_ + 1) * n] = h_scal
+            o_all = torch.zeros(12, dtype=torch.int64).pin_memory()
+
+            def f_sp():
+                capi.check(lib.zkg_msm_bn254_g1_sharded(devs_, world, C.c_void_p(hb_all.data_ptr()), 72, n * world,
+                                                        C.c_void_p(hs_all.data_ptr()), n * world, C.c_void_p(o_all.data_ptr())))
+            f_sp(); f_sp()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                f_sp()
+            t_sp = (time.perf_counter() - t0) / 3
+            exp_sp = point_of_mont_scalar(t_local * world % R_MOD)      # N copies of the same (a, s): N * sum a_i s_i
+            ok_sp = bool((o_all.numpy().view(np.uint64)[:8] == exp_sp).all())
+            one_proc["msm_g1_sharded"] = {"points": n * world, "ms": round(t_sp * 1e3, 3), "Mpts_per_s": round(n * world / t_sp / 1e6, 2),
+                                          "h2d_bytes": n * world * 104, "matches_closed_form": ok_sp,
+                                          "call": "zkg_msm_bn254_g1_sharded(devices[0..N), host pointers, pinned): every GPU's slice crosses its own PCIe link"}
+            hh_ = C.c_uint64(0)
+            capi.check(lib.zkg_bases_register_sharded(devs_, world, 1, C.c_void_p(hb_all.data_ptr()), 72, n * world, C.byref(hh_)))
+
+            def f_spr():
+                capi.check(lib.zkg_msm_bn254_registered(hh_.value, C.c_void_p(hs_all.data_ptr()), n * world, C.c_void_p(o_all.data_ptr())))
+            f_spr(); f_spr()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                f_spr()
+            t_spr = (time.perf_counter() - t0) / 3
+            ok_spr = bool((o_all.numpy().view(np.uint64)[:8] == exp_sp).all())
+            capi.check(lib.zkg_bases_release(hh_.value))
+            one_proc["msm_g1_registered_sharded"] = {"points": n * world, "ms": round(t_spr * 1e3, 3),
+                                                     "Mpts_per_s": round(n * world / t_spr / 1e6, 2), "h2d_bytes": n * world * 32,
+                                                     "matches_closed_form": ok_spr,
+                                                     "call": "zkg_bases_register_sharded + zkg_msm_bn254_registered (host scalars)"}
+            sharded_agree["one_process_msm"] = ok_sp and ok_spr
+            del hb_all, hs_all
+            # king closure and fft1 through the device-list entry points, m = 2^20, against the single-device entry points
+            l_, mbyl_ = 2, 1 << 19
+            dom_ = z.Radix2EvaluationDomain.new(mbyl_ * l_)
+            gen_, g_ = dom_.group_gen(), z.Radix2EvaluationDomain.new(2 * mbyl_ * l_).element(1)
+            pin_in = same_seed_fr(8 * mbyl_, 1700).reshape(8, mbyl_, 4).cpu().pin_memory()
+            pin_rnd = same_seed_fr(2 * mbyl_, 1800).cpu().pin_memory()
+            pin_out = torch.empty((2, 8, mbyl_, 4), dtype=torch.int64).pin_memory()
+            u64p_ = C.POINTER(C.c_uint64)
+            in_arr = (u64p_ * 8)(*[C.cast(pin_in[p_].data_ptr(), u64p_) for p_ in range(8)])
+            out_arr = [(u64p_ * 8)(*[C.cast(pin_out[k_][p_].data_ptr(), u64p_) for p_ in range(8)]) for k_ in range(2)]
+
+            def fk_sp():
+                capi.check(lib.zkg_king_fft2_bn254_sharded(devs_, world, in_arr, None, 8, mbyl_, l_, gen_.ctypes.data, g_.ctypes.data, 1,
+                                                           C.c_void_p(pin_rnd.data_ptr()), out_arr[0]))
+
+            def fk_1():
+                capi.check(lib.zkg_king_fft2_bn254(0, in_arr, None, 8, mbyl_, l_, gen_.ctypes.data, g_.ctypes.data, 1,
+                                                   C.c_void_p(pin_rnd.data_ptr()), out_arr[1]))
+            res_ = {}
+            for name_, fn_ in (("sharded", fk_sp), ("single", fk_1)):
+                fn_(); fn_()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    fn_()
+                res_[name_] = (time.perf_counter() - t0) / 3
+            ok_k = bool((pin_out[0] == pin_out[1]).all())
+            one_proc["king_fft2_sharded_m2^20"] = {"ms": round(res_["sharded"] * 1e3, 3), "single_device_ms": round(res_["single"] * 1e3, 3),
+                                                   "agrees_with_single_device": ok_k, "host_bytes": 2 * 8 * mbyl_ * 32 + 2 * mbyl_ * 32,
+                                                   "call": "zkg_king_fft2_bn254_sharded (host pointers, pinned)"}
+            px_a = same_seed_fr(mbyl_ * 8, 1900).cpu().pin_memory()      # a lane of 2^22 shares
+            px_b = px_a.clone().pin_memory()
+            gen8_ = z.Radix2EvaluationDomain.new(mbyl_ * 8 * l_).group_gen()
+            t0 = time.perf_counter()
+            capi.check(lib.zkg_fft1_bn254_sharded(devs_, world, C.c_void_p(px_a.data_ptr()), mbyl_ * 8, l_, gen8_.ctypes.data, None, None))
+            t_f_sp = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            capi.check(lib.zkg_fft1_bn254(0, C.c_void_p(px_b.data_ptr()), mbyl_ * 8, l_, gen8_.ctypes.data, None, None))
+            t_f_1 = time.perf_counter() - t0
+            ok_f = bool((px_a == px_b).all())
+            one_proc["fft1_sharded_lane2^22"] = {"ms_first_call": round(t_f_sp * 1e3, 3), "single_device_ms_first_call": round(t_f_1 * 1e3, 3),
+                                                 "agrees_with_single_device": ok_f, "call": "zkg_fft1_bn254_sharded (host pointers, pinned)"}
+            sharded_agree["one_process_king"] = ok_k
+            sharded_agree["one_process_fft1"] = ok_f
+            secondary["one_process_device_list"] = one_proc
+            del pin_in, pin_rnd, pin_out, px_a, px_b
+        dist.barrier()
+        flags = [None] * world
+        dist.all_gather_object(flags, sharded_agree)
+        merged = {}
+        for f_ in flags:
+            for k_, v_ in f_.items():
+                merged[k_] = merged.get(k_, True) and bool(v_)
+        sharded_agree = merged
+        if not all(sharded_agree.values()):
+            raise SystemExit(f"bench.py: a sharded path disagrees with the single-GPU result: {sharded_agree}")
 
     # ---- secondary: the SURVEY 8(f) rows built so far, through their host-pointer entry points (PCIe included) ----
     if rank == 0 and not args.no_secondary:
@@ -668,8 +1045,8 @@ def run_ours(args):
     # groth16/src/proving_key.rs:125-176): per party circom_h = 3 d_ifft + 3 d_fft + deg_red (ext_wit.rs:104-181) then
     # 5 d_msm (prove.rs:52,106,154,209,219).  Parties are dealt round-robin to the ranks; the king closures run on rank 0.
     # Device-resident, network excluded; correctness of this dataflow is pinned in tests/test_gpu_protocol.py.
-    if not args.no_secondary and not args.no_prove:
-        lg_m, l_ = 20, 2
+    for lg_m in ((15, 20) if (not args.no_secondary and not args.no_prove) else ()):
+        l_ = 2
         m_ = 1 << lg_m
         mbyl_ = m_ // l_
         dom_ = z.Radix2EvaluationDomain.new(m_)
@@ -719,8 +1096,8 @@ def run_ours(args):
                 for _ in range(3):
                     capi.check(lib.zkg_king_fft2_bn254_dev(ctx, P(kin), None, 8, mbyl_, l_, gen_f.ctypes.data, one_.ctypes.data, 0, P(krand), P(kout)))
             for _p in my_parties:                                   # h = a*b - c on shares, then deg_red
-                capi.check(lib.zkg_field_op_dev(ctx, 0, 0, P(va), P(vb), P(hbuf), mbyl_))
-                capi.check(lib.zkg_field_op_dev(ctx, 0, 2, P(hbuf), P(vc), P(hbuf), mbyl_))
+                # h = (a + out_mask_a)(b + out_mask_b) - (c + out_mask_c): ext_wit.rs:173-177 fused with dfft/mod.rs:313-317
+                capi.check(lib.zkg_qap_h_bn254_dev(ctx, P(va), P(vb), P(vc), P(mask), P(mask), P(mask), None, P(hbuf), mbyl_))
             if rank == 0:
                 capi.check(lib.zkg_deg_red_king_bn254_dev(ctx, P(kin), None, 8, mbyl_, l_, P(krand), P(kout)))
             for st_, _, _ in lanes:                                 # 5 d_msm local MSMs against the registered CRS shares
@@ -741,45 +1118,70 @@ def run_ours(args):
         for _, cx_, _ in lanes:
             lib.zkg_ctx_destroy(cx_)
         if rank == 0:
-            secondary["groth16_prove_emulated_m2^20"] = {
+            secondary[f"groth16_prove_emulated_m2^{lg_m}"] = {
                 "prove_sec": round(t_prove * 1e-3, 5), "parties": 8, "ranks": world, "l": 2,
                 "msm_streams": n_lanes,
-                "what": "6 client fft1 + 5 registered MSMs (S,H,W: 2^19 G1; U: 2^20 G1; V: 2^19 G2) per party, 6 king d_fft "
-                        "closures + 1 deg_red king on rank 0; device-resident, network and pairing check excluded"}
+                "what": f"6 client fft1 + fused h + 5 registered MSMs (S,H,W: 2^{lg_m - 1} G1; U: 2^{lg_m} G1; V: 2^{lg_m - 1} G2) per party, "
+                        "6 king d_fft closures + 1 deg_red king on rank 0; device-resident, network and pairing check excluded"
+                        + ("; BASELINE configs[2] size (sha256 circuit, m ~ 2^15)" if lg_m == 15 else "; BASELINE configs[4] size")}
         del va, vb, vc, mask, hbuf, kin, kout, krand
 
     if rank == 0:
-        hbm_peak, hbm_how, int_peak, int_how = measured_peaks()
         c_ark, W_ark = ark_window(n)
         imad_per_point = 11 * W_ark * 272                        # 11*W modmul x 272 IMAD-class instructions
-        achieved = n * imad_per_point / (acc_ms * 1e-3) / 1e12
-        my_c = int(os.environ.get("ZKG_MSM_PREP_C", "0")) or {19: 20, 20: 20, 21: 20, 22: 20, 23: 20, 24: 20}.get(args.log2n, 20)
+        alg_rate = n * imad_per_point / (acc_ms * 1e-3) / 1e12
+        my_c = int(os.environ.get("ZKG_MSM_PREP_C", "0")) or 20
         my_W = 254 // my_c + 1
         wide_rate = n * my_W * WIDE_MADS_PER_MADD / (acc_ms * 1e-3) / 1e12   # 32x32->64 multiply-adds the kernel actually executes
+        cpu_extra = {}
         if not args.no_cpu and not args.no_secondary:
             secondary["cpu_d_fft_m2^16"] = cpu_dfft_sample(16)
-        cpu_n, cpu_th, cpu_t = cpu_msm_sample(18, 3) if not args.no_cpu else (0, 0, [1.0])
+            secondary["cpu_d_fft_m2^20"] = cpu_dfft_sample(20)
+            if not args.no_prove:
+                secondary["cpu_groth16_prove_emulated_m2^15"] = cpu_prove_sample(15)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as ol_
+            o_ = ol_.oracle()
+            rg_ = np.random.default_rng(2)
+            ng_ = 1 << 15
+            bg_ = np.zeros((ng_, 136), dtype=np.uint8)
+            o_.zko_g2_fixed_base(ol_._p(ol_.rand_fr(rg_, 64)[np.arange(ng_) % 64].copy()), ng_, bg_.ctypes.data, 136)
+            sg_ = ol_.rand_fr(rg_, 256)[np.arange(ng_) % 256].copy()
+            sg_[:, 0] ^= np.arange(ng_, dtype=np.uint64)
+            thg_ = max(1, min(host_threads(), ark_window(ng_)[1]))
+            t0 = time.perf_counter()
+            ol_.o_g2_msm(bg_, sg_, threads=thg_)
+            tg_ = time.perf_counter() - t0
+            secondary["cpu_msm_g2_2^15"] = {"Mpts_per_s": round(ng_ / tg_ / 1e6, 4), "cores": thg_, "kind": "port",
+                                            "sample": "G2 MSM of 2^15 points, one run, oracle port, OpenMP over windows"}
+        cpu_n, cpu_th, cpu_t = cpu_msm_sample(20, 2) if not args.no_cpu else (0, 0, [1.0])
         cpu_val = cpu_n / min(cpu_t) / 1e6
+        cfg = workload_config(args.log2n, world)
+        cfg.update({"l2_policy": "inputs larger than L2 (scalars 128 MiB per step + 13 x 256 MiB window-shifted base table at 2^22)",
+                    "timed_region": "K registered-base MSMs back to back on one stream, CUDA events, max over ranks"})
         line = {
             "metric": "BN254 G1 MSM Mpts/s", "value": round(value, 2), "unit": "Mpts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (8x32-bit Montgomery limbs, IMAD.WIDE)", "data": "synthetic",
-            "config": {"workload": f"d_msm local G1 MSM (dist-primitives/src/dmsm/mod.rs:73), BN254, 2^{args.log2n} points per GPU",
-                       "points_per_gpu": n, "total_points": n * world, "curve": "BN254 G1", "l": 2,
-                       "bases": "registered once (zkg_bases_register_dev: window-shifted table, W copies per base, "
-                                f"{register_s:.2f} s one-time); the e2e leg re-ships unregistered bases every step",
-                       "window_bits": my_c, "windows": my_W,
-                       "l2_policy": "inputs larger than L2 (bases 256 MiB + scalars 128 MiB per step at 2^22)",
-                       "multi_gpu": "point-range sharding; one NCCL all-gather of 128 B partial sums + device add",
-                       "rank_cpu_affinity": affinity},
+            "config": cfg,
+            "impl_config": {"bases": "registered once (zkg_bases_register_dev: window-shifted table, W copies per base, "
+                                     f"{register_s:.2f} s one-time); the e2e leg re-ships unregistered bases every step",
+                            "window_bits": my_c, "windows": my_W,
+                            "multi_gpu": "point-range sharding; one NCCL all-gather of 128 B partial sums + device add",
+                            "rank_cpu_affinity": affinity},
+            "result_matches_closed_form": closed_form_ok,
+            "sharded_paths_agree": (all(sharded_agree.values()) if sharded_agree else None),
+            "sharded_paths_checked": sharded_agree or None,
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 2), "unit": "Mpts/s", "h2d_bytes_per_step": n * (72 + 32),
                     "d2h_bytes_per_step": 96, "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3),
                     "call": "zkg_msm_bn254_g1 (host pointers, pinned; arkworks 72-B affine images + Fr images)",
                     "matches_device_leg": same,
-                    "registered_bases_ms_per_step": round(e2e_reg_ms, 3) if e2e_reg_ms else None,
-                    "registered_bases_Mpts_per_s": round(n / (e2e_reg_ms * 1e-3) / 1e6, 2) if e2e_reg_ms else None,
+                    "registered_bases_ms_per_step": round(e2e_reg_ms, 3),
+                    "registered_bases_Mpts_per_s": round(n * world / (e2e_reg_ms * 1e-3) / 1e6, 2),
+                    "registered_bases_h2d_bytes_per_step": n * 32,
+                    "registered_bases_call": "zkg_msm_bn254_registered (host scalars, pinned; CRS share registered once)",
                     "pageable_host_buffers": e2e_pageable},
             "value_two_streams": {"Mpts_per_s": round(n / (two_stream_ms * 1e-3) / 1e6, 2), "ms_per_step": round(two_stream_ms, 4),
                                   "what": "same K registered MSMs alternating over two contexts/streams (tail of one overlaps "
@@ -789,29 +1191,33 @@ def run_ours(args):
                                  "matches": unprepared_same} if unprepared_ms else None,
             "gpu_launches": int(launches1.value - launches0.value),
             "roofline": {"bound": "int (fmaheavy integer multiply-add pipe; not hbm, not tensor)", "kernel": "k_accumulate<Fq>",
-                         "achieved": round(achieved, 3), "peak": int_peak, "unit": "TIMAD/s",
-                         "frac": round(achieved / int_peak, 4), "peak_source": int_how,
-                         "algorithmic_imad_per_point": imad_per_point,
-                         "note": "SURVEY 8(d) formula k*11*W*272/T with arkworks' W; frac exceeds 1 because the kernel does less "
-                                 "work than the formula charges: 13 windows instead of 15 (prepared table), and an XYZZ mixed "
-                                 "add of 1160 wide multiply-adds (6 products, 2 squarings of 100, one 2-term inner product) "
-                                 "where arkworks' Jacobian madd is 11 products of 128",
-                         "executed_wide_mad_T_per_s": round(wide_rate, 3), "wide_mad_peak_T_per_s": WIDE_MAD_PEAK_T,
-                         "wide_mad_frac": round(wide_rate / WIDE_MAD_PEAK_T, 4),
-                         "wide_mad_note": "the binding unit: IMAD.WIDE.U32 issues at half the 32-bit IMAD rate in every form "
-                                          "(tools/microbench/widemad.cu), so a 254-bit Montgomery product is 128 of them at best",
+                         "achieved": round(wide_rate, 3), "peak": WIDE_MAD_PEAK_T, "unit": "T wide-MAD/s (IMAD.WIDE.U32 executed)",
+                         "frac": round(wide_rate / WIDE_MAD_PEAK_T, 4),
+                         "peak_source": "measured: tools/microbench/widemad.cu -> profiles/r01_widemad_microbench.json (= 148 SMs x 32 lanes x 1.965 GHz); "
+                                        "MEASURED_PEAKS.json has no integer-pipe figure",
+                         "what": "EXECUTED work: points x windows x 1160 wide multiply-adds per XYZZ mixed add (6 products of 128, 2 squarings of 100, "
+                                 "one 2-term inner product of 192) / kernel time; the kernel time comes from CUDA events the library records "
+                                 "around k_accumulate inside the timed region",
+                         "algorithmic_achieved_TIMAD_s": round(alg_rate, 3), "algorithmic_peak_TIMAD_s": int_peak,
+                         "algorithmic_frac": round(alg_rate / int_peak, 4), "algorithmic_imad_per_point": imad_per_point,
+                         "algorithmic_note": "SURVEY 8(d) formula k*11*W*272/T with arkworks' W = 15 against the 32-bit IMAD issue rate; exceeds the "
+                                             "executed fraction because the kernel does less work than the formula charges (13 windows, 1160 wide "
+                                             "MADs per add instead of 11 x 136 limb-MACs)",
                          "kernel_ms": round(acc_ms, 4),
                          "kernel_share_of_step": round(acc_ms / ms_per_step, 4),
                          "phase_ms": {"digits_sort": round(sort_ms, 4), "accumulate": round(acc_ms, 4),
                                       "reduce_final": round(red_ms, 4),
-                                      "note": "CUDA events around the phases of one un-pipelined call; the two launch-heavy "
-                                              "phases include host launch latency (visible when N ranks share the host cores)"},
+                                      "note": "CUDA events recorded by the library at the phase boundaries of the LAST call of the timed, "
+                                              "pipelined region (the GPU is never idle there, so host launch latency is not in them)"},
                          "hbm": {"achieved_gbs": round(96 * n / (acc_ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
                                  "frac": round(96 * n / (acc_ms * 1e-3) / 1e9 / hbm_peak, 4), "peak_source": hbm_how},
                          "traffic": ACC_TRAFFIC_BYTES if args.log2n == 22 else None,
-                         "traffic_note": "ncu dram bytes per launch; 18x the 96 B/point because Pippenger gathers every base once per window (13 gathers that each pull 128 B) -- 0.92 TB/s, 14% of HBM peak, not the bound"},
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch from an ncu --set full capture "
+                                         "(profiles/, not measured in this run); ~18x the 96 B/point because Pippenger gathers every base once per "
+                                         "window (13 gathers that each pull 128 B) -- under 1 TB/s, not the bound"},
             "cpu_baseline": {"value": round(cpu_val, 4), "unit": "Mpts/s", "cores": cpu_th, "kind": "port",
-                             "sample": "G1 MSM of 2^18 points, best of 3, oracle/zkoracle.c (arkworks msm_bigint_wnaf restated), OpenMP over windows"},
+                             "sample": "G1 MSM of 2^20 points (a quarter of the workload), best of 2, oracle/zkoracle.c (arkworks msm_bigint_wnaf "
+                                       "restated), OpenMP over the windows; the full 2^22 workload is what --impl reference times"},
             "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
