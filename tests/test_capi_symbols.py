@@ -71,3 +71,43 @@ def test_host_mirror_argument_checks():
     assert pow(w, 1024, R_MOD) == 1 and pow(w, 512, R_MOD) != 1
     assert fr_value(dom.size_inv()) * 1024 % R_MOD == 1
     assert fr_value(fr_image(R_MOD - 5)) == R_MOD - 5
+
+
+def _c_prototypes():
+    """name -> number of parameters, from the header."""
+    text = open(os.path.join(ROOT, "include", "zksaas_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(zkg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_rust_crate_binds_only_exported_symbols():
+    """rust/zksaas-gpu-sys/src/lib.rs cannot be compiled here (no cargo); keep it honest mechanically: every extern fn
+    it declares exists in the header with the same parameter count, and is exported by the built library."""
+    import zksaas_b200
+    src = open(os.path.join(ROOT, "rust", "zksaas-gpu-sys", "src", "lib.rs")).read()
+    block = src[src.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    block = re.sub(r"//[^\n]*", "", block)
+    protos = _c_prototypes()
+    lib = C.CDLL(zksaas_b200.lib_path())
+    found = re.findall(r"pub fn (zkg_[a-z0-9_]+)\s*\(([^;]*?)\)\s*(?:->\s*[^;]+)?;", block, flags=re.S)
+    assert len(found) >= 35
+    for name, args in found:
+        assert name in protos, f"{name} bound by the Rust crate but not declared in the header"
+        n_args = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
+        assert n_args == protos[name], f"{name}: Rust declares {n_args} parameters, the header {protos[name]}"
+        assert hasattr(lib, name)
+    # every host-pointer entry point of the header is bound (the `_dev` / ctx ones are for device-resident callers)
+    host_api = {s for s in protos if not s.endswith("_dev") and not s.startswith(("zkg_ctx_", "zkg_shared_")) and s not in
+                ("zkg_field_op",)}
+    assert host_api <= {name for name, _ in found}, sorted(host_api - {name for name, _ in found})
+    # the patch touches the five functions it claims to
+    patch = open(os.path.join(ROOT, "rust", "patches", "zk-saas-gpu.patch")).read()
+    for f in ("dmsm/mod.rs", "dfft/mod.rs", "utils/deg_red.rs"):
+        assert f in patch
+    for sym in ("msm_g1_sharded", "zkg_fft1_bn254_sharded", "king_fft2", "zkg_deg_red_king_bn254", "dmsm_king_g1"):
+        assert sym in patch and sym in src

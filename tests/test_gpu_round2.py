@@ -48,8 +48,8 @@ def _scale_jacobian(xyz, lam, g2):
 # ---------------------------------------------------------------------------------------------------
 # king side of d_msm
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("g2", [False, True])
-@pytest.mark.parametrize("l,dropouts", [(2, ()), (2, (7,)), (2, (3,)), (4, ()), (4, (15,)), (4, (0,))])
+@pytest.mark.parametrize("g2,l,dropouts", [(False, 2, ()), (False, 2, (7,)), (False, 2, (3,)), (True, 2, ()), (True, 2, (0,)),
+                                           (False, 4, (15,)), (True, 4, ())])       # l = 4: 16 shares, slow in the big-int model
 def test_pss_unpack2_group_vs_oracle(z, g2, l, dropouts):
     """unpack_missing_shares over points == the packed secrets; the sum is what d_msm's king replicates."""
     rng = random.Random(100 * l + len(dropouts) + g2)

@@ -10,6 +10,10 @@
 //           halves moved to the integer side and accumulated with 64-bit adds (what a 52-bit-limb
 //           multiplier executes per limb product: 2 DFMA + 1 DADD + 2 x 64-bit integer add)
 //   mode 4  DMUL alone; mode 5 DADD alone (do the three FP64 ops share one pipe at one rate?)
+//   k_mix<NW, NL>  the hybrid question: per step NW carry-chained wide MADs (a CIOS row is 8 of them) next to NL Emmart limb
+//           products, reported as 254-bit Montgomery products per second if a product were made of 128 wide MADs (the integer
+//           multiplier of fp.cuh) or 55 limb products (5 x 5 + 5 x (5 + 1) of a 52-bit-limb multiplier):
+//           equivalent = wide_mads / 128 + limb_products / 55.  NL = 0 is the integer multiplier alone.
 // The SASS of every mode is checked with cuobjdump (DFMA / IMAD.WIDE.U32 counts per loop body).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/dfma tools/microbench/dfma.cu && /tmp/dfma
 #include <cstdio>
@@ -59,6 +63,49 @@ __global__ void k_dfma(double* out, double a, double b, uint32_t ia, int iters) 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+template <int NW, int NL>
+__global__ void k_mix(double* out, double a, double b, uint32_t ia, int iters) {
+    uint32_t lo[8], hi[8], m = ia | 1u;
+    double x[4];
+    unsigned long long acc[4];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { lo[c] = threadIdx.x * 7 + c + ia; hi[c] = threadIdx.x * 3 + c + 11; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { x[c] = a + (double)(threadIdx.x * 4 + c) * 1e-9; acc[c] = c; }
+    const double c1 = 4503599627370496.0 * 4503599627370496.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // NW wide MADs as carry chains of 8 (one CIOS row each)
+#pragma unroll
+            for (int r = 0; r < NW / 8; ++r) {
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[0]), "+r"(hi[0]) : "r"(m), "r"(hi[7]));
+#pragma unroll
+                for (int c = 1; c < 8; ++c)
+                    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[c]), "+r"(hi[c]) : "r"(m), "r"(hi[c - 1]));
+                m = lo[7] ^ hi[3];
+            }
+#pragma unroll
+            for (int q = 0; q < NL; ++q) {
+                const int c = q & 3;
+                double h, l, sub;
+                asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(h) : "d"(x[c]), "d"(b), "d"(c1));
+                asm volatile("sub.rn.f64 %0, %1, %2;" : "=d"(sub) : "d"(c1), "d"(h));
+                asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(l) : "d"(x[c]), "d"(b), "d"(sub));
+                acc[c] += (unsigned long long)__double_as_longlong(h);
+                acc[c] += (unsigned long long)__double_as_longlong(l);
+                x[c] = __longlong_as_double((long long)((acc[c] & 0x000fffffffffffffull) | 0x4330000000000000ull));
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += (double)(lo[c] ^ hi[c]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s += x[c] + (double)acc[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s + (double)m;
+}
+
 template <class K>
 static float time_ms(K launch, int reps = 5) {
     cudaEvent_t e0, e1;
@@ -91,6 +138,14 @@ int main() {
     ms = time_ms([&] { k_dfma<3><<<blocks, threads>>>(d, 1.0000001, 0.9999999, 3, iters); }); printf(", \"emmart_limb_products_Tops\": %.3f", base / ms / 1e9);
     ms = time_ms([&] { k_dfma<4><<<blocks, threads>>>(d, 1.0000001, 0.9999999, 3, iters); }); printf(", \"dmul_alone_Tops\": %.3f", base / ms / 1e9);
     ms = time_ms([&] { k_dfma<5><<<blocks, threads>>>(d, 1.0000001, 0.9999999, 3, iters); }); printf(", \"dadd_alone_Tops\": %.3f", base / ms / 1e9);
+    {
+        const double steps = (double)blocks * threads * iters * 4.0;
+#define MIX(NW, NL)                                                                                              \
+        ms = time_ms([&] { k_mix<NW, NL><<<blocks, threads>>>(d, 1.0000001, 0.9999999, 3, iters); });               \
+        printf(", \"mix_%dw_%dl_Gmodmul_equiv\": %.2f", NW, NL, steps * ((NW) / 128.0 + (NL) / 55.0) / ms / 1e6);
+        MIX(32, 0) MIX(32, 1) MIX(32, 2) MIX(32, 4) MIX(32, 8) MIX(16, 8) MIX(0, 8)
+#undef MIX
+    }
     cudaError_t e = cudaDeviceSynchronize();
     printf(", \"cuda_status\": \"%s\"}\n", cudaGetErrorString(e));
     return 0;
