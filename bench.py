@@ -964,14 +964,19 @@ def run_ours(args):
             px_a = same_seed_fr(mbyl_ * 8, 1900).cpu().pin_memory()      # a lane of 2^22 shares
             px_b = px_a.clone().pin_memory()
             gen8_ = z.Radix2EvaluationDomain.new(mbyl_ * 8 * l_).group_gen()
-            t0 = time.perf_counter()
+            px_a0 = px_a.clone()
             capi.check(lib.zkg_fft1_bn254_sharded(devs_, world, C.c_void_p(px_a.data_ptr()), mbyl_ * 8, l_, gen8_.ctypes.data, None, None))
-            t_f_sp = time.perf_counter() - t0
-            t0 = time.perf_counter()
             capi.check(lib.zkg_fft1_bn254(0, C.c_void_p(px_b.data_ptr()), mbyl_ * 8, l_, gen8_.ctypes.data, None, None))
+            px_w = px_a0.clone().pin_memory()                            # second call (peer access and tables set up): timed
+            t0 = time.perf_counter()
+            capi.check(lib.zkg_fft1_bn254_sharded(devs_, world, C.c_void_p(px_w.data_ptr()), mbyl_ * 8, l_, gen8_.ctypes.data, None, None))
+            t_f_sp = time.perf_counter() - t0
+            px_w.copy_(px_a0)
+            t0 = time.perf_counter()
+            capi.check(lib.zkg_fft1_bn254(0, C.c_void_p(px_w.data_ptr()), mbyl_ * 8, l_, gen8_.ctypes.data, None, None))
             t_f_1 = time.perf_counter() - t0
             ok_f = bool((px_a == px_b).all())
-            one_proc["fft1_sharded_lane2^22"] = {"ms_first_call": round(t_f_sp * 1e3, 3), "single_device_ms_first_call": round(t_f_1 * 1e3, 3),
+            one_proc["fft1_sharded_lane2^22"] = {"ms": round(t_f_sp * 1e3, 3), "single_device_ms": round(t_f_1 * 1e3, 3),
                                                  "agrees_with_single_device": ok_f, "call": "zkg_fft1_bn254_sharded (host pointers, pinned)"}
             sharded_agree["one_process_king"] = ok_k
             sharded_agree["one_process_fft1"] = ok_f

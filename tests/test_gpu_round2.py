@@ -266,7 +266,7 @@ def _special_case_inputs(o, g2, n, seed):
 
 
 @pytest.mark.parametrize("g2", [False, True])
-@pytest.mark.parametrize("env_name,env_val", [("ZKG_MSM_BA", "1"), ("ZKG_MSM_COOP_TAIL", "0")])
+@pytest.mark.parametrize("env_name,env_val", [("ZKG_MSM_BA", "1"), ("ZKG_MSM_COOP_TAIL", "0"), ("ZKG_MSM_G2_PAIR", "1"), ("ZKG_MSM_G2_PAIR", "0")])
 @pytest.mark.parametrize("n", [700, 1 << 13])
 def test_optin_msm_kernels_special_cases(z, monkeypatch, g2, env_name, env_val, n):
     o = ol.oracle()

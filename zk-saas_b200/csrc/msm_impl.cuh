@@ -458,6 +458,159 @@ k_accumulate_ba(const Affine<F>* __restrict__ bases, const uint32_t* __restrict_
     store_vec(buckets + slot, acc);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// G2 bucket accumulation on LANE PAIRS (round 2).  One thread per G2 bucket holds 4 x Fq2 of accumulator + an Fq2 point =
+// 96 registers of data before any temporary: k_accumulate<Fq2> needs 168 registers, three blocks per SM, a 1.1 KB stack,
+// and runs its Fq2 routines out of line.  Here two adjacent lanes share a bucket and lane r holds
+// component c_r of every Fq2 value, so the per-lane state is that of the G1 kernel and everything is inlined Fq code:
+//   (a0 + a1 u)(b0 + b1 u):  lane 0 forms a0 b0 - a1 b1, lane 1 forms a0 b1 + a1 b0, each as ONE two-term Montgomery
+//   inner product (fp_dot<2>: 192 wide MADs per lane -- the 384 of a Karatsuba product, split in two) after fetching
+//   the partner's halves with 16 shuffles;  squaring: lane 0 (a0+a1)(a0-a1), lane 1 2 a0 a1 (128 each);
+//   a b - c d: one four-term inner product per lane (320).
+// Same wide-MAD count as the single-thread formulas, half the registers per thread, twice the threads.
+// Control flow is kept WARP-UNIFORM: the bucket loop runs to the longest bucket of the warp (slots are ordered by population, so
+// the 16 buckets of a warp have nearly equal lengths) with finished pairs predicated off, and the special cases of the addition
+// (identity operands, P = Q, P = -Q) are resolved by selects -- a pair that diverged around a shuffle would split the warp for
+// the rest of the loop (measured: 3x slower).  The rare P = +-Q case takes a warp-uniform branch (__any_sync) in which every
+// lane evaluates the doubling and only the affected pair keeps it.
+struct PairLane {
+    bool r;             // false: holds c0, true: holds c1
+};
+static constexpr uint32_t PAIR_FULL = 0xffffffffu;
+__device__ __forceinline__ Fq pair_swap(const Fq& a) {
+    Fq o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = __shfl_xor_sync(PAIR_FULL, a.v[i], 1);
+    return o;
+}
+__device__ __forceinline__ Fq pair_sel(bool c, const Fq& a, const Fq& b) {
+    Fq o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = c ? a.v[i] : b.v[i];
+    return o;
+}
+// both lanes: is the Fq2 value zero?  (the shuffle is executed unconditionally)
+__device__ __forceinline__ bool pair_is_zero(const Fq& a) {
+    const uint32_t own = a.is_zero() ? 1u : 0u;
+    const uint32_t other = __shfl_xor_sync(PAIR_FULL, own, 1);
+    return (own & other) != 0;
+}
+__device__ __forceinline__ Fq pair_mul(const PairLane& L, const Fq& ao, const Fq& bo) {
+    const Fq ap = pair_swap(ao), bp = pair_swap(bo);
+    Fq x[2] = {ao, pair_sel(L.r, ap, fp_neg(ap))};
+    Fq y[2] = {pair_sel(L.r, bp, bo), pair_sel(L.r, bo, bp)};
+    return fp_dot<FqParams, 2>(x, y);
+}
+__device__ __forceinline__ Fq pair_sqr(const PairLane& L, const Fq& ao) {
+    const Fq ap = pair_swap(ao);
+    Fq m = fp_mul(pair_sel(L.r, ao, fp_add(ao, ap)), pair_sel(L.r, ap, fp_sub(ao, ap)));
+    return pair_sel(L.r, fp_dbl(m), m);
+}
+// a b - c d
+__device__ __forceinline__ Fq pair_mulsub(const PairLane& L, const Fq& ao, const Fq& bo, const Fq& co, const Fq& d_o) {
+    const Fq ap = pair_swap(ao), bp = pair_swap(bo), cp = pair_swap(co), dp = pair_swap(d_o);
+    const Fq nco = fp_neg(co);
+    // lane 0:  a0 b0 - a1 b1 - c0 d0 + c1 d1      lane 1 (own = index 1):  a0 b1 + a1 b0 - c0 d1 - c1 d0
+    Fq x[4] = {pair_sel(L.r, ap, ao), pair_sel(L.r, ao, fp_neg(ap)), pair_sel(L.r, fp_neg(cp), nco), pair_sel(L.r, nco, cp)};
+    Fq y[4] = {bo, bp, d_o, dp};
+    return fp_dot<FqParams, 4>(x, y);
+}
+// one() of Fq2 as seen by this lane: (R, 0)
+__device__ __forceinline__ Fq pair_one(const PairLane& L) { return pair_sel(L.r, Fq::zero(), Fq::one()); }
+
+struct PairXYZZ { Fq x, y, zz, zzz; };       // this lane's halves
+__device__ __forceinline__ PairXYZZ pair_sel(bool c, const PairXYZZ& a, const PairXYZZ& b) {
+    PairXYZZ o;
+    o.x = pair_sel(c, a.x, b.x); o.y = pair_sel(c, a.y, b.y); o.zz = pair_sel(c, a.zz, b.zz); o.zzz = pair_sel(c, a.zzz, b.zzz);
+    return o;
+}
+
+// 2 * (affine p)     (mdbl-2008-s-1, a = 0), pair form of xyzz_dbl_affine; out of line: rare
+static __device__ __noinline__ PairXYZZ pair_dbl_affine(bool r, const Fq& px, const Fq& py) {
+    PairLane L; L.r = r;
+    PairXYZZ o;
+    Fq u = fp_dbl(py);
+    Fq v = pair_sqr(L, u);
+    Fq w = pair_mul(L, u, v);
+    Fq s_ = pair_mul(L, px, v);
+    Fq xx = pair_sqr(L, px);
+    Fq m = fp_add(fp_dbl(xx), xx);
+    Fq x3 = fp_sub(fp_sub(pair_sqr(L, m), s_), s_);
+    o.y = pair_mulsub(L, m, fp_sub(s_, x3), w, py);
+    o.x = x3;
+    o.zz = v;
+    o.zzz = w;
+    return o;
+}
+
+// acc += (neg ? -p : p) when `act`      (madd-2008-s), pair form of xyzz_madd; every lane of the warp executes it
+__device__ __forceinline__ void pair_madd(const PairLane& L, PairXYZZ& acc, const Fq& px, const Fq& py_in, bool neg, bool act) {
+    const bool p_inf = pair_is_zero(px) & pair_is_zero(py_in);
+    const Fq py = pair_sel(neg, fp_neg(py_in), py_in);
+    const bool acc_inf = pair_is_zero(acc.zz);
+    Fq u2 = pair_mul(L, px, acc.zz);
+    Fq s2 = pair_mul(L, py, acc.zzz);
+    Fq pp_ = fp_sub(u2, acc.x);
+    Fq rr = fp_sub(s2, acc.y);
+    const bool generic = act && !p_inf && !acc_inf;
+    const bool x_eq = pair_is_zero(pp_);                          // (no short-circuit: every lane executes the shuffles)
+    const bool same_y = pair_is_zero(rr);
+    const bool same_x = generic && x_eq;
+    PairXYZZ res;
+    Fq pp = pair_sqr(L, pp_);
+    Fq ppp = pair_mul(L, pp_, pp);
+    Fq q = pair_mul(L, acc.x, pp);
+    res.x = fp_sub(fp_sub(fp_sub(pair_sqr(L, rr), ppp), q), q);
+    res.y = pair_mulsub(L, rr, fp_sub(q, res.x), acc.y, ppp);
+    res.zz = pair_mul(L, acc.zz, pp);
+    res.zzz = pair_mul(L, acc.zzz, ppp);
+    if (__any_sync(PAIR_FULL, same_x)) {                         // P == Q or P == -Q somewhere in the warp (rare)
+        PairXYZZ d = pair_dbl_affine(L.r, px, py);
+        PairXYZZ inf;
+        inf.x = Fq::zero(); inf.y = Fq::zero(); inf.zz = Fq::zero(); inf.zzz = Fq::zero();
+        res = pair_sel(same_x, pair_sel(same_y, d, inf), res);
+    }
+    PairXYZZ first;                                              // identity + p
+    first.x = px; first.y = py; first.zz = pair_one(L); first.zzz = first.zz;
+    acc = pair_sel(act && !p_inf, pair_sel(acc_inf, first, res), acc);
+}
+
+template <int BLOCKS>
+__global__ void __launch_bounds__(128, BLOCKS)
+k_accumulate_g2pair(const Affine<Fq2>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                    const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
+                    const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
+                    XYZZ<Fq2>* __restrict__ buckets) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t pair = t >> 1;
+    const bool valid = pair < (size_t)W * nb;                // no early exit: every lane takes part in the warp's shuffles
+    PairLane L;
+    L.r = (t & 1) != 0;
+    size_t slot = 0;
+    uint32_t end = 0, cnt = 0;
+    if (valid) { slot = order[pair]; end = cursor_end[slot]; cnt = counts[slot]; }
+    const uint32_t* idx = sorted + (size_t)(slot / nb) * sstride + (end - cnt);
+    const bool heavy = cnt >= SIZE_KEYS - 1;                 // left to k_accumulate_heavy
+    const bool work = valid && !heavy && !(accumulate_into && cnt == 0);
+    const uint32_t my_cnt = work ? cnt : 0u;
+    const uint32_t max_cnt = __reduce_max_sync(PAIR_FULL, my_cnt);
+    Fq* bk = reinterpret_cast<Fq*>(buckets + slot) + (L.r ? 1 : 0);      // x.c_r; y, zz, zzz follow at strides of two Fq
+    PairXYZZ acc;
+    acc.x = Fq::zero(); acc.y = Fq::zero(); acc.zz = Fq::zero(); acc.zzz = Fq::zero();
+    if (work && accumulate_into) { acc.x = load_vec_rw(bk); acc.y = load_vec_rw(bk + 2); acc.zz = load_vec_rw(bk + 4); acc.zzz = load_vec_rw(bk + 6); }
+    for (uint32_t k = 0; k < max_cnt; ++k) {
+        const bool act = k < my_cnt;
+        const uint32_t e = act ? idx[k] : 0u;                // finished pairs re-read base 0 and discard the result
+        const Fq* pb = reinterpret_cast<const Fq*>(bases + (e & 0x7fffffffu)) + (L.r ? 1 : 0);
+        const Fq px = load_vec(pb), py = load_vec(pb + 2);
+        pair_madd(L, acc, px, py, (e >> 31) != 0, act);
+    }
+    if (work || (valid && heavy && !accumulate_into)) {      // heavy buckets start from the identity
+        store_vec(bk, acc.x); store_vec(bk + 2, acc.y); store_vec(bk + 4, acc.zz); store_vec(bk + 6, acc.zzz);
+    }
+}
+
 // Skewed scalar distributions (many equal scalars, boolean witnesses, structured inputs) put thousands
 // of points into one bucket; one thread per bucket would serialise them.  Buckets with at least
 // SIZE_KEYS-1 points are the first hist[SIZE_KEYS-1] entries of `order`: blocks (x = heavy bucket,
@@ -922,6 +1075,18 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const Fr* d_scalars,
     return ZKG_OK;
 }
 
+static inline void msm_launch_g2pair(const Affine<Fq2>* bases, const uint32_t* sorted, const uint32_t* cursor, const uint32_t* counts,
+                                     const uint32_t* order, size_t sstride, uint32_t nb, int Wb, int into, XYZZ<Fq2>* buckets, size_t slots,
+                                     cudaStream_t st) {
+    const unsigned grid = (unsigned)((2 * slots + 127) / 128);
+    if (env_int("ZKG_MSM_G2_PAIR_BLOCKS", 4) == 3)
+        k_accumulate_g2pair<3><<<grid, 128, 0, st>>>(bases, sorted, cursor, counts, order, sstride, nb, Wb, into, buckets);
+    else
+        k_accumulate_g2pair<4><<<grid, 128, 0, st>>>(bases, sorted, cursor, counts, order, sstride, nb, Wb, into, buckets);
+}
+static inline void msm_launch_g2pair(const Affine<Fq>*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, size_t, uint32_t,
+                                     int, int, XYZZ<Fq>*, size_t, cudaStream_t) {}      // never taken: sizeof(Fq) == 32
+
 // second half of a chunk: bucket accumulation of the points sorted by msm_chunk_sort (needs the bases)
 template <class F>
 static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, size_t n) {
@@ -930,7 +1095,12 @@ static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F
     const bool first = pl->chunks_done == 0;
     const size_t sstride = pl->merged ? 0 : n;
     const int use_ba = env_int("ZKG_MSM_BA", 0);            // read per call, like ZKG_MSM_C (tests flip it inside one process)
-    if (use_ba)
+    // G2: the lane-pair kernel wins while the launch is short of threads (2^16 points: accumulate 0.71 -> 0.60 ms) and loses
+    // ~5 % to its shuffles and selects once the one-thread-per-bucket kernel fills the machine (2^19: 3.52 vs 3.70 ms)
+    const int g2_pair = env_int("ZKG_MSM_G2_PAIR", pl->n_total <= ((size_t)1 << 17) ? 1 : 0);
+    if (sizeof(F) > 32 && !use_ba && g2_pair)
+        msm_launch_g2pair(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order, sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets, pl->slots, st);
+    else if (use_ba)
         k_accumulate_ba<F><<<(unsigned)((pl->slots + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, st>>>(
             d_bases, pl->sorted, pl->cursor, pl->counts, pl->order, sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
     else
