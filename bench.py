@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 INT_PEAK_TIMAD = 18.51              # profiles/r01_intpipe_microbench_v2.json: 32-bit IMAD issue rate, B200, 148 SMs @1965 MHz
 WIDE_MAD_PEAK_T = 9.27              # profiles/r01_widemad_microbench.json: IMAD.WIDE.U32 (any form: RZ / addend / .X) issue rate, 10^12/s
 WIDE_MADS_PER_MADD = 6 * 128 + 2 * 100 + 192   # XYZZ mixed add as executed: 6 products, 2 dedicated squarings, one 2-term dot
-ACC_TRAFFIC_BYTES = 7.336e9         # profiles/r01_ncu_k_accumulate_v2.json: dram read+write of one k_accumulate launch at 2^22 (prepared path)
+ACC_TRAFFIC_BYTES = 7.485e9         # profiles/r02_ncu_k_accumulate_g1.json: dram read (7.361 GB) + write (0.124 GB) of one k_accumulate launch at 2^22 (prepared path)
 HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
 
 
@@ -564,6 +564,11 @@ def run_ours(args):
         return {"bound": "int (IMAD pipe); hbm fraction beside it",
                 "fft1": {"int_achieved_TIMAD_s": round(f_int, 3), "int_frac": round(f_int / int_peak, 4),
                          "hbm_achieved_gbs": round(64 * mbyl / (t1_ms * 1e-3) / 1e9, 1), "hbm_frac": round(64 * mbyl / (t1_ms * 1e-3) / 1e9 / hbm_peak, 4)},
+                "executed_note": "wide multiply-adds the kernels execute: fft1 = 1/2 log2(m/l) products of 128 per element (trivial twiddles skipped in "
+                                 "practice: slightly fewer); king (l = 2) = 4 four-term inner products of 320 + 3 products per share column in stage 1 and "
+                                 "1152 per column in the transform-form pack = 1408 per domain element; against the measured 9.27e12/s wide-MAD issue rate",
+                "fft1_executed_wide_mad_frac": round(mbyl * 0.5 * lg * 128 / (t1_ms * 1e-3) / 1e12 / WIDE_MAD_PEAK_T, 4),
+                "king_executed_wide_mad_frac": round(m * 1408 / (tk_ms * 1e-3) / 1e12 / WIDE_MAD_PEAK_T, 4),
                 "king": {"int_achieved_TIMAD_s": round(k_int, 3), "int_frac": round(k_int / int_peak, 4),
                          "hbm_achieved_gbs": round(256 * m / (tk_ms * 1e-3) / 1e9, 1), "hbm_frac": round(256 * m / (tk_ms * 1e-3) / 1e9 / hbm_peak, 4)},
                 "peaks": {"int_TIMAD_s": int_peak, "hbm_gbs": hbm_peak, "hbm_source": hbm_how}}
@@ -1217,8 +1222,8 @@ def run_ours(args):
                          "hbm": {"achieved_gbs": round(96 * n / (acc_ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
                                  "frac": round(96 * n / (acc_ms * 1e-3) / 1e9 / hbm_peak, 4), "peak_source": hbm_how},
                          "traffic": ACC_TRAFFIC_BYTES if args.log2n == 22 else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch from an ncu --set full capture "
-                                         "(profiles/, not measured in this run); ~18x the 96 B/point because Pippenger gathers every base once per "
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch from the ncu --set full capture "
+                                         "profiles/r02_ncu_k_accumulate_g1.json (same code, not measured in this run); ~18x the 96 B/point because Pippenger gathers every base once per "
                                          "window (13 gathers that each pull 128 B) -- under 1 TB/s, not the bound"},
             "cpu_baseline": {"value": round(cpu_val, 4), "unit": "Mpts/s", "cores": cpu_th, "kind": "port",
                              "sample": "G1 MSM of 2^20 points (a quarter of the workload), best of 2, oracle/zkoracle.c (arkworks msm_bigint_wnaf "
