@@ -106,8 +106,10 @@ def test_d_msm_with_dropouts(z, dropouts):
         x_shares.append(aff)
     y_shares = z.transpose(z.pack_vec(y_pub, pp, ol.rand_fr(rng, M // l * pp.t)))
     masks = [z.MsmMask.zero() for _ in range(pp.n)]
-    out = z.d_msm(x_shares, y_shares, masks, pp, z.LocalTestNet(pp.n, dropouts=dropouts))
+    out = z.d_msm(x_shares, y_shares, masks, pp, z.LocalTestNet(pp.n, dropouts=dropouts))       # shares cross as compressed points
     assert all((o_ == should_be).all() for o_ in out)       # the king replicates the clear output (dmsm/mod.rs:87)
+    out2 = z.d_msm(x_shares, y_shares, masks, pp, z.LocalTestNet(pp.n, dropouts=dropouts), wire=False)
+    assert all((o_ == should_be).all() for o_ in out2)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -648,7 +648,7 @@ def d_pp(num_shares, den_shares, masks, pp, net, rand_king, rand_degred):
     return deg_red(out, masks, pp, net, rand_degred)        # :86
 
 
-def d_msm(bases_by_party, scalars_by_party, masks, pp, net, g2=False, device_of_party=None):
+def d_msm(bases_by_party, scalars_by_party, masks, pp, net, g2=False, device_of_party=None, wire=True):
     """dmsm/mod.rs:59-102 for all parties at once.  The king's `unpack_missing_shares` over group elements
     (pss.rs:141-166; the Lagrange path :170-221 when `net` drops parties) and the sum run in
     zkg_pss_unpack2_bn254_g1/g2."""
@@ -658,6 +658,14 @@ def d_msm(bases_by_party, scalars_by_party, masks, pp, net, g2=False, device_of_
         dev = device_of_party(p) if device_of_party else pp.device
         c = msm(bases_by_party[p], scalars_by_party[p], dev)                           # :73
         c_shares.append(group_add(c, masks[p].in_mask, g2, dev))                       # :74
-    recv, parties = net.received(c_shares)
+    if wire:
+        # client_send_or_king_receive_serialized (mpc-net/src/ser_net.rs:25,40): every share crosses as a compressed point
+        frames = [group_to_wire(c, g2, pp.device)[0] for c in c_shares]
+        recv_frames, parties = net.received(frames)
+        recv = list(group_from_wire(np.stack(recv_frames), g2, pp.device))
+    else:
+        recv, parties = net.received(c_shares)
     _, output = pss_unpack2_group(pp, recv, parties, g2, want_unpacked=False)          # :85-86
+    if wire:                                                                           # client_receive_or_king_send_serialized, :112-119
+        output = group_from_wire(group_to_wire(output, g2, pp.device), g2, pp.device)[0]
     return [group_add(output, masks[p].out_mask, g2, pp.device) for p in range(net.n_parties())]  # :98
