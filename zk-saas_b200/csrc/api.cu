@@ -34,6 +34,10 @@ static int32_t ctx_new(int device, void* stream, zkg_ctx** out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {
+        const char* g = getenv("ZKG_L2_FETCH");            // experiment: 32 / 64 / 128-byte L2 fetch granularity
+        if (g && *g) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    }
     *out = c;
     return ZKG_OK;
 }
@@ -48,6 +52,8 @@ static void ctx_free(zkg_ctx* c) {
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < c->copy_ev_count; ++i) cudaEventDestroy(c->copy_ev[i]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 5; ++i) if (c->aux_ev[i]) cudaEventDestroy(c->aux_ev[i]);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -132,6 +138,15 @@ int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events) {
         ZKG_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[ctx->copy_ev_count], cudaEventDisableTiming));
         ctx->copy_ev_count += 1;
     }
+    return ZKG_OK;
+}
+
+int32_t ctx_aux_stream(zkg_ctx* ctx) {
+    if (ctx->aux_stream) return ZKG_OK;
+    int lo = 0, hi = 0;                                    // "greatest" priority is the numerically lowest value
+    ZKG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ZKG_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 5; ++i) ZKG_CUDA(cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming));
     return ZKG_OK;
 }
 

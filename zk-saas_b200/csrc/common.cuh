@@ -70,6 +70,10 @@ struct zkg_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev[16] = {};
     int copy_ev_count = 0;
+    // high-priority side stream + events of the MSM sort pipeline (msm_impl.cuh: the counting sort of chunk k+1 runs
+    // under the bucket accumulation of chunk k)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_ev[5] = {};        // 0: inputs ready (main -> side), 1-2: sorted[set], 3-4: accumulated[set]
     // instrumentation (bench.py): kernels launched so far, and optional per-phase CUDA events
     uint64_t launches = 0;
     bool profile = false;
@@ -87,6 +91,7 @@ struct PooledCtx {
 };
 
 int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events);
+int32_t ctx_aux_stream(zkg_ctx* ctx);
 // host <-> device copies that take pageable host memory at PCIe speed (staging.cu); stream semantics of
 // cudaMemcpyAsync on pageable memory
 int32_t copy_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);

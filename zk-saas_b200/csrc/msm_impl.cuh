@@ -79,28 +79,33 @@ __global__ void k_pack_bases(const uint8_t* __restrict__ ark, size_t stride, siz
 // ------------------------------------------------------------------------------------------
 // scalars -> signed digits + histogram
 // ------------------------------------------------------------------------------------------
-static __global__ void k_digits(const Fr* __restrict__ scalars, size_t n, int c, int W, uint32_t bstride,
+// Emits the digits of windows [w_lo, w_hi) only (a chunk of the sort pipeline may cover a window range); the carry chain
+// is recomputed from window 0, which costs a few shifts per skipped window.  Grid-stride: a sort that runs UNDER another
+// chunk's accumulation is launched with a couple of blocks per SM, so that it takes a thin slice of every SM instead of
+// every slot the accumulation frees (the side stream has the higher priority).
+static __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, size_t n, int c, int W, int w_lo, int w_hi, uint32_t bstride,
                          uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr s = fp_from_mont(load_vec(scalars + i));      // into_bigint()
-    uint32_t carry = 0;
     const uint32_t half = 1u << (c - 1);
-    for (int w = 0; w < W; ++w) {
-        uint32_t coef = msm_window_bits(s.v, w, c) + carry;
-        uint32_t neg = 0;
-        carry = 0;
-        if (w != W - 1 && coef >= half) {
-            if (coef == (1u << c)) coef = 0;
-            else { coef = (1u << c) - coef; neg = 1; }
-            carry = 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        Fr s = fp_from_mont(load_vec(scalars + i));      // into_bigint()
+        uint32_t carry = 0;
+        for (int w = 0; w < w_hi; ++w) {
+            uint32_t coef = msm_window_bits(s.v, w, c) + carry;
+            uint32_t neg = 0;
+            carry = 0;
+            if (w != W - 1 && coef >= half) {
+                if (coef == (1u << c)) coef = 0;
+                else { coef = (1u << c) - coef; neg = 1; }
+                carry = 1;
+            }
+            if (w < w_lo) continue;
+            uint32_t d = MSM_DIGIT_NONE;
+            if (coef != 0) {
+                d = (coef - 1) | (neg << 31);
+                atomicAdd(&counts[(size_t)(w - w_lo) * bstride + (coef - 1)], 1u);      // bstride = 0: windows share the buckets
+            }
+            digits[(size_t)(w - w_lo) * n + i] = d;
         }
-        uint32_t d = MSM_DIGIT_NONE;
-        if (coef != 0) {
-            d = (coef - 1) | (neg << 31);
-            atomicAdd(&counts[(size_t)w * bstride + (coef - 1)], 1u);      // bstride = 0: windows share the buckets
-        }
-        digits[(size_t)w * n + i] = d;
     }
 }
 
@@ -169,16 +174,27 @@ static __global__ void k_scan_final(const uint32_t* __restrict__ counts, uint32_
 }
 
 // bstride / sstride / ioff = (nb, n, 0) for per-window buckets, (0, 0, n_total) for merged windows, where the
-// sorted entry indexes the window-shifted base table (w * n_total + point)
-static __global__ void k_scatter(const uint32_t* __restrict__ digits, size_t n, uint32_t bstride, size_t sstride, size_t ioff,
-                          size_t point0, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t w = blockIdx.y;
-    if (i >= n) return;
-    uint32_t d = digits[(size_t)w * n + i];
-    if (d == MSM_DIGIT_NONE) return;
-    uint32_t pos = atomicAdd(&cursor[(size_t)w * bstride + (d & 0x7fffffffu)], 1u);
-    sorted[(size_t)w * sstride + pos] = (uint32_t)(point0 + i + (size_t)w * ioff) | (d & 0x80000000u);
+// sorted entry indexes the window-shifted base table (w * n_total + point).  Windows are counted from w_lo.
+// One thread takes a point through the chunk's windows, four at a time: the four returned atomics are in flight
+// together, so a launch of a few hundred blocks (a sort hidden under an accumulation) still keeps the L2 busy.
+template <int ILP>
+static __global__ void __launch_bounds__(256, ILP > 4 ? 4 : 8) k_scatter(const uint32_t* __restrict__ digits, size_t n, int wg, uint32_t bstride, size_t sstride, size_t ioff,
+                          size_t point0, int w_lo, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll 1
+        for (int w0 = 0; w0 < wg; w0 += ILP) {
+            uint32_t d[ILP], pos[ILP];
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) d[k] = w0 + k < wg ? digits[(size_t)(w0 + k) * n + i] : MSM_DIGIT_NONE;
+#pragma unroll
+            for (int k = 0; k < ILP; ++k)
+                if (d[k] != MSM_DIGIT_NONE) pos[k] = atomicAdd(&cursor[(size_t)(w0 + k) * bstride + (d[k] & 0x7fffffffu)], 1u);
+#pragma unroll
+            for (int k = 0; k < ILP; ++k)
+                if (d[k] != MSM_DIGIT_NONE)
+                    sorted[(size_t)(w0 + k) * sstride + pos[k]] = (uint32_t)(point0 + i + (size_t)(w0 + k + w_lo) * ioff) | (d[k] & 0x80000000u);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -213,28 +229,39 @@ static __global__ void k_size_scan(const uint32_t* __restrict__ hist, uint32_t* 
     for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x)
         start[SIZE_KEYS - 1 - i] = i ? v[i - 1] : 0;          // exclusive prefix in reversed (descending) order
 }
-static __global__ void k_size_scatter(const uint32_t* __restrict__ counts, size_t slots, uint32_t* __restrict__ start,
+// Block-aggregated: the populations of uniform scalars fall on a few dozen keys, so one global atomic per (warp, key)
+// piles onto the same addresses (42 us for 2^19 slots).  A 1024-thread block ranks its slots in a shared histogram
+// (warp-aggregated), reserves one contiguous range per key it saw, and writes.
+static __global__ void __launch_bounds__(1024) k_size_scatter(const uint32_t* __restrict__ counts, size_t slots, uint32_t* __restrict__ start,
                                       uint32_t* __restrict__ order) {
+    __shared__ uint32_t sh[SIZE_KEYS];
+    for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = t < slots;
     uint32_t key = valid ? min(counts[t], SIZE_KEYS - 1) : 0xffffffffu;
-    // warp-aggregated atomic: lanes with the same key reserve a contiguous range with one atomicAdd
     uint32_t peers = __match_any_sync(0xffffffffu, key);
-    if (!valid) return;
     int leader = __ffs(peers) - 1;
     uint32_t lane = threadIdx.x & 31;
     uint32_t rank = __popc(peers & ((1u << lane) - 1));
     uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(&start[key], (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    order[base + rank] = (uint32_t)t;
+    if (valid && (int)lane == leader) base = atomicAdd(&sh[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank += base;                                          // rank of this slot among the block's slots with its key
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x) {
+        uint32_t c = sh[i];
+        if (c) sh[i] = atomicAdd(&start[i], c);            // the block's range for key i
+    }
+    __syncthreads();
+    if (valid) order[sh[key] + rank] = (uint32_t)t;
 }
 
 // ------------------------------------------------------------------------------------------
 // bucket accumulation: one thread per (window, bucket)
 // ------------------------------------------------------------------------------------------
-template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) > 32 ? 3 : 5)     // G2: three blocks per SM (<= 168 registers); G1: five (<= 102)
+template <class F, int TB = 128>
+__global__ void __launch_bounds__(TB, (sizeof(F) > 32 ? 3 : 5) * 128 / TB)     // G2: three 128-thread blocks per SM (<= 168 registers); G1: five (<= 102)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
              const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
@@ -742,7 +769,10 @@ k_merge_lvl(const XYZZ<F>* __restrict__ in, const XYZZ<F>* __restrict__ in_R0, c
     XYZZ<F> r;
     if (b == 1) {                                          // children are level-0 entries (R_u, A_u)
         if (v == 0) { r = load_vec_rw(in_R0 + lo); xyzz_add(r, load_vec_rw(in_R0 + hi)); }
-        else if (v == 1) { r = load_vec_rw(in_A0 + lo); xyzz_add(r, load_vec_rw(in_A0 + hi)); }
+        else if (v == 1) {
+            if (in_A0) { r = load_vec_rw(in_A0 + lo); xyzz_add(r, load_vec_rw(in_A0 + hi)); }
+            else r = XYZZ<F>::inf();                       // level 0 skipped: the entries are the buckets themselves
+        }
         else r = load_vec_rw(in_R0 + hi);                  // m_0 = total of the odd child
     } else {
         const uint32_t ps = (uint32_t)b + 1;               // slots per child node
@@ -755,18 +785,18 @@ k_merge_lvl(const XYZZ<F>* __restrict__ in, const XYZZ<F>* __restrict__ in_R0, c
 // One block of 32 threads per window: S_w = sumA + 8 * sum_j 2^j m_j + total.  Lane j owns m_j.
 template <class F>
 __global__ void __launch_bounds__(32)
-k_bits_final(const XYZZ<F>* __restrict__ nodes, const XYZZ<F>* __restrict__ R0, const XYZZ<F>* __restrict__ A0, int B,
+k_bits_final(const XYZZ<F>* __restrict__ nodes, const XYZZ<F>* __restrict__ R0, const XYZZ<F>* __restrict__ A0, int B, int lshift,
              XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ Z_out) {
     __shared__ XYZZ<F> sh[32];
     const uint32_t w = blockIdx.x, lane = threadIdx.x;
     XYZZ<F> x = XYZZ<F>::inf();
     if (B == 0) {                                          // a single level-0 entry: u = 0 has weight 0
-        if (lane == 0) { x = load_vec_rw(A0 + w); xyzz_add(x, load_vec_rw(R0 + w)); }
+        if (lane == 0) { x = load_vec_rw(R0 + w); if (A0) xyzz_add(x, load_vec_rw(A0 + w)); }
     } else {
         const XYZZ<F>* nd = nodes + (size_t)w * (B + 2);
         if ((int)lane < B) {
             x = load_vec_rw(nd + 2 + lane);
-            xyzz_dbl_k(x, (int)lane + 3);                                  // 8 * 2^j
+            xyzz_dbl_k(x, (int)lane + lshift);                             // L * 2^j
         } else if ((int)lane == B) {
             x = load_vec_rw(nd);                           // total
             xyzz_add(x, load_vec_rw(nd + 1));              // + sumA
@@ -779,6 +809,201 @@ k_bits_final(const XYZZ<F>* __restrict__ nodes, const XYZZ<F>* __restrict__ R0, 
         __syncthreads();
     }
     if (lane == 0) { store_vec(S_out + w, sh[0]); store_vec(Z_out + w, XYZZ<F>::inf()); }
+}
+
+// ------------------------------------------------------------------------------------------
+// The butterfly levels are a LATENCY chain: level b has only n1/2^b * (b+1) additions, and one thread needs ~11 us for
+// an addition (14 dependent products on a lone warp, ~6 cycles per instruction).  The independent products of an
+// addition can overlap across the four sub-partitions of an SM (the trick of k_final_coop), and a warp instruction costs
+// the same for one lane as for 32 -- so a block of FOUR WARPS evaluates 32 additions at once: lane l of warp w computes
+// product slot w of addition l, the operands and the eight temporaries live in shared memory (word-major, one value per
+// lane: conflict-free), one barrier per formula level (4 for add-2008-s, 3 for dbl-2008-s-1).  ~3.5 us per addition level
+// instead of ~11, same total work.  The exceptional cases (an identity operand, equal or opposite points) are detected
+// per lane by warp 0 at level 2, evaluated there with the plain routine while the operands are still intact, and
+// written over the lane's result after the last level.
+// ------------------------------------------------------------------------------------------
+template <class F> struct ShF { uint32_t w[sizeof(F) / 4][32]; };
+template <class F> struct ShPt { ShF<F> x, y, zz, zzz; };
+
+__device__ __forceinline__ Fq sh_ld(const ShF<Fq>& s, int lane) {
+    Fq r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = s.w[k][lane];
+    return r;
+}
+__device__ __forceinline__ void sh_st(ShF<Fq>& s, int lane, const Fq& a) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s.w[k][lane] = a.v[k];
+}
+__device__ __forceinline__ Fq2 sh_ld(const ShF<Fq2>& s, int lane) {
+    Fq2 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { r.c0.v[k] = s.w[k][lane]; r.c1.v[k] = s.w[8 + k][lane]; }
+    return r;
+}
+__device__ __forceinline__ void sh_st(ShF<Fq2>& s, int lane, const Fq2& a) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s.w[k][lane] = a.c0.v[k]; s.w[8 + k][lane] = a.c1.v[k]; }
+}
+template <class F>
+__device__ __forceinline__ XYZZ<F> sh_ld_pt(const ShPt<F>& p, int lane) {
+    XYZZ<F> r;
+    r.x = sh_ld(p.x, lane); r.y = sh_ld(p.y, lane); r.zz = sh_ld(p.zz, lane); r.zzz = sh_ld(p.zzz, lane);
+    return r;
+}
+template <class F>
+__device__ __forceinline__ void sh_st_pt(ShPt<F>& p, int lane, const XYZZ<F>& a) {
+    sh_st(p.x, lane, a.x); sh_st(p.y, lane, a.y); sh_st(p.zz, lane, a.zz); sh_st(p.zzz, lane, a.zzz);
+}
+// component `comp` (0..3 = x, y, zz, zzz) of a point
+template <class F>
+__device__ __forceinline__ ShF<F>& sh_comp(ShPt<F>& p, int comp) { return comp == 0 ? p.x : comp == 1 ? p.y : comp == 2 ? p.zz : p.zzz; }
+
+// A[lane] += B[lane] for the lanes with `active` (the same value in all four warps); every thread of the 128-thread
+// block calls it.  Inactive lanes touch nothing.
+template <class F>
+__device__ __forceinline__ void coop32_add(ShPt<F>& A, const ShPt<F>& B, ShF<F>* t, int warp, int lane, bool active) {
+    F pp_ = F::zero(), rr_ = F::zero();
+    XYZZ<F> fix = XYZZ<F>::inf();
+    bool special = false;
+    if (active) {
+        if (warp == 0) sh_st(t[0], lane, f_mul(sh_ld(A.x, lane), sh_ld(B.zz, lane)));      // U1
+        if (warp == 1) sh_st(t[1], lane, f_mul(sh_ld(B.x, lane), sh_ld(A.zz, lane)));      // U2
+        if (warp == 2) sh_st(t[2], lane, f_mul(sh_ld(A.y, lane), sh_ld(B.zzz, lane)));     // S1
+        if (warp == 3) sh_st(t[3], lane, f_mul(sh_ld(B.y, lane), sh_ld(A.zzz, lane)));     // S2
+    }
+    __syncthreads();
+    if (active) {
+        if (warp == 0) {
+            pp_ = f_sub(sh_ld(t[1], lane), sh_ld(t[0], lane));
+            special = sh_ld(A.zz, lane).is_zero() || sh_ld(B.zz, lane).is_zero() || pp_.is_zero();
+            if (special) { fix = sh_ld_pt(A, lane); xyzz_add(fix, sh_ld_pt(B, lane)); }
+            sh_st(t[4], lane, f_sqr(pp_));                                                  // PP
+        }
+        if (warp == 1) { rr_ = f_sub(sh_ld(t[3], lane), sh_ld(t[2], lane)); sh_st(t[5], lane, f_sqr(rr_)); }   // RR
+        if (warp == 2) sh_st(t[6], lane, f_mul(sh_ld(A.zz, lane), sh_ld(B.zz, lane)));
+        if (warp == 3) sh_st(t[7], lane, f_mul(sh_ld(A.zzz, lane), sh_ld(B.zzz, lane)));
+    }
+    __syncthreads();
+    if (active) {
+        if (warp == 0) sh_st(t[1], lane, f_mul(pp_, sh_ld(t[4], lane)));                    // PPP (U2 is dead)
+        if (warp == 2) sh_st(t[0], lane, f_mul(sh_ld(t[0], lane), sh_ld(t[4], lane)));      // Q = U1 PP (only this warp reads U1 here)
+        if (warp == 3) sh_st(A.zz, lane, f_mul(sh_ld(t[6], lane), sh_ld(t[4], lane)));      // ZZ3
+    }
+    __syncthreads();
+    if (active) {
+        if (warp == 1) {
+            F ppp = sh_ld(t[1], lane), q = sh_ld(t[0], lane);
+            F x3 = f_sub(f_sub(f_sub(sh_ld(t[5], lane), ppp), q), q);
+            sh_st(A.y, lane, f_mulsub(rr_, f_sub(q, x3), sh_ld(t[2], lane), ppp));
+            sh_st(A.x, lane, x3);
+        }
+        if (warp == 3) sh_st(A.zzz, lane, f_mul(sh_ld(t[7], lane), sh_ld(t[1], lane)));     // ZZZ3
+    }
+    __syncthreads();
+    if (active && warp == 0 && special) sh_st_pt(A, lane, fix);
+    __syncthreads();
+}
+
+// A[lane] = 2 A[lane] for the active lanes   (dbl-2008-s-1, a = 0; three levels)
+template <class F>
+__device__ __forceinline__ void coop32_dbl(ShPt<F>& A, ShF<F>* t, int warp, int lane, bool active) {
+    active = active && !sh_ld(A.zz, lane).is_zero();                                        // 2 * identity: nothing to do
+    if (active) {
+        if (warp == 0) { F u = f_dbl(sh_ld(A.y, lane)); sh_st(t[0], lane, u); sh_st(t[1], lane, f_sqr(u)); }     // U, V
+        if (warp == 1) { F xx = f_sqr(sh_ld(A.x, lane)); sh_st(t[2], lane, f_add(f_dbl(xx), xx)); }              // M
+    }
+    __syncthreads();
+    if (active) {
+        if (warp == 0) sh_st(t[3], lane, f_mul(sh_ld(t[0], lane), sh_ld(t[1], lane)));      // W
+        if (warp == 1) sh_st(t[4], lane, f_mul(sh_ld(A.x, lane), sh_ld(t[1], lane)));       // S
+        if (warp == 2) sh_st(t[5], lane, f_sqr(sh_ld(t[2], lane)));                         // M^2
+        if (warp == 3) sh_st(A.zz, lane, f_mul(sh_ld(t[1], lane), sh_ld(A.zz, lane)));      // ZZ3
+    }
+    __syncthreads();
+    if (active) {
+        if (warp == 0) {
+            F s_ = sh_ld(t[4], lane);
+            F x3 = f_sub(f_sub(sh_ld(t[5], lane), s_), s_);
+            sh_st(A.y, lane, f_mulsub(sh_ld(t[2], lane), f_sub(s_, x3), sh_ld(t[3], lane), sh_ld(A.y, lane)));
+            sh_st(A.x, lane, x3);
+        }
+        if (warp == 1) sh_st(A.zzz, lane, f_mul(sh_ld(t[3], lane), sh_ld(A.zzz, lane)));    // ZZZ3
+    }
+    __syncthreads();
+}
+
+// k_merge_lvl on four-warp blocks: 32 node entries per block.  Warp w moves component w of the operands and results.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_merge_lvl_coop(const XYZZ<F>* __restrict__ in, const XYZZ<F>* __restrict__ in_R0, const XYZZ<F>* __restrict__ in_A0,
+                 XYZZ<F>* __restrict__ out, int b, uint32_t n_prev, int Wb) {
+    __shared__ ShPt<F> A, Bp;
+    __shared__ ShF<F> t[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_new = n_prev >> 1, slots = (uint32_t)b + 2;
+    const size_t e = (size_t)blockIdx.x * 32 + lane;
+    const bool valid = e < (size_t)Wb * n_new * slots;
+    const XYZZ<F>* pa = nullptr;
+    const XYZZ<F>* pb = nullptr;
+    if (valid) {
+        uint32_t v = (uint32_t)(e % slots);
+        size_t node = e / slots;
+        uint32_t w = (uint32_t)(node / n_new), q = (uint32_t)(node % n_new);
+        size_t lo = (size_t)w * n_prev + 2 * (size_t)q, hi = lo + 1;
+        if (b == 1) {
+            if (v == 0) { pa = in_R0 + lo; pb = in_R0 + hi; }
+            else if (v == 1) { if (in_A0) { pa = in_A0 + lo; pb = in_A0 + hi; } }      // no level 0: sumA starts as the identity
+            else pa = in_R0 + hi;
+        } else {
+            const uint32_t ps = (uint32_t)b + 1;
+            if (v == slots - 1) pa = in + hi * ps;
+            else { pa = in + lo * ps + v; pb = in + hi * ps + v; }
+        }
+    }
+    sh_st(sh_comp(A, warp), lane, pa ? load_vec_rw(reinterpret_cast<const F*>(pa) + warp) : F::zero());
+    if (pb) sh_st(sh_comp(Bp, warp), lane, load_vec_rw(reinterpret_cast<const F*>(pb) + warp));
+    __syncthreads();
+    coop32_add(A, Bp, t, warp, lane, pb != nullptr);
+    if (valid) store_vec(reinterpret_cast<F*>(out + e) + warp, sh_ld(sh_comp(A, warp), lane));
+}
+
+// k_bits_final on a four-warp block per window: lane j scales m_j by 2^(j+lshift), L = 2^lshift the level-0 segment (the lanes' doubling chains run together,
+// masked by their lengths), lane B holds total + sumA, then a five-level tree of 32-wide additions.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bits_final_coop(const XYZZ<F>* __restrict__ nodes, const XYZZ<F>* __restrict__ R0, const XYZZ<F>* __restrict__ A0, int B, int lshift,
+                  XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ Z_out) {
+    __shared__ ShPt<F> A, Bp;
+    __shared__ ShF<F> t[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t w = blockIdx.x;
+    // A[lane]: m_lane (lane < B), total (lane == B; sumA is added below), identity otherwise
+    {
+        F a = F::zero(), bb = F::zero();
+        if (B == 0) {
+            if (lane == 0) { a = load_vec_rw(reinterpret_cast<const F*>(R0 + w) + warp); if (A0) bb = load_vec_rw(reinterpret_cast<const F*>(A0 + w) + warp); }
+        } else {
+            const XYZZ<F>* nd = nodes + (size_t)w * (B + 2);
+            if (lane < B) a = load_vec_rw(reinterpret_cast<const F*>(nd + 2 + lane) + warp);
+            else if (lane == B) { a = load_vec_rw(reinterpret_cast<const F*>(nd) + warp); bb = load_vec_rw(reinterpret_cast<const F*>(nd + 1) + warp); }
+        }
+        sh_st(sh_comp(A, warp), lane, a);
+        sh_st(sh_comp(Bp, warp), lane, bb);
+    }
+    __syncthreads();
+    coop32_add(A, Bp, t, warp, lane, B == 0 ? lane == 0 : lane == B);
+    for (int r = 0; r < B - 1 + lshift; ++r) coop32_dbl(A, t, warp, lane, lane < B && r < lane + lshift);
+    for (int off = 16; off > 0; off >>= 1) {
+        // B[lane] = A[lane + off]: every warp copies its component, then the lower half adds
+        if (lane < off) sh_st(sh_comp(Bp, warp), lane, sh_ld(sh_comp(A, warp), lane + off));
+        __syncthreads();
+        coop32_add(A, Bp, t, warp, lane, lane < off);
+    }
+    if (lane == 0) {
+        store_vec(reinterpret_cast<F*>(S_out + w) + warp, sh_ld(sh_comp(A, warp), 0));
+        store_vec(reinterpret_cast<F*>(Z_out + w) + warp, F::zero());
+    }
 }
 
 // Horner over the window sums + normalisation.  mode 0: Jacobian image (x, y, 1) / (1, 1, 0);
@@ -961,11 +1186,26 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-// The pipeline is split in three host-side steps so that the host-pointer entry point can feed it
-// point-range CHUNKS while the next chunk is still crossing PCIe:
-//   msm_plan    window size, workspace carve-up (digit/sort arrays sized for ONE chunk)
-//   msm_chunk   digits -> counting sort -> size ordering -> bucket accumulation INTO the bucket array
-//   msm_finish  bucket reduction + Horner + normalisation
+// The pipeline is split in host-side steps so that one MSM can be fed in CHUNKS -- a point range of the input (the next
+// range still crossing PCIe) and/or a range of the scalar windows:
+//   msm_plan              window size, workspace carve-up (two sets of digit/sort arrays sized for one chunk each)
+//   msm_chunk_sort        digits -> counting sort -> size ordering of the chunk's bucket slots
+//   msm_chunk_accumulate  bucket accumulation INTO the bucket array
+//   msm_finish            bucket reduction + Horner + normalisation
+// Sort pipeline (round 2): the counting sort is bound by L2 atomics (SMs 16 % busy) and the accumulation by the integer
+// multiplier (L2 12 % busy), so when a call has more than one chunk every sort runs on the context's high-priority SIDE
+// stream, into alternating sort sets, and the sort of chunk k+1 hides under the accumulation of chunk k; only the first
+// chunk's sort is exposed.  A device-resident MSM is cut into two WINDOW groups for this (a short first group, so the
+// exposed sort is short); the host-pointer paths pipeline their point-range chunks the same way.
+struct MsmSortSet {
+    uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *cursor = nullptr, *order = nullptr, *shist = nullptr;
+};
+struct MsmChunkDesc {
+    const Fr* d_scalars = nullptr;
+    size_t n = 0, point0 = 0;      // point range [point0, point0 + n) of the call (d_scalars points at its first scalar)
+    int w_lo = 0, w_hi = 0;        // scalar windows covered
+    int into = 0;                  // 1: the chunk's buckets already hold earlier chunks' sums
+};
 template <class F>
 struct MsmPlan {
     size_t n_total = 0, chunk_cap = 0;
@@ -973,22 +1213,27 @@ struct MsmPlan {
     int Wb = 0;                // bucket sets: W (one per window) or 1 (merged: bases carry the window shifts)
     bool merged = false;
     uint32_t nb = 0, n1 = 0;
+    uint32_t L = 8;            // level-0 segment of the bucket reduction (1: no level 0, the butterfly starts on the buckets)
     size_t slots = 0;          // Wb * nb
-    uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *cursor = nullptr, *order = nullptr, *shist = nullptr;
+    MsmSortSet set[2];
+    int n_sets = 1;
+    bool side = false;         // sorts run on ctx->aux_stream (needs n_sets == 2)
     XYZZ<F>* buckets = nullptr;
     XYZZ<F>* Rb[2] = {nullptr, nullptr};
     XYZZ<F>* Cb[2] = {nullptr, nullptr};
-    int chunks_done = 0;
+    int sorts_issued = 0, chunks_done = 0;
 };
 static constexpr uint32_t MSM_REDUCE_L = 8;
 
+// wg0 / wg1: the largest number of windows a chunk sorted into set 0 / set 1 covers (wg1 = 0: one set, no pipelining)
 template <class F>
-static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<F>* pl, int merged_c = 0) {
+static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<F>* pl, int merged_c = 0, int c_forced = 0,
+                        int wg0 = 0, int wg1 = 0) {
     ZKG_REQUIRE(n_total < ((size_t)1 << 31), "msm: n = %zu exceeds 2^31-1", n_total);
     pl->n_total = n_total;
     pl->chunk_cap = chunk_cap;
-    int c = merged_c;
-    if (!merged_c) {
+    int c = merged_c ? merged_c : c_forced;
+    if (!c) {
         c = env_int("ZKG_MSM_C", 0);
         if (c < 2 || c > 22) c = msm_pick_c(n_total);
     }
@@ -999,17 +1244,31 @@ static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<
     ZKG_REQUIRE(!pl->merged || n_total * (size_t)pl->W < ((size_t)1 << 31), "msm: n*W exceeds 2^31-1");
     pl->nb = 1u << (c - 1);
     pl->slots = (size_t)pl->Wb * pl->nb;
-    pl->n1 = (pl->nb + MSM_REDUCE_L - 1) / MSM_REDUCE_L;
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_digits = carve(sizeof(uint32_t) * pl->W * chunk_cap);
-    size_t o_sorted = carve(sizeof(uint32_t) * pl->W * chunk_cap);
-    size_t o_counts = carve(sizeof(uint32_t) * pl->slots);
-    size_t o_cursor = carve(sizeof(uint32_t) * pl->slots);
-    size_t o_order = carve(sizeof(uint32_t) * pl->slots);
+    // Level 0 (running sums over 8 buckets) is 15 DEPENDENT additions per thread, ~165 us on its own however few buckets
+    // there are; small bucket sets skip it and run three more butterfly levels instead (~8 us each on four-warp blocks):
+    // 2^13 G1 points 0.46 -> 0.41 ms, G2 0.92 -> 0.76 ms; from 2^15 buckets up the extra level work costs more than it saves.
+    pl->L = (uint32_t)env_int("ZKG_MSM_REDUCE_L", pl->slots <= ((size_t)1 << 14) ? 1 : (int)MSM_REDUCE_L);
+    if (pl->L != 1) pl->L = MSM_REDUCE_L;
+    pl->n1 = (pl->nb + pl->L - 1) / pl->L;
+    if (wg0 <= 0 || wg0 > pl->W) wg0 = pl->W;
+    if (wg1 < 0 || wg1 > pl->W) wg1 = pl->W;
+    pl->n_sets = wg1 > 0 ? 2 : 1;
+    pl->side = false;
     const uint32_t scan_tiles = (pl->nb + SCAN_TILE - 1) / SCAN_TILE;
     ZKG_REQUIRE(scan_tiles <= 1024, "msm: window of %d bits too large", c);
-    size_t o_shist = carve(sizeof(uint32_t) * (2 * SIZE_KEYS + HEAVY_LOCKS + (size_t)pl->Wb * scan_tiles));   // hist | locks | start | scan tiles
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_set[2][6] = {};
+    for (int k = 0; k < pl->n_sets; ++k) {
+        const size_t wg = (size_t)(k == 0 ? wg0 : wg1);
+        const size_t set_slots = pl->merged ? (size_t)pl->nb : wg * pl->nb;
+        o_set[k][0] = carve(sizeof(uint32_t) * wg * chunk_cap);        // digits
+        o_set[k][1] = carve(sizeof(uint32_t) * wg * chunk_cap);        // sorted
+        o_set[k][2] = carve(sizeof(uint32_t) * set_slots);             // counts
+        o_set[k][3] = carve(sizeof(uint32_t) * set_slots);             // cursor
+        o_set[k][4] = carve(sizeof(uint32_t) * set_slots);             // order
+        o_set[k][5] = carve(sizeof(uint32_t) * (2 * SIZE_KEYS + HEAVY_LOCKS + (pl->merged ? 1 : wg) * scan_tiles));   // hist | locks | start | scan tiles
+    }
     size_t o_buckets = carve(sizeof(XYZZ<F>) * pl->slots);
     size_t o_r0 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
     size_t o_c0 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
@@ -1017,39 +1276,74 @@ static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<
     size_t o_c1 = carve(sizeof(XYZZ<F>) * pl->Wb * pl->n1);
     ZKG_TRY(ctx->ws.reserve(off));
     uint8_t* ws = (uint8_t*)ctx->ws.p;
-    pl->digits = (uint32_t*)(ws + o_digits);
-    pl->sorted = (uint32_t*)(ws + o_sorted);
-    pl->counts = (uint32_t*)(ws + o_counts);
-    pl->cursor = (uint32_t*)(ws + o_cursor);
-    pl->order = (uint32_t*)(ws + o_order);
-    pl->shist = (uint32_t*)(ws + o_shist);
+    for (int k = 0; k < pl->n_sets; ++k) {
+        pl->set[k].digits = (uint32_t*)(ws + o_set[k][0]);
+        pl->set[k].sorted = (uint32_t*)(ws + o_set[k][1]);
+        pl->set[k].counts = (uint32_t*)(ws + o_set[k][2]);
+        pl->set[k].cursor = (uint32_t*)(ws + o_set[k][3]);
+        pl->set[k].order = (uint32_t*)(ws + o_set[k][4]);
+        pl->set[k].shist = (uint32_t*)(ws + o_set[k][5]);
+    }
     pl->buckets = (XYZZ<F>*)(ws + o_buckets);
     pl->Rb[0] = (XYZZ<F>*)(ws + o_r0); pl->Rb[1] = (XYZZ<F>*)(ws + o_r1);
     pl->Cb[0] = (XYZZ<F>*)(ws + o_c0); pl->Cb[1] = (XYZZ<F>*)(ws + o_c1);
+    pl->sorts_issued = 0;
     pl->chunks_done = 0;
     return ZKG_OK;
 }
 
-// accumulate `n` points (n <= chunk_cap) into the plan's buckets.  Merged plans pass the whole
-// window-shifted table as d_bases and the chunk's first point index as point0.
+// Turn the plan's sorts over to the side stream.  `ready` orders them after the call's inputs; the caller records it
+// (msm_side_begin does, on the main stream, for device-resident inputs).
 template <class F>
-static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const Fr* d_scalars, size_t n, size_t point0 = 0) {
-    if (n == 0) return ZKG_OK;
-    cudaStream_t st = ctx->stream;
-    const int TB = 256;
-    const bool first = pl->chunks_done == 0;
-    if (first) phase_mark(ctx, 0);
-    ZKG_CUDA(cudaMemsetAsync(pl->counts, 0, sizeof(uint32_t) * pl->slots, st));
-    ZKG_CUDA(cudaMemsetAsync(pl->shist, 0, sizeof(uint32_t) * (SIZE_KEYS + HEAVY_LOCKS), st));
+static int32_t msm_side_begin(zkg_ctx* ctx, MsmPlan<F>* pl) {
+    if (pl->n_sets != 2 || !env_int("ZKG_MSM_SIDE", 1)) return ZKG_OK;
+    ZKG_TRY(ctx_aux_stream(ctx));
+    ZKG_CUDA(cudaEventRecord(ctx->aux_ev[0], ctx->stream));
+    pl->side = true;
+    return ZKG_OK;
+}
+
+// digits + counting sort + size ordering of one chunk.  ready: event the chunk's scalars wait for (nullptr: aux_ev[0],
+// recorded by msm_side_begin at the start of the call); only used when the sorts run on the side stream.
+template <class F>
+static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunkDesc& ch, cudaEvent_t ready = nullptr) {
+    if (ch.n == 0) return ZKG_OK;
+    const int k = pl->sorts_issued, si = pl->n_sets == 2 ? (k & 1) : 0;
+    const MsmSortSet& ss = pl->set[si];
+    cudaStream_t st = pl->side ? ctx->aux_stream : ctx->stream;
+    const size_t n = ch.n;
+    const int wg = ch.w_hi - ch.w_lo;
+    const int wb = pl->merged ? 1 : wg;                        // bucket sets of this chunk
+    const size_t slots = (size_t)wb * pl->nb;
+    if (k == 0) phase_mark(ctx, 0);
+    if (pl->side) {
+        ZKG_CUDA(cudaStreamWaitEvent(st, ready ? ready : ctx->aux_ev[0], 0));
+        if (k >= 2) ZKG_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[3 + si], 0));      // the set's previous chunk has been accumulated
+    }
+    ZKG_CUDA(cudaMemsetAsync(ss.counts, 0, sizeof(uint32_t) * slots, st));
+    ZKG_CUDA(cudaMemsetAsync(ss.shist, 0, sizeof(uint32_t) * (SIZE_KEYS + HEAVY_LOCKS), st));
     const uint32_t bstride = pl->merged ? 0u : pl->nb;
     const size_t sstride = pl->merged ? 0 : n, ioff = pl->merged ? pl->n_total : 0;
-    k_digits<<<(unsigned)((n + TB - 1) / TB), TB, 0, st>>>(d_scalars, n, pl->c, pl->W, bstride, pl->digits, pl->counts);
+    // a sort that runs under an accumulation (every chunk but the first of a pipelined call) gets a thin grid
+    const bool hidden = pl->side && k > 0;
+    const int TB = hidden ? env_int("ZKG_MSM_SORT_TB_HIDDEN", 256) : 256;
+    unsigned sort_grid = (unsigned)((n + TB - 1) / TB);
+    {
+        const unsigned cap = (unsigned)ctx->sm_count * (unsigned)env_int(hidden ? "ZKG_MSM_SORT_BPS_HIDDEN" : "ZKG_MSM_SORT_BPS", hidden ? (n * (size_t)wg >= ((size_t)1 << 27) ? 2 : 1) : 32);
+        if (cap && sort_grid > cap) sort_grid = cap;
+    }
+    {
+        const int dtb = hidden ? env_int("ZKG_MSM_DIGITS_TB_HIDDEN", TB) : TB;
+        unsigned dgrid = (unsigned)((n + dtb - 1) / dtb);
+        if (dgrid > sort_grid) dgrid = sort_grid;
+        k_digits<<<dgrid, dtb, 0, st>>>(ch.d_scalars, n, pl->c, pl->W, ch.w_lo, ch.w_hi, bstride, ss.digits, ss.counts);
+    }
     {
         const uint32_t tiles = (pl->nb + SCAN_TILE - 1) / SCAN_TILE;      // <= 1024 (nb <= 2^22)
-        uint32_t* tile_sum = pl->shist + 2 * SIZE_KEYS + HEAVY_LOCKS;
-        k_scan_partial<<<dim3(tiles, pl->Wb), 256, 0, st>>>(pl->counts, pl->nb, tiles, tile_sum);
-        k_scan_tiles<<<pl->Wb, 1024, 0, st>>>(tile_sum, tiles);
-        k_scan_final<<<dim3(tiles, pl->Wb), 256, 0, st>>>(pl->counts, pl->nb, tiles, tile_sum, pl->cursor);
+        uint32_t* tile_sum = ss.shist + 2 * SIZE_KEYS + HEAVY_LOCKS;
+        k_scan_partial<<<dim3(tiles, wb), 256, 0, st>>>(ss.counts, pl->nb, tiles, tile_sum);
+        k_scan_tiles<<<wb, 1024, 0, st>>>(tile_sum, tiles);
+        k_scan_final<<<dim3(tiles, wb), 256, 0, st>>>(ss.counts, pl->nb, tiles, tile_sum, ss.cursor);
     }
     // (measured and dropped: scattering one window at a time, to keep the destination region L2-sized, changes nothing --
     //  1.28 vs 1.20 ms at 2^22 -- so the counting sort is not bound by the footprint of its scattered 4-byte stores;
@@ -1062,14 +1356,21 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const Fr* d_scalars,
     //  fixed-capacity bucket lists -- no histogram, no scan, one returned atomic and one store per entry -- bring the
     //  phase from 1.14 to 0.89 ms (5.2 -> 4.3 ms at 2^24) but need an overflow path for every non-uniform input;
     //  2.5 % of a step, not built)
-    k_scatter<<<dim3((unsigned)((n + TB - 1) / TB), pl->W), TB, 0, st>>>(pl->digits, n, bstride, sstride, ioff, point0, pl->cursor, pl->sorted);
-    unsigned hb = (unsigned)((pl->slots + 1023) / 1024);
+    const int ilp = hidden ? env_int("ZKG_MSM_SCATTER_ILP_HIDDEN", 4) : env_int("ZKG_MSM_SCATTER_ILP", 4);
+    if (ilp == 8)
+        k_scatter<8><<<sort_grid, TB, 0, st>>>(ss.digits, n, wg, bstride, sstride, ioff, ch.point0, ch.w_lo, ss.cursor, ss.sorted);
+    else if (ilp == 1)
+        k_scatter<1><<<sort_grid, TB, 0, st>>>(ss.digits, n, wg, bstride, sstride, ioff, ch.point0, ch.w_lo, ss.cursor, ss.sorted);
+    else
+        k_scatter<4><<<sort_grid, TB, 0, st>>>(ss.digits, n, wg, bstride, sstride, ioff, ch.point0, ch.w_lo, ss.cursor, ss.sorted);
+    unsigned hb = (unsigned)((slots + 1023) / 1024);
     if (hb > 592) hb = 592;
-    uint32_t* sstart = pl->shist + SIZE_KEYS + HEAVY_LOCKS;
-    k_size_hist<<<hb, 256, 0, st>>>(pl->counts, pl->slots, pl->shist);
-    k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(pl->shist, sstart);
-    k_size_scatter<<<(unsigned)((pl->slots + 255) / 256), 256, 0, st>>>(pl->counts, pl->slots, sstart, pl->order);
-    if (first) phase_mark(ctx, 1);
+    uint32_t* sstart = ss.shist + SIZE_KEYS + HEAVY_LOCKS;
+    k_size_hist<<<hb, 256, 0, st>>>(ss.counts, slots, ss.shist);
+    k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(ss.shist, sstart);
+    k_size_scatter<<<(unsigned)((slots + 1023) / 1024), 1024, 0, st>>>(ss.counts, slots, sstart, ss.order);
+    if (pl->side) ZKG_CUDA(cudaEventRecord(ctx->aux_ev[1 + si], st));
+    pl->sorts_issued += 1;
     ctx->launches += 8;
     ZKG_CUDA(cudaGetLastError());
     return ZKG_OK;
@@ -1087,46 +1388,81 @@ static inline void msm_launch_g2pair(const Affine<Fq2>* bases, const uint32_t* s
 static inline void msm_launch_g2pair(const Affine<Fq>*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, size_t, uint32_t,
                                      int, int, XYZZ<Fq>*, size_t, cudaStream_t) {}      // never taken: sizeof(Fq) == 32
 
-// second half of a chunk: bucket accumulation of the points sorted by msm_chunk_sort (needs the bases)
+// second half of a chunk: bucket accumulation of the points sorted by msm_chunk_sort (needs the bases).  Chunks are
+// accumulated in the order they were sorted.
 template <class F>
-static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, size_t n) {
-    if (n == 0) return ZKG_OK;
+static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunkDesc& ch, const Affine<F>* d_bases) {
+    if (ch.n == 0) return ZKG_OK;
+    const int k = pl->chunks_done, si = pl->n_sets == 2 ? (k & 1) : 0;
+    const MsmSortSet& ss = pl->set[si];
     cudaStream_t st = ctx->stream;
-    const bool first = pl->chunks_done == 0;
+    const size_t n = ch.n;
+    const int wg = ch.w_hi - ch.w_lo;
+    const int wb = pl->merged ? 1 : wg;
+    const size_t slots = (size_t)wb * pl->nb;
+    XYZZ<F>* buckets = pl->buckets + (pl->merged ? 0 : (size_t)ch.w_lo * pl->nb);
+    if (pl->side) ZKG_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[1 + si], 0));
+    if (k == 0) phase_mark(ctx, 1);
     const size_t sstride = pl->merged ? 0 : n;
     const int use_ba = env_int("ZKG_MSM_BA", 0);            // read per call, like ZKG_MSM_C (tests flip it inside one process)
     // G2: the lane-pair kernel wins while the launch is short of threads (2^16 points: accumulate 0.71 -> 0.60 ms) and loses
     // ~5 % to its shuffles and selects once the one-thread-per-bucket kernel fills the machine (2^19: 3.52 vs 3.70 ms)
     const int g2_pair = env_int("ZKG_MSM_G2_PAIR", pl->n_total <= ((size_t)1 << 17) ? 1 : 0);
     if (sizeof(F) > 32 && !use_ba && g2_pair)
-        msm_launch_g2pair(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order, sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets, pl->slots, st);
+        msm_launch_g2pair(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order, sstride, pl->nb, wb, ch.into, buckets, slots, st);
     else if (use_ba)
-        k_accumulate_ba<F><<<(unsigned)((pl->slots + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, st>>>(
-            d_bases, pl->sorted, pl->cursor, pl->counts, pl->order, sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
+        k_accumulate_ba<F><<<(unsigned)((slots + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, st>>>(
+            d_bases, ss.sorted, ss.cursor, ss.counts, ss.order, sstride, pl->nb, wb, ch.into, buckets);
+    else if (env_int("ZKG_MSM_ACC_TB", 128) == 64)
+        k_accumulate<F, 64><<<(unsigned)((slots + 63) / 64), 64, 0, st>>>(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order,
+                                                                        sstride, pl->nb, wb, ch.into, buckets);
     else
-        k_accumulate<F><<<(unsigned)((pl->slots + 127) / 128), 128, 0, st>>>(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order,
-                                                                           sstride, pl->nb, pl->Wb, first ? 0 : 1, pl->buckets);
+        k_accumulate<F><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order,
+                                                                       sstride, pl->nb, wb, ch.into, buckets);
     {
-        size_t max_heavy = (n * (size_t)pl->W) / (SIZE_KEYS - 1);
-        if (max_heavy > pl->slots) max_heavy = pl->slots;
+        size_t max_heavy = (n * (size_t)wg) / (SIZE_KEYS - 1);
+        if (max_heavy > slots) max_heavy = slots;
         if (max_heavy > 0) {
             unsigned hg = (unsigned)(max_heavy < 74 ? max_heavy : 74);
-            k_accumulate_heavy<F><<<dim3(hg, HEAVY_PARTS), 128, 0, st>>>(d_bases, pl->sorted, pl->cursor, pl->counts, pl->order, pl->shist,
-                                                                       pl->shist + SIZE_KEYS, sstride, pl->nb, pl->buckets);
+            k_accumulate_heavy<F><<<dim3(hg, HEAVY_PARTS), 128, 0, st>>>(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order, ss.shist,
+                                                                       ss.shist + SIZE_KEYS, sstride, pl->nb, buckets);
             ctx->launches += 1;
         }
     }
-    if (first) phase_mark(ctx, 2);
+    if (pl->side) ZKG_CUDA(cudaEventRecord(ctx->aux_ev[3 + si], st));
     ctx->launches += 1;
     pl->chunks_done += 1;
     ZKG_CUDA(cudaGetLastError());
     return ZKG_OK;
 }
 
+// Device-resident inputs: the whole point range at once.  Large MSMs are cut into two WINDOW groups so that the second
+// group's sort hides under the first group's accumulation (merged plans: the groups share the buckets, the second is
+// accumulated into them; per-window plans: the groups own disjoint bucket sets).
+static inline int msm_first_group(size_t n, int W) {
+    int g0 = env_int("ZKG_MSM_GROUP0", -1);
+    // measured at 2^22 G1 points (W = 13): first group of 4 windows 9.76 -> 9.36 ms; below ~2^25 entries the second
+    // sort no longer fits under the first group's accumulation and the split only costs (2^20: 2.96 -> 2.99 ms)
+    if (g0 < 0) g0 = (n * (size_t)W >= ((size_t)1 << 25) && W >= 6) ? (W + 1) / 3 : 0;
+    if (g0 >= W) g0 = 0;
+    return g0;
+}
 template <class F>
-static int32_t msm_chunk(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, size_t point0 = 0) {
-    ZKG_TRY(msm_chunk_sort<F>(ctx, pl, d_scalars, n, point0));
-    return msm_chunk_accumulate<F>(ctx, pl, d_bases, n);
+static int32_t msm_chunks_device(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, int g0) {
+    MsmChunkDesc a, b;
+    a.d_scalars = b.d_scalars = d_scalars;
+    a.n = b.n = n;
+    a.w_lo = 0; a.w_hi = g0 > 0 ? g0 : pl->W; a.into = 0;
+    b.w_lo = a.w_hi; b.w_hi = pl->W; b.into = pl->merged ? 1 : 0;
+    if (g0 > 0) ZKG_TRY(msm_side_begin<F>(ctx, pl));
+    ZKG_TRY(msm_chunk_sort<F>(ctx, pl, a));
+    if (g0 > 0 && pl->side) ZKG_TRY(msm_chunk_sort<F>(ctx, pl, b));
+    ZKG_TRY(msm_chunk_accumulate<F>(ctx, pl, a, d_bases));
+    if (g0 > 0) {
+        if (!pl->side) ZKG_TRY(msm_chunk_sort<F>(ctx, pl, b));
+        ZKG_TRY(msm_chunk_accumulate<F>(ctx, pl, b, d_bases));
+    }
+    return ZKG_OK;
 }
 
 template <class F>
@@ -1138,31 +1474,42 @@ static int32_t msm_finish(zkg_ctx* ctx, MsmPlan<F>* pl, F* d_out, int mode) {
         ZKG_CUDA(cudaGetLastError());
         return ZKG_OK;
     }
+    phase_mark(ctx, 2);                                     // every chunk's accumulation is in the stream by now
     // level 0: running sums over segments of 8 buckets (throughput-bound: two adds per bucket)
     const uint32_t n1 = pl->n1;
-    {
+    const XYZZ<F>* R0 = pl->Rb[0];
+    const XYZZ<F>* A0 = pl->Cb[0];
+    int lshift = 0;
+    if (pl->L > 1) {
         size_t th = (size_t)pl->Wb * n1;
-        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(pl->buckets, nullptr, pl->nb, MSM_REDUCE_L, 0, pl->Wb, pl->Rb[0], pl->Cb[0], n1);
+        k_reduce_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(pl->buckets, nullptr, pl->nb, pl->L, 0, pl->Wb, pl->Rb[0], pl->Cb[0], n1);
         ctx->launches += 1;
+        while (((uint32_t)1 << lshift) < pl->L) ++lshift;
+    } else {
+        R0 = pl->buckets;                                   // n1 = nb entries (R_u = B_u, A_u = identity)
+        A0 = nullptr;
     }
     // log-depth butterfly over the n1 segment results (n1 is a power of two); ping-pong between the
     // two halves of the reduction scratch (each half = 2 * Wb * n1 values, enough for every level)
     int B = 0;
     while (((uint32_t)1 << B) < n1) ++B;
+    const int coop_red = env_int("ZKG_MSM_COOP_REDUCE", 1);  // four-warp blocks for the latency-bound levels
     XYZZ<F>* buf[2] = {pl->Rb[1], pl->Rb[0]};              // level 1 -> second half, level 2 -> first half (level-0 data is dead by then)
     const XYZZ<F>* cur = nullptr;
     uint32_t n_prev = n1;
     for (int lvl = 1; lvl <= B; ++lvl) {
         XYZZ<F>* dst = buf[(lvl - 1) & 1];
         size_t th = (size_t)pl->Wb * (n_prev >> 1) * (lvl + 2);
-        k_merge_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(cur, pl->Rb[0], pl->Cb[0], dst, lvl, n_prev, pl->Wb);
+        if (coop_red) k_merge_lvl_coop<F><<<(unsigned)((th + 31) / 32), 128, 0, st>>>(cur, R0, A0, dst, lvl, n_prev, pl->Wb);
+        else k_merge_lvl<F><<<(unsigned)((th + 127) / 128), 128, 0, st>>>(cur, R0, A0, dst, lvl, n_prev, pl->Wb);
         ctx->launches += 1;
         cur = dst;
         n_prev >>= 1;
     }
     XYZZ<F>* S_arr = B == 0 ? pl->Rb[1] : buf[B & 1];       // the buffer the last level did not write
     XYZZ<F>* Z_arr = S_arr + pl->Wb;
-    k_bits_final<F><<<pl->Wb, 32, 0, st>>>(cur, pl->Rb[0], pl->Cb[0], B, S_arr, Z_arr);
+    if (coop_red) k_bits_final_coop<F><<<pl->Wb, 128, 0, st>>>(cur, R0, A0, B, lshift, S_arr, Z_arr);
+    else k_bits_final<F><<<pl->Wb, 32, 0, st>>>(cur, R0, A0, B, lshift, S_arr, Z_arr);
     ctx->launches += 1;
     const XYZZ<F>* Rin = S_arr;
     const XYZZ<F>* Cin = Z_arr;
@@ -1181,8 +1528,11 @@ template <class F>
 static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, F* d_out, int mode) {
     MsmPlan<F> pl;
     if (n) {
-        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl));
-        ZKG_TRY(msm_chunk<F>(ctx, &pl, d_bases, d_scalars, n));
+        int c = env_int("ZKG_MSM_C", 0);
+        if (c < 2 || c > 22) c = msm_pick_c(n);
+        const int W = msm_num_windows(c), g0 = msm_first_group(n, W);
+        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl, 0, c, g0 > 0 ? g0 : W, g0 > 0 ? W - g0 : 0));
+        ZKG_TRY(msm_chunks_device<F>(ctx, &pl, d_bases, d_scalars, n, g0));
     }
     return msm_finish<F>(ctx, &pl, d_out, mode);
 }
@@ -1220,14 +1570,16 @@ template <class F>
 static int32_t msm_run_prepared(zkg_ctx* ctx, const Affine<F>* d_table, int c, const Fr* d_scalars, size_t n, F* d_out, int mode) {
     MsmPlan<F> pl;
     if (n) {
-        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl, c));
-        ZKG_TRY(msm_chunk<F>(ctx, &pl, d_table, d_scalars, n, 0));
+        const int W = msm_num_windows(c), g0 = msm_first_group(n, W);
+        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl, c, 0, g0 > 0 ? g0 : W, g0 > 0 ? W - g0 : 0));
+        ZKG_TRY(msm_chunks_device<F>(ctx, &pl, d_table, d_scalars, n, g0));
     }
     return msm_finish<F>(ctx, &pl, d_out, mode);
 }
 
 // Registered bases + HOST scalars: the scalars cross PCIe in quarters on the copy stream while the
-// previous quarter is being sorted and accumulated (merged plans take any point range of the table).
+// previous quarter is being sorted and accumulated (merged plans take any point range of the table);
+// the sort of quarter j+1 (side stream) runs under the accumulation of quarter j.
 template <class F>
 static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int c, const uint64_t* h_scalars, size_t n,
                                      F* d_out, int mode = 0) {
@@ -1241,17 +1593,43 @@ static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int
         for (int j = 0; j < K; ++j) if (bounds[j + 1] - bounds[j] > chunk) chunk = bounds[j + 1] - bounds[j];
         ZKG_TRY(ctx->io.reserve(align_up(n * 32, 256) + 512));
         uint8_t* d_sc = (uint8_t*)ctx->io.p;
-        ZKG_TRY(msm_plan<F>(ctx, n, chunk, &pl, c));
+        const int W = msm_num_windows(c);
+        ZKG_TRY(msm_plan<F>(ctx, n, chunk, &pl, c, 0, W, K > 1 ? W : 0));
         ZKG_TRY(ctx_copy_stream(ctx, K));
         ZKG_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
         ZKG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+        if (K > 1) ZKG_TRY(msm_side_begin<F>(ctx, &pl));
+        MsmChunkDesc ch[5];
+        // every copy and every sort first (the sorts wait for their own copy on the side stream), then the accumulations
         for (int j = 0; j < K; ++j) {
             size_t lo = bounds[j], hi = bounds[j + 1];
+            ch[j].d_scalars = (const Fr*)d_sc + lo; ch[j].n = hi - lo; ch[j].point0 = lo;
+            ch[j].w_lo = 0; ch[j].w_hi = W; ch[j].into = 0;
             if (lo >= hi) continue;
             ZKG_TRY(copy_h2d(d_sc + lo * 32, (const uint8_t*)h_scalars + lo * 32, (hi - lo) * 32, ctx->copy_stream));
             ZKG_CUDA(cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
-            ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[j], 0));
-            ZKG_TRY(msm_chunk<F>(ctx, &pl, d_table, (const Fr*)d_sc + lo, hi - lo, lo));
+            if (!pl.side) {
+                ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[j], 0));
+                ch[j].into = pl.chunks_done > 0 ? 1 : 0;
+                ZKG_TRY(msm_chunk_sort<F>(ctx, &pl, ch[j]));
+                ZKG_TRY(msm_chunk_accumulate<F>(ctx, &pl, ch[j], d_table));
+            }
+        }
+        if (pl.side) {
+            // the side stream may run at most two sorts ahead of the accumulations (two sort sets): interleave the enqueues
+            int sorted = 0, accd = 0;
+            auto next = [&](int j) { while (j < K && ch[j].n == 0) ++j; return j; };
+            sorted = next(0); accd = next(0);
+            int ahead = 0;
+            while (accd < K) {
+                while (sorted < K && ahead < 2) {
+                    ZKG_TRY(msm_chunk_sort<F>(ctx, &pl, ch[sorted], ctx->copy_ev[sorted]));
+                    sorted = next(sorted + 1); ++ahead;
+                }
+                ch[accd].into = pl.chunks_done > 0 ? 1 : 0;
+                ZKG_TRY(msm_chunk_accumulate<F>(ctx, &pl, ch[accd], d_table));
+                accd = next(accd + 1); --ahead;
+            }
         }
     }
     return msm_finish<F>(ctx, &pl, d_out, mode);
@@ -1383,28 +1761,36 @@ static int32_t msm_host_enqueue(zkg_ctx* ctx, const void* bases, size_t stride, 
     F* d_out = (F*)(d_pk + pk_bytes);
     MsmPlan<F> pl;
     if (n) {
-        ZKG_TRY(msm_plan<F>(ctx, n, chunk_cap, &pl));
+        int c = env_int("ZKG_MSM_C", 0);
+        if (c < 2 || c > 22) c = msm_pick_c(n);
+        const int W = msm_num_windows(c);
+        ZKG_TRY(msm_plan<F>(ctx, n, chunk_cap, &pl, 0, c, W, K > 1 ? W : 0));
         ZKG_TRY(ctx_copy_stream(ctx, 2 * K));
         // order the copy stream after whatever the compute stream last did with these buffers
         ZKG_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
         ZKG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+        if (K > 1) ZKG_TRY(msm_side_begin<F>(ctx, &pl));
         // copy chunk j, then launch its compute, then copy chunk j+1 ...: with pinned sources the copies
         // simply run ahead on the copy stream; with pageable sources the host thread stages chunk j+1
-        // while the device works on chunk j
+        // while the device works on chunk j.  The sorts go to the side stream: chunk j+1's scalars arrive
+        // right after chunk j's bases, so its sort runs under chunk j's accumulation.
         for (int j = 0; j < K; ++j) {
             size_t lo = bounds[j], hi = bounds[j + 1];
             if (lo >= hi) continue;
+            MsmChunkDesc ch;
+            ch.d_scalars = (const Fr*)d_sc + lo; ch.n = hi - lo; ch.point0 = 0;
+            ch.w_lo = 0; ch.w_hi = W; ch.into = pl.chunks_done > 0 ? 1 : 0;
             // the scalars go first: digits and the counting sort need nothing else, so the chunk's bases cross
             // PCIe while its own sort runs
             ZKG_TRY(copy_h2d(d_sc + lo * 32, (const uint8_t*)scalars + lo * 32, (hi - lo) * 32, ctx->copy_stream));
             ZKG_CUDA(cudaEventRecord(ctx->copy_ev[2 * j], ctx->copy_stream));
-            ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2 * j], 0));
-            ZKG_TRY(msm_chunk_sort<F>(ctx, &pl, (const Fr*)d_sc + lo, hi - lo));      // launched before the (possibly host-staged) bases copy
+            if (!pl.side) ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2 * j], 0));
+            ZKG_TRY(msm_chunk_sort<F>(ctx, &pl, ch, ctx->copy_ev[2 * j]));      // launched before the (possibly host-staged) bases copy
             ZKG_TRY(copy_h2d(d_ark + lo * stride, (const uint8_t*)bases + lo * stride, (hi - lo) * stride, ctx->copy_stream));
             ZKG_CUDA(cudaEventRecord(ctx->copy_ev[2 * j + 1], ctx->copy_stream));
             ZKG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2 * j + 1], 0));
             ZKG_TRY(pack_bases<F>(ctx, d_ark + lo * stride, stride, hi - lo, d_pk + lo * sizeof(Affine<F>)));
-            ZKG_TRY(msm_chunk_accumulate<F>(ctx, &pl, (const Affine<F>*)d_pk + lo, hi - lo));
+            ZKG_TRY(msm_chunk_accumulate<F>(ctx, &pl, ch, (const Affine<F>*)d_pk + lo));
         }
     }
     ZKG_TRY(msm_finish<F>(ctx, &pl, d_out, mode));
