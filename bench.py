@@ -227,13 +227,16 @@ def run_reference(args):
     if rank != 0:
         return
     log2n = args.log2n
-    n, th, times = cpu_msm_sample(log2n, args.warmup + args.steps)
-    timed = times[args.warmup:]
+    # ~2.5 s per step on 15 threads: at most 3 warm-up + 20 timed steps, so the run ends within about a minute
+    k_warm, k_timed = min(args.warmup, 3), min(args.steps, 20)
+    n, th, times = cpu_msm_sample(log2n, k_warm + k_timed)
+    timed = times[k_warm:]
     ms = 1e3 * sum(timed) / len(timed)
     val = n / (ms * 1e-3) / 1e6
     c, W = ark_window(n)
     sample = (f"the full workload: G1 MSM of 2^{log2n} points per step (arkworks window rule c={c}, W={W}), {th} OpenMP threads over "
-              f"the {W} windows (as rayon does under ark-ec's `parallel` feature), {os.cpu_count()} host CPUs visible")
+              f"the {W} windows (as rayon does under ark-ec's `parallel` feature), {os.cpu_count()} host CPUs visible; "
+              f"{k_timed} timed steps after {k_warm} warm-up")
     line = {
         "impl": "reference", "metric": "BN254 G1 MSM Mpts/s", "value": round(val, 4), "unit": "Mpts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
@@ -417,6 +420,27 @@ def run_ours(args):
     closed_form_ok = bool((dev_result.view(np.uint64)[:8] == expect_xy).all())
     if not closed_form_ok:
         raise SystemExit("bench.py: the MSM result differs from the closed form (sum a_i s_i) * G")
+
+    # ---- the same MSM with the sort pipeline switched off (every launch on the one stream, k_accumulate alone on the GPU):
+    #      the kernel's own rate, beside the figure of the timed region where the second window group's sort shares the SMs
+    alone = None
+    if world == 1:
+        os.environ["ZKG_MSM_GROUP0"] = "0"
+        try:
+            for _ in range(2):
+                step_device()
+            capi.check(lib.zkg_ctx_set_profiling(ctx, 1))
+            k_al = max(3, min(args.steps, 10))
+            al_ms = timed(step_device, k_al, collective=False) / k_al
+            al_ph = []
+            for ph in range(3):
+                f = C.c_float(0)
+                capi.check(lib.zkg_ctx_phase_ms(ctx, ph, C.byref(f)))
+                al_ph.append(f.value)
+            capi.check(lib.zkg_ctx_set_profiling(ctx, 0))
+            alone = {"ms_per_step": al_ms, "phases": al_ph, "same": bool((out_xyz.cpu().numpy() == dev_result).all())}
+        finally:
+            del os.environ["ZKG_MSM_GROUP0"]
 
     # ---- same workload with two MSMs in flight (two contexts / streams): the latency-bound tail of one
     #      (bucket reduction) overlaps the bucket accumulation of the next -- how a prover that issues its
@@ -1215,6 +1239,16 @@ def run_ours(args):
                                              "MADs per add instead of 11 x 136 limb-MACs)",
                          "kernel_ms": round(acc_ms, 4),
                          "kernel_share_of_step": round(acc_ms / ms_per_step, 4),
+                         "kernel_launches_per_step": 2,
+                         "pipeline_note": "a step launches k_accumulate twice (window groups 0-3 and 4-12 of the 13 windows); the counting sort of the "
+                                          "second group runs on a high-priority side stream UNDER the first launch, so kernel_ms is the span of both "
+                                          "launches with that sort sharing the SMs (one of five resident blocks per SM displaced while it runs). "
+                                          "sort_pipeline_off is the same step with every launch on one stream: the kernel alone",
+                         "sort_pipeline_off": ({"ms_per_step": round(alone["ms_per_step"], 4), "kernel_ms": round(alone["phases"][1], 4),
+                                                "frac": round(n * my_W * WIDE_MADS_PER_MADD / (alone["phases"][1] * 1e-3) / 1e12 / WIDE_MAD_PEAK_T, 4),
+                                                "phase_ms": {"digits_sort": round(alone["phases"][0], 4), "accumulate": round(alone["phases"][1], 4),
+                                                             "reduce_final": round(alone["phases"][2], 4)},
+                                                "matches": alone["same"]} if alone else None),
                          "phase_ms": {"digits_sort": round(sort_ms, 4), "accumulate": round(acc_ms, 4),
                                       "reduce_final": round(red_ms, 4),
                                       "note": "CUDA events recorded by the library at the phase boundaries of the LAST call of the timed, "
@@ -1241,7 +1275,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=22)

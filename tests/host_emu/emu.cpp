@@ -151,3 +151,4 @@ extern "C" void emu_fr_mul_r29(const uint64_t* a, const uint64_t* b, uint64_t* o
 extern "C" void emu_fq_mul_r29(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
     for (size_t i = 0; i < n; ++i) st(o + 4 * i, fp_mul_r29(ld<Fq>(a + 4 * i), ld<Fq>(b + 4 * i)));
 }
+extern "C" int emu_pick_c_g2(size_t n) { return msm_pick_c(n, true); }

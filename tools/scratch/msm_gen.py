@@ -1,0 +1,34 @@
+"""Device-resident GENERIC (unregistered) MSM at 2^lg points: total and phase times.  argv: lg reps [g2]"""
+import ctypes as C, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import zksaas_b200 as z
+from zksaas_b200 import capi
+lib = z.lib()
+lg = int(sys.argv[1]); reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+g2 = len(sys.argv) > 3
+n = 1 << lg
+st = torch.cuda.Stream(); torch.cuda.set_stream(st)
+ctx = capi.ctx_p(); capi.check(lib.zkg_ctx_create(0, C.c_void_p(st.cuda_stream), C.byref(ctx)))
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+def rnd(k):
+    t = torch.randint(-2**63, 2**63 - 1, (k, 4), dtype=torch.int64, device="cuda", generator=g); t[:, 3] &= (1 << 61) - 1; return t
+a, s = rnd(n), rnd(n)
+b = torch.empty((n, 128 if g2 else 64), dtype=torch.uint8, device="cuda")
+capi.check(lib.zkg_fixed_base_dev(ctx, 2 if g2 else 1, C.c_void_p(s.data_ptr()), n, C.c_void_p(b.data_ptr())))
+o = torch.zeros(24, dtype=torch.int64, device="cuda")
+lib.zkg_ctx_set_profiling(ctx, 1)
+fn = lib.zkg_msm_bn254_g2_dev if g2 else lib.zkg_msm_bn254_g1_dev
+def run():
+    capi.check(fn(ctx, C.c_void_p(b.data_ptr()), C.c_void_p(a.data_ptr()), n, C.c_void_p(o.data_ptr())))
+for _ in range(2): run()
+capi.check(lib.zkg_ctx_sync(ctx))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(st)
+for _ in range(reps): run()
+e1.record(st); e1.synchronize()
+ph = []
+for k in range(3):
+    f = C.c_float(0); lib.zkg_ctx_phase_ms(ctx, k, C.byref(f)); ph.append(round(f.value, 3))
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("ZKG_"))
+print(f"[{tag}] generic {'G2' if g2 else 'G1'} n=2^{lg}: {e0.elapsed_time(e1)/reps:.3f} ms  phases(sort,acc,reduce)={ph}  out={o.cpu().numpy()[:2]}", flush=True)

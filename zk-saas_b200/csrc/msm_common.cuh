@@ -15,28 +15,63 @@ static constexpr uint32_t MSM_DIGIT_NONE = 0xffffffffu;
 // final carry of the signed recoding is absorbed without an extra window.
 ZKG_HD int msm_num_windows(int c) { return MSM_SCALAR_BITS / c + 1; }
 
-// Window size for n points.  Cost model (field multiplications): n*W mixed adds of 10 plus
-// W*2^(c-1) buckets reduced with two 14-multiplication adds each.  The TOP window only holds the
-// r = 254 - (W-1)c leftover bits, so its points fall into just 2^r buckets; one thread walks one
-// bucket, so a small r serialises n/2^r additions on a handful of threads (measured: c = 18 at
-// n = 2^22 has r = 2 and takes 7 s instead of 10 ms).  Window sizes whose top buckets would hold
-// more than 1024 points are therefore excluded.
-ZKG_HD int msm_pick_c(size_t n) {
+// Bucket populations from which a bucket counts as HEAVY (split over a block instead of walked by one thread): well
+// above anything a uniform digit distribution produces, low enough to catch the under-filled top window of small MSMs.
+ZKG_HD uint32_t msm_heavy_key(double mean) {
+    double k = 8.0 * mean + 64.0;
+    return k < 128.0 ? 128u : k > 2047.0 ? 2047u : (uint32_t)k;
+}
+
+// Window size for n points on the per-window path (no prepared table).  Cost model in MICROSECONDS, calibrated on B200
+// window sweeps (tools/scratch/sweep_gen.py, round 2; it reproduces the measured totals within ~10 % from 2^10 to 2^22):
+//   sort        50 + 0.02 ns per (point, window)
+//   accumulate  one thread walks one bucket: (n / buckets) additions at max(7 us, 13 us * threads / 95 k) each -- the
+//               latency of a lone thread, or the share of a full machine; the TOP window only holds r = 254 - (W-1)c
+//               bits, so its 2^r buckets get n / 2^r points each: a serial chain unless they reach the heavy-bucket
+//               threshold and are split over blocks (k_accumulate_heavy: ~110 us of tree and lock per bucket)
+//   reduction   level 0 (two additions per bucket, >= 165 us) or none for small bucket sets, ~8 us per butterfly
+//               level, 70 us for the bit scaling, and the Horner over windows: c (W-1) DEPENDENT doublings at ~2 us
+// (round 1's model counted multiplications only and ignored both latency terms: it chose c = 8 at n = 2^16, where 64
+//  top-window buckets of 1024 points each made the MSM take 7.5 ms; c = 15 takes 1.15 ms.)
+// g2: the same with the measured Fq2 ratios.
+ZKG_HD int msm_pick_c(size_t n, bool g2 = false) {
     int lg = 0;
     while (((size_t)1 << lg) < n) ++lg;
-    int best = 0, fallback = 5, fallback_used = -1;
-    double best_cost = 0;
-    for (int c = 5; c <= 20; ++c) {
-        if (c > lg + 1 && c > 5) break;
-        int W = msm_num_windows(c);
-        int r = MSM_SCALAR_BITS - (W - 1) * c;             // bits in the top window (1..c-1)
-        int used = r < c - 1 ? r : c - 1;                  // log2 of the top window's populated buckets
-        if (used > fallback_used) { fallback = c; fallback_used = used; }
-        if ((n >> used) > 1024) continue;
-        double cost = (double)n * W * 10.0 + (double)W * (double)((size_t)1 << (c - 1)) * 28.0 + (double)((c - 1 + 2) / 3) * 13e6;
-        if (best == 0 || cost < best_cost) { best = c; best_cost = cost; }
+    const double lat_min = g2 ? 15.0 : 7.0, lat_full = g2 ? 29.0 : 13.0, thr_full = g2 ? 56800.0 : 95000.0;
+    const double add_ns = g2 ? 0.75 : 0.25, lvl_us = g2 ? 16.0 : 8.0, bits_us = g2 ? 190.0 : 70.0, dbl_us = g2 ? 6.5 : 2.0;
+    int best = 5;
+    double best_cost = -1.0;
+    for (int c = 4; c <= 20; ++c) {
+        if (c > lg + 2 && c > 4) break;
+        const int W = msm_num_windows(c);
+        const int r = MSM_SCALAR_BITS - (W - 1) * c;             // bits in the top window (1..c)
+        const int used = r < c - 1 ? r : c - 1;                  // log2 of the top window's populated buckets
+        const double nb = (double)((size_t)1 << (c - 1)), slots = nb * W, mean = (double)n / nb;
+        const double lat = lat_full * slots / thr_full > lat_min ? lat_full * slots / thr_full : lat_min;
+        double acc = mean * lat;
+        const double top = (double)n / (double)((size_t)1 << used);
+        if (top >= (double)msm_heavy_key(mean)) {
+            double parts = top / 4096.0;
+            parts = parts < 1.0 ? 1.0 : parts > 32.0 ? 32.0 : parts;
+            double hb = (double)((size_t)1 << used);                 // heavy buckets; the launch walks them 148 at a time
+            double rounds = hb / 148.0;
+            rounds = rounds < 1.0 ? 1.0 : rounds;
+            const double hthreads = (hb < 148.0 ? hb : 148.0) * parts * 128.0;
+            const double lat_h = lat_full * hthreads / thr_full > lat_min ? lat_full * hthreads / thr_full : lat_min;
+            acc += rounds * (top / (parts * 128.0) * lat_h + (g2 ? 300.0 : 110.0));
+        } else if (top * lat > acc) acc = top * lat;
+        const double sort = 50.0 + (double)n * W * 0.02e-3;
+        double red;
+        if (slots <= 16384.0) red = (c - 1) * lvl_us;
+        else {
+            double l0 = slots * 2.0 * add_ns * 1e-3;
+            red = (l0 > 165.0 ? l0 : 165.0) + (c - 4) * lvl_us + slots / 8.0 * 3.0 * add_ns * 1e-3;
+        }
+        red += bits_us + (double)c * (W - 1) * dbl_us + W * 1.5 + 60.0;
+        const double cost = sort + acc + red;
+        if (best_cost < 0 || cost < best_cost) { best = c; best_cost = cost; }
     }
-    return best ? best : fallback;      // huge n: no window meets the bound, take the best-filled top window
+    return best;
 }
 
 // Window size when the bases come with precomputed window shifts 2^(cw) * P (static CRS shares):

@@ -83,7 +83,8 @@ __global__ void k_pack_bases(const uint8_t* __restrict__ ark, size_t stride, siz
 // is recomputed from window 0, which costs a few shifts per skipped window.  Grid-stride: a sort that runs UNDER another
 // chunk's accumulation is launched with a couple of blocks per SM, so that it takes a thin slice of every SM instead of
 // every slot the accumulation frees (the side stream has the higher priority).
-static __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, size_t n, int c, int W, int w_lo, int w_hi, uint32_t bstride,
+template <int THIN>      // THIN: at most 32 registers, so that a 128-thread block fits beside five resident k_accumulate blocks
+static __global__ void __launch_bounds__(THIN ? 128 : 256, THIN ? 16 : 1) k_digits(const Fr* __restrict__ scalars, size_t n, int c, int W, int w_lo, int w_hi, uint32_t bstride,
                          uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
     const uint32_t half = 1u << (c - 1);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -204,12 +205,12 @@ static __global__ void __launch_bounds__(256, ILP > 4 ? 4 : 8) k_scatter(const u
 // ------------------------------------------------------------------------------------------
 static constexpr uint32_t SIZE_KEYS = 2048;
 
-static __global__ void k_size_hist(const uint32_t* __restrict__ counts, size_t slots, uint32_t* __restrict__ hist) {
+static __global__ void k_size_hist(const uint32_t* __restrict__ counts, size_t slots, uint32_t hkey, uint32_t* __restrict__ hist) {
     __shared__ uint32_t h[SIZE_KEYS];
     for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x) h[i] = 0;
     __syncthreads();
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots; t += (size_t)gridDim.x * blockDim.x)
-        atomicAdd(&h[min(counts[t], SIZE_KEYS - 1)], 1u);
+        atomicAdd(&h[min(counts[t], hkey)], 1u);
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x)
         if (h[i]) atomicAdd(&hist[i], h[i]);
@@ -232,14 +233,14 @@ static __global__ void k_size_scan(const uint32_t* __restrict__ hist, uint32_t* 
 // Block-aggregated: the populations of uniform scalars fall on a few dozen keys, so one global atomic per (warp, key)
 // piles onto the same addresses (42 us for 2^19 slots).  A 1024-thread block ranks its slots in a shared histogram
 // (warp-aggregated), reserves one contiguous range per key it saw, and writes.
-static __global__ void __launch_bounds__(1024) k_size_scatter(const uint32_t* __restrict__ counts, size_t slots, uint32_t* __restrict__ start,
+static __global__ void __launch_bounds__(1024) k_size_scatter(const uint32_t* __restrict__ counts, size_t slots, uint32_t hkey, uint32_t* __restrict__ start,
                                       uint32_t* __restrict__ order) {
     __shared__ uint32_t sh[SIZE_KEYS];
     for (uint32_t i = threadIdx.x; i < SIZE_KEYS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = t < slots;
-    uint32_t key = valid ? min(counts[t], SIZE_KEYS - 1) : 0xffffffffu;
+    uint32_t key = valid ? min(counts[t], hkey) : 0xffffffffu;
     uint32_t peers = __match_any_sync(0xffffffffu, key);
     int leader = __ffs(peers) - 1;
     uint32_t lane = threadIdx.x & 31;
@@ -264,7 +265,7 @@ template <class F, int TB = 128>
 __global__ void __launch_bounds__(TB, (sizeof(F) > 32 ? 3 : 5) * 128 / TB)     // G2: three 128-thread blocks per SM (<= 168 registers); G1: five (<= 102)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
-             const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
+             const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into, uint32_t hkey,
              XYZZ<F>* __restrict__ buckets) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)W * nb) return;
@@ -274,7 +275,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
     uint32_t end = cursor_end[slot], cnt = counts[slot];
     const uint32_t* idx = sorted + (size_t)w * sstride;
     if (accumulate_into && cnt == 0) return;                 // nothing new for this bucket in this chunk
-    if (cnt >= SIZE_KEYS - 1) {                              // heavy bucket: left to k_accumulate_heavy
+    if (cnt >= hkey) {                                       // heavy bucket: left to k_accumulate_heavy
         if (!accumulate_into) store_vec(buckets + slot, XYZZ<F>::inf());
         return;
     }
@@ -369,7 +370,7 @@ template <class F>
 __global__ void __launch_bounds__(BA_THREADS, 3)
 k_accumulate_ba(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
                 const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
-                const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
+                const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into, uint32_t hkey,
                 XYZZ<F>* __restrict__ buckets) {
     __shared__ __align__(16) unsigned char raw_pre[BA_THREADS * sizeof(F)];
     __shared__ __align__(16) unsigned char raw_suf[BA_THREADS * sizeof(F)];
@@ -397,7 +398,7 @@ k_accumulate_ba(const Affine<F>* __restrict__ bases, const uint32_t* __restrict_
 
     if (cnt0 > 2 * BA_MAXP || cnt0 < BA_MIN) {     // block-uniform: plain chain (heavy buckets are skipped as in k_accumulate)
         if (!valid || (accumulate_into && cnt == 0)) return;
-        if (cnt >= SIZE_KEYS - 1) {
+        if (cnt >= hkey) {
             if (!accumulate_into) store_vec(buckets + slot, XYZZ<F>::inf());
             return;
         }
@@ -607,7 +608,7 @@ template <int BLOCKS>
 __global__ void __launch_bounds__(128, BLOCKS)
 k_accumulate_g2pair(const Affine<Fq2>* __restrict__ bases, const uint32_t* __restrict__ sorted,
                     const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
-                    const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into,
+                    const uint32_t* __restrict__ order, size_t sstride, uint32_t nb, int W, int accumulate_into, uint32_t hkey,
                     XYZZ<Fq2>* __restrict__ buckets) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t pair = t >> 1;
@@ -618,7 +619,7 @@ k_accumulate_g2pair(const Affine<Fq2>* __restrict__ bases, const uint32_t* __res
     uint32_t end = 0, cnt = 0;
     if (valid) { slot = order[pair]; end = cursor_end[slot]; cnt = counts[slot]; }
     const uint32_t* idx = sorted + (size_t)(slot / nb) * sstride + (end - cnt);
-    const bool heavy = cnt >= SIZE_KEYS - 1;                 // left to k_accumulate_heavy
+    const bool heavy = cnt >= hkey;                          // left to k_accumulate_heavy
     const bool work = valid && !heavy && !(accumulate_into && cnt == 0);
     const uint32_t my_cnt = work ? cnt : 0u;
     const uint32_t max_cnt = __reduce_max_sync(PAIR_FULL, my_cnt);
@@ -654,10 +655,10 @@ __global__ void __launch_bounds__(128)
 k_accumulate_heavy(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
                    const uint32_t* __restrict__ cursor_end, const uint32_t* __restrict__ counts,
                    const uint32_t* __restrict__ order, const uint32_t* __restrict__ size_hist,
-                   uint32_t* __restrict__ locks, size_t sstride, uint32_t nb, XYZZ<F>* buckets) {
+                   uint32_t* __restrict__ locks, size_t sstride, uint32_t nb, uint32_t hkey, XYZZ<F>* buckets) {
     __shared__ __align__(16) unsigned char raw[128 * sizeof(XYZZ<F>)];
     XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(raw);
-    const uint32_t n_heavy = size_hist[SIZE_KEYS - 1];
+    const uint32_t n_heavy = size_hist[hkey];
     const uint32_t tid = threadIdx.x, part = blockIdx.y;
     for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
         size_t slot = order[h];
@@ -1216,6 +1217,7 @@ struct MsmPlan {
     uint32_t L = 8;            // level-0 segment of the bucket reduction (1: no level 0, the butterfly starts on the buckets)
     size_t slots = 0;          // Wb * nb
     MsmSortSet set[2];
+    uint32_t hkey[2] = {SIZE_KEYS - 1, SIZE_KEYS - 1};      // heavy-bucket threshold of the chunk sorted into each set
     int n_sets = 1;
     bool side = false;         // sorts run on ctx->aux_stream (needs n_sets == 2)
     XYZZ<F>* buckets = nullptr;
@@ -1235,7 +1237,7 @@ static int32_t msm_plan(zkg_ctx* ctx, size_t n_total, size_t chunk_cap, MsmPlan<
     int c = merged_c ? merged_c : c_forced;
     if (!c) {
         c = env_int("ZKG_MSM_C", 0);
-        if (c < 2 || c > 22) c = msm_pick_c(n_total);
+        if (c < 2 || c > 22) c = msm_pick_c(n_total, sizeof(F) > 32);
     }
     pl->c = c;
     pl->W = msm_num_windows(c);
@@ -1315,6 +1317,11 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunkDesc& 
     const int wg = ch.w_hi - ch.w_lo;
     const int wb = pl->merged ? 1 : wg;                        // bucket sets of this chunk
     const size_t slots = (size_t)wb * pl->nb;
+    {
+        const int hk = env_int("ZKG_MSM_HEAVY_KEY", 0);
+        pl->hkey[si] = hk >= 2 && hk < (int)SIZE_KEYS ? (uint32_t)hk : msm_heavy_key((double)n * wg / (double)slots);
+    }
+    const uint32_t hkey = pl->hkey[si];
     if (k == 0) phase_mark(ctx, 0);
     if (pl->side) {
         ZKG_CUDA(cudaStreamWaitEvent(st, ready ? ready : ctx->aux_ev[0], 0));
@@ -1336,7 +1343,8 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunkDesc& 
         const int dtb = hidden ? env_int("ZKG_MSM_DIGITS_TB_HIDDEN", TB) : TB;
         unsigned dgrid = (unsigned)((n + dtb - 1) / dtb);
         if (dgrid > sort_grid) dgrid = sort_grid;
-        k_digits<<<dgrid, dtb, 0, st>>>(ch.d_scalars, n, pl->c, pl->W, ch.w_lo, ch.w_hi, bstride, ss.digits, ss.counts);
+        if (dtb <= 128) k_digits<1><<<dgrid, dtb, 0, st>>>(ch.d_scalars, n, pl->c, pl->W, ch.w_lo, ch.w_hi, bstride, ss.digits, ss.counts);
+        else k_digits<0><<<dgrid, dtb, 0, st>>>(ch.d_scalars, n, pl->c, pl->W, ch.w_lo, ch.w_hi, bstride, ss.digits, ss.counts);
     }
     {
         const uint32_t tiles = (pl->nb + SCAN_TILE - 1) / SCAN_TILE;      // <= 1024 (nb <= 2^22)
@@ -1366,9 +1374,9 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunkDesc& 
     unsigned hb = (unsigned)((slots + 1023) / 1024);
     if (hb > 592) hb = 592;
     uint32_t* sstart = ss.shist + SIZE_KEYS + HEAVY_LOCKS;
-    k_size_hist<<<hb, 256, 0, st>>>(ss.counts, slots, ss.shist);
+    k_size_hist<<<hb, 256, 0, st>>>(ss.counts, slots, hkey, ss.shist);
     k_size_scan<<<1, SIZE_KEYS / 2, 0, st>>>(ss.shist, sstart);
-    k_size_scatter<<<(unsigned)((slots + 1023) / 1024), 1024, 0, st>>>(ss.counts, slots, sstart, ss.order);
+    k_size_scatter<<<(unsigned)((slots + 1023) / 1024), 1024, 0, st>>>(ss.counts, slots, hkey, sstart, ss.order);
     if (pl->side) ZKG_CUDA(cudaEventRecord(ctx->aux_ev[1 + si], st));
     pl->sorts_issued += 1;
     ctx->launches += 8;
@@ -1377,16 +1385,16 @@ static int32_t msm_chunk_sort(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunkDesc& 
 }
 
 static inline void msm_launch_g2pair(const Affine<Fq2>* bases, const uint32_t* sorted, const uint32_t* cursor, const uint32_t* counts,
-                                     const uint32_t* order, size_t sstride, uint32_t nb, int Wb, int into, XYZZ<Fq2>* buckets, size_t slots,
+                                     const uint32_t* order, size_t sstride, uint32_t nb, int Wb, int into, uint32_t hkey, XYZZ<Fq2>* buckets, size_t slots,
                                      cudaStream_t st) {
     const unsigned grid = (unsigned)((2 * slots + 127) / 128);
     if (env_int("ZKG_MSM_G2_PAIR_BLOCKS", 4) == 3)
-        k_accumulate_g2pair<3><<<grid, 128, 0, st>>>(bases, sorted, cursor, counts, order, sstride, nb, Wb, into, buckets);
+        k_accumulate_g2pair<3><<<grid, 128, 0, st>>>(bases, sorted, cursor, counts, order, sstride, nb, Wb, into, hkey, buckets);
     else
-        k_accumulate_g2pair<4><<<grid, 128, 0, st>>>(bases, sorted, cursor, counts, order, sstride, nb, Wb, into, buckets);
+        k_accumulate_g2pair<4><<<grid, 128, 0, st>>>(bases, sorted, cursor, counts, order, sstride, nb, Wb, into, hkey, buckets);
 }
 static inline void msm_launch_g2pair(const Affine<Fq>*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, size_t, uint32_t,
-                                     int, int, XYZZ<Fq>*, size_t, cudaStream_t) {}      // never taken: sizeof(Fq) == 32
+                                     int, int, uint32_t, XYZZ<Fq>*, size_t, cudaStream_t) {}      // never taken: sizeof(Fq) == 32
 
 // second half of a chunk: bucket accumulation of the points sorted by msm_chunk_sort (needs the bases).  Chunks are
 // accumulated in the order they were sorted.
@@ -1401,6 +1409,7 @@ static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunk
     const int wb = pl->merged ? 1 : wg;
     const size_t slots = (size_t)wb * pl->nb;
     XYZZ<F>* buckets = pl->buckets + (pl->merged ? 0 : (size_t)ch.w_lo * pl->nb);
+    const uint32_t hkey = pl->hkey[si];
     if (pl->side) ZKG_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[1 + si], 0));
     if (k == 0) phase_mark(ctx, 1);
     const size_t sstride = pl->merged ? 0 : n;
@@ -1409,23 +1418,23 @@ static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunk
     // ~5 % to its shuffles and selects once the one-thread-per-bucket kernel fills the machine (2^19: 3.52 vs 3.70 ms)
     const int g2_pair = env_int("ZKG_MSM_G2_PAIR", pl->n_total <= ((size_t)1 << 17) ? 1 : 0);
     if (sizeof(F) > 32 && !use_ba && g2_pair)
-        msm_launch_g2pair(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order, sstride, pl->nb, wb, ch.into, buckets, slots, st);
+        msm_launch_g2pair(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order, sstride, pl->nb, wb, ch.into, hkey, buckets, slots, st);
     else if (use_ba)
         k_accumulate_ba<F><<<(unsigned)((slots + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, st>>>(
-            d_bases, ss.sorted, ss.cursor, ss.counts, ss.order, sstride, pl->nb, wb, ch.into, buckets);
+            d_bases, ss.sorted, ss.cursor, ss.counts, ss.order, sstride, pl->nb, wb, ch.into, hkey, buckets);
     else if (env_int("ZKG_MSM_ACC_TB", 128) == 64)
         k_accumulate<F, 64><<<(unsigned)((slots + 63) / 64), 64, 0, st>>>(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order,
-                                                                        sstride, pl->nb, wb, ch.into, buckets);
+                                                                        sstride, pl->nb, wb, ch.into, hkey, buckets);
     else
         k_accumulate<F><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order,
-                                                                       sstride, pl->nb, wb, ch.into, buckets);
+                                                                       sstride, pl->nb, wb, ch.into, hkey, buckets);
     {
-        size_t max_heavy = (n * (size_t)wg) / (SIZE_KEYS - 1);
+        size_t max_heavy = (n * (size_t)wg) / hkey;
         if (max_heavy > slots) max_heavy = slots;
         if (max_heavy > 0) {
-            unsigned hg = (unsigned)(max_heavy < 74 ? max_heavy : 74);
+            unsigned hg = (unsigned)(max_heavy < 148 ? max_heavy : 148);
             k_accumulate_heavy<F><<<dim3(hg, HEAVY_PARTS), 128, 0, st>>>(d_bases, ss.sorted, ss.cursor, ss.counts, ss.order, ss.shist,
-                                                                       ss.shist + SIZE_KEYS, sstride, pl->nb, buckets);
+                                                                       ss.shist + SIZE_KEYS, sstride, pl->nb, hkey, buckets);
             ctx->launches += 1;
         }
     }
@@ -1436,33 +1445,54 @@ static int32_t msm_chunk_accumulate(zkg_ctx* ctx, MsmPlan<F>* pl, const MsmChunk
     return ZKG_OK;
 }
 
-// Device-resident inputs: the whole point range at once.  Large MSMs are cut into two WINDOW groups so that the second
-// group's sort hides under the first group's accumulation (merged plans: the groups share the buckets, the second is
+// Device-resident inputs: the whole point range at once.  Large MSMs are cut into WINDOW groups so that each group's
+// sort hides under the previous group's accumulation (merged plans: the groups share the buckets, later groups are
 // accumulated into them; per-window plans: the groups own disjoint bucket sets).
-static inline int msm_first_group(size_t n, int W) {
+// groups[]: window boundaries 0 = g[0] < g[1] < ... < g[ng] = W; ng = 1: no pipelining.
+static inline int msm_window_groups(size_t n, int W, int* g) {
     int g0 = env_int("ZKG_MSM_GROUP0", -1);
+    const int ng_env = env_int("ZKG_MSM_GROUPS", 2);
     // measured at 2^22 G1 points (W = 13): first group of 4 windows 9.76 -> 9.36 ms; below ~2^25 entries the second
     // sort no longer fits under the first group's accumulation and the split only costs (2^20: 2.96 -> 2.99 ms)
     if (g0 < 0) g0 = (n * (size_t)W >= ((size_t)1 << 25) && W >= 6) ? (W + 1) / 3 : 0;
-    if (g0 >= W) g0 = 0;
-    return g0;
+    g[0] = 0;
+    if (g0 <= 0 || g0 >= W) { g[1] = W; return 1; }
+    if (ng_env >= 3 && W - g0 >= 2) { g[1] = g0; g[2] = g0 + (W - g0) / 2; g[3] = W; return 3; }
+    g[1] = g0; g[2] = W;
+    return 2;
 }
 template <class F>
-static int32_t msm_chunks_device(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, int g0) {
-    MsmChunkDesc a, b;
-    a.d_scalars = b.d_scalars = d_scalars;
-    a.n = b.n = n;
-    a.w_lo = 0; a.w_hi = g0 > 0 ? g0 : pl->W; a.into = 0;
-    b.w_lo = a.w_hi; b.w_hi = pl->W; b.into = pl->merged ? 1 : 0;
-    if (g0 > 0) ZKG_TRY(msm_side_begin<F>(ctx, pl));
-    ZKG_TRY(msm_chunk_sort<F>(ctx, pl, a));
-    if (g0 > 0 && pl->side) ZKG_TRY(msm_chunk_sort<F>(ctx, pl, b));
-    ZKG_TRY(msm_chunk_accumulate<F>(ctx, pl, a, d_bases));
-    if (g0 > 0) {
-        if (!pl->side) ZKG_TRY(msm_chunk_sort<F>(ctx, pl, b));
-        ZKG_TRY(msm_chunk_accumulate<F>(ctx, pl, b, d_bases));
+static int32_t msm_chunks_device(zkg_ctx* ctx, MsmPlan<F>* pl, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, const int* g, int ng) {
+    MsmChunkDesc ch[4];
+    for (int k = 0; k < ng; ++k) {
+        ch[k].d_scalars = d_scalars; ch[k].n = n; ch[k].point0 = 0;
+        ch[k].w_lo = g[k]; ch[k].w_hi = g[k + 1];
+        ch[k].into = (k > 0 && pl->merged) ? 1 : 0;
+    }
+    if (ng > 1) ZKG_TRY(msm_side_begin<F>(ctx, pl));
+    if (!pl->side) {
+        for (int k = 0; k < ng; ++k) {
+            ZKG_TRY(msm_chunk_sort<F>(ctx, pl, ch[k]));
+            ZKG_TRY(msm_chunk_accumulate<F>(ctx, pl, ch[k], d_bases));
+        }
+        return ZKG_OK;
+    }
+    // two sort sets: the side stream runs at most two sorts ahead of the accumulations
+    int sorted = 0;
+    for (int k = 0; k < ng; ++k) {
+        while (sorted < ng && sorted < k + 2) ZKG_TRY(msm_chunk_sort<F>(ctx, pl, ch[sorted++]));
+        ZKG_TRY(msm_chunk_accumulate<F>(ctx, pl, ch[k], d_bases));
     }
     return ZKG_OK;
+}
+// largest window count of the groups sorted into set 0 (even groups) / set 1 (odd groups)
+static inline void msm_group_caps(const int* g, int ng, int W, int* wg0, int* wg1) {
+    *wg0 = 0; *wg1 = 0;
+    for (int k = 0; k < ng; ++k) {
+        int w = g[k + 1] - g[k];
+        if (k & 1) { if (w > *wg1) *wg1 = w; } else { if (w > *wg0) *wg0 = w; }
+    }
+    if (ng == 1) { *wg0 = W; *wg1 = 0; }
 }
 
 template <class F>
@@ -1514,6 +1544,8 @@ static int32_t msm_finish(zkg_ctx* ctx, MsmPlan<F>* pl, F* d_out, int mode) {
     const XYZZ<F>* Rin = S_arr;
     const XYZZ<F>* Cin = Z_arr;
     const int coop_tail = env_int("ZKG_MSM_COOP_TAIL", 1);
+    // (the same Horner on the 32-wide word-major primitives of the merge levels measured no faster: 0.75 vs 0.74 ms at c = 5,
+    //  W = 51, and 0.17 ms slower on G2 -- a lone chain is bound by the product latency, not by the operand traffic)
     if (!pl->merged && pl->Wb > 1 && pl->Wb <= 64 && coop_tail)
         k_final_coop<F><<<1, 128, 0, st>>>(Rin, Cin, pl->c, pl->Wb, mode, d_out);       // Horner over windows on four warps
     else
@@ -1529,10 +1561,13 @@ static int32_t msm_run(zkg_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scala
     MsmPlan<F> pl;
     if (n) {
         int c = env_int("ZKG_MSM_C", 0);
-        if (c < 2 || c > 22) c = msm_pick_c(n);
-        const int W = msm_num_windows(c), g0 = msm_first_group(n, W);
-        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl, 0, c, g0 > 0 ? g0 : W, g0 > 0 ? W - g0 : 0));
-        ZKG_TRY(msm_chunks_device<F>(ctx, &pl, d_bases, d_scalars, n, g0));
+        if (c < 2 || c > 22) c = msm_pick_c(n, sizeof(F) > 32);
+        const int W = msm_num_windows(c);
+        int g[5], wg0, wg1;
+        const int ng = msm_window_groups(n, W, g);
+        msm_group_caps(g, ng, W, &wg0, &wg1);
+        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl, 0, c, wg0, wg1));
+        ZKG_TRY(msm_chunks_device<F>(ctx, &pl, d_bases, d_scalars, n, g, ng));
     }
     return msm_finish<F>(ctx, &pl, d_out, mode);
 }
@@ -1570,9 +1605,12 @@ template <class F>
 static int32_t msm_run_prepared(zkg_ctx* ctx, const Affine<F>* d_table, int c, const Fr* d_scalars, size_t n, F* d_out, int mode) {
     MsmPlan<F> pl;
     if (n) {
-        const int W = msm_num_windows(c), g0 = msm_first_group(n, W);
-        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl, c, 0, g0 > 0 ? g0 : W, g0 > 0 ? W - g0 : 0));
-        ZKG_TRY(msm_chunks_device<F>(ctx, &pl, d_table, d_scalars, n, g0));
+        const int W = msm_num_windows(c);
+        int g[5], wg0, wg1;
+        const int ng = msm_window_groups(n, W, g);
+        msm_group_caps(g, ng, W, &wg0, &wg1);
+        ZKG_TRY(msm_plan<F>(ctx, n, n, &pl, c, 0, wg0, wg1));
+        ZKG_TRY(msm_chunks_device<F>(ctx, &pl, d_table, d_scalars, n, g, ng));
     }
     return msm_finish<F>(ctx, &pl, d_out, mode);
 }
@@ -1762,7 +1800,7 @@ static int32_t msm_host_enqueue(zkg_ctx* ctx, const void* bases, size_t stride, 
     MsmPlan<F> pl;
     if (n) {
         int c = env_int("ZKG_MSM_C", 0);
-        if (c < 2 || c > 22) c = msm_pick_c(n);
+        if (c < 2 || c > 22) c = msm_pick_c(n, sizeof(F) > 32);
         const int W = msm_num_windows(c);
         ZKG_TRY(msm_plan<F>(ctx, n, chunk_cap, &pl, 0, c, W, K > 1 ? W : 0));
         ZKG_TRY(ctx_copy_stream(ctx, 2 * K));
