@@ -209,6 +209,41 @@ def test_msm_registered_dev_closed_form(env, group, log2n):
     capi.check(lib.zkg_bases_release(h.value))
 
 
+@pytest.mark.parametrize("group", [1, 2])
+@pytest.mark.parametrize("envs", ["ZKG_MSM_GROUP0=2", "ZKG_MSM_GROUP0=3;ZKG_MSM_SIDE=0", "ZKG_MSM_GROUP0=1;ZKG_MSM_GROUPS=3",
+                                  "ZKG_MSM_GROUP0=2;ZKG_MSM_SORT_BPS_HIDDEN=4;ZKG_MSM_SCATTER_ILP_HIDDEN=1;ZKG_MSM_DIGITS_TB_HIDDEN=128",
+                                  "ZKG_MSM_GROUP0=2;ZKG_MSM_SCATTER_ILP_HIDDEN=8;ZKG_MSM_HEAVY_KEY=3",
+                                  "ZKG_MSM_HEAVY_KEY=2", "ZKG_MSM_REDUCE_L=1", "ZKG_MSM_REDUCE_L=8;ZKG_MSM_COOP_REDUCE=0"])
+def test_msm_device_resident_switches(env, monkeypatch, group, envs):
+    """The sort pipeline (window groups, side stream, thin hidden sorts), the heavy-bucket threshold and the reduction shapes
+    change the schedule of a device-resident MSM, never the group element: registered and generic path, closed form."""
+    z, capi, torch, ctx = env
+    o = ol.oracle()
+    lib = z.lib()
+    n = (1 << 13) + 77
+    a, s = _rand_dev(torch, n, 7100 + group), _rand_dev(torch, n, 7200 + group)
+    a[0::5] = a[0]                                        # long buckets
+    a[3] = 0
+    pk = 64 if group == 1 else 128
+    bases = torch.empty((n, pk), dtype=torch.uint8, device="cuda")
+    capi.check(lib.zkg_fixed_base_dev(ctx, group, C.c_void_p(s.data_ptr()), n, C.c_void_p(bases.data_ptr())))
+    exp = _closed_form(o, a.cpu().numpy().view(np.uint64).copy(), s.cpu().numpy().view(np.uint64).copy(), g2=(group == 2))
+    h = C.c_uint64(0)
+    capi.check(lib.zkg_bases_register_dev(ctx, group, C.c_void_p(bases.data_ptr()), n, C.byref(h)))
+    fn = lib.zkg_msm_bn254_g1_dev if group == 1 else lib.zkg_msm_bn254_g2_dev
+    for kv in envs.split(";"):
+        monkeypatch.setenv(*kv.split("="))
+    for _ in range(2):                                    # twice: the second call reuses the sort sets and events
+        out = torch.zeros(12 * group, dtype=torch.int64, device="cuda")
+        plain = torch.zeros(12 * group, dtype=torch.int64, device="cuda")
+        capi.check(lib.zkg_msm_bn254_registered_dev(ctx, h.value, C.c_void_p(a.data_ptr()), n, C.c_void_p(out.data_ptr()), 0))
+        capi.check(fn(ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(a.data_ptr()), n, C.c_void_p(plain.data_ptr())))
+        capi.check(lib.zkg_ctx_sync(ctx))
+        assert (out.cpu().numpy().view(np.uint64) == exp).all()
+        assert (plain.cpu().numpy().view(np.uint64) == exp).all()
+    capi.check(lib.zkg_bases_release(h.value))
+
+
 def test_d_fft_2p24_sampled_against_the_dft_definition(env):
     """The top of the north_star range (bench.py reports d_fft at m = 2^24): one d_fft round through the host-pointer
     C ABI -- QAP-style packing (zkg_pss_pack_vec layout 1), client fft1 per party, king pipeline -- then sampled output

@@ -268,15 +268,23 @@ def _special_case_inputs(o, g2, n, seed):
 
 
 @pytest.mark.parametrize("g2", [False, True])
-@pytest.mark.parametrize("env_name,env_val", [("ZKG_MSM_BA", "1"), ("ZKG_MSM_COOP_TAIL", "0"), ("ZKG_MSM_G2_PAIR", "1"), ("ZKG_MSM_G2_PAIR", "0")])
+@pytest.mark.parametrize("envs", ["ZKG_MSM_BA=1", "ZKG_MSM_COOP_TAIL=0", "ZKG_MSM_G2_PAIR=1", "ZKG_MSM_G2_PAIR=0",
+                                  # round 2, second session: sort pipeline (window groups on the side stream / on one stream, three
+                                  # groups), heavy-bucket threshold (nearly every bucket heavy / the default rule), both reduction
+                                  # shapes with and without the four-warp levels
+                                  "ZKG_MSM_GROUP0=2", "ZKG_MSM_GROUP0=2;ZKG_MSM_SIDE=0", "ZKG_MSM_GROUP0=1;ZKG_MSM_GROUPS=3",
+                                  "ZKG_MSM_HEAVY_KEY=2", "ZKG_MSM_HEAVY_KEY=24",
+                                  "ZKG_MSM_REDUCE_L=1", "ZKG_MSM_REDUCE_L=8", "ZKG_MSM_COOP_REDUCE=0;ZKG_MSM_REDUCE_L=1",
+                                  "ZKG_MSM_COOP_REDUCE=0;ZKG_MSM_REDUCE_L=8"])
 @pytest.mark.parametrize("n", [700, 1 << 13])
-def test_optin_msm_kernels_special_cases(z, monkeypatch, g2, env_name, env_val, n):
+def test_optin_msm_kernels_special_cases(z, monkeypatch, g2, envs, n):
     o = ol.oracle()
     bases, sc = _special_case_inputs(o, g2, n, 17 + g2)
     msm, omsm = (z.msm_g2, ol.o_g2_msm) if g2 else (z.msm_g1, ol.o_g1_msm)
     exp = omsm(bases, sc, threads=8)
     assert (msm(bases, sc) == exp).all()
-    monkeypatch.setenv(env_name, env_val)
+    for kv in envs.split(";"):
+        monkeypatch.setenv(*kv.split("="))
     monkeypatch.setenv("ZKG_MSM_CHUNKS", "3")              # the chunked accumulate_into path as well
     assert (msm(bases, sc) == exp).all()
     monkeypatch.setenv("ZKG_MSM_C", "6")                   # long buckets: the batched-affine tree runs several rounds
