@@ -1,0 +1,121 @@
+"""CPU: the reference's end-to-end acceptance test (groth16/examples/sha256.rs: the distributed proof VERIFIES,
+:400-415) run over the ORACLE's restatements of the path -- pyref's d_fft / d_ifft / deg_red / pack / unpack2 and the C
+oracle's MSM and group packing -- with the clear-text Groth16 model of tests/groth16_ref.py and the pairing that is
+pinned to the reference's vk_alphabeta_12.  It ties the oracle's PROTOCOL-level functions (not only its field and curve
+arithmetic) to the property the reference itself tests, and it is the CPU twin of tests/test_gpu_groth16.py.
+Masks are zero here (they are additive and cancel; FftMask / DegRedMask / MsmMask sampling has its own tests)."""
+import random
+
+import numpy as np
+
+import groth16_ref as gr
+import oracle_lib as ol
+from oracle_lib import _p, pyref
+
+R = pyref.R_MOD
+
+
+def test_clear_text_groth16_model_verifies():
+    cs, w = gr.synthetic_circuit(60, 2, seed=7)
+    pk, vk = gr.setup(cs, seed=11)
+    proof = gr.prove_clear(pk, cs, w, 12345, 67890)
+    assert gr.verify(vk, w[1:2], proof)
+    assert not gr.verify(vk, [(w[1] + 1) % R], proof)                   # wrong public input
+    A, B, C = proof
+    assert not gr.verify(vk, w[1:2], (A, B, pyref.G1.add(C, A)))        # tampered proof
+    assert not gr.verify(vk, w[1:2], (A, pyref.G2.add(B, B), C))
+
+
+def test_oracle_distributed_groth16_proof_verifies():
+    o = ol.oracle()
+    l = 2
+    rnd = random.Random(20260)
+    cs, w = gr.synthetic_circuit(28, 2, seed=5)
+    pk, vk = gr.setup(cs, seed=6)
+    r, s = rnd.randrange(R), rnd.randrange(R)
+    clear = gr.prove_clear(pk, cs, w, r, s)
+    pp = pyref.PackedSharingParams(l)
+    n, t = pp.n, pp.t
+    m = pk.domain_size
+    mbyl = m // l
+    rand_cols = lambda cols=mbyl: [[rnd.randrange(R) for _ in range(t)] for _ in range(cols)]
+    parties = list(range(n))
+
+    def qap_pss_pack(x):                                                # groth16/src/qap.rs:99-112
+        x = pyref.fft_in_place_rearrange(x)
+        rc = rand_cols()
+        return pyref.transpose([pp.pack(x[i::mbyl][:l], rc[i]) for i in range(mbyl)])
+
+    def pack_from_witness(v):                                           # sha256.rs:131-156
+        v = list(v) + [0] * ((-len(v)) % l)
+        return pyref.transpose(pyref.pack_vec(v, pp, rand_cols(len(v) // l)))
+
+    def crs_det_pack(bases, g2):                                        # groth16/src/proving_key.rs:72-104
+        words = 24 if g2 else 12
+        bases = gr.pad_to_chunks(bases, l)
+        out = [np.zeros((bases.shape[0] // l, bases.shape[1]), dtype=np.uint8) for _ in range(n)]
+        for j in range(bases.shape[0] // l):
+            sec = np.concatenate([gr.aff_to_xyz(bases[j * l + k], g2) for k in range(l)])
+            sh = np.zeros(n * words, dtype=np.uint64)
+            (o.zko_pss_pack_g2 if g2 else o.zko_pss_pack_g1)(l, _p(sec), None, _p(sh))
+            for p in range(n):
+                out[p][j] = gr.xyz_to_aff(sh[p * words:(p + 1) * words], g2)
+        return out
+
+    def gadd(a, b, g2=False):
+        out = np.zeros_like(a)
+        (o.zko_g2_add if g2 else o.zko_g1_add)(_p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(out))
+        return out
+
+    def gmul(a, k, g2=False):
+        out = np.zeros_like(a)
+        (o.zko_g2_mul if g2 else o.zko_g1_mul)(_p(np.ascontiguousarray(a)), _p(ol.fr_np([k % R])), _p(out))
+        return out
+
+    def unpack2(shares, g2=False):                                      # pss.rs:141-166 over group elements
+        words = 24 if g2 else 12
+        u = np.zeros(l * words, dtype=np.uint64)
+        (o.zko_pss_unpack2_g2 if g2 else o.zko_pss_unpack2_g1)(l, _p(np.concatenate(shares)), _p(u))
+        return [u[i * words:(i + 1) * words].copy() for i in range(l)]
+
+    def d_msm(bases_by_party, scalars_by_party, g2=False):              # dmsm/mod.rs:59-102, zero masks
+        msm = ol.o_g2_msm if g2 else ol.o_g1_msm
+        c = [msm(bases_by_party[p], ol.fr_np(scalars_by_party[p])) for p in range(n)]     # :73
+        res = unpack2(c, g2)                                                                # :85
+        out = res[0]
+        for x in res[1:]:
+            out = gadd(out, x, g2)                                                          # :86
+        return [out.copy() for _ in range(n)]                                               # :87
+
+    # dealer
+    qa, qb, qc = (qap_pss_pack(v) for v in gr.qap_witness(cs, w))
+    crs = {k: crs_det_pack(v, g2) for k, v, g2 in (("s", pk.a_query[1:], False), ("u", pk.h_query, False),
+                                                    ("w", pk.l_query, False), ("h", pk.b_g1_query[1:], False),
+                                                    ("v", pk.b_g2_query[1:], True))}
+    a_sh, ax_sh = pack_from_witness(w[1:]), pack_from_witness(w[cs.num_instance:])
+    # circom_h (groth16/src/ext_wit.rs:104-181)
+    zero = [[0] * mbyl for _ in range(n)]
+    root = pyref.Radix2Domain(2 * m).element(1)
+    coeff = [pyref.d_fft_round(q, zero, zero, True, m, pp, rand_cols(), inverse=True, g=root) for q in (qa, qb, qc)]
+    ev = [pyref.d_fft_round(cf, zero, zero, False, m, pp, rand_cols()) for cf in coeff]
+    h_eval = [[(x * y - v) % R for x, y, v in zip(ev[0][p], ev[1][p], ev[2][p])] for p in range(n)]
+    h_sh = pyref.deg_red_king(h_eval, parties, pp, rand_cols())
+    # the shares of h unpack to circom_ref's h (ext_wit.rs:532-537)
+    got_h = sum((pp.unpack(col) for col in pyref.transpose(h_sh)), [])
+    assert got_h == gr.circom_h(*gr.qap_witness(cs, w))
+    # A, B, C (groth16/src/prove.rs)
+    J = gr.aff_to_xyz
+    L, N, AG1, BG1 = J(pk.a_query[0]), J(pk.delta_g1), J(pk.alpha_g1), J(pk.beta_g1)
+    Z1, Z2, K2, BG2 = J(pk.b_g1_query[0]), J(pk.b_g2_query[0], True), J(pk.delta_g2, True), J(pk.beta_g2, True)
+    prod_a, prod_b1 = d_msm(crs["s"], a_sh), d_msm(crs["h"], a_sh)
+    prod_b2 = d_msm(crs["v"], a_sh, True)
+    prod_w, prod_u = d_msm(crs["w"], ax_sh), d_msm(crs["u"], h_sh)
+    A_sh = [gadd(gadd(gadd(L, gmul(N, r)), prod_a[p]), AG1) for p in range(n)]
+    B1_sh = [gadd(gadd(gadd(Z1, gmul(N, s)), prod_b1[p]), BG1) for p in range(n)]
+    B2_sh = [gadd(gadd(gadd(Z2, gmul(K2, s, True), True), prod_b2[p], True), BG2, True) for p in range(n)]
+    C_sh = [gadd(gadd(gadd(gadd(gmul(A_sh[p], s), gmul(B1_sh[p], r)), gmul(N, -(r * s))), prod_w[p]), prod_u[p])
+            for p in range(n)]
+    proof = (ol.g1_xyz_to_point(unpack2(A_sh)[0]), ol.g2_xyz_to_point(unpack2(B2_sh, True)[0]),
+             ol.g1_xyz_to_point(unpack2(C_sh)[0]))                       # sha256.rs:375-377
+    assert proof == clear
+    assert gr.verify(vk, w[1:cs.num_instance], proof)                   # sha256.rs:409-415
