@@ -1217,6 +1217,26 @@ static int env_int(const char* name, int dflt) {
 struct MsmSortSet {
     uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *cursor = nullptr, *order = nullptr, *shist = nullptr;
 };
+// ZKG_MSM_BOUNDS (experiment switch of the host-pointer paths): cumulative chunk ends in 64ths of the point range,
+// e.g. "1,4,12,28,46,64"; at most 8 chunks.  Returns the number of chunks (0: not set) and fills bounds[0..K].
+static inline int msm_env_bounds(size_t n, size_t* bounds) {
+    const char* plan = getenv("ZKG_MSM_BOUNDS");
+    if (!plan || !*plan || n < 4096) return 0;
+    int K = 0;
+    bounds[0] = 0;
+    for (const char* q = plan; *q && K < 7;) {
+        char* end = nullptr;
+        long v = strtol(q, &end, 10);
+        if (end == q) break;
+        if (v > 64) v = 64;
+        size_t b = v == 64 ? n : n / 64 * (size_t)v;
+        if (b > bounds[K]) bounds[++K] = b;
+        q = *end ? end + 1 : end;
+    }
+    if (K == 0 || bounds[K] != n) bounds[++K] = n;
+    return K;
+}
+
 struct MsmChunkDesc {
     const Fr* d_scalars = nullptr;
     size_t n = 0, point0 = 0;      // point range [point0, point0 + n) of the call (d_scalars points at its first scalar)
@@ -1637,9 +1657,13 @@ static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int
     MsmPlan<F> pl;
     if (n) {
         // graded chunks (1/16, 3/16, 1/4, 1/4, 1/4): the first copy, which nothing hides, is short
-        size_t bounds[6] = {0, n, n, n, n, n};
-        int K = 1;
-        if (n >= ((size_t)1 << 18)) { K = 5; bounds[1] = n / 16; bounds[2] = n / 4; bounds[3] = n / 2; bounds[4] = n / 4 * 3; }
+        size_t bounds[10] = {0, n, n, n, n, n, n, n, n, n};
+        int K = msm_env_bounds(n, bounds);
+        if (K == 0) {
+            K = 1;
+            bounds[1] = n;
+            if (n >= ((size_t)1 << 18)) { K = 5; bounds[1] = n / 16; bounds[2] = n / 4; bounds[3] = n / 2; bounds[4] = n / 4 * 3; bounds[5] = n; }
+        }
         size_t chunk = 0;
         for (int j = 0; j < K; ++j) if (bounds[j + 1] - bounds[j] > chunk) chunk = bounds[j + 1] - bounds[j];
         ZKG_TRY(ctx->io.reserve(align_up(n * 32, 256) + 512));
@@ -1650,7 +1674,7 @@ static int32_t msm_run_prepared_host(zkg_ctx* ctx, const Affine<F>* d_table, int
         ZKG_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
         ZKG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
         if (K > 1) ZKG_TRY(msm_side_begin<F>(ctx, &pl));
-        MsmChunkDesc ch[5];
+        MsmChunkDesc ch[8];
         // every copy and every sort first (the sorts wait for their own copy on the side stream), then the accumulations
         for (int j = 0; j < K; ++j) {
             size_t lo = bounds[j], hi = bounds[j + 1];
@@ -1783,15 +1807,23 @@ static int32_t msm_host_enqueue(zkg_ctx* ctx, const void* bases, size_t stride, 
                                 F** d_result) {
     ZKG_REQUIRE(n == 0 || (bases && scalars), "msm: NULL input");
     ZKG_REQUIRE(n == 0 || stride >= sizeof(Affine<F>) + 1, "base stride %zu too small", stride);
-    // Chunk boundaries (1/16, 3/16, 1/4, 1/4, 1/4): the first copy, which nothing can hide, is short;
-    // every later copy (2 ms per quarter at 2^22 over PCIe 5) is covered by the ~3.4 ms the previous
-    // quarter spends in digits/sort/accumulate.
-    // ZKG_MSM_CHUNKS=k forces k equal chunks.
+    // Chunk boundaries (2^20 points: 1/16, 3/16, 1/4, 1/4, 1/4; from 2^21: eight graded chunks): the first copy,
+    // which nothing can hide, is short; every later copy is covered by the previous chunk's digits/sort/accumulate.
+    // ZKG_MSM_CHUNKS=k forces k equal chunks, ZKG_MSM_BOUNDS an explicit plan.
     size_t bounds[18];
     int K = env_int("ZKG_MSM_CHUNKS", 0);
     if (K > 8) K = 8;
-    if (K > 0) {
+    const int Kenv = msm_env_bounds(n, bounds);
+    if (Kenv > 0) {
+        K = Kenv;
+    } else if (K > 0) {
         for (int j = 0; j <= K; ++j) bounds[j] = n * (size_t)j / (size_t)K;
+    } else if (n >= ((size_t)1 << 21)) {
+        // the accumulation (2.25 ns/point) is slower than the copy (1.9 ns/point): a tiny first chunk starts the compute
+        // stream early and growing chunks keep it fed -- measured at 2^22: 12.13 ms against 12.53 ms with five chunks
+        static const int ends[9] = {0, 1, 3, 8, 16, 28, 40, 52, 64};
+        K = 8;
+        for (int j = 0; j <= K; ++j) bounds[j] = ends[j] == 64 ? n : n / 64 * (size_t)ends[j];
     } else if (n >= ((size_t)1 << 20)) {
         K = 5;
         bounds[0] = 0; bounds[1] = n / 16; bounds[2] = n / 4; bounds[3] = n / 2; bounds[4] = n / 4 * 3; bounds[5] = n;
