@@ -34,10 +34,10 @@ def rand_points(rnd, k, g2=False):
     return [gr.aff_to_xyz(p, g2) for p in gr.fixed_base([rnd.randrange(1, R) for _ in range(k)], g2)]
 
 
-@pytest.mark.parametrize("num_constraints,num_instance,dropouts", [(60, 2, ()), (60, 2, (7,)), (1000, 3, ())])
-def test_distributed_groth16_proof_verifies(z, num_constraints, num_instance, dropouts):
+@pytest.mark.parametrize("num_constraints,num_instance,dropouts,l",
+                         [(60, 2, (), 2), (60, 2, (7,), 2), (1000, 3, (), 2), (120, 2, (), 4), (120, 2, (15,), 4)])
+def test_distributed_groth16_proof_verifies(z, num_constraints, num_instance, dropouts, l):
     from zksaas_b200 import api
-    l = 2
     rnd = random.Random(1000 * num_constraints + len(dropouts))
     rng = np.random.default_rng(num_constraints + 17 * len(dropouts))
     cs, w = gr.synthetic_circuit(num_constraints, num_instance, seed=rnd.randrange(1 << 30))

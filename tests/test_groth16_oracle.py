@@ -7,6 +7,7 @@ Masks are zero here (they are additive and cancel; FftMask / DegRedMask / MsmMas
 import random
 
 import numpy as np
+import pytest
 
 import groth16_ref as gr
 import oracle_lib as ol
@@ -26,9 +27,9 @@ def test_clear_text_groth16_model_verifies():
     assert not gr.verify(vk, w[1:2], (A, pyref.G2.add(B, B), C))
 
 
-def test_oracle_distributed_groth16_proof_verifies():
+@pytest.mark.parametrize("l", [2, 4])
+def test_oracle_distributed_groth16_proof_verifies(l):
     o = ol.oracle()
-    l = 2
     rnd = random.Random(20260)
     cs, w = gr.synthetic_circuit(28, 2, seed=5)
     pk, vk = gr.setup(cs, seed=6)
