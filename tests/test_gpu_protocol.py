@@ -4,6 +4,7 @@
   dist-primitives/src/utils/deg_red.rs   :142-191 (degree reduction of squared sharings, L = 4, with a dropout)
   dist-primitives/examples/dmsm_test.rs  :13-53   (d_msm output unpacks to the plain MSM)
   groth16/src/ext_wit.rs                 :411-538 circom_dummy_ext_witness (expected h = golden circom_ref)
+                                         :287-409 libsnark_dummy_ext_witness (expected h = golden libsnark_ref)
 plus the committed golden fixtures (tests/golden) through the GPU entry points."""
 import numpy as np
 import pytest
@@ -193,6 +194,35 @@ def test_circom_h_dataflow_vs_golden(z):
     h_red = z.deg_red(h, dmask, pp, net, rp())                                                     # :179
     got = unpack_all(z, pp, h_red, two=True)                                                       # test :532-535
     exp = ol.fr_np(gu.ints(gu.load("ext_wit.json")[str(m)]["circom_h"]))
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("m", [32, 1 << 10])
+def test_libsnark_h_dataflow_vs_golden(z, m):
+    """groth16/src/ext_wit.rs:14-102 `libsnark_h` + its test :287-409 (a = b = (0..m), c = a*b; m = 32 there): coset
+    d_ifft x3 (rearrange), d_fft x3 (rearrange), h = (ab - c) / Z(g) fused (zkg_qap_h_bn254 with the factor), coset d_ifft
+    back to coefficients; the unpack2'ed result must equal libsnark_ref's h (tests/golden/ext_wit.json)."""
+    from zksaas_b200 import api
+    l = 2
+    rng = np.random.default_rng(32 + m)
+    pp = z.PackedSharingParams.new(l)
+    dom = z.Radix2EvaluationDomain.new(m)
+    net = z.LocalTestNet(pp.n)
+    a = ol.fr_np(list(range(m)))
+    c = api.fr_mul(a, a)
+    one = api.fr_image(1)
+    g, ginv = api.fr_image(5), api.fr_image(pow(5, -1, R))                     # coset_dom.coset_offset() / _inv(), :29
+    rp = lambda: ol.rand_fr(rng, m // l * pp.t)
+    sh = {k: pack_rearranged(z, rng, pp, v) for k, v in (("a", a), ("b", a), ("c", c))}            # QAP::pss
+    coeff = {k: z.d_ifft(sh[k], sample_fft_mask(z, rng, True, g, dom.group_gen_inv(), m, pp), True, dom, g, pp, net, rp())
+             for k in "abc"}                                                                       # :31-64
+    ev = {k: z.d_fft(coeff[k], sample_fft_mask(z, rng, True, one, dom.group_gen(), m, pp), True, dom, pp, net, rp())
+          for k in "abc"}                                                                          # :66-75
+    vinv = api.fr_image(pow((pow(5, m, R) - 1) % R, -1, R))                                        # :78-81
+    h_eval = [api.qap_h(ev["a"][p], ev["b"][p], ev["c"][p], factor=vinv) for p in range(pp.n)]     # :83-88
+    h = z.d_ifft(h_eval, sample_fft_mask(z, rng, False, ginv, dom.group_gen_inv(), m, pp), False, dom, ginv, pp, net, rp())  # :91-100
+    got = unpack_all(z, pp, h, two=True)                                                           # test :403-406
+    exp = ol.fr_np(gu.ints(gu.load("ext_wit.json")[str(m)]["libsnark_h"]))
     assert (got == exp).all()
 
 

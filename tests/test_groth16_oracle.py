@@ -120,3 +120,33 @@ def test_oracle_distributed_groth16_proof_verifies(l):
              ol.g1_xyz_to_point(unpack2(C_sh)[0]))                       # sha256.rs:375-377
     assert proof == clear
     assert gr.verify(vk, w[1:cs.num_instance], proof)                   # sha256.rs:409-415
+
+
+def test_oracle_libsnark_h_dataflow_vs_golden():
+    """groth16/src/ext_wit.rs:14-102 `libsnark_h` + its test :287-409 over pyref's d_ifft / d_fft rounds (m = 32, zero
+    masks): the unpack2'ed coefficients equal libsnark_ref's h (tests/golden/ext_wit.json) -- the CPU twin of
+    tests/test_gpu_protocol.py::test_libsnark_h_dataflow_vs_golden."""
+    import golden_util as gu
+    m, l = 32, 2
+    pp = pyref.PackedSharingParams(l)
+    n, mbyl = pp.n, m // l
+    rnd = random.Random(1)
+    rc = lambda: [[rnd.randrange(R) for _ in range(pp.t)] for _ in range(mbyl)]
+    a = list(range(m))
+    c = [x * x % R for x in a]
+
+    def pss(x):
+        x = pyref.fft_in_place_rearrange(x)
+        r = rc()
+        return pyref.transpose([pp.pack(x[i::mbyl][:l], r[i]) for i in range(mbyl)])
+
+    zero = [[0] * mbyl for _ in range(n)]
+    sh = {k: pss(v) for k, v in (("a", a), ("b", a), ("c", c))}
+    g, ginv = 5, pow(5, -1, R)
+    coeff = {k: pyref.d_fft_round(sh[k], zero, zero, True, m, pp, rc(), inverse=True, g=g) for k in "abc"}
+    ev = {k: pyref.d_fft_round(coeff[k], zero, zero, True, m, pp, rc()) for k in "abc"}
+    vinv = pow((pow(5, m, R) - 1) % R, -1, R)
+    h_eval = [[(x * y - w) * vinv % R for x, y, w in zip(ev["a"][p], ev["b"][p], ev["c"][p])] for p in range(n)]
+    h = pyref.d_fft_round(h_eval, zero, zero, False, m, pp, rc(), inverse=True, g=ginv)
+    got = sum((pp.unpack2(col) for col in pyref.transpose(h)), [])
+    assert got == gu.ints(gu.load("ext_wit.json")[str(m)]["libsnark_h"])
