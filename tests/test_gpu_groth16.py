@@ -35,7 +35,8 @@ def rand_points(rnd, k, g2=False):
 
 
 @pytest.mark.parametrize("num_constraints,num_instance,dropouts,l",
-                         [(60, 2, (), 2), (60, 2, (7,), 2), (1000, 3, (), 2), (120, 2, (), 4), (120, 2, (15,), 4)])
+                         [(60, 2, (), 2), (60, 2, (7,), 2), (1000, 3, (), 2), (120, 2, (), 4), (120, 2, (15,), 4),
+                          (32700, 2, (), 2)])        # the last: m = 2^15, the size of BASELINE configs[2] (sha256 circuit)
 def test_distributed_groth16_proof_verifies(z, num_constraints, num_instance, dropouts, l):
     from zksaas_b200 import api
     rnd = random.Random(1000 * num_constraints + len(dropouts))
