@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 INT_PEAK_TIMAD = 18.51              # profiles/r01_intpipe_microbench_v2.json: 32-bit IMAD issue rate, B200, 148 SMs @1965 MHz
 WIDE_MAD_PEAK_T = 9.27              # profiles/r01_widemad_microbench.json: IMAD.WIDE.U32 (any form: RZ / addend / .X) issue rate, 10^12/s
 WIDE_MADS_PER_MADD = 6 * 128 + 2 * 100 + 192   # XYZZ mixed add as executed: 6 products, 2 dedicated squarings, one 2-term dot
-ACC_TRAFFIC_BYTES = 7.485e9         # profiles/r02_ncu_k_accumulate_g1.json: dram read (7.361 GB) + write (0.124 GB) of one k_accumulate launch at 2^22 (prepared path)
+ACC_TRAFFIC_BYTES = 7.95e9          # profiles/r02c_ncu_k_accumulate_g1.json: dram read (2.377 + 5.303 GB) + write (0.108 + 0.162 GB) of the two k_accumulate launches (window groups 0-3, 4-12) of one 2^22 MSM (prepared path)
 HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
 
 
@@ -1256,8 +1256,8 @@ def run_ours(args):
                          "hbm": {"achieved_gbs": round(96 * n / (acc_ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
                                  "frac": round(96 * n / (acc_ms * 1e-3) / 1e9 / hbm_peak, 4), "peak_source": hbm_how},
                          "traffic": ACC_TRAFFIC_BYTES if args.log2n == 22 else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch from the ncu --set full capture "
-                                         "profiles/r02_ncu_k_accumulate_g1.json (same code, not measured in this run); ~18x the 96 B/point because Pippenger gathers every base once per "
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the k_accumulate launches of ONE MSM (two window groups; kernel_ms is their sum too) from the ncu --set full capture "
+                                         "profiles/r02c_ncu_k_accumulate_g1.json (same code, not measured in this run); ~19x the 96 B/point because Pippenger gathers every base once per "
                                          "window (13 gathers that each pull 128 B) -- under 1 TB/s, not the bound"},
             "cpu_baseline": {"value": round(cpu_val, 4), "unit": "Mpts/s", "cores": cpu_th, "kind": "port",
                              "sample": "G1 MSM of 2^20 points (a quarter of the workload), best of 2, oracle/zkoracle.c (arkworks msm_bigint_wnaf "
