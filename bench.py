@@ -291,6 +291,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        # CPU-side group: while rank 0 drives every GPU from one process (device-list legs) the other ranks must wait WITHOUT
+        # a kernel on their GPU -- an NCCL barrier spins on the device and the GPU then time-slices between the two processes
+        cpu_group = dist.new_group(backend="gloo")
     lib = z.lib()
     # One explicit (non-default) stream for everything: the library launches on it, torch's events
     # and NCCL collectives are recorded on it, so CUDA-event timings see the kernels they bracket.
@@ -918,8 +921,9 @@ def run_ours(args):
         del a_s, s_s, b_s
 
         # -- the same operations from ONE process through the device-list C-ABI entry points (what the unchanged Rust caller binds):
-        #    rank 0 drives all N GPUs with host buffers; the other ranks wait at the barrier
-        dist.barrier()
+        #    rank 0 drives all N GPUs with host buffers; the other ranks wait at a CPU (gloo) barrier with their GPU idle
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             devs_ = (C.c_int32 * world)(*range(world))
             one_proc = {}
@@ -1011,7 +1015,7 @@ def run_ours(args):
             sharded_agree["one_process_fft1"] = ok_f
             secondary["one_process_device_list"] = one_proc
             del pin_in, pin_rnd, pin_out, px_a, px_b
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         flags = [None] * world
         dist.all_gather_object(flags, sharded_agree)
         merged = {}
