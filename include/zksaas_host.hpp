@@ -16,6 +16,8 @@
 //   dist-primitives/src/dfft/mod.rs:99-175    d_fft / d_ifft     d_fft, d_ifft                 (all parties of a LocalTestNet at once)
 //   dist-primitives/src/dfft/mod.rs:178-335   fft1 / fft2 / ...  fft1_in_place, fft2_in_place, fft_in_place_rearrange
 //   dist-primitives/src/utils/deg_red.rs:14-126                  DegRedMask::sample, deg_red
+//   dist-primitives/src/dpp/mod.rs:15-87      d_pp               d_pp
+//   groth16/src/proving_key.rs:72-104, qap.rs:99-112            crs_det_pack<G>, qap_pss_pack
 //   dist-primitives/src/dmsm/mod.rs:10-102    MsmMask, d_msm     MsmMask<G>::sample, d_msm<G>
 //   G::msm(bases, scalars) -> Result<G, usize>                   msm<G>(bases, scalars)        (throws MsmLengthMismatch{min_len})
 //   mpc-net/src/multi.rs LocalTestNet (+ lossy round :330-363)   LocalTestNet{n, dropouts}
@@ -191,6 +193,19 @@ inline Projective<W> lincomb(const std::vector<Projective<W>>& points, const std
 template <int W>
 inline Projective<W> add(const Projective<W>& a, const Projective<W>& b, int32_t device = 0) {
     return lincomb<W>({a, b}, {Fr::one(), Fr::one()}, device);
+}
+
+// pack_from_arkworks_proving_key's inner step (groth16/src/proving_key.rs:72-104): `pp.det_pack::<G>(chunk)` for every l-chunk of
+// a CRS query (bases.size() a multiple of l; pad a short last chunk with the identity), returned as the n parties' share vectors
+template <int W>
+inline std::vector<std::vector<Affine<W>>> crs_det_pack(const std::vector<Affine<W>>& bases, uint32_t l, int32_t device = 0) {
+    if (bases.size() % l) throw Error(ZKG_ERR_BAD_ARG, "crs_det_pack: a multiple of l bases expected");
+    const size_t chunks = bases.size() / l;
+    std::vector<std::vector<Affine<W>>> out(4 * l, std::vector<Affine<W>>(chunks));
+    std::vector<void*> p;
+    for (auto& v : out) p.push_back(v.data());
+    check(zkg_crs_det_pack_bn254(device, detail::group_tag<W>::id, bases.data(), sizeof(Affine<W>), bases.size(), l, p.data(), sizeof(Affine<W>)));
+    return out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -497,6 +512,28 @@ inline Shares deg_red(const Shares& x_shares, const std::vector<DegRedMask>& mas
     Shares out = deg_red_king(recv, parties, pp, rand_points);
     for (uint32_t p = 0; p < net.n; ++p) out[p] = detail::vec_add(out[p], masks[p].out_mask, pp.device);
     return out;
+}
+// dist-primitives/src/dpp/mod.rs:15-87 (partial products of num / den; the dummy randomness s = 1 of :24-25 included):
+// the king unpacks, divides (a zero denominator is ZKG_ERR_BAD_ARG where the reference's `.inverse().unwrap()` panics),
+// takes the running product over all secrets and re-packs (:41-76); then deg_red (:86)
+inline Shares dpp_king(const Shares& recv, const std::vector<uint32_t>& parties, const PackedSharingParams& pp, const std::vector<Fr>& rand_points) {
+    if (recv.empty() || recv.size() != parties.size() || recv[0].size() % 2) throw Error(ZKG_ERR_BAD_ARG, "dpp_king: num || den share vectors expected");
+    const size_t cols = recv[0].size() / 2;
+    if (rand_points.size() != cols * pp.t) throw Error(ZKG_ERR_BAD_ARG, "dpp_king: cols * t random points expected");
+    Shares out(pp.n, std::vector<Fr>(cols));
+    auto pi = detail::cptrs(recv);
+    auto po = detail::ptrs(out);
+    check(zkg_dpp_king_bn254(pp.device, pi.data(), parties.data(), (uint32_t)parties.size(), cols, pp.l, (const uint64_t*)rand_points.data(), po.data()));
+    return out;
+}
+inline Shares d_pp(const Shares& num, const Shares& den, const std::vector<DegRedMask>& masks, const PackedSharingParams& pp, const LocalTestNet& net,
+                   const std::vector<Fr>& rand_king, const std::vector<Fr>& rand_degred) {
+    Shares sent(net.n);
+    for (uint32_t p = 0; p < net.n; ++p) { sent[p] = num[p]; sent[p].insert(sent[p].end(), den[p].begin(), den[p].end()); }    // :31-32
+    const auto parties = net.parties();
+    Shares recv;
+    for (uint32_t p : parties) recv.push_back(sent[p]);
+    return deg_red(dpp_king(recv, parties, pp, rand_king), masks, pp, net, rand_degred);
 }
 // share-wise h = (a * b - c) [* factor]: groth16/src/ext_wit.rs:173-177 / :82-86
 inline std::vector<Fr> qap_h(const std::vector<Fr>& a, const std::vector<Fr>& b, const std::vector<Fr>& c, const Fr* factor = nullptr, int32_t device = 0) {

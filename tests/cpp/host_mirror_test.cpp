@@ -156,6 +156,49 @@ static void test_d_msm(Rng& rng, size_t M, std::vector<uint32_t> dropouts, const
     EXPECT(ok, name);
 }
 
+static void test_d_pp(Rng& rng) {                                          // examples/dpp_test.rs: d_pp(x, x) == all ones; plus a random num / den
+    const uint32_t l = 2;
+    const size_t m = 1 << 5, cols = m / l;
+    auto pp = PackedSharingParams::new_(l);
+    LocalTestNet net{pp.n, {}};
+    std::vector<Fr> x(m);
+    for (size_t i = 0; i < m; ++i) x[i] = Fr::from_u64(i + 1);
+    auto px = pack_vec(x, pp, rng.frs(cols * pp.t));
+    auto masks = DegRedMask::sample(pp, cols, rng.frs(cols * l), rng.frs(cols * pp.t), rng.frs(cols * pp.t));
+    auto out = d_pp(px, px, masks, pp, net, rng.frs(cols * pp.t), rng.frs(cols * pp.t));
+    EXPECT(unpack_all(pp, out) == std::vector<Fr>(m, Fr::one()), "d_pp(x, x) == ones (dpp_test.rs)");
+    auto num = rng.frs(m), den = rng.frs(m);
+    auto out2 = d_pp(pack_vec(num, pp, rng.frs(cols * pp.t)), pack_vec(den, pp, rng.frs(cols * pp.t)), masks, pp, net, rng.frs(cols * pp.t), rng.frs(cols * pp.t));
+    std::vector<Fr> exp(m);
+    Fr run = Fr::one();
+    for (size_t i = 0; i < m; ++i) { run = run * num[i] * den[i].inverse(); exp[i] = run; }    // host arithmetic: prefix products of num/den
+    EXPECT(unpack_all(pp, out2) == exp, "d_pp: prefix products of num / den");
+}
+
+template <int W>
+static void test_crs_det_pack(Rng& rng, const char* name) {                // groth16/src/proving_key.rs:72-104
+    const uint32_t l = 2;
+    const size_t n = 2 * 9;
+    auto pp = PackedSharingParams::new_(l);
+    auto fixed = W == 4 ? zko_g1_fixed_base : zko_g2_fixed_base;
+    std::vector<Affine<W>> bases(n);
+    auto dl = rng.frs(n);
+    fixed((const uint64_t*)dl.data(), n, bases.data(), sizeof(Affine<W>));
+    std::memset(&bases[5], 0, sizeof bases[5]);
+    bases[5].infinity = 1;                                                  // an identity among the secrets
+    auto shares = crs_det_pack<W>(bases, l);
+    std::vector<uint32_t> all(pp.n);
+    for (uint32_t i = 0; i < pp.n; ++i) all[i] = i;
+    bool ok = true;
+    for (size_t c = 0; c < n / l; ++c) {
+        std::vector<Projective<W>> col;
+        for (uint32_t p = 0; p < pp.n; ++p) col.push_back(into_group(shares[p][c]));
+        auto sec = pp.unpack_missing_shares<W>(col, all);                   // degree < l + t: unpack2 recovers the secrets
+        for (uint32_t j = 0; j < l; ++j) ok &= sec[j] == into_group(bases[c * l + j]);
+    }
+    EXPECT(ok, name);
+}
+
 static void test_length_mismatch(Rng& rng) {
     std::vector<G1Affine> bases(5);
     auto s = rng.frs(5);
@@ -213,6 +256,9 @@ int main(int argc, char** argv) {
         test_d_ifft_d_fft(rng, 4, 64);
         test_ifft_then_fft(rng);
         test_deg_red(rng);
+        test_d_pp(rng);
+        test_crs_det_pack<4>(rng, "crs det_pack over G1 chunks unpacks to the CRS elements");
+        test_crs_det_pack<8>(rng, "crs det_pack over G2 chunks unpacks to the CRS elements");
         test_d_msm<4>(rng, 1 << 10, {}, "d_msm G1 2^10 points, sampled masks, compressed wire == plain MSM");
         test_d_msm<4>(rng, 1 << 8, {3}, "d_msm G1 with a dropped party == plain MSM");
         test_d_msm<8>(rng, 1 << 6, {}, "d_msm G2 == plain MSM");
