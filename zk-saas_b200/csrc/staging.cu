@@ -11,6 +11,7 @@
 // stream); copy_d2h returns when the destination holds the data.
 #include <condition_variable>
 #include <cstring>
+#include <emmintrin.h>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -21,7 +22,27 @@ namespace zkg {
 
 namespace {
 
-constexpr size_t SLOT_BYTES = 8u << 20;
+static size_t SLOT_BYTES = 8u << 20;    // ZKG_STAGING_SLOT_MB
+static int g_nt = 1;                     // ZKG_STAGING_NT: streaming stores into the pinned slot (no read-for-ownership of the destination)
+
+// user memory -> pinned slot with streaming stores: the slot is written once and read only by the DMA engine, so the stores
+// bypass the cache and skip the read-for-ownership of the destination.
+// Pageable 2^22-point MSM: 18.3 -> 13.5 ms (pinned: 12.2).  Falls back to memcpy for a destination that is not 16-byte aligned.
+static void copy_in(uint8_t* d, const uint8_t* s, size_t n) {
+    size_t i = 0;
+    if (g_nt && ((uintptr_t)d & 15) == 0) {
+        for (; i + 64 <= n; i += 64) {
+            __m128i a = _mm_loadu_si128((const __m128i*)(s + i)), b = _mm_loadu_si128((const __m128i*)(s + i + 16));
+            __m128i c = _mm_loadu_si128((const __m128i*)(s + i + 32)), e = _mm_loadu_si128((const __m128i*)(s + i + 48));
+            _mm_stream_si128((__m128i*)(d + i), a);
+            _mm_stream_si128((__m128i*)(d + i + 16), b);
+            _mm_stream_si128((__m128i*)(d + i + 32), c);
+            _mm_stream_si128((__m128i*)(d + i + 48), e);
+        }
+        _mm_sfence();
+    }
+    if (i < n) memcpy(d + i, s + i, n - i);
+}
 constexpr int N_SLOTS = 4;
 constexpr int MAX_DEV = 16;
 constexpr size_t STAGE_MIN = 1u << 20;       // below this the driver's path is as good
@@ -29,7 +50,7 @@ constexpr size_t STAGE_MIN = 1u << 20;       // below this the driver's path is 
 // persistent helpers that split one memcpy; heap-allocated and never destroyed (threads are detached
 // and sleep on the condition variable until the process exits)
 struct CopyPool {
-    struct Job { uint8_t* d; const uint8_t* s; size_t n; };
+    struct Job { uint8_t* d; const uint8_t* s; size_t n; bool in; };
     std::mutex m;
     std::condition_variable cv, done_cv;
     std::vector<Job> jobs;
@@ -56,22 +77,22 @@ struct CopyPool {
                 cv.wait(lk, [&] { return next < jobs.size(); });
                 pop(&j);
             }
-            memcpy(j.d, j.s, j.n);
+            if (j.in) copy_in(j.d, j.s, j.n); else memcpy(j.d, j.s, j.n);
             finish_one();
         }
     }
     // one caller at a time (the stager's mutex serialises callers)
-    void run(uint8_t* d, const uint8_t* s, size_t n) {
+    void run(uint8_t* d, const uint8_t* s, size_t n, bool in = false) {
         const size_t part_min = 256u << 10;
         size_t parts = n / part_min;
         if (parts > (size_t)n_threads + 1) parts = (size_t)n_threads + 1;
-        if (parts <= 1) { memcpy(d, s, n); return; }
+        if (parts <= 1) { if (in) copy_in(d, s, n); else memcpy(d, s, n); return; }
         const size_t per = (n / parts + 63) & ~(size_t)63;
         {
             std::lock_guard<std::mutex> lk(m);
             jobs.clear();
             next = 0;
-            for (size_t off = 0; off < n; off += per) jobs.push_back({d + off, s + off, off + per <= n ? per : n - off});
+            for (size_t off = 0; off < n; off += per) jobs.push_back({d + off, s + off, off + per <= n ? per : n - off, in});
             pending = jobs.size();
         }
         cv.notify_all();
@@ -81,7 +102,7 @@ struct CopyPool {
                 std::lock_guard<std::mutex> lk(m);
                 if (!pop(&j)) break;
             }
-            memcpy(j.d, j.s, j.n);
+            if (j.in) copy_in(j.d, j.s, j.n); else memcpy(j.d, j.s, j.n);
             finish_one();
         }
         std::unique_lock<std::mutex> lk(m);
@@ -102,12 +123,14 @@ struct Stager {
         if (ready) return ZKG_OK;
         const char* e = getenv("ZKG_STAGING");
         enabled = !(e && e[0] == '0');
+        if (const char* mb = getenv("ZKG_STAGING_SLOT_MB")) { int v = atoi(mb); if (v >= 1 && v <= 256) SLOT_BYTES = (size_t)v << 20; }
+        if (const char* nt = getenv("ZKG_STAGING_NT")) g_nt = nt[0] != '0';
         for (int s = 0; s < N_SLOTS; ++s) {
             ZKG_CUDA(cudaHostAlloc((void**)&slot[s], SLOT_BYTES, cudaHostAllocPortable));
             slot_dev[s] = -1;
         }
         unsigned hc = std::thread::hardware_concurrency();
-        int threads = hc >= 16 ? 7 : hc >= 8 ? 5 : hc >= 4 ? 3 : 1;
+        int threads = hc >= 16 ? 11 : hc >= 8 ? 5 : hc >= 4 ? 3 : 1;   // 16 cores, 2^22-point pageable MSM: 7 helpers 13.8-14.9 ms, 11 13.2-13.9, 15 13.3-13.4
         const char* t = getenv("ZKG_STAGING_THREADS");
         if (t && atoi(t) >= 0 && atoi(t) <= 32) threads = atoi(t);
         pool = new CopyPool(threads);
@@ -162,7 +185,7 @@ int32_t copy_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) 
         const int s = k % N_SLOTS;
         const size_t len = off + SLOT_BYTES <= bytes ? SLOT_BYTES : bytes - off;
         ZKG_TRY(S->wait_slot(s));
-        S->pool->run(S->slot[s], (const uint8_t*)h_src + off, len);
+        S->pool->run(S->slot[s], (const uint8_t*)h_src + off, len, true);
         ZKG_CUDA(cudaMemcpyAsync((uint8_t*)d_dst + off, S->slot[s], len, cudaMemcpyHostToDevice, st));
         cudaEvent_t e;
         ZKG_TRY(S->event_for(dev, s, &e));
@@ -205,7 +228,7 @@ int32_t copy_d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) 
             const int s = (int)(j % N_SLOTS);
             const size_t off = j * SLOT_BYTES, len = off + SLOT_BYTES <= bytes ? SLOT_BYTES : bytes - off;
             ZKG_TRY(S->wait_slot(s));
-            S->pool->run((uint8_t*)h_dst + off, S->slot[s], len);
+            S->pool->run((uint8_t*)h_dst + off, S->slot[s], len);           // (streaming stores measured no faster in this direction)
         }
     }
     return ZKG_OK;
