@@ -18,6 +18,7 @@
 //   dist-primitives/src/utils/deg_red.rs:14-126                  DegRedMask::sample, deg_red
 //   dist-primitives/src/dpp/mod.rs:15-87      d_pp               d_pp
 //   groth16/src/proving_key.rs:72-104, qap.rs:99-112            crs_det_pack<G>, qap_pss_pack
+//   groth16/src/ext_wit.rs:14-181   libsnark_h, circom_h         libsnark_h, circom_h
 //   dist-primitives/src/dmsm/mod.rs:10-102    MsmMask, d_msm     MsmMask<G>::sample, d_msm<G>
 //   G::msm(bases, scalars) -> Result<G, usize>                   msm<G>(bases, scalars)        (throws MsmLengthMismatch{min_len})
 //   mpc-net/src/multi.rs LocalTestNet (+ lossy round :330-363)   LocalTestNet{n, dropouts}
@@ -542,6 +543,46 @@ inline std::vector<Fr> qap_h(const std::vector<Fr>& a, const std::vector<Fr>& b,
     check(zkg_qap_h_bn254(device, (const uint64_t*)a.data(), (const uint64_t*)b.data(), (const uint64_t*)c.data(), nullptr, nullptr, nullptr,
                           factor ? factor->v : nullptr, (uint64_t*)out.data(), a.size()));
     return out;
+}
+
+// groth16/src/ext_wit.rs:104-181 `circom_h`: three d_ifft (coset shift w_2m on the way out, rearranged), three d_fft,
+// h = a*b - c share-wise, deg_red.  qap_shares[party] = {a, b, c} share vectors of a PackedQAPShare (qap.rs:30-41);
+// fft_masks: 3 ifft + 3 fft masks, each for all parties; rand: the king's packing draws of the seven rounds (m/l * t each).
+struct PackedQAPShare { std::vector<Fr> a, b, c; };
+inline Shares circom_h(const std::vector<PackedQAPShare>& qap_shares, const std::vector<std::vector<FftMask>>& fft_masks,
+                       const std::vector<DegRedMask>& degred_mask, const Radix2EvaluationDomain& domain, const PackedSharingParams& pp,
+                       const LocalTestNet& net, const std::vector<std::vector<Fr>>& rand) {
+    if (qap_shares.size() != net.n || fft_masks.size() != 6 || rand.size() != 7) throw Error(ZKG_ERR_BAD_ARG, "circom_h: n QAP shares, 6 FFT masks, 7 draw vectors expected");
+    const Fr root_of_unity = Radix2EvaluationDomain::new_(2 * domain.size()).element(1);          // :117-122
+    Shares in[3];
+    for (const auto& q : qap_shares) { in[0].push_back(q.a); in[1].push_back(q.b); in[2].push_back(q.c); }
+    Shares ev[3];
+    for (int k = 0; k < 3; ++k) {
+        Shares coeff = d_ifft(in[k], fft_masks[k], true, domain, root_of_unity, pp, net, rand[k]);   // :124-159
+        ev[k] = d_fft(coeff, fft_masks[3 + k], false, domain, pp, net, rand[3 + k]);                 // :161-170
+    }
+    Shares h(net.n);
+    for (uint32_t p = 0; p < net.n; ++p) h[p] = qap_h(ev[0][p], ev[1][p], ev[2][p], nullptr, pp.device);   // :173-177
+    return deg_red(h, degred_mask, pp, net, rand[6]);                                               // :179
+}
+// groth16/src/ext_wit.rs:14-102 `libsnark_h`: coset (offset = F::GENERATOR) d_ifft x3 and d_fft x3 (all rearranged),
+// h = (a*b - c) / Z(g), coset d_ifft back to coefficients (fft_masks: 7; rand: 7)
+inline Shares libsnark_h(const std::vector<PackedQAPShare>& qap_shares, const std::vector<std::vector<FftMask>>& fft_masks,
+                         const Radix2EvaluationDomain& domain, const PackedSharingParams& pp, const LocalTestNet& net,
+                         const std::vector<std::vector<Fr>>& rand) {
+    if (qap_shares.size() != net.n || fft_masks.size() != 7 || rand.size() != 7) throw Error(ZKG_ERR_BAD_ARG, "libsnark_h: n QAP shares, 7 FFT masks, 7 draw vectors expected");
+    const Fr g = Fr::generator(), ginv = g.inverse();                                                // coset_dom.coset_offset(), :29
+    Shares in[3];
+    for (const auto& q : qap_shares) { in[0].push_back(q.a); in[1].push_back(q.b); in[2].push_back(q.c); }
+    Shares ev[3];
+    for (int k = 0; k < 3; ++k) {
+        Shares coeff = d_ifft(in[k], fft_masks[k], true, domain, g, pp, net, rand[k]);               // :31-64
+        ev[k] = d_fft(coeff, fft_masks[3 + k], true, domain, pp, net, rand[3 + k]);                  // :66-75
+    }
+    const Fr vinv = (g.pow((uint64_t)domain.size()) - Fr::one()).inverse();                          // evaluate_vanishing_polynomial(g)^-1, :78-81
+    Shares h(net.n);
+    for (uint32_t p = 0; p < net.n; ++p) h[p] = qap_h(ev[0][p], ev[1][p], ev[2][p], &vinv, pp.device);     // :83-88
+    return d_ifft(h, fft_masks[6], false, domain, ginv, pp, net, rand[6]);                           // :91-100
 }
 
 // dist-primitives/src/dmsm/mod.rs:59-102 for all parties at once.  Every share crosses the "network" as an ark-serialize

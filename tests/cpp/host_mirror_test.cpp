@@ -4,6 +4,7 @@
 //   dist-primitives/src/utils/deg_red.rs     :142-191 (squared sharings, L = 4, lossy round)
 //   dist-primitives/src/dmsm/mod.rs          :127-180 / examples/dmsm_test.rs:13-93 (d_msm output unpacks to the plain MSM)
 //   secret-sharing/src/pss.rs                :250-311 (pack/unpack, det_pack, multiplication)
+//   groth16/src/ext_wit.rs                   :287-538 (libsnark_h / circom_h against the plain pipelines), examples/dpp_test.rs
 // plus what a compiled host must get right at the boundary: Err(min_len) on a length mismatch, and concurrent calls
 // from OS threads (mpc-net/src/multi.rs:320-325 polls one task per party).
 // Expected values: the reference's own assertions (plain fft / plain msm through the same library) AND the CPU oracle
@@ -199,6 +200,51 @@ static void test_crs_det_pack(Rng& rng, const char* name) {                // gr
     EXPECT(ok, name);
 }
 
+// groth16/src/ext_wit.rs:287-409 libsnark_dummy_ext_witness / :411-538 circom_dummy_ext_witness: a = b = (0..m), c = a*b;
+// expected h from the plain pipelines libsnark_ref / circom_ref (:204-285) run through the library's own fft / powers
+static void test_ext_witness(Rng& rng, size_t m) {
+    const uint32_t l = 2;
+    auto pp = PackedSharingParams::new_(l);
+    auto dom = Radix2EvaluationDomain::new_(m);
+    LocalTestNet net{pp.n, {}};
+    const size_t mbyl = m / l;
+    std::vector<Fr> a(m), c(m);
+    for (size_t i = 0; i < m; ++i) { a[i] = Fr::from_u64(i); c[i] = a[i] * a[i]; }
+    // QAP::pss (groth16/src/qap.rs:92-134)
+    Shares pa = qap_pss_pack(a, pp, rng.frs(mbyl * pp.t)), pb = qap_pss_pack(a, pp, rng.frs(mbyl * pp.t)), pc = qap_pss_pack(c, pp, rng.frs(mbyl * pp.t));
+    std::vector<PackedQAPShare> qap;
+    for (uint32_t p = 0; p < pp.n; ++p) qap.push_back(PackedQAPShare{pa[p], pb[p], pc[p]});
+    auto draws = [&] { std::vector<std::vector<Fr>> r; for (int i = 0; i < 7; ++i) r.push_back(rng.frs(mbyl * pp.t)); return r; };
+    {   // circom
+        const Fr root = Radix2EvaluationDomain::new_(2 * m).element(1);
+        std::vector<std::vector<FftMask>> fm;
+        for (int i = 0; i < 3; ++i) fm.push_back(sample_fft_mask(rng, true, root, dom.group_gen_inv(), m, pp));
+        for (int i = 0; i < 3; ++i) fm.push_back(sample_fft_mask(rng, false, Fr::one(), dom.group_gen(), m, pp));
+        auto dm = DegRedMask::sample(pp, mbyl, rng.frs(mbyl * l), rng.frs(mbyl * pp.t), rng.frs(mbyl * pp.t));
+        auto h = circom_h(qap, fm, dm, dom, pp, net, draws());
+        auto coset_eval = [&](std::vector<Fr> v) { dom.ifft_in_place(v); distribute_powers(v, root); dom.fft_in_place(v); return v; };   // circom_ref :239-285
+        auto ae = coset_eval(a), ce = coset_eval(c);
+        std::vector<Fr> exp(m);
+        for (size_t i = 0; i < m; ++i) exp[i] = ae[i] * ae[i] - ce[i];
+        EXPECT(unpack_all(pp, h, true) == exp, "circom_h == circom_ref (ext_wit.rs:411-538)");
+    }
+    {   // libsnark
+        const Fr g = Fr::generator(), ginv = g.inverse();
+        std::vector<std::vector<FftMask>> fm;
+        for (int i = 0; i < 3; ++i) fm.push_back(sample_fft_mask(rng, true, g, dom.group_gen_inv(), m, pp));
+        for (int i = 0; i < 3; ++i) fm.push_back(sample_fft_mask(rng, true, Fr::one(), dom.group_gen(), m, pp));
+        fm.push_back(sample_fft_mask(rng, false, ginv, dom.group_gen_inv(), m, pp));
+        auto h = libsnark_h(qap, fm, dom, pp, net, draws());
+        auto coset5 = [&](std::vector<Fr> v) { dom.ifft_in_place(v); dom.fft_in_place(v, &g); return v; };                            // libsnark_ref :204-237
+        auto ae = coset5(a), ce = coset5(c);
+        const Fr vinv = (g.pow((uint64_t)m) - Fr::one()).inverse();
+        std::vector<Fr> exp(m);
+        for (size_t i = 0; i < m; ++i) exp[i] = (ae[i] * ae[i] - ce[i]) * vinv;
+        dom.ifft_in_place(exp, &g);
+        EXPECT(unpack_all(pp, h, true) == exp, "libsnark_h == libsnark_ref (ext_wit.rs:287-409)");
+    }
+}
+
 static void test_length_mismatch(Rng& rng) {
     std::vector<G1Affine> bases(5);
     auto s = rng.frs(5);
@@ -257,6 +303,8 @@ int main(int argc, char** argv) {
         test_ifft_then_fft(rng);
         test_deg_red(rng);
         test_d_pp(rng);
+        test_ext_witness(rng, 32);
+        test_ext_witness(rng, 1 << 10);
         test_crs_det_pack<4>(rng, "crs det_pack over G1 chunks unpacks to the CRS elements");
         test_crs_det_pack<8>(rng, "crs det_pack over G2 chunks unpacks to the CRS elements");
         test_d_msm<4>(rng, 1 << 10, {}, "d_msm G1 2^10 points, sampled masks, compressed wire == plain MSM");
