@@ -343,3 +343,18 @@ def test_pairing_bilinearity_pins_scalar_multiplication(o):
     t = [rnd.randrange(R) for _ in range(2)]
     q = ol.g2_xyz_to_point(ol.o_g2_msm(ol.g2_aff_np([beta, pyref.G2_GEN_PT]), ol.fr_np(t)))
     assert pairing.pairing(alpha, q, fuentes=True) == gt.pow(t[0]) * pairing.pairing(alpha, pyref.G2_GEN_PT, fuentes=True).pow(t[1])
+
+
+def test_pss_initialize_and_eval_interpolate():
+    """secret-sharing/src/pss.rs:239-248 test_initialize and :313-324 test_eval_interpolate (degree 32, xs = 1..64), on the
+    oracle's PackedSharingParams and lagrange_interpolate (utils.rs:78-116)."""
+    for l in (2, 4, 8):
+        pp = pyref.PackedSharingParams(l)
+        assert (pp.t, pp.l, pp.n) == (l, l, 4 * l)
+        assert (pp.share.size, pp.secret.size, pp.secret2.size) == (4 * l, 2 * l, 4 * l)
+    rng = random.Random(11)
+    degree = 32
+    p = [rng.randrange(R) for _ in range(degree)]
+    xs = list(range(1, 2 * degree + 1))
+    ys = [sum(c * pow(x, i, R) for i, c in enumerate(p)) % R for x in xs]
+    assert pyref.lagrange_interpolate(xs, ys, R, pyref.field_ops(R)) == p
