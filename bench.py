@@ -577,6 +577,27 @@ def run_ours(args):
             res[name + "_ms_per_step"] = round(ms, 3)
             res[name + "_Mpts_per_s"] = round(n / ms / 1e3, 2)
             same = same and bool((pg_out.view(dev_result.dtype) == dev_result).all())
+        # opt-in transparent registration for the unchanged caller (ZKG_AUTO_REGISTER=1, csrc/msm_api.cu): the SAME strict call;
+        # from the third call on the bases are still shipped in full (436 MB H2D per step) but only compared on the device with
+        # the registered copy while the MSM runs against the prepared table.  Reported beside the strict figures, not as `e2e`.
+        os.environ["ZKG_AUTO_REGISTER"] = "1"
+        try:
+            for name, bptr, sptr, optr, view in (("pinned", h_bases.data_ptr(), h_scal.data_ptr(), h_out.data_ptr(), lambda: h_out.numpy()),
+                                                 ("pageable", pg_bases.ctypes.data, pg_scal.ctypes.data, pg_out.ctypes.data, lambda: pg_out)):
+                call = lambda: lib.zkg_msm_bn254_g1(local, C.c_void_p(bptr), 72, n, C.c_void_p(sptr), n, C.c_void_p(optr))
+                for _ in range(4):                       # sighting, preparation (one-time, ~0.4 s), two served calls
+                    capi.check(call())
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    capi.check(call())
+                ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+                res["auto_registered_" + name + "_ms_per_step"] = round(ms, 3)
+                res["auto_registered_" + name + "_Mpts_per_s"] = round(n / ms / 1e3, 2)
+                same = same and bool((view().view(dev_result.dtype)[:12] == dev_result).all())
+            res["auto_registered_note"] = ("ZKG_AUTO_REGISTER=1 (opt-in): same zkg_msm_bn254_g1 call and the same 436 MB H2D per step; the shipped "
+                                           "bases are verified byte for byte on the device against the registered copy, a mismatch falls back to the ordinary path")
+        finally:
+            os.environ.pop("ZKG_AUTO_REGISTER", None)
         e2e_pageable = res
         del pg_bases, pg_scal
 

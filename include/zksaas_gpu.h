@@ -70,7 +70,10 @@ int32_t zkg_shutdown(void);
 
 /* ---- MSM: replaces `G::msm(bases, scalars)` at dist-primitives/src/dmsm/mod.rs:73 ---------
  * (ark-ec 0.4.2 VariableBaseMSM::msm for ark_bn254::{G1,G2}Projective; callers
- * groth16/src/prove.rs:52,106,154,209,219).  scalars: Fr Montgomery images. */
+ * groth16/src/prove.rs:52,106,154,209,219).  scalars: Fr Montgomery images.
+ * Environment ZKG_AUTO_REGISTER=1 (opt-in): a base vector seen again behind the same pointer is registered transparently; every
+ * later call still ships the bases, which are compared byte for byte on the device with the registered copy (a mismatch falls
+ * back to the ordinary path), while the MSM runs against the prepared table -- see zkg_bases_register below. */
 int32_t zkg_msm_bn254_g1(int32_t device, const void *bases, size_t base_stride, size_t n_bases,
                          const uint64_t *scalars, size_t n_scalars, uint64_t out_xyz[12]);
 int32_t zkg_msm_bn254_g2(int32_t device, const void *bases, size_t base_stride, size_t n_bases,

@@ -478,3 +478,48 @@ def test_sharded_entry_points_with_one_device_match(z):
     assert (g_ == e).all()
     bad = (C.c_int32 * 2)(0, 0)
     assert lib.zkg_fft1_bn254_sharded(bad, 2, _p(g_), mbyl, l, _p(dom.group_gen()), None, None) == capi.ZKG_ERR_BAD_ARG
+
+
+# ------------------------------------------------------------------------------------------------
+# Opt-in transparent registration for the unchanged d_msm caller (ZKG_AUTO_REGISTER=1, msm_api.cu): the same host
+# pointer seen again is served from a prepared table, the shipped bases being compared on the device with the registered copy
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("g2", [False, True])
+def test_auto_register_serves_the_same_results_and_detects_changed_bases(z, monkeypatch, g2):
+    o = ol.oracle()
+    n = 1 << 16
+    rng = np.random.default_rng(77 + g2)
+    stride = 136 if g2 else 72
+    fixed = o.zko_g2_fixed_base if g2 else o.zko_g1_fixed_base
+    msm = z.msm_g2 if g2 else z.msm_g1
+    bases = np.zeros((n, stride), dtype=np.uint8)
+    fixed(_p(ol.rand_fr(rng, n)), n, bases.ctypes.data, stride)
+    bases[5] = 0
+    bases[5, stride - 8] = 1                                             # an identity among the bases
+    sc = [ol.rand_fr(rng, n) for _ in range(3)]
+    monkeypatch.delenv("ZKG_AUTO_REGISTER", raising=False)
+    want = [msm(bases, s) for s in sc]                                   # ordinary path
+    monkeypatch.setenv("ZKG_AUTO_REGISTER", "1")
+    # call 1: first sighting; call 2: pays the preparation; calls 3..: served from the table (different scalars each time)
+    got = [msm(bases, sc[k % 3]) for k in range(6)]
+    for k in range(6):
+        assert (got[k] == want[k % 3]).all(), k
+    # the memory behind the SAME pointer changes: one coordinate byte, one whole point, the infinity flag
+    other = np.zeros((3, stride), dtype=np.uint8)
+    fixed(_p(ol.rand_fr(rng, 3)), 3, other.ctypes.data, stride)
+    for mutate in ("byte", "point", "flag"):
+        saved = bases[n - 7].copy()
+        if mutate == "byte":
+            bases[n - 7] = other[0]
+        elif mutate == "point":
+            bases[n - 7] = other[1]
+        else:
+            bases[n - 7, stride - 8] = 1
+        monkeypatch.delenv("ZKG_AUTO_REGISTER", raising=False)
+        ref = msm(bases.copy(), sc[0])                                   # a fresh buffer: never cached
+        monkeypatch.setenv("ZKG_AUTO_REGISTER", "1")
+        for _ in range(4):                                               # detect + drop, re-sight, re-prepare, serve
+            assert (msm(bases, sc[0]) == ref).all(), mutate
+        bases[n - 7] = saved
+        for _ in range(4):
+            assert (msm(bases, sc[0]) == want[0]).all(), mutate

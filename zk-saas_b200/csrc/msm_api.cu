@@ -160,6 +160,213 @@ static int32_t msm_registered_sharded(const BaseSet& bs, const uint64_t* scalars
     return first;
 }
 
+static int32_t base_set_create_fwd(zkg_ctx* ctx, int32_t group, const void* d_packed, size_t n, uint64_t* handle);
+
+// ------------------------------------------------------------------------------------------------------------
+// Opt-in (ZKG_AUTO_REGISTER=1): transparent registration for the UNCHANGED caller.  `d_msm(bases, scalars)`
+// (dist-primitives/src/dmsm/mod.rs:59-73) hands over the same static CRS share on every proof
+// (groth16/src/proving_key.rs:15-45) but has no place to keep a handle.  With the switch on, the second call that shows the
+// same (device, pointer, stride, length) registers the bases (one-time table preparation) and keeps a packed device copy;
+// later calls still ship the bases -- every byte the caller passed crosses PCIe, on a second stream -- but only to be
+// COMPARED on the device with that copy, while the MSM itself runs against the prepared table with the caller's scalars.
+// A single differing byte sets a flag; the call then drops the entry and recomputes through the ordinary path, so the result is
+// the reference's for any input (tests/test_gpu_round2.py::test_auto_register_*).
+// ------------------------------------------------------------------------------------------------------------
+template <int WORDS16>      // 16-byte words per packed base: 4 (G1) or 8 (G2)
+__global__ void k_verify_bases(const uint8_t* __restrict__ ark, size_t stride, size_t n, const uint4* __restrict__ packed, int* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = ark + i * stride;
+    const bool inf = p[WORDS16 * 16] != 0;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < WORDS16; ++k) {
+        uint4 want = packed[i * WORDS16 + k];
+        uint4 got = make_uint4(0, 0, 0, 0);
+        if (!inf) {
+            if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+                const uint2* q = reinterpret_cast<const uint2*>(p + 16 * k);
+                uint2 a = q[0], b = q[1];
+                got = make_uint4(a.x, a.y, b.x, b.y);
+            } else {
+                uint32_t w[4];
+                for (int j = 0; j < 4; ++j) {
+                    const uint8_t* b = p + 16 * k + 4 * j;
+                    w[j] = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+                }
+                got = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        bad |= got.x != want.x || got.y != want.y || got.z != want.z || got.w != want.w;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
+struct AutoEntry {
+    int device = 0, group = 0;
+    const void* ptr = nullptr;
+    size_t stride = 0, n = 0;
+    int seen = 0;
+    bool busy = false;
+    uint64_t handle = 0;
+    uint8_t* d_packed = nullptr;     // packed copy of the registered bases (what the table was built from)
+    uint8_t* d_ark = nullptr;        // landing area of the bases shipped by each call + the flag
+    cudaStream_t vstream = nullptr;
+    int* h_flag = nullptr;           // pinned
+};
+static std::mutex g_auto_mu;
+static std::vector<AutoEntry*> g_auto;
+
+static bool auto_register_enabled() {
+    const char* e = getenv("ZKG_AUTO_REGISTER");
+    return e && e[0] == '1';
+}
+static void auto_entry_free(AutoEntry* e) {          // caller holds no lock; the entry is already unlinked
+    DeviceGuard dg(e->device);
+    if (e->handle) zkg_bases_release(e->handle);
+    if (e->d_packed) cudaFree(e->d_packed);
+    if (e->d_ark) cudaFree(e->d_ark);
+    if (e->vstream) cudaStreamDestroy(e->vstream);
+    if (e->h_flag) cudaFreeHost(e->h_flag);
+    delete e;
+}
+// Registers the bases of `e` (table + packed copy + landing area).  Called without the lock, with e->busy set.
+static int32_t auto_entry_prepare(AutoEntry* e, const void* bases) {
+    DeviceGuard dg(e->device);
+    const size_t pk = e->n * packed_bytes(e->group), ark = align_up(e->n * e->stride, 256);
+    PooledCtx pc;
+    ZKG_TRY(pc.acquire(e->device));
+    zkg_ctx* ctx = pc.ctx;
+    ZKG_TRY(ctx->io.reserve(ark + pk + 256));
+    uint8_t* d_ark = (uint8_t*)ctx->io.p;
+    uint8_t* d_pk = d_ark + ark;
+    ZKG_TRY(copy_h2d(d_ark, bases, e->n * e->stride, ctx->stream));
+    ZKG_TRY(e->group == 1 ? pack_bases_g1(ctx, d_ark, e->stride, e->n, d_pk) : pack_bases_g2(ctx, d_ark, e->stride, e->n, d_pk));
+    ZKG_CUDA(cudaMalloc(&e->d_packed, pk));
+    ZKG_CUDA(cudaMemcpyAsync(e->d_packed, d_pk, pk, cudaMemcpyDeviceToDevice, ctx->stream));
+    ZKG_TRY(base_set_create_fwd(ctx, e->group, d_pk, e->n, &e->handle));
+    ZKG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZKG_CUDA(cudaMalloc(&e->d_ark, ark + 256));
+    int prio_lo = 0, prio_hi = 0;                        // the comparison kernel takes the first slot an accumulation block frees
+    ZKG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    ZKG_CUDA(cudaStreamCreateWithPriority(&e->vstream, cudaStreamNonBlocking, prio_hi));
+    ZKG_CUDA(cudaHostAlloc((void**)&e->h_flag, sizeof(int), cudaHostAllocPortable));
+    return ZKG_OK;
+}
+void auto_register_clear() {                         // zkg_shutdown: drop every transparent registration that is not in use
+    std::vector<AutoEntry*> gone;
+    {
+        std::lock_guard<std::mutex> lk(g_auto_mu);
+        for (size_t i = 0; i < g_auto.size();) {
+            if (g_auto[i]->busy) { ++i; continue; }
+            gone.push_back(g_auto[i]);
+            g_auto.erase(g_auto.begin() + i);
+        }
+    }
+    for (AutoEntry* e : gone) auto_entry_free(e);
+}
+// Returns ZKG_OK with *handled = true when the call was served from a verified registration; *handled = false means
+// "run the ordinary path" (first sightings, a busy entry, a failed verification, any set-up error).
+static int32_t msm_host_auto(int group, int device, const void* bases, size_t stride, size_t n, const uint64_t* scalars, uint64_t* out_xyz,
+                             bool* handled) {
+    *handled = false;
+    AutoEntry* e = nullptr;
+    bool prepare = false;
+    {
+        std::lock_guard<std::mutex> lk(g_auto_mu);
+        for (AutoEntry* x : g_auto)
+            if (x->device == device && x->group == group && x->ptr == bases && x->stride == stride && x->n == n) e = x;
+        if (!e) {
+            if (g_auto.size() >= 16) return ZKG_OK;                       // a handful of CRS shares per prover; never grow without bound
+            e = new AutoEntry();
+            e->device = device; e->group = group; e->ptr = bases; e->stride = stride; e->n = n; e->seen = 1;
+            g_auto.push_back(e);
+            return ZKG_OK;
+        }
+        if (e->busy) return ZKG_OK;
+        if (!e->handle) {
+            e->seen += 1;
+            if (e->seen < 2) return ZKG_OK;
+            prepare = true;
+        }
+        e->busy = true;
+    }
+    auto unbusy = [&] { std::lock_guard<std::mutex> lk(g_auto_mu); e->busy = false; };
+    auto drop = [&] {
+        { std::lock_guard<std::mutex> lk(g_auto_mu); for (size_t i = 0; i < g_auto.size(); ++i) if (g_auto[i] == e) { g_auto.erase(g_auto.begin() + i); break; } }
+        auto_entry_free(e);
+    };
+    if (prepare) {
+        // this call pays the one-time preparation and then runs the ordinary path; the next one is served from the table
+        if (auto_entry_prepare(e, bases) != ZKG_OK) { drop(); return ZKG_OK; }
+        unbusy();
+        return ZKG_OK;
+    }
+    int32_t rc = ZKG_OK;
+    bool mismatch = false;
+    {
+        DeviceGuard dg(device);
+        // (1) the MSM against the prepared table, with the caller's scalars (enqueued first: with pageable scalars the
+        //     staging of this thread is then interleaved with the accumulations, not with the verification copies)
+        BaseRef ref;
+        rc = ref.acquire(e->handle);
+        PooledCtx pc;
+        if (rc == ZKG_OK) rc = pc.acquire(device);
+        zkg_ctx* ctx = pc.ctx;
+        void* d_out = nullptr;
+        if (rc == ZKG_OK) {
+            const size_t sc_bytes = align_up(n * 32, 256);
+            rc = ctx->io.reserve(sc_bytes + 512);
+            d_out = (uint8_t*)ctx->io.p + sc_bytes;
+        }
+        const char* dbg0 = getenv("ZKG_AUTO_DEBUG_SKIP");
+        if (rc == ZKG_OK && !(dbg0 && dbg0[0] == '2'))
+            rc = group == 1 ? msm_run_prepared_host_g1(ctx, ref.bs->d_table, ref.bs->c, scalars, n, d_out, 0)
+                            : msm_run_prepared_host_g2(ctx, ref.bs->d_table, ref.bs->c, scalars, n, d_out, 0);
+        // (2) the bases the caller passed: shipped in full on the entry's own stream and compared with the registered copy
+        const char* dbg = getenv("ZKG_AUTO_DEBUG_SKIP");      // measurement aid only: 1 = skip the verification copies, 2 = skip the MSM
+        if (rc == ZKG_OK && !(dbg && dbg[0] == '1')) {
+            const size_t ark = align_up(n * stride, 256);
+            int* d_flag = (int*)(e->d_ark + ark);
+            cudaError_t ce = cudaMemsetAsync(d_flag, 0, sizeof(int), e->vstream);
+            // every copy first, ONE comparison kernel after them: a kernel queued between two copies would wait for a free
+            // slot under the resident accumulation blocks and hold back the copies behind it (measured: 12.9 ms instead of 9.7)
+            const int K = 8;
+            for (int j = 0; j < K && rc == ZKG_OK; ++j) {
+                const size_t lo = n * (size_t)j / K, hi = n * (size_t)(j + 1) / K;
+                if (lo < hi) rc = copy_h2d(e->d_ark + lo * stride, (const uint8_t*)bases + lo * stride, (hi - lo) * stride, e->vstream);
+            }
+            if (ce == cudaSuccess && rc == ZKG_OK) {
+                const unsigned blocks = (unsigned)((n + 255) / 256);
+                if (group == 1) k_verify_bases<4><<<blocks, 256, 0, e->vstream>>>(e->d_ark, stride, n, (const uint4*)e->d_packed, d_flag);
+                else k_verify_bases<8><<<blocks, 256, 0, e->vstream>>>(e->d_ark, stride, n, (const uint4*)e->d_packed, d_flag);
+                ce = cudaGetLastError();
+            }
+            if (ce == cudaSuccess && rc == ZKG_OK) ce = cudaMemcpyAsync(e->h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->vstream);
+            // the result comes back only now: a copy into PAGEABLE caller memory blocks this thread until the MSM has finished,
+            // which must not hold back the verification copies above
+            if (ce == cudaSuccess && rc == ZKG_OK && !(dbg0 && dbg0[0] == '2')) rc = copy_d2h(out_xyz, d_out, group == 1 ? 96 : 192, ctx->stream);
+            if (ce == cudaSuccess && rc == ZKG_OK) ce = cudaStreamSynchronize(e->vstream);
+            if (ce != cudaSuccess && rc == ZKG_OK) { set_error("auto-register verification failed: %s", cudaGetErrorString(ce)); rc = ZKG_ERR_CUDA; }
+            if (rc == ZKG_OK) mismatch = *e->h_flag != 0;
+        }
+        if (rc == ZKG_OK && dbg && dbg[0] == '1') rc = copy_d2h(out_xyz, d_out, group == 1 ? 96 : 192, ctx->stream);
+        if (ctx) {
+            cudaError_t se = cudaStreamSynchronize(ctx->stream);
+            if (rc == ZKG_OK && se != cudaSuccess) { set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(se)); rc = ZKG_ERR_CUDA; }
+        }
+    }
+    if (rc != ZKG_OK || mismatch) {
+        // the memory behind the pointer changed (or something failed): forget the entry and let the ordinary path answer
+        cudaGetLastError();
+        drop();
+        return ZKG_OK;
+    }
+    unbusy();
+    *handled = true;
+    return ZKG_OK;
+}
+
 }  // namespace zkg
 
 using namespace zkg;
@@ -168,10 +375,20 @@ extern "C" {
 
 int32_t zkg_msm_bn254_g1(int32_t device, const void* bases, size_t base_stride, size_t n_bases, const uint64_t* scalars,
                          size_t n_scalars, uint64_t out_xyz[12]) {
+    if (n_bases == n_scalars && n_bases >= ((size_t)1 << 16) && bases && scalars && out_xyz && auto_register_enabled()) {
+        bool handled = false;
+        msm_host_auto(1, device, bases, base_stride, n_bases, scalars, out_xyz, &handled);
+        if (handled) return ZKG_OK;
+    }
     return msm_host_g1(device, bases, base_stride, n_bases, scalars, n_scalars, out_xyz);
 }
 int32_t zkg_msm_bn254_g2(int32_t device, const void* bases, size_t base_stride, size_t n_bases, const uint64_t* scalars,
                          size_t n_scalars, uint64_t out_xyz[24]) {
+    if (n_bases == n_scalars && n_bases >= ((size_t)1 << 16) && bases && scalars && out_xyz && auto_register_enabled()) {
+        bool handled = false;
+        msm_host_auto(2, device, bases, base_stride, n_bases, scalars, out_xyz, &handled);
+        if (handled) return ZKG_OK;
+    }
     return msm_host_g2(device, bases, base_stride, n_bases, scalars, n_scalars, out_xyz);
 }
 
@@ -258,6 +475,14 @@ static int32_t base_set_create(zkg_ctx* ctx, int32_t group, const void* d_packed
     *handle = ((uint64_t)bs->generation << 32) | (uint64_t)(slot + 1);
     return ZKG_OK;
 }
+
+}  // extern "C"
+namespace zkg {
+static int32_t base_set_create_fwd(zkg_ctx* ctx, int32_t group, const void* d_packed, size_t n, uint64_t* handle) {
+    return base_set_create(ctx, group, d_packed, n, handle);
+}
+}  // namespace zkg
+extern "C" {
 
 int32_t zkg_crs_det_pack_bn254(int32_t device, int32_t group, const void* bases, size_t base_stride, size_t n, uint32_t l,
                                void* const* out_by_party, size_t out_stride) {
