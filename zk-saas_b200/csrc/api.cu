@@ -248,7 +248,6 @@ int32_t zkg_ctx_phase_ms(zkg_ctx* ctx, int32_t phase, float* ms) {
     return ZKG_OK;
 }
 
-namespace zkg { void auto_register_clear(); }
 int32_t zkg_shutdown(void) {
     zkg::auto_register_clear();             // tables kept by ZKG_AUTO_REGISTER (msm_api.cu)
     std::vector<zkg_ctx*> all;

@@ -90,6 +90,7 @@ struct PooledCtx {
     ~PooledCtx();
 };
 
+void auto_register_clear();             // msm_api.cu: drops the transparent registrations of ZKG_AUTO_REGISTER (zkg_shutdown)
 int32_t ctx_copy_stream(zkg_ctx* ctx, int n_events);
 int32_t ctx_aux_stream(zkg_ctx* ctx);
 // host <-> device copies that take pageable host memory at PCIe speed (staging.cu); stream semantics of
