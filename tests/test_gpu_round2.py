@@ -523,3 +523,36 @@ def test_auto_register_serves_the_same_results_and_detects_changed_bases(z, monk
         bases[n - 7] = saved
         for _ in range(4):
             assert (msm(bases, sc[0]) == want[0]).all(), mutate
+
+
+def test_auto_register_budget_and_many_pointers(z, monkeypatch):
+    """The transparent registrations are bounded: a byte budget (ZKG_AUTO_REGISTER_MAX_MB; least recently used sets are dropped,
+    a set that cannot fit is never registered) and a bounded list of sighted pointers.  Results stay the ordinary path's."""
+    o = ol.oracle()
+    n = 1 << 16
+    rng = np.random.default_rng(99)
+    sets = []
+    for _ in range(3):
+        b = np.zeros((n, 72), dtype=np.uint8)
+        o.zko_g1_fixed_base(_p(ol.rand_fr(rng, n)), n, b.ctypes.data, 72)
+        sets.append(b)
+    sc = ol.rand_fr(rng, n)
+    monkeypatch.delenv("ZKG_AUTO_REGISTER", raising=False)
+    want = [z.msm_g1(b, sc) for b in sets]
+    monkeypatch.setenv("ZKG_AUTO_REGISTER", "1")
+    monkeypatch.setenv("ZKG_AUTO_REGISTER_MAX_MB", "1")                  # nothing fits: every call takes the ordinary path
+    for _ in range(3):
+        for b, w in zip(sets, want):
+            assert (z.msm_g1(b, sc) == w).all()
+    # room for ONE set of 2^16 points (table 13 x 4 MiB + copies): the three sets keep evicting each other
+    monkeypatch.setenv("ZKG_AUTO_REGISTER_MAX_MB", "80")
+    for _ in range(4):
+        for b, w in zip(sets, want):
+            assert (z.msm_g1(b, sc) == w).all()
+    # more distinct pointers than the sighting list holds
+    monkeypatch.setenv("ZKG_AUTO_REGISTER_MAX_MB", "32768")
+    many = [sets[0][: n - 64 * k].copy() for k in range(1, 20)]
+    for b in many:
+        got = z.msm_g1(b, sc[: b.shape[0]])
+    monkeypatch.delenv("ZKG_AUTO_REGISTER", raising=False)
+    assert (got == z.msm_g1(many[-1].copy(), sc[: many[-1].shape[0]])).all()

@@ -209,6 +209,8 @@ struct AutoEntry {
     int seen = 0;
     bool busy = false;
     uint64_t handle = 0;
+    size_t bytes = 0;                // device memory held (table + packed copy + landing area)
+    uint64_t last_use = 0;
     uint8_t* d_packed = nullptr;     // packed copy of the registered bases (what the table was built from)
     uint8_t* d_ark = nullptr;        // landing area of the bases shipped by each call + the flag
     cudaStream_t vstream = nullptr;
@@ -216,6 +218,12 @@ struct AutoEntry {
 };
 static std::mutex g_auto_mu;
 static std::vector<AutoEntry*> g_auto;
+static uint64_t g_auto_clock = 0;
+static size_t auto_budget_bytes() {                  // ZKG_AUTO_REGISTER_MAX_MB (default 32 GiB of the 180 GB): least recently used sets go first
+    const char* e = getenv("ZKG_AUTO_REGISTER_MAX_MB");
+    long mb = e ? atol(e) : 32768;
+    return (size_t)(mb < 0 ? 0 : mb) << 20;
+}
 
 static bool auto_register_enabled() {
     const char* e = getenv("ZKG_AUTO_REGISTER");
@@ -271,26 +279,61 @@ static int32_t msm_host_auto(int group, int device, const void* bases, size_t st
                              bool* handled) {
     *handled = false;
     AutoEntry* e = nullptr;
-    bool prepare = false;
+    bool prepare = false, give_up = false;
+    std::vector<AutoEntry*> evicted;
     {
         std::lock_guard<std::mutex> lk(g_auto_mu);
         for (AutoEntry* x : g_auto)
             if (x->device == device && x->group == group && x->ptr == bases && x->stride == stride && x->n == n) e = x;
         if (!e) {
-            if (g_auto.size() >= 16) return ZKG_OK;                       // a handful of CRS shares per prover; never grow without bound
+            if (g_auto.size() >= 16) {
+                // a handful of CRS shares per prover: never grow without bound; the oldest pointer that was seen only once goes
+                size_t victim = g_auto.size();
+                for (size_t i = 0; i < g_auto.size(); ++i)
+                    if (!g_auto[i]->handle && !g_auto[i]->busy && (victim == g_auto.size() || g_auto[i]->last_use < g_auto[victim]->last_use)) victim = i;
+                if (victim == g_auto.size()) return ZKG_OK;
+                delete g_auto[victim];
+                g_auto.erase(g_auto.begin() + victim);
+            }
             e = new AutoEntry();
             e->device = device; e->group = group; e->ptr = bases; e->stride = stride; e->n = n; e->seen = 1;
+            e->last_use = ++g_auto_clock;
             g_auto.push_back(e);
             return ZKG_OK;
         }
         if (e->busy) return ZKG_OK;
         if (!e->handle) {
             e->seen += 1;
+            e->last_use = ++g_auto_clock;
             if (e->seen < 2) return ZKG_OK;
-            prepare = true;
+            // device memory the registration will hold; make room by dropping the least recently used idle sets, or give up
+            int c = msm_pick_c_merged_host(n);
+            while (c < 23 && n * (size_t)(254 / c + 1) >= ((size_t)1 << 31)) ++c;
+            e->bytes = n * (size_t)(254 / c + 1) * packed_bytes(group) + n * packed_bytes(group) + align_up(n * stride, 256) + 256;
+            const size_t budget = auto_budget_bytes();
+            if (e->bytes > budget) return ZKG_OK;
+            for (;;) {
+                size_t held = 0;
+                AutoEntry* lru = nullptr;
+                for (AutoEntry* x : g_auto) {
+                    if (!x->handle) continue;
+                    held += x->bytes;
+                    if (!x->busy && (!lru || x->last_use < lru->last_use)) lru = x;
+                }
+                if (held + e->bytes <= budget) break;
+                if (!lru) { give_up = true; break; }                      // everything that could go is in use
+                for (size_t i = 0; i < g_auto.size(); ++i) if (g_auto[i] == lru) { g_auto.erase(g_auto.begin() + i); break; }
+                evicted.push_back(lru);
+            }
+            prepare = !give_up;
         }
-        e->busy = true;
+        if (!give_up) {
+            e->busy = true;
+            e->last_use = ++g_auto_clock;
+        }
     }
+    for (AutoEntry* x : evicted) auto_entry_free(x);
+    if (give_up) return ZKG_OK;
     auto unbusy = [&] { std::lock_guard<std::mutex> lk(g_auto_mu); e->busy = false; };
     auto drop = [&] {
         { std::lock_guard<std::mutex> lk(g_auto_mu); for (size_t i = 0; i < g_auto.size(); ++i) if (g_auto[i] == e) { g_auto.erase(g_auto.begin() + i); break; } }
