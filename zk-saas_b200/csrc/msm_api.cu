@@ -341,7 +341,11 @@ static int32_t msm_host_auto(int group, int device, const void* bases, size_t st
     };
     if (prepare) {
         // this call pays the one-time preparation and then runs the ordinary path; the next one is served from the table
-        if (auto_entry_prepare(e, bases) != ZKG_OK) { drop(); return ZKG_OK; }
+        if (auto_entry_prepare(e, bases) != ZKG_OK) {
+            cudaGetLastError();                              // e.g. out of memory: not this call's error -- the ordinary path answers
+            drop();
+            return ZKG_OK;
+        }
         unbusy();
         return ZKG_OK;
     }
