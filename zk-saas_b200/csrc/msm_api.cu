@@ -366,13 +366,11 @@ static int32_t msm_host_auto(int group, int device, const void* bases, size_t st
             rc = ctx->io.reserve(sc_bytes + 512);
             d_out = (uint8_t*)ctx->io.p + sc_bytes;
         }
-        const char* dbg0 = getenv("ZKG_AUTO_DEBUG_SKIP");
-        if (rc == ZKG_OK && !(dbg0 && dbg0[0] == '2'))
+        if (rc == ZKG_OK)
             rc = group == 1 ? msm_run_prepared_host_g1(ctx, ref.bs->d_table, ref.bs->c, scalars, n, d_out, 0)
                             : msm_run_prepared_host_g2(ctx, ref.bs->d_table, ref.bs->c, scalars, n, d_out, 0);
         // (2) the bases the caller passed: shipped in full on the entry's own stream and compared with the registered copy
-        const char* dbg = getenv("ZKG_AUTO_DEBUG_SKIP");      // measurement aid only: 1 = skip the verification copies, 2 = skip the MSM
-        if (rc == ZKG_OK && !(dbg && dbg[0] == '1')) {
+        if (rc == ZKG_OK) {
             const size_t ark = align_up(n * stride, 256);
             int* d_flag = (int*)(e->d_ark + ark);
             cudaError_t ce = cudaMemsetAsync(d_flag, 0, sizeof(int), e->vstream);
@@ -392,12 +390,11 @@ static int32_t msm_host_auto(int group, int device, const void* bases, size_t st
             if (ce == cudaSuccess && rc == ZKG_OK) ce = cudaMemcpyAsync(e->h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->vstream);
             // the result comes back only now: a copy into PAGEABLE caller memory blocks this thread until the MSM has finished,
             // which must not hold back the verification copies above
-            if (ce == cudaSuccess && rc == ZKG_OK && !(dbg0 && dbg0[0] == '2')) rc = copy_d2h(out_xyz, d_out, group == 1 ? 96 : 192, ctx->stream);
+            if (ce == cudaSuccess && rc == ZKG_OK) rc = copy_d2h(out_xyz, d_out, group == 1 ? 96 : 192, ctx->stream);
             if (ce == cudaSuccess && rc == ZKG_OK) ce = cudaStreamSynchronize(e->vstream);
             if (ce != cudaSuccess && rc == ZKG_OK) { set_error("auto-register verification failed: %s", cudaGetErrorString(ce)); rc = ZKG_ERR_CUDA; }
             if (rc == ZKG_OK) mismatch = *e->h_flag != 0;
         }
-        if (rc == ZKG_OK && dbg && dbg[0] == '1') rc = copy_d2h(out_xyz, d_out, group == 1 ? 96 : 192, ctx->stream);
         if (ctx) {
             cudaError_t se = cudaStreamSynchronize(ctx->stream);
             if (rc == ZKG_OK && se != cudaSuccess) { set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(se)); rc = ZKG_ERR_CUDA; }
