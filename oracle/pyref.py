@@ -408,6 +408,31 @@ def d_fft_round(pcoeff_shares, in_masks, out_masks, rearrange, m, pp, rand, inve
     return [[(x + mk) % p for x, mk in zip(out[party], out_masks[party])] for party in range(pp.n)]  # :313-317
 
 
+def fft_mask_sample(rearrange, g, gen, m, pp: PackedSharingParams, mask_values, rand_in, rand_out, p=R_MOD):
+    """FftMask::sample, dist-primitives/src/dfft/mod.rs:30-85, with the draws passed in: mask_values (m), rand_in[i] /
+    rand_out[i] = the t packing draws of column i.  Returns (in_mask_shares, out_mask_shares), party-major."""
+    mbyl = m // pp.l
+    in_shares = transpose(pack_vec(list(mask_values), pp, rand_in))                  # :41-42
+    s = fft2_in_place(list(mask_values), pp, gen, p)                                 # :44
+    if g % p != 1:
+        s = distribute_powers(s, g, p)                                               # :46-48
+    s = [(-v) % p for v in s]                                                        # :51
+    if rearrange:                                                                    # :55-72
+        s = fft_in_place_rearrange(s)
+        out_shares = transpose([pp.pack(s[i::mbyl][: pp.l], rand_out[i]) for i in range(mbyl)])
+    else:
+        out_shares = transpose(pack_vec(s, pp, rand_out))                            # :74
+    return in_shares, out_shares
+
+
+def deg_red_mask_sample(pp: PackedSharingParams, num, mask_values, rand_in, rand_out, p=R_MOD):
+    """DegRedMask::sample over F with gen = 1, dist-primitives/src/utils/deg_red.rs:40-66: in = pack(values), out = pack(-values)."""
+    assert len(mask_values) == num * pp.l
+    in_shares = transpose(pack_vec(list(mask_values), pp, rand_in))
+    out_shares = transpose(pack_vec([(-v) % p for v in mask_values], pp, rand_out))
+    return in_shares, out_shares
+
+
 def deg_red_king(shares_by_party, parties, pp, rand):
     """King closure of deg_red, dist-primitives/src/utils/deg_red.rs:103-111."""
     cols = transpose(shares_by_party)

@@ -3,7 +3,8 @@
 oracle's MSM and group packing -- with the clear-text Groth16 model of tests/groth16_ref.py and the pairing that is
 pinned to the reference's vk_alphabeta_12.  It ties the oracle's PROTOCOL-level functions (not only its field and curve
 arithmetic) to the property the reference itself tests, and it is the CPU twin of tests/test_gpu_groth16.py.
-Masks are zero here (they are additive and cancel; FftMask / DegRedMask / MsmMask sampling has its own tests)."""
+The FFT, degree-reduction and MSM masks are SAMPLED as the reference samples them (dfft/mod.rs:30-85, deg_red.rs:40-66,
+dmsm/mod.rs:21-48), so the test also checks that they cancel."""
 import random
 
 import numpy as np
@@ -79,14 +80,30 @@ def test_oracle_distributed_groth16_proof_verifies(l):
         (o.zko_pss_unpack2_g2 if g2 else o.zko_pss_unpack2_g1)(l, _p(np.concatenate(shares)), _p(u))
         return [u[i * words:(i + 1) * words].copy() for i in range(l)]
 
-    def d_msm(bases_by_party, scalars_by_party, g2=False):              # dmsm/mod.rs:59-102, zero masks
+    def msm_mask_sample(g2=False):                                      # MsmMask::sample, dmsm/mod.rs:21-48
+        words = 24 if g2 else 12
+        gen = gr.aff_to_xyz(gr.fixed_base([1], g2)[0], g2)
+        rand_pts = lambda: np.concatenate([gr.aff_to_xyz(a, g2) for a in gr.fixed_base([rnd.randrange(1, R) for _ in range(t)], g2)])
+        values = [gmul(gen, rnd.randrange(R), g2) for _ in range(l)]                        # :27-31 gen * x_i
+        total = values[0]
+        for v in values[1:]:
+            total = gadd(total, v, g2)
+        out_value = gmul(total, R - 1, g2)                                                  # :38 -(sum of the mask values)
+        pack = o.zko_pss_pack_g2 if g2 else o.zko_pss_pack_g1
+        ins, outs = np.zeros(n * words, dtype=np.uint64), np.zeros(n * words, dtype=np.uint64)
+        pack(l, _p(np.concatenate(values)), _p(rand_pts()), _p(ins))                        # :34 pack(mask values)
+        pack(l, _p(np.concatenate([out_value] * l)), _p(rand_pts()), _p(outs))              # :40-41 pack([out; l])
+        return [(ins[p * words:(p + 1) * words].copy(), outs[p * words:(p + 1) * words].copy()) for p in range(n)]
+
+    def d_msm(bases_by_party, scalars_by_party, g2=False):              # dmsm/mod.rs:59-102 with sampled masks
         msm = ol.o_g2_msm if g2 else ol.o_g1_msm
-        c = [msm(bases_by_party[p], ol.fr_np(scalars_by_party[p])) for p in range(n)]     # :73
+        masks = msm_mask_sample(g2)
+        c = [gadd(msm(bases_by_party[p], ol.fr_np(scalars_by_party[p])), masks[p][0], g2) for p in range(n)]   # :73-74
         res = unpack2(c, g2)                                                                # :85
         out = res[0]
         for x in res[1:]:
             out = gadd(out, x, g2)                                                          # :86
-        return [out.copy() for _ in range(n)]                                               # :87
+        return [gadd(out, masks[p][1], g2) for p in range(n)]                               # :87, :98
 
     # dealer
     qa, qb, qc = (qap_pss_pack(v) for v in gr.qap_witness(cs, w))
@@ -95,12 +112,18 @@ def test_oracle_distributed_groth16_proof_verifies(l):
                                                     ("v", pk.b_g2_query[1:], True))}
     a_sh, ax_sh = pack_from_witness(w[1:]), pack_from_witness(w[cs.num_instance:])
     # circom_h (groth16/src/ext_wit.rs:104-181)
-    zero = [[0] * mbyl for _ in range(n)]
+    dom = pyref.Radix2Domain(m)
     root = pyref.Radix2Domain(2 * m).element(1)
-    coeff = [pyref.d_fft_round(q, zero, zero, True, m, pp, rand_cols(), inverse=True, g=root) for q in (qa, qb, qc)]
-    ev = [pyref.d_fft_round(cf, zero, zero, False, m, pp, rand_cols()) for cf in coeff]
+    fmask = lambda rearr, g_, gen_: pyref.fft_mask_sample(rearr, g_, gen_, m, pp, [rnd.randrange(R) for _ in range(m)], rand_cols(), rand_cols())
+    im = [fmask(True, root, dom.group_gen_inv) for _ in range(3)]                                   # sha256.rs:218-267
+    fm = [fmask(False, 1, dom.group_gen) for _ in range(3)]
+    coeff = [pyref.d_fft_round(q, im[k][0], im[k][1], True, m, pp, rand_cols(), inverse=True, g=root) for k, q in enumerate((qa, qb, qc))]
+    ev = [pyref.d_fft_round(cf, fm[k][0], fm[k][1], False, m, pp, rand_cols()) for k, cf in enumerate(coeff)]
     h_eval = [[(x * y - v) % R for x, y, v in zip(ev[0][p], ev[1][p], ev[2][p])] for p in range(n)]
-    h_sh = pyref.deg_red_king(h_eval, parties, pp, rand_cols())
+    dm_in, dm_out = pyref.deg_red_mask_sample(pp, mbyl, [rnd.randrange(R) for _ in range(mbyl * l)], rand_cols(), rand_cols())
+    masked = [[(x + k) % R for x, k in zip(h_eval[p], dm_in[p])] for p in range(n)]                 # deg_red.rs:94-97
+    h_sh = pyref.deg_red_king(masked, parties, pp, rand_cols())
+    h_sh = [[(x + k) % R for x, k in zip(h_sh[p], dm_out[p])] for p in range(n)]                    # :120-124
     # the shares of h unpack to circom_ref's h (ext_wit.rs:532-537)
     got_h = sum((pp.unpack(col) for col in pyref.transpose(h_sh)), [])
     assert got_h == gr.circom_h(*gr.qap_witness(cs, w))
