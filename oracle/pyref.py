@@ -389,10 +389,11 @@ def king_fft2(shares_by_party, parties, pp: PackedSharingParams, gen, g, rearran
     return transpose(pack_vec(s1, pp, rand))                     # :302
 
 
-def d_fft_round(pcoeff_shares, in_masks, out_masks, rearrange, m, pp, rand, inverse=False, g=1, p=R_MOD):
+def d_fft_round(pcoeff_shares, in_masks, out_masks, rearrange, m, pp, rand, inverse=False, g=1, p=R_MOD, parties=None):
     """In-process n-party emulation of d_fft (dfft/mod.rs:99-134) / d_ifft (:137-175).
 
     pcoeff_shares[party] = that party's share vector (length m/l); in_masks/out_masks likewise.
+    parties: the parties whose message reaches the king (default all; a lossy round, mpc-net/src/multi.rs:330-363, drops some).
     """
     dom = Radix2Domain(m, 1, p)
     gen = dom.group_gen_inv if inverse else dom.group_gen
@@ -404,7 +405,8 @@ def d_fft_round(pcoeff_shares, in_masks, out_masks, rearrange, m, pp, rand, inve
         v = fft1_in_place(v, pp, gen, p)                         # :121 / :162
         v = [(x + mk) % p for x, mk in zip(v, in_masks[party])]  # :254-258
         sent.append(v)
-    out = king_fft2(sent, list(range(pp.n)), pp, gen, g, rearrange, rand, p)
+    parties = list(range(pp.n)) if parties is None else list(parties)
+    out = king_fft2([sent[q] for q in parties], parties, pp, gen, g, rearrange, rand, p)
     return [[(x + mk) % p for x, mk in zip(out[party], out_masks[party])] for party in range(pp.n)]  # :313-317
 
 

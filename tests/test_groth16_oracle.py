@@ -28,8 +28,8 @@ def test_clear_text_groth16_model_verifies():
     assert not gr.verify(vk, w[1:2], (A, pyref.G2.add(B, B), C))
 
 
-@pytest.mark.parametrize("l", [2, 4])
-def test_oracle_distributed_groth16_proof_verifies(l):
+@pytest.mark.parametrize("l,dropouts", [(2, ()), (4, ()), (2, (7,))])
+def test_oracle_distributed_groth16_proof_verifies(l, dropouts):
     o = ol.oracle()
     rnd = random.Random(20260)
     cs, w = gr.synthetic_circuit(28, 2, seed=5)
@@ -41,7 +41,7 @@ def test_oracle_distributed_groth16_proof_verifies(l):
     m = pk.domain_size
     mbyl = m // l
     rand_cols = lambda cols=mbyl: [[rnd.randrange(R) for _ in range(t)] for _ in range(cols)]
-    parties = list(range(n))
+    parties = [q for q in range(n) if q not in dropouts]      # whose messages reach the king (lossy round: multi.rs:330-363)
 
     def qap_pss_pack(x):                                                # groth16/src/qap.rs:99-112
         x = pyref.fft_in_place_rearrange(x)
@@ -74,8 +74,13 @@ def test_oracle_distributed_groth16_proof_verifies(l):
         (o.zko_g2_mul if g2 else o.zko_g1_mul)(_p(np.ascontiguousarray(a)), _p(ol.fr_np([k % R])), _p(out))
         return out
 
-    def unpack2(shares, g2=False):                                      # pss.rs:141-166 over group elements
+    def unpack2(shares, g2=False, who=None):                            # pss.rs:141-166 / :210-221 over group elements
         words = 24 if g2 else 12
+        if who is not None and len(who) < n:                            # unpack_missing_shares -> lagrange_unpack (:170-207)
+            curve = pyref.G2 if g2 else pyref.G1
+            to_pt, to_img = (ol.g2_xyz_to_point, ol.g2_point_to_xyz) if g2 else (ol.g1_xyz_to_point, ol.g1_point_to_xyz)
+            pts = pp.unpack_missing_shares([to_pt(x) for x in shares], list(who), pyref.group_ops(curve))
+            return [to_img(q) for q in pts]
         u = np.zeros(l * words, dtype=np.uint64)
         (o.zko_pss_unpack2_g2 if g2 else o.zko_pss_unpack2_g1)(l, _p(np.concatenate(shares)), _p(u))
         return [u[i * words:(i + 1) * words].copy() for i in range(l)]
@@ -99,7 +104,7 @@ def test_oracle_distributed_groth16_proof_verifies(l):
         msm = ol.o_g2_msm if g2 else ol.o_g1_msm
         masks = msm_mask_sample(g2)
         c = [gadd(msm(bases_by_party[p], ol.fr_np(scalars_by_party[p])), masks[p][0], g2) for p in range(n)]   # :73-74
-        res = unpack2(c, g2)                                                                # :85
+        res = unpack2([c[q] for q in parties], g2, parties)                                 # :85
         out = res[0]
         for x in res[1:]:
             out = gadd(out, x, g2)                                                          # :86
@@ -117,12 +122,12 @@ def test_oracle_distributed_groth16_proof_verifies(l):
     fmask = lambda rearr, g_, gen_: pyref.fft_mask_sample(rearr, g_, gen_, m, pp, [rnd.randrange(R) for _ in range(m)], rand_cols(), rand_cols())
     im = [fmask(True, root, dom.group_gen_inv) for _ in range(3)]                                   # sha256.rs:218-267
     fm = [fmask(False, 1, dom.group_gen) for _ in range(3)]
-    coeff = [pyref.d_fft_round(q, im[k][0], im[k][1], True, m, pp, rand_cols(), inverse=True, g=root) for k, q in enumerate((qa, qb, qc))]
-    ev = [pyref.d_fft_round(cf, fm[k][0], fm[k][1], False, m, pp, rand_cols()) for k, cf in enumerate(coeff)]
+    coeff = [pyref.d_fft_round(q, im[k][0], im[k][1], True, m, pp, rand_cols(), inverse=True, g=root, parties=parties) for k, q in enumerate((qa, qb, qc))]
+    ev = [pyref.d_fft_round(cf, fm[k][0], fm[k][1], False, m, pp, rand_cols(), parties=parties) for k, cf in enumerate(coeff)]
     h_eval = [[(x * y - v) % R for x, y, v in zip(ev[0][p], ev[1][p], ev[2][p])] for p in range(n)]
     dm_in, dm_out = pyref.deg_red_mask_sample(pp, mbyl, [rnd.randrange(R) for _ in range(mbyl * l)], rand_cols(), rand_cols())
     masked = [[(x + k) % R for x, k in zip(h_eval[p], dm_in[p])] for p in range(n)]                 # deg_red.rs:94-97
-    h_sh = pyref.deg_red_king(masked, parties, pp, rand_cols())
+    h_sh = pyref.deg_red_king([masked[q] for q in parties], parties, pp, rand_cols())
     h_sh = [[(x + k) % R for x, k in zip(h_sh[p], dm_out[p])] for p in range(n)]                    # :120-124
     # the shares of h unpack to circom_ref's h (ext_wit.rs:532-537)
     got_h = sum((pp.unpack(col) for col in pyref.transpose(h_sh)), [])
